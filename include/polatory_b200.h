@@ -1,0 +1,148 @@
+/*
+ * polatory_b200 -- C ABI of the B200-native RBF fast-multipole evaluator.
+ *
+ * This is the drop-in boundary for Polatory's src/fmm evaluator interface
+ * (SURVEY.md section 8b).  One handle replaces one instance of
+ *
+ *   polatory::fmm::FmmGenericEvaluatorBase<Dim>          include/polatory/fmm/fmm_evaluator.hpp:17-41
+ *   polatory::fmm::FmmGenericSymmetricEvaluatorBase<Dim>  include/polatory/fmm/fmm_symmetric_evaluator.hpp:16-37
+ *
+ * as returned by the six factories
+ *
+ *   make_fmm_evaluator / make_fmm_gradient_evaluator / make_fmm_gradient_transpose_evaluator /
+ *   make_fmm_hessian_evaluator                            include/polatory/fmm/fmm_evaluator.hpp:92-106
+ *   make_fmm_symmetric_evaluator / make_fmm_hessian_symmetric_evaluator
+ *                                                         include/polatory/fmm/fmm_symmetric_evaluator.hpp:80-86
+ *
+ * Conventions (same as the reference, SURVEY.md 8b "Data conventions"):
+ *   - points:  contiguous row-major N x dim doubles in ORIGINAL coordinates; the
+ *              evaluator applies the anisotropy (src/fmm/fmm_evaluator.hpp:120-157);
+ *   - weights: km doubles per source point, point-major (km*idx + i);
+ *   - result:  kn doubles per target point, point-major, in caller order;
+ *   - km/kn:   K 1/1, F dim/1, FT 1/dim, H dim/dim
+ *              (include/polatory/fmm/kernel.hpp:29-30, gradient_kernel.hpp:28-29,
+ *               gradient_transpose_kernel.hpp:29-30, hessian_kernel.hpp:28-29).
+ *   - every pointer argument may be a host pointer OR a device pointer of the
+ *     handle's device (CUDA unified addressing decides); data are copied in, nothing is
+ *     borrowed after the call returns.  Work is issued on the handle's stream
+ *     (default: the legacy default stream); calls taking host output pointers
+ *     synchronise that stream before returning.
+ *   - no exceptions cross this boundary: every call returns a status code and
+ *     plt_last_error() gives the message a C++ shim rethrows as std::runtime_error.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     PLT_ERR_CUDA.
+ */
+#ifndef POLATORY_B200_H_
+#define POLATORY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plt_eval plt_eval;
+
+/* Status codes. */
+enum {
+  PLT_OK = 0,
+  PLT_ERR_INVALID = 1,   /* bad argument (unknown RBF, bad dim, size mismatch, ...)        */
+  PLT_ERR_CUDA = 2,      /* CUDA runtime failure (incl. "no device")                        */
+  PLT_ERR_ACCURACY = 3,  /* "failed to construct an evaluator that meets the desired
+                            accuracy"  src/fmm/fmm_accuracy_estimator.hpp:120               */
+  PLT_ERR_UNSUPPORTED = 4 /* e.g. Hessian of cov_spherical / cov_cubic
+                            include/polatory/rbf/cov_spherical.hpp:53-55                    */
+};
+
+/* Kernel kinds = the four kernel functors of include/polatory/fmm/. */
+enum { PLT_KIND_K = 0, PLT_KIND_F = 1, PLT_KIND_FT = 2, PLT_KIND_H = 3 };
+
+/* RBF ids = the 16 runtime RBFs of include/polatory/rbf/make_rbf.hpp:30-45. */
+enum {
+  PLT_RBF_BH3 = 0, PLT_RBF_TH3 = 1, PLT_RBF_BH2 = 2, PLT_RBF_TH2 = 3,
+  PLT_RBF_EXP = 4, PLT_RBF_GAU = 5,
+  PLT_RBF_GC3 = 6, PLT_RBF_GC5 = 7, PLT_RBF_GC7 = 8, PLT_RBF_GC9 = 9,
+  PLT_RBF_SP3 = 10, PLT_RBF_SP5 = 11, PLT_RBF_SP7 = 12, PLT_RBF_SP9 = 13,
+  PLT_RBF_SPH = 14, PLT_RBF_CUB = 15
+};
+
+/* Spheroidal split (include/polatory/rbf/cov_spheroidal3.hpp:113-123): the full RBF is
+ * evaluated as direct part (compact) + fast part (FMM), src/fmm/spheroidal_evaluator.hpp:24-29.
+ * PLT_PART_FULL on a spheroidal id performs that split internally. */
+enum { PLT_PART_FULL = 0, PLT_PART_DIRECT = 1, PLT_PART_FAST = 2 };
+
+/* Interpolator configuration, src/fmm/interpolator_configuration.hpp:9-19. */
+typedef struct plt_config {
+  int tree_height; /* 0 => brute-force branch (src/fmm/fmm_evaluator.hpp:226-234) */
+  int order;
+  int d;           /* -1 = classic polynomial; 0..order-1 = Floater-Hormann degree */
+} plt_config;
+
+/* Replaces the six factories: ctor(rbf, bbox) of FmmGenericEvaluator<Kernel> /
+ * FmmGenericSymmetricEvaluator<Kernel> (src/fmm/fmm_evaluator.hpp:71-76,
+ * src/fmm/fmm_symmetric_evaluator.hpp:59-64).  params: the RBF's parameters()
+ * (n_params 0..2; polyharmonics default to {1, 0}, polyharmonic_odd.hpp:87-99);
+ * aniso: dim*dim row-major anisotropy matrix (NULL = identity);
+ * bbox_min/max: dim doubles each, must contain all sources and targets. */
+int plt_eval_create(int kind, int symmetric, int dim, int rbf_id, int rbf_part,
+                    const double* params, int n_params, const double* aniso,
+                    const double* bbox_min, const double* bbox_max, plt_eval** out);
+
+void plt_eval_destroy(plt_eval* h);
+
+/* FmmGenericEvaluatorBase::set_source_points / set_target_points
+ * (include/polatory/fmm/fmm_evaluator.hpp:36-38).  Invalid on a symmetric handle. */
+int plt_eval_set_source_points(plt_eval* h, const double* points, int64_t n);
+int plt_eval_set_target_points(plt_eval* h, const double* points, int64_t n);
+
+/* FmmGenericSymmetricEvaluatorBase::set_points (fmm_symmetric_evaluator.hpp:33). */
+int plt_eval_set_points(plt_eval* h, const double* points, int64_t n);
+
+/* set_weights (fmm_evaluator.hpp:40): len must be km * n_sources. */
+int plt_eval_set_weights(plt_eval* h, const double* weights, int64_t len);
+
+/* set_accuracy (fmm_evaluator.hpp:34): +inf => order 6 polynomial, 0 => order 12 / d 8,
+ * finite => search order 8,10,...,20 (src/fmm/fmm_accuracy_estimator.hpp:74-121). */
+int plt_eval_set_accuracy(plt_eval* h, double accuracy);
+
+/* evaluate (fmm_evaluator.hpp:32): writes kn * n_targets doubles. */
+int plt_eval_evaluate(plt_eval* h, double* out, int64_t len);
+
+/* Additions with no reference counterpart. */
+
+/* Bypass the accuracy search with a fixed (order, d); order 0 restores the search.
+ * tree_height is always derived from the point counts (src/fmm/utility.hpp:12-16)
+ * unless tree_height_override > 0. */
+int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_override);
+
+/* The configuration used by the last evaluate() (tree_height 0 = brute force). */
+int plt_eval_get_config(plt_eval* h, plt_config* out);
+
+/* Issue all work of this handle on the given cudaStream_t (NULL = legacy default). */
+int plt_eval_set_stream(plt_eval* h, void* cuda_stream);
+
+/* Restrict evaluate() to the targets [begin, end) of the Morton-sorted target order
+ * (multi-GPU sharding by Morton range); outputs of other targets are
+ * written as 0 so that a sum over ranks reassembles the full result.
+ * begin = 0, end = -1 restores the full range. */
+int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size);
+
+/* Per-phase device time of the last evaluate() in milliseconds (CUDA events on the
+ * handle's stream).  names/ms: arrays of capacity cap; returns the number of phases. */
+int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap);
+
+/* Number of kernels launched by this handle since creation. */
+int64_t plt_eval_launch_count(plt_eval* h);
+
+/* Message of the last failure on this handle (h == NULL: last plt_eval_create failure
+ * on the calling thread).  Never NULL. */
+const char* plt_last_error(plt_eval* h);
+
+/* Library/ABI version and a device probe (returns PLT_ERR_CUDA without a usable GPU). */
+int plt_version(void);
+int plt_device_check(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLATORY_B200_H_ */

@@ -1,0 +1,119 @@
+// Brute-force O(N*M) near-field kernel: the reference's full_direct
+// (src/fmm/full_direct.hpp:7-52), used for small problems
+// (src/fmm/fmm_evaluator.hpp:226-234, fmm_symmetric_evaluator.hpp:222-230) and as the exact
+// side of the accuracy search (src/fmm/fmm_accuracy_estimator.hpp:107).
+//
+// Mapping: one thread owns kTPT targets (registers), a CTA streams source tiles through
+// shared memory (broadcast reads), the source range is split across blockIdx.y so that
+// few-target/many-source shapes (the 10k x N accuracy search) still fill 148 SMs; partial
+// sums are reduced in a fixed order (deterministic).
+#include "direct.cuh"
+#include "dispatch.cuh"
+
+namespace plt {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kTPT = 2;
+constexpr int kTile = 128;
+
+template <int FAM, int KIND, int DIM>
+__global__ void __launch_bounds__(kThreads) k_direct(DirectArgs a) {
+  constexpr int KM = KindTraits<KIND, DIM>::km;
+  constexpr int KN = KindTraits<KIND, DIM>::kn;
+  __shared__ double s_pos[DIM][kTile];
+  __shared__ double s_w[KM][kTile];
+  const int tid = threadIdx.x;
+  const int64_t t_base = static_cast<int64_t>(blockIdx.x) * (kThreads * kTPT);
+  double tp[kTPT][DIM];
+  int64_t ti[kTPT];
+  double v[kTPT][KN];
+#pragma unroll
+  for (int u = 0; u < kTPT; ++u) {
+    ti[u] = t_base + u * kThreads + tid;
+    int64_t tc = ti[u] < a.nt ? ti[u] : a.nt - 1;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) tp[u][c] = a.tpos[c * a.nt + tc];
+#pragma unroll
+    for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
+  }
+  const int64_t s0 = static_cast<int64_t>(blockIdx.y) * a.chunk;
+  const int64_t s1 = s0 + a.chunk < a.ns ? s0 + a.chunk : a.ns;
+  for (int64_t tile = s0; tile < s1; tile += kTile) {
+    const int cnt = static_cast<int>(s1 - tile < kTile ? s1 - tile : kTile);
+    __syncthreads();
+    if (tid < cnt) {
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) s_pos[c][tid] = a.spos[c * a.ns + tile + tid];
+#pragma unroll
+      for (int m = 0; m < KM; ++m) s_w[m][tid] = a.swt[m * a.ns + tile + tid];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      double sp[DIM], w[KM];
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) sp[c] = s_pos[c][j];
+#pragma unroll
+      for (int m = 0; m < KM; ++m) w[m] = s_w[m][j];
+#pragma unroll
+      for (int u = 0; u < kTPT; ++u) {
+        if (a.symmetric && tile + j == ti[u]) continue;  // full_direct.hpp:17-19
+        double d[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) d[c] = tp[u][c] - sp[c];
+        pair_accumulate<FAM, KIND, DIM>(a.k, d, w, v[u]);
+      }
+    }
+  }
+  double* dst = a.n_chunks > 1 ? a.partial + static_cast<int64_t>(blockIdx.y) * KN * a.nt : a.out;
+#pragma unroll
+  for (int u = 0; u < kTPT; ++u) {
+    if (ti[u] < a.nt) {
+#pragma unroll
+      for (int b = 0; b < KN; ++b) dst[b * a.nt + ti[u]] = v[u][b];
+    }
+  }
+}
+
+__global__ void k_reduce_chunks(const double* __restrict__ partial, int n_chunks, int64_t len,
+                                double* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < n_chunks; ++c) s += partial[c * len + i];
+  out[i] = s;
+}
+
+}  // namespace
+
+int direct_plan_chunks(int64_t ns, int64_t nt) {
+  const int64_t t_blocks = (nt + kThreads * kTPT - 1) / (kThreads * kTPT);
+  const int64_t want = 4 * kNumSM;
+  int64_t chunks = (want + t_blocks - 1) / t_blocks;
+  const int64_t max_chunks = std::max<int64_t>(1, ns / 1024);
+  chunks = std::max<int64_t>(1, std::min(chunks, max_chunks));
+  return static_cast<int>(std::min<int64_t>(chunks, 65535));
+}
+
+void launch_direct(int kind, int dim, DirectArgs a, cudaStream_t stream, LaunchCounter& ctr) {
+  if (a.nt == 0) return;
+  const int kn = (kind == KIND_FT || kind == KIND_H) ? dim : 1;
+  if (a.ns == 0) {
+    PLT_CUDA(cudaMemsetAsync(a.out, 0, sizeof(double) * kn * a.nt, stream));
+    return;
+  }
+  PLT_REQUIRE(a.n_chunks >= 1, "n_chunks");
+  a.chunk = (a.ns + a.n_chunks - 1) / a.n_chunks;
+  a.chunk = (a.chunk + kTile - 1) / kTile * kTile;
+  dim3 grid(ceil_div(a.nt, kThreads * kTPT), a.n_chunks);
+  dispatch_fkd(a.k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
+    PLT_LAUNCH(ctr, (k_direct<fam.value, knd.value, dm.value>), grid, kThreads, 0, stream, a);
+  });
+  if (a.n_chunks > 1) {
+    const int64_t len = static_cast<int64_t>(kn) * a.nt;
+    PLT_LAUNCH(ctr, k_reduce_chunks, ceil_div(len, 256), 256, 0, stream, a.partial, a.n_chunks, len, a.out);
+  }
+}
+
+}  // namespace plt

@@ -1,0 +1,27 @@
+#pragma once
+
+#include "common.cuh"
+#include "rbf.cuh"
+
+namespace plt {
+
+struct DirectArgs {
+  RbfConst k;
+  const double* spos;  // SoA [dim][ns], isotropic space
+  const double* swt;   // SoA [km][ns], anisotropy folded in
+  int64_t ns;
+  const double* tpos;  // SoA [dim][nt]
+  int64_t nt;
+  double* out;         // SoA [kn][nt] raw (pre-output-transform) sums
+  double* partial;     // [n_chunks][kn][nt] scratch when n_chunks > 1
+  int n_chunks;
+  int64_t chunk;       // filled by launch_direct
+  int symmetric;       // skip source index == target index
+};
+
+// Number of source chunks (blockIdx.y) that fills the GPU for this shape.
+int direct_plan_chunks(int64_t ns, int64_t nt);
+
+void launch_direct(int kind, int dim, DirectArgs a, cudaStream_t stream, LaunchCounter& ctr);
+
+}  // namespace plt

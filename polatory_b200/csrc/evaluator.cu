@@ -1,0 +1,909 @@
+// Host-side evaluator: the state machine behind the C ABI (include/polatory_b200.h).
+//
+// Mirrors FmmGenericEvaluator<Kernel>::Impl (src/fmm/fmm_evaluator.hpp:32-293) and
+// FmmGenericSymmetricEvaluator<Kernel>::Impl (src/fmm/fmm_symmetric_evaluator.hpp:31-275):
+// same setters, same brute-force thresholds, same tree-height rule, same accuracy ->
+// (order, d) policy; everything below that line is device-resident and new.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "direct.cuh"
+#include "fmm_ops.cuh"
+#include "interp.hpp"
+#include "rbf_host.hpp"
+#include "tree.cuh"
+
+namespace plt {
+namespace {
+
+constexpr int kClassic = -1;
+constexpr int64_t kMaxSearchTargets = 10000;  // fmm_accuracy_estimator.hpp:71
+
+__global__ void k_max_abs_diff(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                               unsigned long long* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  double d = 0.0;
+  if (i < n) {
+    d = fabs(a[i] - b[i]);
+    if (!(d == d)) d = INFINITY;  // NaN -> inf so that it never passes the accuracy test
+  }
+  for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+  if ((threadIdx.x & 31) == 0 && d > 0.0) atomicMax(out, static_cast<unsigned long long>(__double_as_longlong(d)));
+}
+
+__global__ void k_gather_soa(const double* __restrict__ src, int64_t n_src, const int* __restrict__ idx,
+                             int64_t n, int dim, double* __restrict__ dst) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int j = idx[i];
+  for (int a = 0; a < dim; ++a) dst[a * n + i] = src[a * n_src + j];
+}
+
+__global__ void k_add(const double* __restrict__ a, int64_t n, double* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] += a[i];
+}
+
+// Per-level compact-cell ranges covering the leaves [leaf_lo, leaf_hi) of a tree.
+__global__ void k_level_ranges(TreeView tr, int leaf_lo, int leaf_hi, int* __restrict__ lo, int* __restrict__ hi) {
+  int l = threadIdx.x;
+  if (l >= tr.height) return;
+  const int leaf = tr.height - 1;
+  if (leaf_hi <= leaf_lo) {
+    lo[l] = hi[l] = 0;
+    return;
+  }
+  uint32_t k0 = tr.keys[tr.cell_off[leaf] + leaf_lo] >> (tr.dim * (leaf - l));
+  uint32_t k1 = tr.keys[tr.cell_off[leaf] + leaf_hi - 1] >> (tr.dim * (leaf - l));
+  lo[l] = tr.dense[tr.dense_off[l] + k0];
+  hi[l] = tr.dense[tr.dense_off[l] + k1] + 1;
+}
+
+// First leaf whose point range starts at or after `point` (leaf-granular shard boundary).
+__global__ void k_find_leaf(const int* __restrict__ leaf_start, int n_leaf, int point, int* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_leaf) return;
+  int s = leaf_start[i];
+  int prev = i == 0 ? -1 : leaf_start[i - 1];
+  if (s >= point && prev < point) *out = i;
+}
+
+struct PhaseTimer {
+  struct Rec {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      PLT_CUDA(cudaEventCreate(&e));
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void reset() {
+    recs.clear();
+    used = 0;
+  }
+  void begin(const char* name, cudaStream_t s) {
+    Rec r{name, get(), get()};
+    PLT_CUDA(cudaEventRecord(r.e0, s));
+    recs.push_back(r);
+  }
+  void end(cudaStream_t s) { PLT_CUDA(cudaEventRecord(recs.back().e1, s)); }
+  ~PhaseTimer() {
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+struct ConfigKey {
+  int height, order, d;
+  bool operator<(const ConfigKey& o) const { return std::tie(height, order, d) < std::tie(o.height, o.order, o.d); }
+};
+
+// Device-resident interpolator for one (height, order, d): tables + per-level M2L operators.
+// Counterpart of scalfmm::interpolation::interpolator(kernel, order, tree_height, box_width, d)
+// cached like the reference's LruCache<InterpolatorConfiguration, Interpolator>(2)
+// (src/fmm/fmm_evaluator.hpp:249-252,292).
+struct Interpolator {
+  InterpTables host;
+  DevBuf<double> beta, child;
+  DevBuf<double2> tw;
+  DevBuf<double2> khat;  // [levels 2..height-1][7^dim][kn][km][F]
+  size_t khat_level_stride = 0;
+  InterpDev dev{};
+  uint64_t last_use = 0;
+};
+
+}  // namespace
+}  // namespace plt
+
+using namespace plt;
+
+struct plt_eval {
+  int kind = 0, symmetric = 0, dim = 3, km = 1, kn = 1;
+  int rbf_id = 0, rbf_part = 0;
+  RbfHost rbf;
+  std::vector<double> params;
+  double aniso[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+  Box box;
+  double accuracy = std::numeric_limits<double>::infinity();
+  int force_order = 0, force_d = kClassic, force_height = 0;
+  cudaStream_t stream = nullptr;
+  LaunchCounter ctr;
+  std::string err;
+  PhaseTimer timer;
+
+  // Spheroidal split (src/fmm/spheroidal_evaluator.hpp:17-29).
+  std::unique_ptr<plt_eval> direct_part, fast_part;
+
+  int64_t n_src = 0, n_trg = 0;
+  DevBuf<double> src_pos_c, trg_pos_c;  // caller order, transformed, SoA
+  DevBuf<double> w_caller;              // weights as given [km * n_src]
+  bool have_weights = false;
+
+  Tree src_tree, trg_tree;
+  bool multipole_dirty = true;
+  int up_order = 0, up_d = 0;  // configuration the cached multipoles were built with
+  DevBuf<double> wt_sorted;    // [km][n_src] folded, sorted
+  bool wt_dirty = true;
+  DevBuf<double> M;
+  DevBuf<double2> Mhat;
+
+  std::map<ConfigKey, std::unique_ptr<Interpolator>> interp_cache;
+  uint64_t use_clock = 0;
+  std::map<int, plt_config> best_config;  // per tree height (fmm_evaluator.hpp:187-197)
+  plt_config config{0, 0, kClassic};
+
+  int shard_rank = 0, shard_world = 1;
+
+  // -------------------------------------------------------------------------------
+  const Tree& target_tree() const { return symmetric ? src_tree : trg_tree; }
+  int64_t targets() const { return symmetric ? n_src : n_trg; }
+  const double* target_pos_c() const { return symmetric ? src_pos_c.get() : trg_pos_c.get(); }
+
+  void init(int kind_, int symmetric_, int dim_, int rbf_id_, int part_, const double* params_, int n_params,
+            const double* aniso_, const double* bmin, const double* bmax) {
+    PLT_REQUIRE(dim_ >= 1 && dim_ <= 3, "dim must be 1, 2 or 3");
+    PLT_REQUIRE(kind_ >= 0 && kind_ <= 3, "unknown kernel kind");
+    PLT_REQUIRE(bmin && bmax, "bbox is required");
+    kind = kind_;
+    symmetric = symmetric_ ? 1 : 0;
+    dim = dim_;
+    rbf_id = rbf_id_;
+    rbf_part = part_;
+    km = (kind == KIND_F || kind == KIND_H) ? dim : 1;
+    kn = (kind == KIND_FT || kind == KIND_H) ? dim : 1;
+    // Symmetric evaluators exist only for K and H (fmm_symmetric_evaluator.hpp:74-78).
+    PLT_REQUIRE(!symmetric || kind == KIND_K || kind == KIND_H, "symmetric evaluators are K or H only");
+    try {
+      rbf = make_rbf_const(rbf_id, part_, params_, n_params);
+    } catch (const std::invalid_argument& e) {
+      throw Error(PLT_ERR_INVALID, e.what());
+    }
+    if (kind == KIND_H && !rbf.has_hessian)
+      throw Error(PLT_ERR_UNSUPPORTED, "evaluate_hessian_isotropic is not implemented for this RBF");
+    params.assign(params_, params_ + n_params);
+    for (int i = 0; i < dim * dim; ++i) aniso[i] = aniso_ ? aniso_[i] : (i / dim == i % dim ? 1.0 : 0.0);
+    // rbf_base.hpp:73-75
+    double det = dim == 1 ? aniso[0]
+                 : dim == 2 ? aniso[0] * aniso[3] - aniso[1] * aniso[2]
+                            : aniso[0] * (aniso[4] * aniso[8] - aniso[5] * aniso[7]) -
+                                  aniso[1] * (aniso[3] * aniso[8] - aniso[5] * aniso[6]) +
+                                  aniso[2] * (aniso[3] * aniso[7] - aniso[4] * aniso[6]);
+    PLT_REQUIRE(det > 0.0, "aniso must have a positive determinant");
+    for (int a = 0; a < dim; ++a) {
+      bbox_min[a] = bmin[a];
+      bbox_max[a] = bmax[a];
+    }
+    make_box();
+    int ndev = 0;
+    PLT_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) throw Error(PLT_ERR_CUDA, "no CUDA device");
+    if (rbf.spheroidal && part_ == PLT_PART_FULL) {
+      direct_part = std::make_unique<plt_eval>();
+      direct_part->init(kind, symmetric, dim, rbf_id, PLT_PART_DIRECT, params_, n_params, aniso_, bmin, bmax);
+      fast_part = std::make_unique<plt_eval>();
+      fast_part->init(kind, symmetric, dim, rbf_id, PLT_PART_FAST, params_, n_params, aniso_, bmin, bmax);
+    }
+  }
+
+  // src/fmm/utility.hpp:18-33: bbox.transform(aniso) = bbox of the transformed corners.
+  void make_box() {
+    double lo[3], hi[3];
+    for (int a = 0; a < dim; ++a) {
+      lo[a] = std::numeric_limits<double>::infinity();
+      hi[a] = -lo[a];
+    }
+    for (int c = 0; c < (1 << dim); ++c) {
+      double p[3];
+      for (int b = 0; b < dim; ++b) p[b] = ((c >> b) & 1) ? bbox_max[b] : bbox_min[b];
+      for (int a = 0; a < dim; ++a) {
+        double s = 0.0;
+        for (int b = 0; b < dim; ++b) s += p[b] * aniso[a * dim + b];
+        lo[a] = std::min(lo[a], s);
+        hi[a] = std::max(hi[a], s);
+      }
+    }
+    double width = 0.0;
+    for (int a = 0; a < dim; ++a) width = std::max(width, hi[a] - lo[a]);
+    width *= 1.01;
+    if (width == 0.0) width = 1.0;
+    box.width = width;
+    for (int a = 0; a < dim; ++a) box.center[a] = lo[a] + 0.5 * (hi[a] - lo[a]);
+  }
+
+  // Copy caller data (host or device pointer) in; host sources are fully consumed on return.
+  void copy_in(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    cudaPointerAttributes attr{};
+    bool dev = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+               (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    PLT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream));
+    if (!dev) PLT_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // -------------------------------------------------------------------------------
+  void set_points_impl(const double* pts, int64_t n, bool source) {
+    PLT_REQUIRE(n >= 0 && (n == 0 || pts), "points");
+    PLT_REQUIRE(n < (int64_t{1} << 31), "too many points");
+    if (direct_part) {
+      direct_part->set_points_impl(pts, n, source);
+      fast_part->set_points_impl(pts, n, source);
+    }
+    DevBuf<double> staged;
+    staged.alloc(static_cast<size_t>(n) * dim, stream);
+    copy_in(staged.get(), pts, sizeof(double) * n * dim);
+    DevBuf<double>& pos = source ? src_pos_c : trg_pos_c;
+    pos.alloc(static_cast<size_t>(n) * dim, stream);
+    launch_transform_points(dim, aniso, staged.get(), n, pos.get(), stream, ctr);
+    if (source) {
+      n_src = n;
+      src_tree.reset();
+      best_config.clear();   // fmm_evaluator.hpp:136-138
+      multipole_dirty = true;
+      wt_dirty = true;
+      have_weights = false;
+    } else {
+      n_trg = n;
+      trg_tree.reset();      // fmm_evaluator.hpp:155-156
+    }
+  }
+
+  void set_weights(const double* w, int64_t len) {
+    PLT_REQUIRE(len == km * n_src, "weights.rows() must be km * n_src_points");
+    if (direct_part) {
+      direct_part->set_weights(w, len);
+      fast_part->set_weights(w, len);
+    }
+    w_caller.alloc(len, stream);
+    copy_in(w_caller.get(), w, sizeof(double) * len);
+    have_weights = true;
+    wt_dirty = true;
+    multipole_dirty = true;  // fmm_evaluator.hpp:181
+  }
+
+  void set_accuracy(double a) {
+    accuracy = a;
+    best_config.clear();  // fmm_evaluator.hpp:114-118
+    if (direct_part) {
+      direct_part->set_accuracy(a);
+      fast_part->set_accuracy(a);
+    }
+  }
+
+  // -------------------------------------------------------------------------------
+  Interpolator& interpolator(int height, int order, int d) {
+    ConfigKey key{height, order, d};
+    auto it = interp_cache.find(key);
+    if (it == interp_cache.end()) {
+      // LRU(2), src/fmm/lru_cache.hpp.
+      while (interp_cache.size() >= 2) {
+        auto victim = interp_cache.begin();
+        for (auto j = interp_cache.begin(); j != interp_cache.end(); ++j)
+          if (j->second->last_use < victim->second->last_use) victim = j;
+        interp_cache.erase(victim);
+      }
+      auto ip = std::make_unique<Interpolator>();
+      PLT_REQUIRE(order >= 2 && order <= kMaxOrder, "interpolation order out of range");
+      ip->host = make_interp_tables(order, d);
+      const auto& h = ip->host;
+      ip->beta.alloc(h.beta.size(), stream);
+      ip->child.alloc(h.child.size(), stream);
+      ip->tw.alloc(h.nf, stream);
+      PLT_CUDA(cudaMemcpyAsync(ip->beta.get(), h.beta.data(), sizeof(double) * h.beta.size(), cudaMemcpyHostToDevice, stream));
+      PLT_CUDA(cudaMemcpyAsync(ip->child.get(), h.child.data(), sizeof(double) * h.child.size(), cudaMemcpyHostToDevice, stream));
+      PLT_CUDA(cudaMemcpyAsync(ip->tw.get(), h.tw.data(), sizeof(double2) * h.nf, cudaMemcpyHostToDevice, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));  // host tables are about to go out of scope of the copy
+      ip->dev = InterpDev{order, h.nf, ip->beta.get(), ip->child.get(), ip->tw.get()};
+      const size_t F = freqs_per_cell(order, dim);
+      ip->khat_level_stride = static_cast<size_t>(ipow(7, dim)) * kn * km * F;
+      const int n_levels = std::max(0, height - 2);
+      ip->khat.alloc(ip->khat_level_stride * n_levels, stream);
+      ip->khat.zero(stream);
+      for (int l = 2; l < height; ++l)
+        launch_tabulate_m2l(kind, dim, rbf.k, box, l, ip->dev, ip->khat.get() + ip->khat_level_stride * (l - 2),
+                            stream, ctr);
+      it = interp_cache.emplace(key, std::move(ip)).first;
+    }
+    it->second->last_use = ++use_clock;
+    return *it->second;
+  }
+
+  void ensure_sorted_weights() {
+    if (!wt_dirty) return;
+    PLT_REQUIRE(have_weights, "set_weights must be called before evaluate");
+    wt_sorted.alloc(static_cast<size_t>(km) * n_src, stream);
+    launch_prepare_weights(kind, dim, aniso, w_caller.get(), src_tree.perm(), n_src, wt_sorted.get(), stream, ctr);
+    wt_dirty = false;
+  }
+
+  // P2M + M2M + multipole DFT (the reference's `fmm(src_tree, op, p2m | m2m)`,
+  // src/fmm/fmm_evaluator.hpp:83-88).
+  void upward(const Tree& st, const double* wt, Interpolator& ip, DevBuf<double>& M_, DevBuf<double2>& Mhat_,
+              bool timed) {
+    const int order = ip.host.order;
+    const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
+    TreeView sv = st.view();
+    M_.alloc(static_cast<size_t>(st.total_cells()) * km * P, stream);
+    if (timed) timer.begin("p2m", stream);
+    launch_p2m(dim, km, sv, box, ip.dev, wt, M_.get(), stream, ctr);
+    if (timed) timer.end(stream);
+    if (timed) timer.begin("m2m", stream);
+    for (int l = st.height() - 2; l >= 2; --l) launch_m2m(dim, km, sv, l, ip.dev, M_.get(), stream, ctr);
+    if (timed) timer.end(stream);
+    size_t far_cells = 0;
+    for (int l = 2; l < st.height(); ++l) far_cells += st.n_cells(l);
+    Mhat_.alloc(far_cells * km * F, stream);
+    if (timed) timer.begin("m2hat", stream);
+    launch_m2hat(dim, km, sv, ip.dev, M_.get(), Mhat_.get(), stream, ctr);
+    if (timed) timer.end(stream);
+  }
+
+  // M2L + L2L + L2P + P2P for the target leaves [leaf_lo, leaf_hi) -> vt (SoA [kn][n_trg], sorted).
+  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const Tree& tt,
+                Interpolator& ip, double* vt, int leaf_lo, int leaf_hi, bool timed) {
+    const int order = ip.host.order;
+    const int height = tt.height();
+    const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
+    TreeView sv = st.view(), tv = tt.view();
+    if (leaf_hi <= leaf_lo) return;
+
+    // per-level compact ranges of the ancestors of the shard's leaves
+    std::vector<int> lo(height, 0), hi(height, 0);
+    if (leaf_lo == 0 && leaf_hi == tt.n_cells(height - 1)) {
+      for (int l = 0; l < height; ++l) hi[l] = tt.n_cells(l);
+    } else {
+      DevBuf<int> d_lo, d_hi;
+      d_lo.alloc(height, stream);
+      d_hi.alloc(height, stream);
+      PLT_LAUNCH(ctr, k_level_ranges, 1, 32, 0, stream, tv, leaf_lo, leaf_hi, d_lo.get(), d_hi.get());
+      PLT_CUDA(cudaMemcpyAsync(lo.data(), d_lo.get(), sizeof(int) * height, cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaMemcpyAsync(hi.data(), d_hi.get(), sizeof(int) * height, cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    DevBuf<double> L;
+    if (height > 2) {
+      L.alloc(static_cast<size_t>(tt.total_cells()) * kn * P, stream);
+      L.zero(stream);
+      DevBuf<int> flags, active, d_count;
+      DevBuf<unsigned char> cub_tmp;
+      DevBuf<double2> Lhat;
+      d_count.alloc(1, stream);
+      const size_t per_parent = static_cast<size_t>(1 << dim) * kn * F;
+      const size_t budget = (size_t{2} << 30) / sizeof(double2);
+      const int chunk_parents = static_cast<int>(std::max<size_t>(1, budget / per_parent));
+      for (int l = 2; l < height; ++l) {
+        const int np = hi[l - 1] - lo[l - 1];
+        if (np <= 0) continue;
+        if (timed) timer.begin("m2l_list", stream);
+        flags.alloc(tt.n_cells(l - 1), stream);
+        active.alloc(tt.n_cells(l - 1), stream);
+        launch_m2l_mark_active(dim, sv, tv, l, flags.get(), stream, ctr);
+        size_t tmp_bytes = 0;
+        cub::CountingInputIterator<int> iota(lo[l - 1]);
+        PLT_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.get() + lo[l - 1], active.get(),
+                                            d_count.get(), np, stream));
+        cub_tmp.alloc(tmp_bytes, stream);
+        PLT_CUDA(cub::DeviceSelect::Flagged(cub_tmp.get(), tmp_bytes, iota, flags.get() + lo[l - 1], active.get(),
+                                            d_count.get(), np, stream));
+        ctr.n += 1;
+        int n_active = 0;
+        PLT_CUDA(cudaMemcpyAsync(&n_active, d_count.get(), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaStreamSynchronize(stream));
+        if (timed) timer.end(stream);
+        if (timed) timer.begin("m2l", stream);
+        for (int c0 = 0; c0 < n_active; c0 += chunk_parents) {
+          const int nc = std::min(chunk_parents, n_active - c0);
+          Lhat.alloc(static_cast<size_t>(nc) * per_parent, stream);
+          M2LArgs a{};
+          a.src = sv;
+          a.trg = tv;
+          a.level = l;
+          a.order = order;
+          a.dim = dim;
+          a.km = km;
+          a.kn = kn;
+          a.Mhat = Mhat_.get();
+          a.Khat = ip.khat.get() + ip.khat_level_stride * (l - 2);
+          a.active = active.get() + c0;
+          a.n_active = nc;
+          a.Lhat = Lhat.get();
+          a.L = L.get();
+          launch_m2l_hadamard(a, stream, ctr);
+          launch_m2l_idft(a, ip.dev, stream, ctr);
+        }
+        if (timed) timer.end(stream);
+        if (l > 2) {
+          if (timed) timer.begin("l2l", stream);
+          launch_l2l(dim, kn, tv, l, ip.dev, L.get(), lo[l], hi[l], stream, ctr);
+          if (timed) timer.end(stream);
+        }
+      }
+      if (timed) timer.begin("l2p", stream);
+      launch_l2p(dim, kn, tv, box, ip.dev, L.get(), vt, leaf_lo, leaf_hi, stream, ctr);
+      if (timed) timer.end(stream);
+    }
+    if (timed) timer.begin("p2p", stream);
+    launch_p2p(kind, dim, rbf.k, sv, wt, tv, vt, symmetric, height > 2 ? 1 : 0, leaf_lo, leaf_hi, stream, ctr);
+    if (timed) timer.end(stream);
+  }
+
+  // Brute force in caller order: the tree_height == 0 branch.
+  void brute_force(const double* spos, const double* w_c, int64_t ns, const double* tpos, int64_t nt,
+                   double* out_caller) {
+    DevBuf<double> wt, vt, partial;
+    wt.alloc(static_cast<size_t>(km) * ns, stream);
+    vt.alloc(static_cast<size_t>(kn) * nt, stream);
+    launch_prepare_weights(kind, dim, aniso, w_c, nullptr, ns, wt.get(), stream, ctr);
+    DirectArgs a{};
+    a.k = rbf.k;
+    a.spos = spos;
+    a.swt = wt.get();
+    a.ns = ns;
+    a.tpos = tpos;
+    a.nt = nt;
+    a.out = vt.get();
+    a.n_chunks = (ns > 0 && nt > 0) ? direct_plan_chunks(ns, nt) : 1;
+    if (a.n_chunks > 1) partial.alloc(static_cast<size_t>(a.n_chunks) * kn * nt, stream);
+    a.partial = partial.get();
+    a.symmetric = 0;
+    launch_direct(kind, dim, a, stream, ctr);
+    launch_finish_outputs(kind, dim, aniso, vt.get(), nullptr, nt, 0, nt, out_caller, stream, ctr);
+  }
+
+  // src/fmm/fmm_accuracy_estimator.hpp:74-121.
+  plt_config find_best_configuration(int height) {
+    if (force_order > 0) return {height, force_order, force_d};
+    auto it = best_config.find(height);
+    if (it != best_config.end()) return it->second;
+    plt_config c{height, 0, kClassic};
+    if (std::isinf(accuracy) && accuracy > 0) {
+      c = {height, 6, kClassic};
+    } else if (accuracy == 0.0) {
+      c = {height, 12, 8};
+    } else {
+      c = search_configuration(height);
+    }
+    best_config[height] = c;
+    return c;
+  }
+
+  plt_config search_configuration(int height) {
+    // "Errors at the data points are larger than those at randomly distributed points":
+    // sample min(n_src, 10000) source points (of the Morton-sorted container) as targets.
+    const int64_t nt = std::min<int64_t>(n_src, kMaxSearchTargets);
+    std::mt19937 gen;
+    std::vector<int> idx(n_src);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::shuffle(idx.begin(), idx.end(), gen);
+    DevBuf<int> d_idx;
+    d_idx.alloc(nt, stream);
+    PLT_CUDA(cudaMemcpyAsync(d_idx.get(), idx.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, stream));
+    DevBuf<double> tpos;
+    tpos.alloc(static_cast<size_t>(dim) * nt, stream);
+    PLT_LAUNCH(ctr, k_gather_soa, ceil_div(nt, 256), 256, 0, stream, src_tree.pos(), n_src, d_idx.get(), nt, dim,
+               tpos.get());
+    PLT_CUDA(cudaStreamSynchronize(stream));
+    ensure_sorted_weights();
+
+    // exact: brute force over the sorted sources with the folded sorted weights
+    DevBuf<double> exact_raw, approx_raw, partial;
+    exact_raw.alloc(static_cast<size_t>(kn) * nt, stream);
+    approx_raw.alloc(static_cast<size_t>(kn) * nt, stream);
+    DirectArgs a{};
+    a.k = rbf.k;
+    a.spos = src_tree.pos();
+    a.swt = wt_sorted.get();
+    a.ns = n_src;
+    a.tpos = tpos.get();
+    a.nt = nt;
+    a.out = exact_raw.get();
+    a.n_chunks = direct_plan_chunks(n_src, nt);
+    if (a.n_chunks > 1) partial.alloc(static_cast<size_t>(a.n_chunks) * kn * nt, stream);
+    a.partial = partial.get();
+    launch_direct(kind, dim, a, stream, ctr);
+    DevBuf<double> exact, approx;
+    exact.alloc(static_cast<size_t>(kn) * nt, stream);
+    approx.alloc(static_cast<size_t>(kn) * nt, stream);
+    launch_finish_outputs(kind, dim, aniso, exact_raw.get(), nullptr, nt, 0, nt, exact.get(), stream, ctr);
+
+    Tree sample_tree;
+    sample_tree.build(dim, height, box, tpos.get(), nt, stream, ctr);
+    DevBuf<unsigned long long> d_err;
+    d_err.alloc(1, stream);
+    DevBuf<double> M_;
+    DevBuf<double2> Mhat_;
+    for (int order = 8; order <= 20; order += 2) {
+      const int min_d = order >= 12 ? 7 : kClassic;
+      const int max_d = order >= 12 ? 9 : kClassic;
+      for (int d = min_d; d <= max_d; ++d) {
+        Interpolator& ip = interpolator(height, order, d);
+        upward(src_tree, wt_sorted.get(), ip, M_, Mhat_, false);
+        downward(src_tree, wt_sorted.get(), Mhat_, sample_tree, ip, approx_raw.get(), 0,
+                 sample_tree.n_cells(height - 1), false);
+        launch_finish_outputs(kind, dim, aniso, approx_raw.get(), sample_tree.perm(), nt, 0, nt, approx.get(),
+                              stream, ctr);
+        d_err.zero(stream);
+        PLT_LAUNCH(ctr, k_max_abs_diff, ceil_div(kn * nt, 256), 256, 0, stream, approx.get(), exact.get(), kn * nt,
+                   d_err.get());
+        unsigned long long bits = 0;
+        PLT_CUDA(cudaMemcpyAsync(&bits, d_err.get(), sizeof(bits), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaStreamSynchronize(stream));
+        double err_abs;
+        std::memcpy(&err_abs, &bits, sizeof(double));
+        if (err_abs <= accuracy) return {height, order, d};
+      }
+    }
+    throw Error(PLT_ERR_ACCURACY, "failed to construct an evaluator that meets the desired accuracy");
+  }
+
+  // Compact-support kernels (cov_spherical, cov_cubic, spheroidal direct parts): the reference
+  // uses a kd-tree radius search (src/fmm/direct_evaluator.hpp:41-68); here a uniform cell list
+  // with cell width >= support radius, i.e. the P2P kernel alone on a tree of suitable height.
+  int compact_height() const {
+    const double r = rbf.support_radius;
+    int level = 0;
+    while (level < 10 && box.width / static_cast<double>(1 << (level + 1)) >= r) ++level;
+    const int cap = fmm_tree_height(dim, std::max<int64_t>(std::max(n_src, targets()), 2)) + 1;
+    return std::max(2, std::min(level + 1, cap));
+  }
+
+  void evaluate(double* out, int64_t len) {
+    const int64_t nt = targets();
+    PLT_REQUIRE(len == kn * nt, "output length must be kn * n_trg_points");
+    PLT_REQUIRE(have_weights || n_src == 0, "set_weights must be called before evaluate");
+    timer.reset();
+    DevBuf<double> out_dev;
+    cudaPointerAttributes attr{};
+    bool out_is_device = false;
+    if (out && cudaPointerGetAttributes(&attr, out) == cudaSuccess)
+      out_is_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    cudaGetLastError();
+    double* dst = out;
+    if (!out_is_device) {
+      out_dev.alloc(len, stream);
+      dst = out_dev.get();
+    }
+    evaluate_device(dst);
+    if (!out_is_device) {
+      if (len) PLT_CUDA(cudaMemcpyAsync(out, dst, sizeof(double) * len, cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+    }
+  }
+
+  void shard_leaves(const Tree& tt, int& leaf_lo, int& leaf_hi) {
+    const int n_leaf = tt.n_cells(tt.height() - 1);
+    leaf_lo = 0;
+    leaf_hi = n_leaf;
+    if (shard_world <= 1) return;
+    TreeView tv = tt.view();
+    DevBuf<int> d;
+    d.alloc(2, stream);
+    int bounds[2] = {0, n_leaf};
+    PLT_CUDA(cudaMemcpyAsync(d.get(), bounds, sizeof(bounds), cudaMemcpyHostToDevice, stream));
+    const int64_t n = tt.n();
+    const int p0 = static_cast<int>(n * shard_rank / shard_world);
+    const int p1 = static_cast<int>(n * (shard_rank + 1) / shard_world);
+    if (shard_rank > 0)
+      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p0, d.get());
+    if (shard_rank + 1 < shard_world)
+      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p1, d.get() + 1);
+    PLT_CUDA(cudaMemcpyAsync(bounds, d.get(), sizeof(bounds), cudaMemcpyDeviceToHost, stream));
+    PLT_CUDA(cudaStreamSynchronize(stream));
+    leaf_lo = bounds[0];
+    leaf_hi = bounds[1];
+  }
+
+  void evaluate_device(double* out) {
+    const int64_t nt = targets();
+    const int64_t len = kn * nt;
+    if (direct_part) {
+      // src/fmm/spheroidal_evaluator.hpp:24-29
+      direct_part->stream = fast_part->stream = stream;
+      direct_part->shard_rank = fast_part->shard_rank = shard_rank;
+      direct_part->shard_world = fast_part->shard_world = shard_world;
+      direct_part->timer.reset();
+      fast_part->timer.reset();
+      DevBuf<double> tmp;
+      tmp.alloc(len, stream);
+      direct_part->evaluate_device(out);
+      fast_part->evaluate_device(tmp.get());
+      if (len) PLT_LAUNCH(ctr, k_add, ceil_div(len, 256), 256, 0, stream, tmp.get(), len, out);
+      config = fast_part->config;
+      return;
+    }
+    if (nt == 0) return;
+    if (n_src == 0) {
+      PLT_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * len, stream));
+      config = {0, 0, kClassic};
+      return;
+    }
+
+    const bool compact = std::isfinite(rbf.support_radius);
+    // src/fmm/fmm_evaluator.hpp:226-234 / fmm_symmetric_evaluator.hpp:222-230
+    const bool small = symmetric ? n_src < 1024 : n_src * nt < int64_t{1024} * 1024;
+    if ((small && !compact && force_height == 0) || (compact && compact_height() <= 2 && shard_world == 1)) {
+      if (shard_world > 1) {
+        // brute force is not sharded: rank 0 computes it, other ranks contribute zeros
+        if (shard_rank != 0) {
+          PLT_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * len, stream));
+          config = {0, 0, kClassic};
+          return;
+        }
+      }
+      timer.begin("direct", stream);
+      brute_force(src_pos_c.get(), w_caller.get(), n_src, target_pos_c(), nt, out);
+      timer.end(stream);
+      config = {0, 0, kClassic};
+      return;
+    }
+
+    int height = compact ? compact_height()
+                         : fmm_tree_height(dim, symmetric ? n_src : std::max(n_src, nt));
+    if (force_height > 0) height = force_height;
+
+    timer.begin("tree", stream);
+    if (!src_tree.built() || src_tree.height() != height) {
+      src_tree.build(dim, height, box, src_pos_c.get(), n_src, stream, ctr);
+      wt_dirty = true;
+      multipole_dirty = true;
+    }
+    if (!symmetric && (!trg_tree.built() || trg_tree.height() != height))
+      trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, stream, ctr);
+    ensure_sorted_weights();
+    timer.end(stream);
+    const Tree& tt = target_tree();
+
+    int leaf_lo, leaf_hi;
+    shard_leaves(tt, leaf_lo, leaf_hi);
+
+    DevBuf<double> vt;
+    vt.alloc(static_cast<size_t>(kn) * nt, stream);
+    vt.zero(stream);
+    if (compact) {
+      config = {height, 0, kClassic};
+      timer.begin("p2p", stream);
+      launch_p2p(kind, dim, rbf.k, src_tree.view(), wt_sorted.get(), tt.view(), vt.get(), symmetric, 0, leaf_lo,
+                 leaf_hi, stream, ctr);
+      timer.end(stream);
+    } else {
+      plt_config c = find_best_configuration(height);
+      Interpolator& ip = interpolator(height, c.order, c.d);
+      if (height > 2 && (multipole_dirty || up_order != c.order || up_d != c.d)) {
+        upward(src_tree, wt_sorted.get(), ip, M, Mhat, true);
+        multipole_dirty = false;
+        up_order = c.order;
+        up_d = c.d;
+      }
+      downward(src_tree, wt_sorted.get(), Mhat, tt, ip, vt.get(), leaf_lo, leaf_hi, true);
+      config = c;
+    }
+    timer.begin("finish", stream);
+    TreeView tv = tt.view();
+    int p_lo = 0, p_hi = static_cast<int>(nt);
+    if (shard_world > 1) {
+      int b[2];
+      PLT_CUDA(cudaMemcpyAsync(&b[0], tv.leaf_start + leaf_lo, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaMemcpyAsync(&b[1], tv.leaf_start + leaf_hi, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+      p_lo = b[0];
+      p_hi = b[1];
+    }
+    launch_finish_outputs(kind, dim, aniso, vt.get(), tt.perm(), nt, p_lo, p_hi, out, stream, ctr);
+    timer.end(stream);
+  }
+};
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+namespace {
+thread_local std::string g_create_error;
+
+template <class F>
+int guarded(plt_eval* h, F&& f) {
+  if (!h) return PLT_ERR_INVALID;
+  try {
+    f();
+    return PLT_OK;
+  } catch (const Error& e) {
+    h->err = e.what();
+    return e.status;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return PLT_ERR_INVALID;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int plt_version(void) { return 100; }
+
+int plt_device_check(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return PLT_ERR_CUDA;
+  }
+  return PLT_OK;
+}
+
+int plt_eval_create(int kind, int symmetric, int dim, int rbf_id, int rbf_part, const double* params,
+                    int n_params, const double* aniso, const double* bbox_min, const double* bbox_max,
+                    plt_eval** out) {
+  if (!out) return PLT_ERR_INVALID;
+  *out = nullptr;
+  auto h = std::make_unique<plt_eval>();
+  try {
+    h->init(kind, symmetric, dim, rbf_id, rbf_part, params, n_params, aniso, bbox_min, bbox_max);
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    return e.status;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return PLT_ERR_INVALID;
+  }
+  *out = h.release();
+  return PLT_OK;
+}
+
+void plt_eval_destroy(plt_eval* h) { delete h; }
+
+int plt_eval_set_source_points(plt_eval* h, const double* points, int64_t n) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(!h->symmetric, "set_source_points is not available on a symmetric evaluator");
+    h->set_points_impl(points, n, true);
+  });
+}
+
+int plt_eval_set_target_points(plt_eval* h, const double* points, int64_t n) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(!h->symmetric, "set_target_points is not available on a symmetric evaluator");
+    h->set_points_impl(points, n, false);
+  });
+}
+
+int plt_eval_set_points(plt_eval* h, const double* points, int64_t n) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(h->symmetric, "set_points is only available on a symmetric evaluator");
+    h->set_points_impl(points, n, true);
+  });
+}
+
+int plt_eval_set_weights(plt_eval* h, const double* weights, int64_t len) {
+  return guarded(h, [&] { h->set_weights(weights, len); });
+}
+
+int plt_eval_set_accuracy(plt_eval* h, double accuracy) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(accuracy >= 0.0, "accuracy must be non-negative");
+    h->set_accuracy(accuracy);
+  });
+}
+
+int plt_eval_evaluate(plt_eval* h, double* out, int64_t len) {
+  return guarded(h, [&] { h->evaluate(out, len); });
+}
+
+int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_override) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(order == 0 || (order >= 2 && order <= kMaxOrder), "order out of range");
+    PLT_REQUIRE(d >= -1 && d < std::max(order, 1), "d out of range");
+    auto apply = [&](plt_eval* e) {
+      e->force_order = order;
+      e->force_d = d;
+      e->force_height = tree_height_override;
+      e->best_config.clear();
+    };
+    apply(h);
+    if (h->direct_part) {
+      apply(h->fast_part.get());
+    }
+  });
+}
+
+int plt_eval_get_config(plt_eval* h, plt_config* out) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(out, "out");
+    *out = h->config;
+  });
+}
+
+int plt_eval_set_stream(plt_eval* h, void* cuda_stream) {
+  return guarded(h, [&] { h->stream = static_cast<cudaStream_t>(cuda_stream); });
+}
+
+int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad shard");
+    h->shard_rank = rank;
+    h->shard_world = world_size;
+  });
+}
+
+int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap) {
+  if (!h) return 0;
+  int n = 0;
+  try {
+    PLT_CUDA(cudaStreamSynchronize(h->stream));
+    auto collect = [&](plt_eval* e) {
+      for (auto& r : e->timer.recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) {
+          cudaGetLastError();
+          continue;
+        }
+        // merge phases of the same name (per-level records)
+        int j = 0;
+        for (; j < n; ++j)
+          if (std::strcmp(names[j], r.name) == 0) break;
+        if (j == n) {
+          if (n == cap) continue;
+          names[n] = r.name;
+          ms[n] = 0.0;
+          ++n;
+        }
+        ms[j] += t;
+      }
+    };
+    collect(h);
+    if (h->direct_part) {
+      collect(h->direct_part.get());
+      collect(h->fast_part.get());
+    }
+  } catch (const std::exception& e) {
+    h->err = e.what();
+  }
+  return n;
+}
+
+int64_t plt_eval_launch_count(plt_eval* h) {
+  if (!h) return 0;
+  int64_t n = h->ctr.n;
+  if (h->direct_part) n += h->direct_part->ctr.n + h->fast_part->ctr.n;
+  return n;
+}
+
+const char* plt_last_error(plt_eval* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"

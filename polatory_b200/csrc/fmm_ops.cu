@@ -1,0 +1,773 @@
+// FMM operator kernels that do not depend on the RBF: P2M, M2M, multipole DFT, the
+// Fourier-space M2L (Hadamard + inverse DFT), L2L, L2P, and the point pre/post passes.
+// (RBF-dependent kernels -- P2P and the M2L operator tabulation -- are in fmm_rbf_ops.cu.)
+//
+// Layouts (all FP64):
+//   M, L   : [cell][k][P]      P = order^dim nodes, node index row-major (axis 0 slowest)
+//   Mhat   : [cell][km][F]     F = nf^(dim-1) * order half-spectrum, double2 (re, im)
+//   Khat   : [7^dim offsets][kn][km][F]
+//   points : SoA [dim][n]; weights SoA [km][n]; raw outputs SoA [kn][n]
+#include "fmm_ops.cuh"
+
+namespace plt {
+namespace {
+
+constexpr int kBlock = 128;
+
+struct Mat3 {
+  double a[9];
+};
+
+// ------------------------------------------------------------------------------------
+// Point pre/post processing
+// ------------------------------------------------------------------------------------
+__global__ void k_transform_points(int dim, Mat3 A, const double* __restrict__ pts, int64_t n,
+                                   double* __restrict__ pos) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  double p[3] = {0, 0, 0};
+  for (int b = 0; b < dim; ++b) p[b] = pts[i * dim + b];
+  for (int a = 0; a < dim; ++a) {
+    // geometry/point3d.hpp:36-40: p * A^T  => component a = sum_b A[a][b] p[b]
+    double s = 0.0;
+    for (int b = 0; b < dim; ++b) s += p[b] * A.a[a * dim + b];
+    pos[a * n + i] = s;
+  }
+}
+
+__global__ void k_prepare_weights(int km, int fold, int dim, Mat3 A, const double* __restrict__ w,
+                                  const int* __restrict__ perm, int64_t n, double* __restrict__ wt) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int64_t j = perm ? perm[i] : i;
+  if (!fold) {
+    for (int m = 0; m < km; ++m) wt[m * n + i] = w[j * km + m];
+  } else {
+    // w' = A w  (gradient_kernel.hpp:53: grad_iso * A contracted with w)
+    double v[3] = {0, 0, 0};
+    for (int b = 0; b < dim; ++b) v[b] = w[j * dim + b];
+    for (int a = 0; a < dim; ++a) {
+      double s = 0.0;
+      for (int b = 0; b < dim; ++b) s += A.a[a * dim + b] * v[b];
+      wt[a * n + i] = s;
+    }
+  }
+}
+
+__global__ void k_finish_outputs(int kn, int fold, int dim, Mat3 A, const double* __restrict__ vt,
+                                 const int* __restrict__ perm, int64_t n, int64_t lo, int64_t hi,
+                                 double* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int64_t j = perm ? perm[i] : i;
+  const bool in = i >= lo && i < hi;
+  if (!fold) {
+    for (int b = 0; b < kn; ++b) out[j * kn + b] = in ? vt[b * n + i] : 0.0;
+  } else {
+    // out = A^T v
+    double v[3] = {0, 0, 0};
+    for (int a = 0; a < dim; ++a) v[a] = in ? vt[a * n + i] : 0.0;
+    for (int b = 0; b < dim; ++b) {
+      double s = 0.0;
+      for (int a = 0; a < dim; ++a) s += A.a[a * dim + b] * v[a];
+      out[j * dim + b] = s;
+    }
+  }
+}
+
+Mat3 make_mat3(int dim, const double* aniso) {
+  Mat3 m{};
+  for (int i = 0; i < dim * dim; ++i) m.a[i] = aniso[i];
+  return m;
+}
+
+// ------------------------------------------------------------------------------------
+// Interpolation helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double node_pos(int i, int order) { return -1.0 + 2.0 * i / (order - 1); }
+
+// Barycentric basis values S_i(t), i < order, written with the given stride.
+__device__ void bary_basis(int order, const double* __restrict__ beta, double t, double* s) {
+  int hit = -1;
+  double sum = 0.0;
+  for (int i = 0; i < order; ++i) {
+    double dt = t - node_pos(i, order);
+    if (dt == 0.0) hit = i;
+    double q = beta[i] / dt;
+    s[i] = q;
+    sum += q;
+  }
+  if (hit >= 0) {
+    for (int i = 0; i < order; ++i) s[i] = i == hit ? 1.0 : 0.0;
+  } else {
+    double inv = 1.0 / sum;
+    for (int i = 0; i < order; ++i) s[i] *= inv;
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void cell_center(const Box& box, int level, uint32_t key, double (&c)[DIM],
+                                            double& half) {
+  int ci[DIM];
+  morton_decode<DIM>(key, ci);
+  const double w = box.width / static_cast<double>(1 << level);
+  half = 0.5 * w;
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) c[a] = box.center[a] - 0.5 * box.width + (ci[a] + 0.5) * w;
+}
+
+template <int DIM>
+__device__ __forceinline__ void node_decode(int n, int order, int (&ni)[DIM]) {
+#pragma unroll
+  for (int a = DIM - 1; a >= 0; --a) {
+    ni[a] = n % order;
+    n /= order;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// P2M: M_c[m][n] = sum_j S_n(x_j) w_j[m]          (one CTA per source leaf)
+// ------------------------------------------------------------------------------------
+constexpr int kPointBatch = 32;
+
+template <int DIM>
+__global__ void __launch_bounds__(kBlock) k_p2m(TreeView tr, Box box, InterpDev it, int km,
+                                                const double* __restrict__ wt, double* __restrict__ M) {
+  extern __shared__ double sm[];
+  const int p = it.order;
+  double* s_beta = sm;                          // [p]
+  double* s_basis = s_beta + p;                 // [batch][DIM][p]
+  double* s_w = s_basis + kPointBatch * DIM * p;  // [batch][km]
+  const int leaf = tr.height - 1;
+  const int cell = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p; i += kBlock) s_beta[i] = it.beta[i];
+  double c[DIM], half;
+  cell_center<DIM>(box, leaf, tr.keys[tr.cell_off[leaf] + cell], c, half);
+  const double inv_half = 1.0 / half;
+  const int i0 = tr.leaf_start[cell], i1 = tr.leaf_start[cell + 1];
+  int P = 1;
+  for (int a = 0; a < DIM; ++a) P *= p;
+  double* Mc = M + static_cast<size_t>(tr.cell_off[leaf] + cell) * km * P;
+  __syncthreads();
+  for (int b0 = i0; b0 < i1; b0 += kPointBatch) {
+    const int nb = min(kPointBatch, i1 - b0);
+    for (int e = tid; e < nb * DIM; e += kBlock) {
+      int j = e / DIM, a = e % DIM;
+      double t = (tr.pos[a * tr.n + b0 + j] - c[a]) * inv_half;
+      bary_basis(p, s_beta, t, s_basis + (j * DIM + a) * p);
+    }
+    for (int e = tid; e < nb * km; e += kBlock) {
+      int j = e / km, m = e % km;
+      s_w[j * km + m] = wt[m * tr.n + b0 + j];
+    }
+    __syncthreads();
+    for (int n = tid; n < P; n += kBlock) {
+      int ni[DIM];
+      node_decode<DIM>(n, p, ni);
+      for (int m = 0; m < km; ++m) {
+        double acc = b0 == i0 ? 0.0 : Mc[m * P + n];
+        for (int j = 0; j < nb; ++j) {
+          double s = s_w[j * km + m];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) s *= s_basis[(j * DIM + a) * p + ni[a]];
+          acc += s;
+        }
+        Mc[m * P + n] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Per-axis p x p contraction used by M2M and L2L.
+//   out[o][r][i] = sum_q T(r, q) in[o][q][i],  array viewed as [outer][p][inner]
+//   T(r, q) = tm[r * p + q] (transpose == false) or tm[q * p + r] (transpose == true)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void axis_contract(const double* __restrict__ in, double* out, int outer, int p,
+                                              int inner, const double* __restrict__ tm, bool transpose,
+                                              bool accumulate) {
+  const int total = outer * p * inner;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int i = e % inner;
+    int r = (e / inner) % p;
+    int o = e / (inner * p);
+    const double* src = in + static_cast<size_t>(o) * p * inner + i;
+    double acc = 0.0;
+    if (!transpose) {
+      for (int q = 0; q < p; ++q) acc += tm[r * p + q] * src[q * inner];
+    } else {
+      for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q * inner];
+    }
+    if (accumulate) out[e] += acc; else out[e] = acc;
+  }
+}
+
+// M2M: M_parent[m] = sum_children sum_n S_m^parent(y_n^child) M_child[n]   (CTA per parent cell)
+template <int DIM>
+__global__ void __launch_bounds__(kBlock) k_m2m(TreeView tr, int level, InterpDev it, int km,
+                                                double* __restrict__ M) {
+  extern __shared__ double sm[];
+  const int p = it.order;
+  int P = 1;
+  for (int a = 0; a < DIM; ++a) P *= p;
+  double* s_t = sm;               // [2][p][p]
+  double* s_acc = s_t + 2 * p * p;  // [P]
+  double* s_b0 = s_acc + P;
+  double* s_b1 = s_b0 + P;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * p * p; i += kBlock) s_t[i] = it.child[i];
+  const int cell = blockIdx.x;
+  const uint32_t key = tr.keys[tr.cell_off[level] + cell];
+  const int* dense_child = tr.dense + tr.dense_off[level + 1];
+  double* Mp = M + static_cast<size_t>(tr.cell_off[level] + cell) * km * P;
+  for (int m = 0; m < km; ++m) {
+    for (int n = tid; n < P; n += kBlock) s_acc[n] = 0.0;
+    for (int ch = 0; ch < (1 << DIM); ++ch) {
+      int cidx = dense_child[(key << DIM) | ch];
+      if (cidx < 0) continue;
+      const double* Mc = M + (static_cast<size_t>(tr.cell_off[level + 1] + cidx) * km + m) * P;
+      __syncthreads();
+      for (int n = tid; n < P; n += kBlock) s_b0[n] = Mc[n];
+      __syncthreads();
+      double* in = s_b0;
+      double* out = s_b1;
+      int outer = 1, inner = P / p;
+      for (int a = 0; a < DIM; ++a) {
+        int side = (ch >> (DIM - 1 - a)) & 1;
+        bool last = a == DIM - 1;
+        // parent node r <- child node q: T(r, q) = child[side][r][q]
+        axis_contract(in, last ? s_acc : out, outer, p, inner, s_t + side * p * p, false, last);
+        __syncthreads();
+        double* t = in; in = out; out = t;
+        outer *= p;
+        inner /= p;
+      }
+    }
+    __syncthreads();
+    for (int n = tid; n < P; n += kBlock) Mp[m * P + n] = s_acc[n];
+    __syncthreads();
+  }
+}
+
+// L2L: L_child[n] += sum_m S_m^parent(x_n^child) L_parent[m]   (CTA per child cell)
+template <int DIM>
+__global__ void __launch_bounds__(kBlock) k_l2l(TreeView tr, int level, InterpDev it, int kn,
+                                                double* __restrict__ L, int cell_lo) {
+  extern __shared__ double sm[];
+  const int p = it.order;
+  int P = 1;
+  for (int a = 0; a < DIM; ++a) P *= p;
+  double* s_t = sm;
+  double* s_b0 = s_t + 2 * p * p;
+  double* s_b1 = s_b0 + P;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * p * p; i += kBlock) s_t[i] = it.child[i];
+  const int cell = cell_lo + blockIdx.x;
+  const uint32_t key = tr.keys[tr.cell_off[level] + cell];
+  const int pidx = tr.dense[tr.dense_off[level - 1] + (key >> DIM)];
+  const int ch = key & ((1 << DIM) - 1);
+  for (int b = 0; b < kn; ++b) {
+    const double* Lp = L + (static_cast<size_t>(tr.cell_off[level - 1] + pidx) * kn + b) * P;
+    double* Lc = L + (static_cast<size_t>(tr.cell_off[level] + cell) * kn + b) * P;
+    __syncthreads();
+    for (int n = tid; n < P; n += kBlock) s_b0[n] = Lp[n];
+    __syncthreads();
+    double* in = s_b0;
+    double* out = s_b1;
+    int outer = 1, inner = P / p;
+    for (int a = 0; a < DIM; ++a) {
+      int side = (ch >> (DIM - 1 - a)) & 1;
+      bool last = a == DIM - 1;
+      // child node r <- parent node q: T(r, q) = child[side][q][r]
+      axis_contract(in, last ? Lc : out, outer, p, inner, s_t + side * p * p, true, last);
+      __syncthreads();
+      double* t = in; in = out; out = t;
+      outer *= p;
+      inner /= p;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// L2P: v_i[b] = sum_n S_n(x_i) L_c[b][n]     (CTA per target leaf, warp per point)
+// ------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev it, int kn,
+                                                const double* __restrict__ L, double* __restrict__ vt,
+                                                int leaf_lo) {
+  extern __shared__ double sm[];
+  const int p = it.order;
+  double* s_beta = sm;           // [p]
+  double* s_basis = s_beta + p;  // [warps][DIM][p]
+  const int leaf = tr.height - 1;
+  const int cell = leaf_lo + blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < p; i += kBlock) s_beta[i] = it.beta[i];
+  double c[DIM], half;
+  cell_center<DIM>(box, leaf, tr.keys[tr.cell_off[leaf] + cell], c, half);
+  const double inv_half = 1.0 / half;
+  const int i0 = tr.leaf_start[cell], i1 = tr.leaf_start[cell + 1];
+  int P = 1;
+  for (int a = 0; a < DIM; ++a) P *= p;
+  const double* Lc = L + static_cast<size_t>(tr.cell_off[leaf] + cell) * kn * P;
+  double* basis = s_basis + warp * DIM * p;
+  __syncthreads();
+  for (int i = i0 + warp; i < i1; i += kBlock / 32) {
+    if (lane < DIM) {
+      double t = (tr.pos[lane * tr.n + i] - c[lane]) * inv_half;
+      bary_basis(p, s_beta, t, basis + lane * p);
+    }
+    __syncwarp();
+    double acc[kMaxDim] = {0, 0, 0};
+    for (int n = lane; n < P; n += 32) {
+      int ni[DIM];
+      node_decode<DIM>(n, p, ni);
+      double s = 1.0;
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) s *= basis[a * p + ni[a]];
+      for (int b = 0; b < kn; ++b) acc[b] += s * Lc[b * P + n];
+    }
+    for (int b = 0; b < kn; ++b) {
+      double v = acc[b];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) vt[b * tr.n + i] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Small dense DFT stages (generic pointers: shared or global).
+//   out[o][k][i] = sum_n in[o][n][i] * W^(k n),   W = e^{-2 pi i / nf} (or its conjugate)
+// ------------------------------------------------------------------------------------
+template <bool IN_REAL>
+__device__ __forceinline__ void dft_stage(const void* in_, double2* out, int outer, int n_in, int n_out,
+                                          int inner, const double2* __restrict__ tw, int nf, bool conj) {
+  const int total = outer * n_out * inner;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int i = e % inner;
+    int k = (e / inner) % n_out;
+    int o = e / (inner * n_out);
+    double re = 0.0, im = 0.0;
+    int idx = 0;
+    const size_t base = static_cast<size_t>(o) * n_in * inner + i;
+    for (int n = 0; n < n_in; ++n) {
+      double2 w = tw[idx];
+      if (conj) w.y = -w.y;
+      if constexpr (IN_REAL) {
+        double v = static_cast<const double*>(in_)[base + static_cast<size_t>(n) * inner];
+        re = fma(v, w.x, re);
+        im = fma(v, w.y, im);
+      } else {
+        double2 v = static_cast<const double2*>(in_)[base + static_cast<size_t>(n) * inner];
+        re = fma(v.x, w.x, re);
+        re = fma(-v.y, w.y, re);
+        im = fma(v.x, w.y, im);
+        im = fma(v.y, w.x, im);
+      }
+      idx += k;
+      if (idx >= nf) idx -= nf;
+    }
+    out[e] = make_double2(re, im);
+  }
+}
+
+// Last inverse stage, half spectrum -> real: out[o][m] = Re in[o][0] + 2 sum_{k>=1} Re(in[o][k] e^{+i th k m})
+__device__ __forceinline__ void idft_stage_c2r(const double2* in, double* out, int outer, int p,
+                                               const double2* __restrict__ tw, int nf, bool accumulate) {
+  const int total = outer * p;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int m = e % p;
+    int o = e / p;
+    const double2* src = in + static_cast<size_t>(o) * p;
+    double acc = src[0].x;
+    int idx = m;
+    for (int k = 1; k < p; ++k) {
+      double2 w = tw[idx];  // (cos, -sin); Re(v e^{+i th}) = v.x cos - v.y sin = v.x w.x + v.y w.y
+      acc = fma(2.0 * src[k].x, w.x, acc);
+      acc = fma(2.0 * src[k].y, w.y, acc);
+      idx += m;
+      if (idx >= nf) idx -= nf;
+    }
+    if (accumulate) out[e] += acc; else out[e] = acc;
+  }
+}
+
+// M -> Mhat for all cells of levels >= 2 (CTA grid-strides over cells).
+// Shared (or global scratch) buffers: real P, complex bufA, complex bufB.
+template <int DIM>
+__global__ void __launch_bounds__(kBlock) k_m2hat(int first_cell, int n_cells, InterpDev it, int km,
+                                                  const double* __restrict__ M, double2* __restrict__ Mhat,
+                                                  double2* gscratch, int scratch_elems) {
+  extern __shared__ double2 sm2[];
+  const int p = it.order, nf = it.nf;
+  int P = 1, F = p;
+  for (int a = 0; a < DIM; ++a) P *= p;
+  for (int a = 0; a + 1 < DIM; ++a) F *= nf;
+  double2* s_tw = sm2;  // [nf]
+  double2* bufA = gscratch ? gscratch + static_cast<size_t>(blockIdx.x) * 2 * scratch_elems : sm2 + nf;
+  double2* bufB = bufA + scratch_elems;
+  for (int i = threadIdx.x; i < nf; i += kBlock) s_tw[i] = it.tw[i];
+  __syncthreads();
+  for (int cell = blockIdx.x; cell < n_cells * km; cell += gridDim.x) {
+    const double* Mc = M + static_cast<size_t>(first_cell) * km * P + static_cast<size_t>(cell) * P;
+    double2* out = Mhat + static_cast<size_t>(cell) * F;
+    // last axis: real -> half spectrum
+    if constexpr (DIM == 1) {
+      dft_stage<true>(Mc, out, 1, p, p, 1, s_tw, nf, false);
+    } else {
+      dft_stage<true>(Mc, bufA, P / p, p, p, 1, s_tw, nf, false);
+      __syncthreads();
+      // remaining axes, last-1 down to 0
+      double2* in = bufA;
+      double2* ob = bufB;
+      int outer = P / p / p;  // p^(axis)
+      int inner = p;          // already transformed tail
+      for (int a = DIM - 2; a >= 0; --a) {
+        double2* dst = a == 0 ? out : ob;
+        dft_stage<false>(in, dst, outer, p, nf, inner, s_tw, nf, false);
+        __syncthreads();
+        double2* t = in; in = ob; ob = t;
+        inner *= nf;
+        outer /= p;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// M2L, Fourier space.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_m2l_mark_active(TreeView src, TreeView trg, int level, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pl = level - 1;
+  if (i >= trg.n_cells[pl]) return;
+  int c[DIM];
+  morton_decode<DIM>(trg.keys[trg.cell_off[pl] + i], c);
+  const int nside = 1 << pl;
+  const int* sd = src.dense + src.dense_off[pl];
+  int nn = 1;
+  for (int a = 0; a < DIM; ++a) nn *= 3;
+  int found = 0;
+  for (int e = 0; e < nn && !found; ++e) {
+    int q[DIM], r = e;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = c[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (ok && sd[morton_encode<DIM>(q)] >= 0) found = 1;
+  }
+  flags[i] = found;
+}
+
+// Hadamard accumulation, one CTA per active target parent, threads over frequencies.
+//   Lhat[slot][ct][b][f] = sum_{cs in list(ct)} sum_a Khat[o(ct,cs)][b][a][f] * Mhat[cs][a][f]
+template <int DIM, int KN, int KM>
+__global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
+  constexpr int NC = 1 << DIM;        // children per cell
+  constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  constexpr int NOFF = DIM == 1 ? 7 : (DIM == 2 ? 49 : 343);
+  __shared__ int s_src[NN * NC];  // global compact id (within Mhat) of source child or -1
+  __shared__ int s_trg[NC];       // 1 if the target child exists
+  const int slot = blockIdx.x;
+  const int pl = a.level - 1;
+  const int pidx = a.active[slot];
+  const uint32_t pkey = a.trg.keys[a.trg.cell_off[pl] + pidx];
+  int pc[DIM];
+  morton_decode<DIM>(pkey, pc);
+  const int nside_p = 1 << pl;
+  const int* sdense = a.src.dense + a.src.dense_off[a.level];
+  const int* tdense = a.trg.dense + a.trg.dense_off[a.level];
+  for (int e = threadIdx.x; e < NN * NC; e += blockDim.x) {
+    int nb = e / NC, ch = e % NC;
+    int q[DIM], r = nb;
+    bool ok = true;
+#pragma unroll
+    for (int d = DIM - 1; d >= 0; --d) {
+      q[d] = pc[d] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[d] >= 0 && q[d] < nside_p;
+    }
+    int id = -1;
+    if (ok) {
+      uint32_t ck = (morton_encode<DIM>(q) << DIM) | ch;
+      int ci = sdense[ck];
+      if (ci >= 0) id = a.src.cell_off[a.level] + ci - a.src.cell_off[2];
+    }
+    s_src[e] = id;
+  }
+  for (int e = threadIdx.x; e < NC; e += blockDim.x) s_trg[e] = tdense[(pkey << DIM) | e] >= 0;
+  __syncthreads();
+
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    double2 acc[NC][KN];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int b = 0; b < KN; ++b) acc[c][b] = make_double2(0.0, 0.0);
+    for (int nb = 0; nb < NN; ++nb) {
+      int e3[DIM], r = nb;
+#pragma unroll
+      for (int d = DIM - 1; d >= 0; --d) {
+        e3[d] = (r % 3) - 1;
+        r /= 3;
+      }
+#pragma unroll
+      for (int cs = 0; cs < NC; ++cs) {
+        const int sid = s_src[nb * NC + cs];
+        if (sid < 0) continue;
+        double2 mh[KM];
+#pragma unroll
+        for (int m = 0; m < KM; ++m) mh[m] = a.Mhat[(static_cast<size_t>(sid) * KM + m) * F + f];
+#pragma unroll
+        for (int ct = 0; ct < NC; ++ct) {
+          if (!s_trg[ct]) continue;
+          // offset o = source child coord - target child coord, per axis in [-3, 3]
+          int oi = 0, far = 0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            int o = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) - ((ct >> (DIM - 1 - d)) & 1);
+            far |= (o > 1 || o < -1);
+            oi = oi * 7 + (o + 3);
+          }
+          if (!far) continue;
+          const double2* kh = a.Khat + static_cast<size_t>(oi) * KN * KM * F + f;
+#pragma unroll
+          for (int b = 0; b < KN; ++b)
+#pragma unroll
+            for (int m = 0; m < KM; ++m) {
+              double2 kv = kh[static_cast<size_t>(b * KM + m) * F];
+              acc[ct][b].x = fma(kv.x, mh[m].x, acc[ct][b].x);
+              acc[ct][b].x = fma(-kv.y, mh[m].y, acc[ct][b].x);
+              acc[ct][b].y = fma(kv.x, mh[m].y, acc[ct][b].y);
+              acc[ct][b].y = fma(kv.y, mh[m].x, acc[ct][b].y);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < NC; ++ct)
+#pragma unroll
+      for (int b = 0; b < KN; ++b)
+        a.Lhat[((static_cast<size_t>(slot) * NC + ct) * KN + b) * F + f] = acc[ct][b];
+  }
+}
+
+// Inverse DFT of the accumulated spectra, pruned to the order^dim nodes:  L[cell][b][:] = IDFT(Lhat)
+// One CTA per (slot, child, b).
+template <int DIM>
+__global__ void __launch_bounds__(kBlock) k_m2l_idft(M2LArgs a, InterpDev it, double2* gscratch,
+                                                     int scratch_elems) {
+  extern __shared__ double2 sm2[];
+  constexpr int NC = 1 << DIM;
+  const int p = it.order, nf = it.nf;
+  int P = 1, F = p;
+  for (int d = 0; d < DIM; ++d) P *= p;
+  for (int d = 0; d + 1 < DIM; ++d) F *= nf;
+  double2* s_tw = sm2;
+  double2* bufA = gscratch ? gscratch + static_cast<size_t>(blockIdx.x) * 2 * scratch_elems : sm2 + nf;
+  double2* bufB = bufA + scratch_elems;
+  for (int i = threadIdx.x; i < nf; i += kBlock) s_tw[i] = it.tw[i];
+  __syncthreads();
+  const int total = a.n_active * NC * a.kn;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int b = w % a.kn;
+    const int ct = (w / a.kn) % NC;
+    const int slot = w / (a.kn * NC);
+    const int pidx = a.active[slot];
+    const uint32_t pkey = a.trg.keys[a.trg.cell_off[a.level - 1] + pidx];
+    const int cidx = a.trg.dense[a.trg.dense_off[a.level] + ((pkey << DIM) | ct)];
+    if (cidx < 0) continue;  // uniform across the CTA
+    const double2* in0 = a.Lhat + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * F;
+    double* Lc = a.L + (static_cast<size_t>(a.trg.cell_off[a.level] + cidx) * a.kn + b) * P;
+    if constexpr (DIM == 1) {
+      idft_stage_c2r(in0, Lc, 1, p, s_tw, nf, false);
+    } else {
+      const double2* in = in0;
+      double2* ob = bufA;
+      int outer = 1;
+      int inner = F / nf;  // nf^(DIM-2) * p
+      for (int d = 0; d + 1 < DIM; ++d) {
+        dft_stage<false>(in, ob, outer, nf, p, inner, s_tw, nf, true);
+        __syncthreads();
+        in = ob;
+        ob = ob == bufA ? bufB : bufA;
+        outer *= p;
+        inner /= nf;
+      }
+      idft_stage_c2r(in, Lc, P / p, p, s_tw, nf, false);
+    }
+    __syncthreads();
+  }
+}
+
+size_t smem_opt_in(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    PLT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  }
+  return bytes;
+}
+
+constexpr size_t kSmemCap = 200 * 1024;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------
+void launch_transform_points(int dim, const double* aniso, const double* pts, int64_t n, double* pos,
+                             cudaStream_t s, LaunchCounter& c) {
+  if (n == 0) return;
+  PLT_LAUNCH(c, k_transform_points, ceil_div(n, 256), 256, 0, s, dim, make_mat3(dim, aniso), pts, n, pos);
+}
+
+void launch_prepare_weights(int kind, int dim, const double* aniso, const double* w, const int* perm, int64_t n,
+                            double* wt, cudaStream_t s, LaunchCounter& c) {
+  if (n == 0) return;
+  const int fold = kind == KIND_F || kind == KIND_H;
+  const int km = fold ? dim : 1;
+  PLT_LAUNCH(c, k_prepare_weights, ceil_div(n, 256), 256, 0, s, km, fold, dim, make_mat3(dim, aniso), w, perm, n, wt);
+}
+
+void launch_finish_outputs(int kind, int dim, const double* aniso, const double* vt, const int* perm, int64_t n,
+                           int64_t lo, int64_t hi, double* out, cudaStream_t s, LaunchCounter& c) {
+  if (n == 0) return;
+  const int fold = kind == KIND_FT || kind == KIND_H;
+  const int kn = fold ? dim : 1;
+  PLT_LAUNCH(c, k_finish_outputs, ceil_div(n, 256), 256, 0, s, kn, fold, dim, make_mat3(dim, aniso), vt, perm, n,
+             lo, hi, out);
+}
+
+void launch_p2m(int dim, int km, const TreeView& tr, const Box& box, const InterpDev& it, const double* wt,
+                double* M, cudaStream_t s, LaunchCounter& c) {
+  const int leaf = tr.height - 1;
+  const int n = tr.n_cells[leaf];
+  if (n == 0) return;
+  size_t smem = sizeof(double) * (it.order + kPointBatch * dim * it.order + kPointBatch * km);
+  if (dim == 1) PLT_LAUNCH(c, k_p2m<1>, n, kBlock, smem, s, tr, box, it, km, wt, M);
+  if (dim == 2) PLT_LAUNCH(c, k_p2m<2>, n, kBlock, smem, s, tr, box, it, km, wt, M);
+  if (dim == 3) PLT_LAUNCH(c, k_p2m<3>, n, kBlock, smem, s, tr, box, it, km, wt, M);
+}
+
+void launch_m2m(int dim, int km, const TreeView& tr, int level, const InterpDev& it, double* M, cudaStream_t s,
+                LaunchCounter& c) {
+  const int n = tr.n_cells[level];
+  if (n == 0) return;
+  const int P = nodes_per_cell(it.order, dim);
+  size_t smem = sizeof(double) * (2 * it.order * it.order + 3 * static_cast<size_t>(P));
+  PLT_REQUIRE(smem <= kSmemCap, "interpolation order too large for M2M shared-memory staging");
+  if (dim == 1) { smem_opt_in((const void*)k_m2m<1>, smem); PLT_LAUNCH(c, k_m2m<1>, n, kBlock, smem, s, tr, level, it, km, M); }
+  if (dim == 2) { smem_opt_in((const void*)k_m2m<2>, smem); PLT_LAUNCH(c, k_m2m<2>, n, kBlock, smem, s, tr, level, it, km, M); }
+  if (dim == 3) { smem_opt_in((const void*)k_m2m<3>, smem); PLT_LAUNCH(c, k_m2m<3>, n, kBlock, smem, s, tr, level, it, km, M); }
+}
+
+void launch_l2l(int dim, int kn, const TreeView& tr, int level, const InterpDev& it, double* L, int cell_lo,
+                int cell_hi, cudaStream_t s, LaunchCounter& c) {
+  const int n = cell_hi - cell_lo;
+  if (n <= 0) return;
+  const int P = nodes_per_cell(it.order, dim);
+  size_t smem = sizeof(double) * (2 * it.order * it.order + 2 * static_cast<size_t>(P));
+  PLT_REQUIRE(smem <= kSmemCap, "interpolation order too large for L2L shared-memory staging");
+  if (dim == 1) { smem_opt_in((const void*)k_l2l<1>, smem); PLT_LAUNCH(c, k_l2l<1>, n, kBlock, smem, s, tr, level, it, kn, L, cell_lo); }
+  if (dim == 2) { smem_opt_in((const void*)k_l2l<2>, smem); PLT_LAUNCH(c, k_l2l<2>, n, kBlock, smem, s, tr, level, it, kn, L, cell_lo); }
+  if (dim == 3) { smem_opt_in((const void*)k_l2l<3>, smem); PLT_LAUNCH(c, k_l2l<3>, n, kBlock, smem, s, tr, level, it, kn, L, cell_lo); }
+}
+
+void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
+                double* vt, int64_t leaf_lo, int64_t leaf_hi, cudaStream_t s, LaunchCounter& c) {
+  const int n = static_cast<int>(leaf_hi - leaf_lo);
+  if (n <= 0) return;
+  size_t smem = sizeof(double) * (it.order + (kBlock / 32) * dim * it.order);
+  if (dim == 1) PLT_LAUNCH(c, k_l2p<1>, n, kBlock, smem, s, tr, box, it, kn, L, vt, static_cast<int>(leaf_lo));
+  if (dim == 2) PLT_LAUNCH(c, k_l2p<2>, n, kBlock, smem, s, tr, box, it, kn, L, vt, static_cast<int>(leaf_lo));
+  if (dim == 3) PLT_LAUNCH(c, k_l2p<3>, n, kBlock, smem, s, tr, box, it, kn, L, vt, static_cast<int>(leaf_lo));
+}
+
+namespace {
+// Scratch policy for the DFT kernels: shared memory when the two complex stage buffers fit,
+// otherwise a per-CTA slice of a global scratch buffer (generic addressing, same code).
+struct DftScratch {
+  int elems;           // complex elements per stage buffer
+  size_t smem;         // dynamic shared memory bytes
+  bool global;
+  int grid;
+  DevBuf<double2> buf;
+};
+
+DftScratch plan_dft_scratch(int order, int dim, int work_items, cudaStream_t s) {
+  DftScratch d;
+  const int nf = 2 * order - 1;
+  // largest intermediate: order^(dim-1) * nf^(dim-2)... bounded by order * nf^(dim-2) * order * ... use generous bound
+  int elems = order;
+  for (int a = 0; a + 1 < dim; ++a) elems *= (a == 0 ? order : nf);
+  // dim 1: order; dim 2: order*order; dim 3: order*order*nf
+  d.elems = elems;
+  size_t smem = sizeof(double2) * (nf + 2 * static_cast<size_t>(elems));
+  d.global = smem > kSmemCap;
+  d.smem = d.global ? sizeof(double2) * nf : smem;
+  d.grid = std::max(1, std::min(work_items, d.global ? 4 * kNumSM : work_items));
+  if (d.global) d.buf.alloc(static_cast<size_t>(d.grid) * 2 * elems, s);
+  return d;
+}
+}  // namespace
+
+void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, const double* M, double2* Mhat,
+                  cudaStream_t s, LaunchCounter& c) {
+  if (tr.height <= 2) return;
+  const int first = tr.cell_off[2];
+  int n_cells = 0;
+  for (int l = 2; l < tr.height; ++l) n_cells += tr.n_cells[l];
+  if (n_cells == 0) return;
+  DftScratch d = plan_dft_scratch(it.order, dim, n_cells * km, s);
+  if (dim == 1) { smem_opt_in((const void*)k_m2hat<1>, d.smem); PLT_LAUNCH(c, k_m2hat<1>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
+  if (dim == 2) { smem_opt_in((const void*)k_m2hat<2>, d.smem); PLT_LAUNCH(c, k_m2hat<2>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
+  if (dim == 3) { smem_opt_in((const void*)k_m2hat<3>, d.smem); PLT_LAUNCH(c, k_m2hat<3>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
+}
+
+void launch_m2l_mark_active(int dim, const TreeView& src, const TreeView& trg, int level, int* flags,
+                            cudaStream_t s, LaunchCounter& c) {
+  const int n = trg.n_cells[level - 1];
+  if (n == 0) return;
+  if (dim == 1) PLT_LAUNCH(c, k_m2l_mark_active<1>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
+  if (dim == 2) PLT_LAUNCH(c, k_m2l_mark_active<2>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
+  if (dim == 3) PLT_LAUNCH(c, k_m2l_mark_active<3>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
+}
+
+void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
+  if (a.n_active == 0) return;
+  const int F = freqs_per_cell(a.order, a.dim);
+  const int threads = F >= 256 ? 256 : ((F + 31) / 32 * 32);
+#define PLT_HAD(D, KN, KM) PLT_LAUNCH(c, (k_m2l_hadamard<D, KN, KM>), a.n_active, threads, 0, s, a, F)
+  const int key = a.dim * 100 + a.kn * 10 + a.km;
+  switch (key) {
+    case 111: PLT_HAD(1, 1, 1); break;
+    case 211: PLT_HAD(2, 1, 1); break;
+    case 212: PLT_HAD(2, 1, 2); break;
+    case 221: PLT_HAD(2, 2, 1); break;
+    case 222: PLT_HAD(2, 2, 2); break;
+    case 311: PLT_HAD(3, 1, 1); break;
+    case 313: PLT_HAD(3, 1, 3); break;
+    case 331: PLT_HAD(3, 3, 1); break;
+    case 333: PLT_HAD(3, 3, 3); break;
+    default: throw Error(PLT_ERR_INVALID, "unsupported (dim, kn, km)");
+  }
+#undef PLT_HAD
+}
+
+void launch_m2l_idft(const M2LArgs& a, const InterpDev& it, cudaStream_t s, LaunchCounter& c) {
+  if (a.n_active == 0) return;
+  const int work = a.n_active * (1 << a.dim) * a.kn;
+  DftScratch d = plan_dft_scratch(it.order, a.dim, work, s);
+  if (a.dim == 1) { smem_opt_in((const void*)k_m2l_idft<1>, d.smem); PLT_LAUNCH(c, k_m2l_idft<1>, d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems); }
+  if (a.dim == 2) { smem_opt_in((const void*)k_m2l_idft<2>, d.smem); PLT_LAUNCH(c, k_m2l_idft<2>, d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems); }
+  if (a.dim == 3) { smem_opt_in((const void*)k_m2l_idft<3>, d.smem); PLT_LAUNCH(c, k_m2l_idft<3>, d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems); }
+}
+
+}  // namespace plt

@@ -1,0 +1,241 @@
+// RBF-dependent FMM kernels: leaf-level near field (P2P) and tabulation of the
+// Fourier-space M2L operators.
+#include "dispatch.cuh"
+#include "fmm_ops.cuh"
+
+namespace plt {
+namespace {
+
+// ------------------------------------------------------------------------------------
+// P2P over the 3^dim adjacent source leaves (separation criterion 1,
+// include/polatory/fmm/kernel.hpp:71; list = build_p2p_interaction_list(src, trg, 1, mutual),
+// src/fmm/fmm_evaluator.hpp:95-97).
+//
+// One warp per target leaf.  Lanes own sources (32 at a time, coalesced loads of the
+// Morton-sorted SoA arrays); targets are processed in register groups of kTG, partial sums
+// stay in registers across all neighbour leaves and are reduced with warp shuffles once per
+// group.  The symmetric variant needs no special casing: the i == j pair evaluated at d = 0
+// is exactly the k(0,0) w_i self term of src/fmm/fmm_symmetric_evaluator.hpp:163-193.
+// ------------------------------------------------------------------------------------
+constexpr int kP2PWarps = 4;
+constexpr int kTG = 8;
+
+template <int FAM, int KIND, int DIM>
+__global__ void __launch_bounds__(kP2PWarps * 32)
+k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, double* __restrict__ vt,
+      int accumulate, int leaf_lo, int leaf_hi) {
+  constexpr int KM = KindTraits<KIND, DIM>::km;
+  constexpr int KN = KindTraits<KIND, DIM>::kn;
+  constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  const int lane = threadIdx.x & 31;
+  const int cell = leaf_lo + blockIdx.x * kP2PWarps + (threadIdx.x >> 5);
+  if (cell >= leaf_hi) return;
+  const int leaf = trg.height - 1;
+  const int nside = 1 << leaf;
+  int tc[DIM];
+  morton_decode<DIM>(trg.keys[trg.cell_off[leaf] + cell], tc);
+  const int t0 = trg.leaf_start[cell], t1 = trg.leaf_start[cell + 1];
+  const int* sdense = src.dense + src.dense_off[leaf];
+
+  for (int tb = t0; tb < t1; tb += kTG) {
+    double tp[kTG][DIM];
+    double v[kTG][KN];
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) {
+      int t = min(tb + u, t1 - 1);
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) tp[u][a] = trg.pos[a * trg.n + t];
+#pragma unroll
+      for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
+    }
+    const int nt = min(kTG, t1 - tb);
+    for (int nb = 0; nb < NN; ++nb) {
+      int q[DIM], r = nb;
+      bool ok = true;
+#pragma unroll
+      for (int a = DIM - 1; a >= 0; --a) {
+        q[a] = tc[a] + (r % 3) - 1;
+        r /= 3;
+        ok = ok && q[a] >= 0 && q[a] < nside;
+      }
+      if (!ok) continue;
+      const int sc = sdense[morton_encode<DIM>(q)];
+      if (sc < 0) continue;
+      const int s0 = src.leaf_start[sc], s1 = src.leaf_start[sc + 1];
+      for (int sb = s0; sb < s1; sb += 32) {
+        const int j = sb + lane;
+        if (j < s1) {
+          double sp[DIM], w[KM];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
+#pragma unroll
+          for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j];
+#pragma unroll
+          for (int u = 0; u < kTG; ++u) {
+            if (u < nt) {
+              double d[DIM];
+#pragma unroll
+              for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
+              pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) {
+#pragma unroll
+      for (int b = 0; b < KN; ++b) {
+        double x = v[u][b];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && u < nt) {
+          double* dst = vt + b * trg.n + tb + u;
+          *dst = accumulate ? *dst + x : x;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// M2L operator tabulation.  For level l, cell width w, node spacing h = w / (order - 1) and
+// cell offset o (source minus target, in cells) the operator is Toeplitz in the node index
+// difference delta:  k(h * delta - w * o).  It is embedded in a circulant of length
+// nf = 2 * order - 1 per axis and diagonalised:  Khat[o][b][a][f] = DFT(T)[f] / nf^dim.
+// One CTA per offset; scratch in global memory (one-off precompute per configuration).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void dft_r2c_last(const double* in, double2* out, int outer, int nf, int p,
+                                             const double2* __restrict__ tw) {
+  const int total = outer * p;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int kq = e % p, o = e / p;
+    double re = 0.0, im = 0.0;
+    int idx = 0;
+    for (int n = 0; n < nf; ++n) {
+      double v = in[static_cast<size_t>(o) * nf + n];
+      double2 w = tw[idx];
+      re = fma(v, w.x, re);
+      im = fma(v, w.y, im);
+      idx += kq;
+      if (idx >= nf) idx -= nf;
+    }
+    out[e] = make_double2(re, im);
+  }
+}
+
+__device__ __forceinline__ void dft_c2c_axis(const double2* in, double2* out, int outer, int nf, int inner,
+                                             const double2* __restrict__ tw) {
+  const int total = outer * nf * inner;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int i = e % inner, kq = (e / inner) % nf, o = e / (inner * nf);
+    double re = 0.0, im = 0.0;
+    int idx = 0;
+    for (int n = 0; n < nf; ++n) {
+      double2 v = in[(static_cast<size_t>(o) * nf + n) * inner + i];
+      double2 w = tw[idx];
+      re = fma(v.x, w.x, re);
+      re = fma(-v.y, w.y, re);
+      im = fma(v.x, w.y, im);
+      im = fma(v.y, w.x, im);
+      idx += kq;
+      if (idx >= nf) idx -= nf;
+    }
+    out[e] = make_double2(re, im);
+  }
+}
+
+template <int FAM, int KIND, int DIM>
+__global__ void __launch_bounds__(128) k_tabulate_m2l(RbfConst k, double cell_w, InterpDev it,
+                                                      double2* __restrict__ Khat, double* scratch_t,
+                                                      double2* scratch_c) {
+  constexpr int KM = KindTraits<KIND, DIM>::km;
+  constexpr int KN = KindTraits<KIND, DIM>::kn;
+  const int p = it.order, nf = it.nf;
+  int o3[DIM], r = blockIdx.x;
+  bool near = true;
+#pragma unroll
+  for (int a = DIM - 1; a >= 0; --a) {
+    o3[a] = (r % 7) - 3;
+    r /= 7;
+    near = near && o3[a] >= -1 && o3[a] <= 1;
+  }
+  if (near) return;
+  int NT = 1, F = p;
+  for (int a = 0; a < DIM; ++a) NT *= nf;
+  for (int a = 0; a + 1 < DIM; ++a) F *= nf;
+  double* T = scratch_t + static_cast<size_t>(blockIdx.x) * NT;
+  double2* bufA = scratch_c + static_cast<size_t>(blockIdx.x) * 2 * F;
+  double2* bufB = bufA + F;
+  const double h = cell_w / (p - 1);
+  double scale = 1.0;
+  for (int a = 0; a < DIM; ++a) scale /= nf;
+  for (int comp = 0; comp < KN * KM; ++comp) {
+    for (int e = threadIdx.x; e < NT; e += blockDim.x) {
+      double d[DIM];
+      int rr = e;
+#pragma unroll
+      for (int a = DIM - 1; a >= 0; --a) {
+        int ia = rr % nf;
+        rr /= nf;
+        int delta = ia < p ? ia : ia - nf;
+        d[a] = h * delta - cell_w * o3[a];
+      }
+      double blk[KN * KM];
+      kernel_block<FAM, KIND, DIM>(k, d, blk);
+      T[e] = blk[comp] * scale;
+    }
+    __syncthreads();
+    double2* dst = Khat + (static_cast<size_t>(blockIdx.x) * KN * KM + comp) * F;
+    if constexpr (DIM == 1) {
+      dft_r2c_last(T, dst, 1, nf, p, it.tw);
+    } else {
+      dft_r2c_last(T, bufA, NT / nf, nf, p, it.tw);
+      __syncthreads();
+      double2* in = bufA;
+      double2* ob = bufB;
+      int outer = NT / nf / nf;
+      int inner = p;
+      for (int a = DIM - 2; a >= 0; --a) {
+        dft_c2c_axis(in, a == 0 ? dst : ob, outer, nf, inner, it.tw);
+        __syncthreads();
+        double2* t = in; in = ob; ob = t;
+        inner *= nf;
+        outer /= nf;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const double* swt, const TreeView& trg,
+                double* vt, int symmetric, int accumulate, int64_t leaf_lo, int64_t leaf_hi, cudaStream_t s,
+                LaunchCounter& c) {
+  (void)symmetric;
+  const int n = static_cast<int>(leaf_hi - leaf_lo);
+  if (n <= 0) return;
+  dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
+    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), ceil_div(n, kP2PWarps), kP2PWarps * 32, 0, s, k, src,
+               swt, trg, vt, accumulate, static_cast<int>(leaf_lo), static_cast<int>(leaf_hi));
+  });
+}
+
+void launch_tabulate_m2l(int kind, int dim, const RbfConst& k, const Box& box, int level, const InterpDev& it,
+                         double2* Khat_level, cudaStream_t s, LaunchCounter& c) {
+  const int nf = it.nf;
+  const int noff = ipow(7, dim);
+  const size_t NT = ipow(nf, dim);
+  const size_t F = freqs_per_cell(it.order, dim);
+  DevBuf<double> st;
+  DevBuf<double2> sc;
+  st.alloc(noff * NT, s);
+  sc.alloc(noff * 2 * F, s);
+  const double cell_w = box.width / static_cast<double>(1 << level);
+  dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
+    PLT_LAUNCH(c, (k_tabulate_m2l<fam.value, knd.value, dm.value>), noff, 128, 0, s, k, cell_w, it, Khat_level,
+               st.get(), sc.get());
+  });
+}
+
+}  // namespace plt

@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's FMM evaluator interface, over the C ABI.
+
+  FmmGenericEvaluatorBase<Dim>          include/polatory/fmm/fmm_evaluator.hpp:17-41
+  FmmGenericSymmetricEvaluatorBase<Dim> include/polatory/fmm/fmm_symmetric_evaluator.hpp:16-37
+  make_fmm_*evaluator factories         include/polatory/fmm/fmm_evaluator.hpp:92-106,
+                                        include/polatory/fmm/fmm_symmetric_evaluator.hpp:80-86
+
+Same method names, argument meaning and error behaviour (exceptions carry the reference's
+messages).  Points / weights may be numpy arrays (host) or CUDA torch tensors (device
+resident, zero-copy across the ABI); `evaluate()` returns a numpy vector, or fills `out`
+when a CUDA tensor is passed.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .rbf import Rbf
+
+KIND_K, KIND_F, KIND_FT, KIND_H = 0, 1, 2, 3
+PART_FULL, PART_DIRECT, PART_FAST = 0, 1, 2
+kClassic = -1
+
+
+class Bbox:
+    """geometry::Bbox<Dim> (include/polatory/geometry/bbox3d.hpp): min / max corners."""
+
+    def __init__(self, min_, max_):
+        self.min = np.asarray(min_, dtype=np.float64).reshape(-1)
+        self.max = np.asarray(max_, dtype=np.float64).reshape(-1)
+
+    @staticmethod
+    def from_points(points):
+        points = np.asarray(points, dtype=np.float64)
+        return Bbox(points.min(axis=0), points.max(axis=0))
+
+    def convex_hull(self, other):
+        return Bbox(np.minimum(self.min, other.min), np.maximum(self.max, other.max))
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _as_ptr(x, keep):
+    """Pointer + element count of a contiguous float64 numpy array or CUDA tensor."""
+    if _is_torch_cuda(x):
+        import torch
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            x = x.to(torch.float64).contiguous()
+        keep.append(x)
+        return ctypes.c_void_p(x.data_ptr()), x.numel()
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    keep.append(a)
+    return ctypes.c_void_p(a.ctypes.data), a.size
+
+
+class _EvaluatorBase:
+    _symmetric = False
+
+    def __init__(self, kind, rbf: Rbf, bbox: Bbox, part=PART_FULL):
+        if not isinstance(rbf, Rbf):
+            raise RuntimeError("not implemented")  # make_fmm_evaluator.cpp:68
+        self._lib = _lib.load()
+        self.kind = kind
+        self.dim = rbf.dim
+        self.km = rbf.dim if kind in (KIND_F, KIND_H) else 1
+        self.kn = rbf.dim if kind in (KIND_FT, KIND_H) else 1
+        self._n_src = 0
+        self._n_trg = 0
+        params = np.asarray(rbf.parameters(), dtype=np.float64)
+        aniso = np.ascontiguousarray(rbf.anisotropy(), dtype=np.float64)
+        bmin = np.ascontiguousarray(bbox.min, dtype=np.float64)
+        bmax = np.ascontiguousarray(bbox.max, dtype=np.float64)
+        if bmin.size != self.dim or bmax.size != self.dim:
+            raise ValueError("bbox dimension mismatch")
+        h = ctypes.c_void_p()
+        st = self._lib.plt_eval_create(kind, int(self._symmetric), self.dim, rbf.rbf_id, part,
+                                       params.ctypes.data, params.size, aniso.ctypes.data,
+                                       bmin.ctypes.data, bmax.ctypes.data, ctypes.byref(h))
+        if st != _lib.PLT_OK:
+            msg = self._lib.plt_last_error(None)
+            raise _lib.PolatoryB200Error(st, msg.decode() if msg else f"status {st}")
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.plt_eval_destroy(h)
+            self._h = None
+
+    # -- reference interface ---------------------------------------------------------
+    def set_accuracy(self, accuracy):
+        _lib.check(self._h, self._lib.plt_eval_set_accuracy(self._h, float(accuracy)))
+
+    def set_weights(self, weights):
+        keep = []
+        p, n = _as_ptr(weights, keep)
+        _lib.check(self._h, self._lib.plt_eval_set_weights(self._h, p, n))
+
+    def evaluate(self, out=None):
+        n = self.kn * (self._n_src if self._symmetric else self._n_trg)
+        if out is not None and _is_torch_cuda(out):
+            import torch
+            assert out.dtype == torch.float64 and out.is_contiguous() and out.numel() == n
+            _lib.check(self._h, self._lib.plt_eval_evaluate(self._h, ctypes.c_void_p(out.data_ptr()), n))
+            return out
+        res = np.empty(n, dtype=np.float64) if out is None else out
+        assert res.dtype == np.float64 and res.flags.c_contiguous and res.size == n
+        _lib.check(self._h, self._lib.plt_eval_evaluate(self._h, ctypes.c_void_p(res.ctypes.data), n))
+        return res
+
+    # -- additions (no reference counterpart) ------------------------------------------
+    def force_config(self, order, d=kClassic, tree_height=0):
+        _lib.check(self._h, self._lib.plt_eval_force_config(self._h, int(order), int(d), int(tree_height)))
+
+    def config(self):
+        c = _lib.PltConfig()
+        _lib.check(self._h, self._lib.plt_eval_get_config(self._h, ctypes.byref(c)))
+        return {"tree_height": c.tree_height, "order": c.order, "d": c.d}
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(self._h, self._lib.plt_eval_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def set_target_shard(self, rank, world_size):
+        _lib.check(self._h, self._lib.plt_eval_set_target_shard(self._h, int(rank), int(world_size)))
+
+    def phase_times(self):
+        cap = 32
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_double * cap)()
+        n = self._lib.plt_eval_phase_times(self._h, names, ms, cap)
+        return {names[i].decode(): ms[i] for i in range(n)}
+
+    def launch_count(self):
+        return int(self._lib.plt_eval_launch_count(self._h))
+
+    def _points(self, points):
+        keep = []
+        p, n = _as_ptr(points, keep)
+        if n % self.dim != 0:
+            raise ValueError("points must be N x dim")
+        return p, n // self.dim, keep
+
+
+class FmmGenericEvaluator(_EvaluatorBase):
+    """FmmGenericEvaluator<Kernel> (src/fmm/fmm_evaluator.hpp:32-293)."""
+
+    def set_source_points(self, points):
+        p, n, keep = self._points(points)
+        _lib.check(self._h, self._lib.plt_eval_set_source_points(self._h, p, n))
+        self._n_src = n
+
+    def set_target_points(self, points):
+        p, n, keep = self._points(points)
+        _lib.check(self._h, self._lib.plt_eval_set_target_points(self._h, p, n))
+        self._n_trg = n
+
+
+class FmmGenericSymmetricEvaluator(_EvaluatorBase):
+    """FmmGenericSymmetricEvaluator<Kernel> (src/fmm/fmm_symmetric_evaluator.hpp:31-275)."""
+
+    _symmetric = True
+
+    def set_points(self, points):
+        p, n, keep = self._points(points)
+        _lib.check(self._h, self._lib.plt_eval_set_points(self._h, p, n))
+        self._n_src = n
+
+
+# -- the six factories ------------------------------------------------------------------
+def make_fmm_evaluator(rbf, bbox):
+    return FmmGenericEvaluator(KIND_K, rbf, bbox)
+
+
+def make_fmm_gradient_evaluator(rbf, bbox):
+    return FmmGenericEvaluator(KIND_F, rbf, bbox)
+
+
+def make_fmm_gradient_transpose_evaluator(rbf, bbox):
+    return FmmGenericEvaluator(KIND_FT, rbf, bbox)
+
+
+def make_fmm_hessian_evaluator(rbf, bbox):
+    return FmmGenericEvaluator(KIND_H, rbf, bbox)
+
+
+def make_fmm_symmetric_evaluator(rbf, bbox):
+    return FmmGenericSymmetricEvaluator(KIND_K, rbf, bbox)
+
+
+def make_fmm_hessian_symmetric_evaluator(rbf, bbox):
+    return FmmGenericSymmetricEvaluator(KIND_H, rbf, bbox)
