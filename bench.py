@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: FMM evaluation throughput, BASELINE.json metric
+"FMM eval Mtargets/s (1M src biharmonic3d)" on config #3 (1M-source biharmonic3d interpolant
+sampled at ~10M grid points).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port, host cores)
+
+One step = one pass of the hot path over one batch: set_weights(1M weights) +
+set_target_points(10M targets) + evaluate() -> 10M values; i.e. upward pass (P2M, M2M, multipole
+DFT), target tree build, M2L, L2L, L2P, P2P and the scatter to caller order, every step.
+`value` is measured with inputs/outputs resident in HBM; `e2e` through the same public calls
+with pinned HOST buffers (H2D of targets + weights and D2H of the result inside the timed
+region).  Weak scaling: every rank evaluates its own 10M-target grid (a sub-cell shifted copy
+of the lattice, the isosurface sampler's many-batches pattern) against the same 1M sources;
+no data-path collective is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SOURCES = 1_000_000
+GRID = (216, 216, 215)
+METRIC = "FMM eval Mtargets/s (1M src biharmonic3d)"
+UNIT = "Mtargets/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--accuracy", type=float, default=float("inf"),
+                    help="evaluation accuracy (reference default: infinity -> order 6)")
+    ap.add_argument("--n-sources", type=int, default=N_SOURCES)
+    ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-layers", type=int, default=21,
+                    help="x-layers of the target grid (central slab) the CPU arm evaluates per step")
+    return ap.parse_args()
+
+
+def workload(args, rank=0, world=1):
+    from polatory_b200 import workloads as wl
+    src, w, trg, lo, hi = wl.c3_isosurface_field(args.n_sources, tuple(args.grid))
+    if world > 1:
+        # rank r samples the lattice shifted by r/world of a grid step (still inside the bbox)
+        step = (hi - lo) / (np.asarray(args.grid) - 1)
+        trg = trg + (rank / world) * step * 0.999
+        hi = hi + step
+    return src, w, trg, lo, hi
+
+
+def config_dict(args, n_src, n_trg, cfg, world):
+    return {
+        "workload": "config #3: isosurface field evaluation, biharmonic3d (s=1, c=0) interpolant with "
+                    f"{n_src} sources (unit-sphere surface + normal-offset SDF points) sampled at "
+                    f"{n_trg} grid targets ({'x'.join(map(str, args.grid))}) over 1.1 x bbox"
+                    + (f", per rank ({world} ranks, sub-cell shifted lattices)" if world > 1 else ""),
+        "rbf": "bh3", "kernel_kind": "K", "dim": 3,
+        "accuracy": "inf" if np.isinf(args.accuracy) else args.accuracy,
+        "tree_height": cfg.get("tree_height"), "order": cfg.get("order"), "d": cfg.get("d"),
+        "step": "set_weights + set_target_points + evaluate (upward pass, target tree, M2L, L2L, L2P, P2P)",
+        "cache_policy": "inputs larger than L2 (240 MB targets, >4 GB expansions per step)",
+        "parallelism": f"targets-dp{world}",
+    }
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ---------------------------------------------------------------------------------------
+def cpu_sample(args, src, w, trg, lo, hi):
+    """Bounded sample of the same workload for the CPU arm: all sources, the central x-slab of
+    the target grid, the tree height of the FULL problem."""
+    g = args.grid
+    layers = min(args.cpu_sample_layers, g[0])
+    x0 = (g[0] - layers) // 2
+    per_layer = g[1] * g[2]
+    sub = trg[x0 * per_layer:(x0 + layers) * per_layer]
+    from oracle import fmm as ofmm
+    height = ofmm.tree_height(3, max(len(src), len(trg)))
+    desc = (f"oracle port (oracle/fmm_oracle.c, OpenMP): all {len(src)} sources -> central slab of "
+            f"{layers} x-layers = {len(sub)} of the {len(trg)} targets, tree height {height} of the full "
+            f"problem, order/d as the GPU arm; whole evaluate() incl. tree build and upward pass")
+    return sub, height, desc
+
+
+def run_cpu_once(args, src, w, sub, lo, hi, height, order, d):
+    from oracle import fmm as ofmm
+    t0 = time.perf_counter()
+    out = ofmm.fmm("bh3", [1.0, 0.0], 3, 0, lo, hi, src, sub, w, order, d, height)
+    dt = time.perf_counter() - t0
+    return dt, out
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores.
+    The reference itself cannot be built in this image (ScalFMM3 / Eigen absent), so
+    this is the oracle port, labelled as such."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import fmm as ofmm
+    src, w, trg, lo, hi = workload(args)
+    order, d = (6, -1) if np.isinf(args.accuracy) else ((12, 8) if args.accuracy == 0 else (10, -1))
+    sub, height, desc = cpu_sample(args, src, w, trg, lo, hi)
+    for _ in range(args.warmup):
+        run_cpu_once(args, src, w, sub, lo, hi, height, order, d)
+    times = [run_cpu_once(args, src, w, sub, lo, hi, height, order, d)[0] for _ in range(args.steps)]
+    t = float(np.mean(times))
+    value = len(sub) / t / 1e6
+    cores = ofmm.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, len(src), len(trg), {"tree_height": height, "order": order, "d": d}, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    import polatory_b200 as pb
+    from polatory_b200 import _lib
+
+    src, w, trg, lo, hi = workload(args, rank, world)
+    n_src, n_trg = len(src), len(trg)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0, 0.0]), pb.Bbox(lo, hi))
+    ev.set_accuracy(args.accuracy)
+    d_src = torch.from_numpy(src).to(dev)
+    d_w = torch.from_numpy(w).to(dev)
+    d_trg = torch.from_numpy(trg).to(dev)
+    d_out = torch.empty(n_trg, dtype=torch.float64, device=dev)
+    ev.set_source_points(d_src)
+
+    def step_device():
+        ev.set_weights(d_w)
+        ev.set_target_points(d_trg)
+        ev.evaluate(d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()  # the library issues on the legacy default stream = torch's current stream
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = ev.launch_count()
+    ms_total = timed(step_device, args.steps)
+    launches = ev.launch_count() - launches0
+    clocks = sampler.stop()
+    phases = ev.phase_times()
+    cfg = ev.config()
+    ms_step = ms_total / args.steps
+    value = world * n_trg / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e: same calls, pinned host buffers, H2D + D2H inside the timed region ----
+    h_trg = torch.from_numpy(trg).pin_memory()
+    h_w = torch.from_numpy(w).pin_memory()
+    h_out = torch.empty(n_trg, dtype=torch.float64).pin_memory()
+
+    def step_host():
+        ev.set_weights(h_w.numpy())
+        ev.set_target_points(h_trg.numpy())
+        ev.evaluate(h_out.numpy())
+
+    for _ in range(2):
+        step_host()
+    e2e_ms = timed(step_host, args.steps) / args.steps
+    e2e_value = world * n_trg / (e2e_ms * 1e-3) / 1e6
+    host_ok = bool(np.allclose(h_out.numpy()[:1000], d_out[:1000].cpu().numpy(), rtol=0, atol=0))
+
+    # ---- roofline of the dominant kernel (live CUDA-event time of the last timed step) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    _lib.load().plt_measure_fp64_peak(ctypes.byref(tf))
+    fp64_peak = float(tf.value)
+    dominant = max(phases, key=phases.get) if phases else None
+    roofline = roofline_for(dominant, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, ev)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, n_src, n_trg, cfg, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(trg.nbytes + w.nbytes), "d2h_bytes_per_step": int(8 * n_trg),
+                "matches_device_path": host_ok},
+        "gpu_launches": int(launches),
+        "phases_ms": {k: round(v, 4) for k, v in phases.items()},
+        "roofline": roofline,
+        "fp64_peak_tflops_measured": fp64_peak,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sub, height, desc = cpu_sample(args, src, w, trg, lo, hi)
+        order, d = cfg["order"], cfg["d"]
+        dt, out_cpu = run_cpu_once(args, src, w, sub, lo, hi, height, order, d)
+        from oracle import fmm as ofmm
+        # parity of the bench's own output against the oracle on the sample
+        g = args.grid
+        layers = min(args.cpu_sample_layers, g[0])
+        x0 = (g[0] - layers) // 2
+        got = d_out[x0 * g[1] * g[2]:(x0 + layers) * g[1] * g[2]].cpu().numpy()
+        rel = float(np.max(np.abs(got - out_cpu)) / np.max(np.abs(out_cpu)))
+        line["cpu_baseline"] = {"value": len(sub) / dt / 1e6, "unit": UNIT, "cores": ofmm.num_threads(),
+                                "kind": "port", "sample": desc, "seconds": dt,
+                                "gpu_vs_cpu_port_max_rel_diff": rel}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_for(name, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, ev):
+    """Algorithmic work of the dominant kernel / its CUDA-event time."""
+    if not name:
+        return None
+    ms = phases[name]
+    p = cfg.get("order") or 0
+    stats = ev.work_stats()
+    out = {"kernel": name, "ms": ms, "work": stats}
+    F = (2 * p - 1) ** 2 * p
+    P = p ** 3
+    if name == "m2l_hadamard" and stats.get("m2l_pairs"):
+        flops = 8.0 * F * stats["m2l_pairs"]  # one complex multiply-add per frequency and pair
+        ach = flops / (ms * 1e-3) / 1e12
+        out.update({"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                    "peak_source": "DFMA-chain microbenchmark in this run (plt_measure_fp64_peak)",
+                    "algorithmic": f"8 flop x F={F} frequencies x {stats['m2l_pairs']} M2L pairs"})
+    elif name == "m2l_idft" and stats.get("m2l_target_cells"):
+        nb = (16.0 * F + 8.0 * P) * stats["m2l_target_cells"]
+        ach = nb / (ms * 1e-3) / 1e9
+        out.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_source": hbm_src,
+                    "algorithmic": f"(16 F + 8 P) bytes x {stats['m2l_target_cells']} target cells"})
+    else:
+        nb = 8.0 * (3 + 1) * n_trg
+        ach = nb / (ms * 1e-3) / 1e9
+        out.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_source": hbm_src, "algorithmic": "32 bytes per target"})
+    return out
+
+
+if __name__ == "__main__":
+    main()

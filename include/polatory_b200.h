@@ -131,12 +131,21 @@ int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size);
  * handle's stream).  names/ms: arrays of capacity cap; returns the number of phases. */
 int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap);
 
+/* Algorithmic work of the current (source tree, target tree) pair, counted on the device:
+ * M2L cell pairs, target cells with a non-empty M2L list (all levels), P2P point pairs.
+ * Diagnostic (feeds the roofline figures); valid after an evaluate() on the FMM branch. */
+int plt_eval_work_stats(plt_eval* h, int64_t* m2l_pairs, int64_t* m2l_target_cells, int64_t* p2p_pairs);
+
 /* Number of kernels launched by this handle since creation. */
 int64_t plt_eval_launch_count(plt_eval* h);
 
 /* Message of the last failure on this handle (h == NULL: last plt_eval_create failure
  * on the calling thread).  Never NULL. */
 const char* plt_last_error(plt_eval* h);
+
+/* FP64 FMA peak of the current device, measured with a DFMA-chain microbenchmark (TFLOP/s);
+ * the denominator of the FP64 roofline. */
+int plt_measure_fp64_peak(double* tflops);
 
 /* Library/ABI version and a device probe (returns PLT_ERR_CUDA without a usable GPU). */
 int plt_version(void);

@@ -39,8 +39,11 @@ SYMBOLS = [
     ("plt_eval_set_stream", ctypes.c_int, [_vp, _vp]),
     ("plt_eval_set_target_shard", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     ("plt_eval_phase_times", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), _c_double_p, ctypes.c_int]),
+    ("plt_eval_work_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_int64)]),
     ("plt_eval_launch_count", ctypes.c_int64, [_vp]),
     ("plt_last_error", ctypes.c_char_p, [_vp]),
+    ("plt_measure_fp64_peak", ctypes.c_int, [_c_double_p]),
     ("plt_version", ctypes.c_int, []),
     ("plt_device_check", ctypes.c_int, []),
 ]

@@ -216,6 +216,16 @@ struct plt_eval {
     int ndev = 0;
     PLT_CUDA(cudaGetDeviceCount(&ndev));
     if (ndev == 0) throw Error(PLT_ERR_CUDA, "no CUDA device");
+    {
+      // Keep freed blocks in the stream-ordered pool (default threshold 0 returns them to the
+      // driver at every synchronisation, which turns each evaluate() into GBs of cudaMalloc).
+      int dev = 0;
+      PLT_CUDA(cudaGetDevice(&dev));
+      cudaMemPool_t pool;
+      PLT_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = UINT64_MAX;
+      PLT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     if (rbf.spheroidal && part_ == PLT_PART_FULL) {
       direct_part = std::make_unique<plt_eval>();
       direct_part->init(kind, symmetric, dim, rbf_id, PLT_PART_DIRECT, params_, n_params, aniso_, bmin, bmax);
@@ -430,10 +440,9 @@ struct plt_eval {
         PLT_CUDA(cudaMemcpyAsync(&n_active, d_count.get(), sizeof(int), cudaMemcpyDeviceToHost, stream));
         PLT_CUDA(cudaStreamSynchronize(stream));
         if (timed) timer.end(stream);
-        if (timed) timer.begin("m2l", stream);
+        Lhat.alloc(static_cast<size_t>(std::min(chunk_parents, std::max(n_active, 1))) * per_parent, stream);
         for (int c0 = 0; c0 < n_active; c0 += chunk_parents) {
           const int nc = std::min(chunk_parents, n_active - c0);
-          Lhat.alloc(static_cast<size_t>(nc) * per_parent, stream);
           M2LArgs a{};
           a.src = sv;
           a.trg = tv;
@@ -448,10 +457,13 @@ struct plt_eval {
           a.n_active = nc;
           a.Lhat = Lhat.get();
           a.L = L.get();
+          if (timed) timer.begin("m2l_hadamard", stream);
           launch_m2l_hadamard(a, stream, ctr);
+          if (timed) timer.end(stream);
+          if (timed) timer.begin("m2l_idft", stream);
           launch_m2l_idft(a, ip.dev, stream, ctr);
+          if (timed) timer.end(stream);
         }
-        if (timed) timer.end(stream);
         if (l > 2) {
           if (timed) timer.begin("l2l", stream);
           launch_l2l(dim, kn, tv, l, ip.dev, L.get(), lo[l], hi[l], stream, ctr);
@@ -895,6 +907,26 @@ int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap) {
     h->err = e.what();
   }
   return n;
+}
+
+int plt_eval_work_stats(plt_eval* h, int64_t* m2l_pairs, int64_t* m2l_target_cells, int64_t* p2p_pairs) {
+  return guarded(h, [&] {
+    plt_eval* e = h->fast_part ? h->fast_part.get() : h;
+    unsigned long long host[3] = {0, 0, 0};
+    const Tree& tt = e->target_tree();
+    if (e->src_tree.built() && tt.built()) {
+      DevBuf<unsigned long long> d;
+      d.alloc(3, e->stream);
+      d.zero(e->stream);
+      LaunchCounter scratch;  // diagnostic launches are not part of the evaluation count
+      launch_count_work(e->dim, e->src_tree.view(), tt.view(), d.get(), e->stream, scratch);
+      PLT_CUDA(cudaMemcpyAsync(host, d.get(), sizeof(host), cudaMemcpyDeviceToHost, e->stream));
+      PLT_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    if (m2l_pairs) *m2l_pairs = static_cast<int64_t>(host[0]);
+    if (m2l_target_cells) *m2l_target_cells = static_cast<int64_t>(host[1]);
+    if (p2p_pairs) *p2p_pairs = static_cast<int64_t>(host[2]);
+  });
 }
 
 int64_t plt_eval_launch_count(plt_eval* h) {

@@ -608,6 +608,77 @@ __global__ void __launch_bounds__(kBlock) k_m2l_idft(M2LArgs a, InterpDev it, do
   }
 }
 
+// Work counters for the roofline figures (not on the timed path): M2L pairs and target cells
+// with a non-empty list at one level; P2P pairs at the leaves.
+template <int DIM>
+__global__ void k_count_m2l(TreeView src, TreeView trg, int level, unsigned long long* __restrict__ counters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long pairs = 0;
+  if (i < trg.n_cells[level]) {
+    int c[DIM], pc[DIM];
+    morton_decode<DIM>(trg.keys[trg.cell_off[level] + i], c);
+    const int nside_p = 1 << (level - 1);
+    const int* sd = src.dense + src.dense_off[level];
+    int nn = 1;
+    for (int a = 0; a < DIM; ++a) { nn *= 3; pc[a] = c[a] >> 1; }
+    for (int e = 0; e < nn; ++e) {
+      int q[DIM], r = e;
+      bool ok = true;
+#pragma unroll
+      for (int a = DIM - 1; a >= 0; --a) {
+        q[a] = pc[a] + (r % 3) - 1;
+        r /= 3;
+        ok = ok && q[a] >= 0 && q[a] < nside_p;
+      }
+      if (!ok) continue;
+      for (int ch = 0; ch < (1 << DIM); ++ch) {
+        int s[DIM];
+        bool far = false;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+          s[a] = 2 * q[a] + ((ch >> (DIM - 1 - a)) & 1);
+          int o = s[a] - c[a];
+          far = far || o > 1 || o < -1;
+        }
+        if (far && sd[morton_encode<DIM>(s)] >= 0) ++pairs;
+      }
+    }
+  }
+  if (pairs) {
+    atomicAdd(&counters[0], pairs);
+    atomicAdd(&counters[1], 1ull);
+  }
+}
+
+template <int DIM>
+__global__ void k_count_p2p(TreeView src, TreeView trg, unsigned long long* __restrict__ counters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int leaf = trg.height - 1;
+  if (i >= trg.n_cells[leaf]) return;
+  int c[DIM];
+  morton_decode<DIM>(trg.keys[trg.cell_off[leaf] + i], c);
+  const int nside = 1 << leaf;
+  const int* sd = src.dense + src.dense_off[leaf];
+  int nn = 1;
+  for (int a = 0; a < DIM; ++a) nn *= 3;
+  unsigned long long ns = 0;
+  for (int e = 0; e < nn; ++e) {
+    int q[DIM], r = e;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = c[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (!ok) continue;
+    int sc = sd[morton_encode<DIM>(q)];
+    if (sc >= 0) ns += src.leaf_start[sc + 1] - src.leaf_start[sc];
+  }
+  unsigned long long nt = trg.leaf_start[i + 1] - trg.leaf_start[i];
+  if (ns) atomicAdd(&counters[2], ns * nt);
+}
+
 size_t smem_opt_in(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
     PLT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
@@ -738,6 +809,22 @@ void launch_m2l_mark_active(int dim, const TreeView& src, const TreeView& trg, i
   if (dim == 1) PLT_LAUNCH(c, k_m2l_mark_active<1>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
   if (dim == 2) PLT_LAUNCH(c, k_m2l_mark_active<2>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
   if (dim == 3) PLT_LAUNCH(c, k_m2l_mark_active<3>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
+}
+
+void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
+                       cudaStream_t s, LaunchCounter& c) {
+  for (int l = 2; l < trg.height; ++l) {
+    const int n = trg.n_cells[l];
+    if (n == 0) continue;
+    if (dim == 1) PLT_LAUNCH(c, k_count_m2l<1>, ceil_div(n, 256), 256, 0, s, src, trg, l, counters);
+    if (dim == 2) PLT_LAUNCH(c, k_count_m2l<2>, ceil_div(n, 256), 256, 0, s, src, trg, l, counters);
+    if (dim == 3) PLT_LAUNCH(c, k_count_m2l<3>, ceil_div(n, 256), 256, 0, s, src, trg, l, counters);
+  }
+  const int n = trg.n_cells[trg.height - 1];
+  if (n == 0) return;
+  if (dim == 1) PLT_LAUNCH(c, k_count_p2p<1>, ceil_div(n, 256), 256, 0, s, src, trg, counters);
+  if (dim == 2) PLT_LAUNCH(c, k_count_p2p<2>, ceil_div(n, 256), 256, 0, s, src, trg, counters);
+  if (dim == 3) PLT_LAUNCH(c, k_count_p2p<3>, ceil_div(n, 256), 256, 0, s, src, trg, counters);
 }
 
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {

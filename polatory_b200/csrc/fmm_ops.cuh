@@ -72,6 +72,9 @@ struct M2LArgs {
 void launch_m2l_mark_active(int dim, const TreeView& src, const TreeView& trg, int level, int* flags,
                             cudaStream_t s, LaunchCounter& c);
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
+// counters[0] += M2L pairs, [1] += target cells with a non-empty M2L list, [2] += P2P pairs.
+void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
+                       cudaStream_t s, LaunchCounter& c);
 void launch_m2l_idft(const M2LArgs& a, const InterpDev& it, cudaStream_t s, LaunchCounter& c);
 
 // ---- downward ----

@@ -134,6 +134,11 @@ class _EvaluatorBase:
         n = self._lib.plt_eval_phase_times(self._h, names, ms, cap)
         return {names[i].decode(): ms[i] for i in range(n)}
 
+    def work_stats(self):
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._h, self._lib.plt_eval_work_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"m2l_pairs": a.value, "m2l_target_cells": b.value, "p2p_pairs": c.value}
+
     def launch_count(self):
         return int(self._lib.plt_eval_launch_count(self._h))
 

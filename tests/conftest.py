@@ -1,0 +1,36 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def random_anisotropy(dim, rng):
+    """test/utility.hpp:13-42 with a seeded generator: scaling 10^(+-0.5) (det 1) x rotation."""
+    q, _ = np.linalg.qr(rng.standard_normal((dim, dim)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] *= -1.0
+    s = 10.0 ** (0.5 * rng.uniform(-1.0, 1.0, dim))
+    s /= np.prod(s) ** (1.0 / dim)
+    return np.diag(s) @ q
+
+
+ALL_RBFS = ["bh3", "th3", "bh2", "th2", "exp", "gau", "gc3", "gc5", "gc7", "gc9", "sp3", "sp5", "sp7", "sp9",
+            "sph", "cub"]
+
+
+def default_params(name):
+    return [1.3, 0.1] if name in ("bh3", "th3", "bh2", "th2") else [1.1, 0.7]
+
+
+@pytest.fixture
+def rng():
+    return np.random.default_rng(12345)

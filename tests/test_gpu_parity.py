@@ -1,0 +1,362 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle.
+
+Tolerances (FP64):
+  * brute-force / P2P-only paths vs exact direct sum ............ 1e-12 * max|ref|
+  * GPU FMM vs the CPU restatement with the same (height, order, d): 1e-10 * max|ref|
+    (north_star's relative tolerance; only the summation order differs)
+  * GPU FMM vs exact direct sum ................................. the requested absolute
+    `accuracy`, the reference's own criterion (test/interpolation/test_evaluator.cpp:70-75)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ALL_RBFS, default_params, random_anisotropy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import polatory_b200
+    from polatory_b200 import _lib
+    assert _lib.load().plt_device_check() == 0
+    return polatory_b200
+
+
+def _oracle():
+    from oracle import direct as odir
+    from oracle import fmm as ofmm
+    from oracle import rbf as orbf
+    return odir, ofmm, orbf
+
+
+def _relerr(got, ref):
+    return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+# ---------------------------------------------------------------------------------------
+# 1. every RBF x kernel kind x dimension on the committed golden vectors (brute-force branch)
+# ---------------------------------------------------------------------------------------
+def test_golden_direct_cases(pb):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "direct_golden.npz"))
+    worst = 0.0
+    for key in g["cases"]:
+        name, dim, kind = key.split("_")
+        dim, kind = int(dim), int(kind)
+        rbf = pb.make_rbf(name, default_params(name), dim, g[key + "_aniso"])
+        ev = pb.FmmGenericEvaluator(kind, rbf, pb.Bbox(-np.ones(dim), np.ones(dim)))
+        ev.set_source_points(g[key + "_src"])
+        ev.set_target_points(g[key + "_trg"])
+        ev.set_weights(g[key + "_w"])
+        got = ev.evaluate()
+        assert ev.config()["tree_height"] == 0  # n_src * n_trg < 1024^2 -> full_direct
+        ref = g[key + "_out"]
+        if np.isnan(ref).any():
+            assert (np.isnan(ref) == np.isnan(got)).all(), key
+            continue
+        tol = 1e-10 if (dim == 1 and kind == 3) else 1e-12  # 1-D Hessians cancel to ~0
+        err = _relerr(got, ref)
+        worst = max(worst, err)
+        assert err < tol, (key, err)
+    print("worst golden rel err", worst)
+
+
+# ---------------------------------------------------------------------------------------
+# 2. GPU FMM == CPU restatement with the same discretisation
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,n", [(3, 12000), (2, 12000), (1, 4000)])
+@pytest.mark.parametrize("name,params", [("bh3", [1.0, 0.0]), ("th3", [1.0, 0.01]), ("bh2", [1.0, 0.0]),
+                                         ("exp", [1.0, 0.5]), ("gc5", [1.2, 0.8])])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_fmm_matches_cpu_restatement(pb, dim, n, name, params, kind, rng):
+    odir, ofmm, _ = _oracle()
+    if dim == 1 and kind == 3 and name == "bh3":
+        pytest.skip("the 1-D Hessian of |x| vanishes identically")
+    a = random_anisotropy(dim, rng)
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (n // 2, dim))
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    ev = pb.FmmGenericEvaluator(kind, pb.make_rbf(name, params, dim, a), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    for order, d in ((6, -1), (12, 8)):
+        ev.force_config(order, d)
+        got = ev.evaluate()
+        cfg = ev.config()
+        assert cfg["order"] == order and cfg["d"] == d and cfg["tree_height"] == ofmm.tree_height(dim, n)
+        ref = ofmm.fmm(name, params, dim, kind, -np.ones(dim), np.ones(dim), src, trg, w, order, d, 0, a)
+        assert _relerr(got, ref) < 1e-10, (order, d, _relerr(got, ref))
+
+
+# ---------------------------------------------------------------------------------------
+# 3. the reference's own test shapes
+# ---------------------------------------------------------------------------------------
+def test_reference_evaluator_test_shape(pb, rng):
+    """test/interpolation/test_evaluator.cpp:27-75: th3, random anisotropy, 1024 points + 1024
+    gradient points -> 1024 + 1024 gradient targets in [-1,1]^3, accuracy 1e-4 (values and
+    gradients), composed exactly as interpolation::Evaluator does (evaluator.hpp:65-81)."""
+    odir, ofmm, orbf = _oracle()
+    dim, n = 3, 1024
+    accuracy = 1e-4
+    a = random_anisotropy(dim, rng)
+    pts, gpts, epts, gepts = (rng.uniform(-1, 1, (n, dim)) for _ in range(4))
+    w = rng.uniform(-1, 1, n + dim * n)
+    rbf = pb.make_rbf("th3", [1.0], dim, a)
+    bbox = pb.Bbox(-np.ones(dim), np.ones(dim))
+    ea, ef = pb.make_fmm_evaluator(rbf, bbox), pb.make_fmm_gradient_evaluator(rbf, bbox)
+    eft, eh = pb.make_fmm_gradient_transpose_evaluator(rbf, bbox), pb.make_fmm_hessian_evaluator(rbf, bbox)
+    for e, s, t in ((ea, pts, epts), (ef, gpts, epts), (eft, pts, gepts), (eh, gpts, gepts)):
+        e.set_source_points(s)
+        e.set_target_points(t)
+        e.set_accuracy(accuracy / 2.0)  # evaluator.hpp:95-97 (sigma > 0 halves the accuracy)
+    ea.set_weights(w[:n]); eft.set_weights(w[:n])
+    ef.set_weights(w[n:]); eh.set_weights(w[n:])
+    values = ea.evaluate() + ef.evaluate()
+    grads = eft.evaluate() + eh.evaluate()
+    assert ea.config()["tree_height"] == 3  # 1024 * 1024 is not < 1024^2 -> FMM branch
+    ref = odir.direct_evaluator(orbf.make_rbf("th3", [1.0], dim, a), 0.0, pts, gpts, w, epts, gepts)
+    assert np.max(np.abs(values - ref[:n])) < accuracy
+    assert np.max(np.abs(grads - ref[n:])) < accuracy
+
+
+@pytest.mark.parametrize("kind", [0, 3])
+def test_reference_symmetric_evaluator_test_shape(pb, kind, rng):
+    """test/interpolation/test_symmetric_evaluator.cpp:24-62 (sources == targets, 1024 >= 1024 ->
+    FMM branch) incl. the self interaction of fmm_symmetric_evaluator.hpp:163-193."""
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 1024
+    a = random_anisotropy(dim, rng)
+    pts = rng.uniform(-1, 1, (n, dim))
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    rbf = pb.make_rbf("th3", [1.0, 0.05], dim, a)
+    ev = pb.FmmGenericSymmetricEvaluator(kind, rbf, pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_points(pts)
+    ev.set_accuracy(1e-4)
+    ev.set_weights(w)
+    got = ev.evaluate()
+    assert ev.config()["tree_height"] == 3
+    ref = ofmm.direct("th3", [1.0, 0.05], dim, kind, pts, None, w, a, symmetric=True)
+    assert np.max(np.abs(got - ref)) < 1e-4
+    # below 1024 points: brute-force branch, exact
+    ev.set_points(pts[:500])
+    ev.set_weights(w[:500 * odir.kind_km(kind, dim)])
+    got = ev.evaluate()
+    assert ev.config()["tree_height"] == 0
+    ref = ofmm.direct("th3", [1.0, 0.05], dim, kind, pts[:500], None, w[:500 * odir.kind_km(kind, dim)], a,
+                      symmetric=True)
+    assert _relerr(got, ref) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------
+# 4. accuracy -> (order, d) policy (src/fmm/fmm_accuracy_estimator.hpp:74-121)
+# ---------------------------------------------------------------------------------------
+def test_accuracy_policy(pb, rng):
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 20000
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (3000, dim))
+    w = rng.uniform(-1, 1, n)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    ref = ofmm.direct("bh3", [1.0, 0.0], dim, 0, src, trg, w)
+    ev.evaluate()
+    assert (ev.config()["order"], ev.config()["d"]) == (6, -1)  # default accuracy = infinity
+    ev.set_accuracy(0.0)
+    ev.evaluate()
+    assert (ev.config()["order"], ev.config()["d"]) == (12, 8)
+    for acc in (1e-2, 1e-5):
+        ev.set_accuracy(acc)
+        got = ev.evaluate()
+        cfg = ev.config()
+        assert cfg["order"] >= 8 and cfg["order"] % 2 == 0
+        assert (cfg["d"] == -1) == (cfg["order"] < 12)
+        assert np.max(np.abs(got - ref)) <= 10 * acc  # searched on sampled source points
+    ev.set_accuracy(1e-30)
+    from polatory_b200 import _lib
+    with pytest.raises(_lib.PolatoryB200Error) as e:
+        ev.evaluate()
+    assert e.value.status == _lib.PLT_ERR_ACCURACY
+    assert "desired accuracy" in str(e.value)
+
+
+# ---------------------------------------------------------------------------------------
+# 5. compact-support RBFs and the spheroidal split
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,params", [("sph", [1.1, 0.3]), ("cub", [0.9, 0.25])])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_compact_support_evaluators(pb, name, params, kind, rng):
+    """src/fmm/direct_evaluator.hpp:41-68 (kd-tree radius search) -> device cell list; exact."""
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 20000
+    a = random_anisotropy(dim, rng)
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (5000, dim))
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    ev = pb.FmmGenericEvaluator(kind, pb.make_rbf(name, params, dim, a), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    got = ev.evaluate()
+    assert ev.config()["tree_height"] > 2 and ev.config()["order"] == 0  # P2P only
+    ref = ofmm.direct(name, params, dim, kind, src, trg, w, a)
+    assert _relerr(got, ref) < 1e-12
+
+
+def test_compact_hessian_is_unsupported(pb):
+    from polatory_b200 import _lib
+    with pytest.raises(_lib.PolatoryB200Error) as e:
+        pb.make_fmm_hessian_evaluator(pb.make_rbf("sph", [1.0, 1.0]), pb.Bbox(-np.ones(3), np.ones(3)))
+    assert e.value.status == _lib.PLT_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["sp3", "sp9"])
+@pytest.mark.parametrize("kind", [0, 3])
+def test_spheroidal_split(pb, name, kind, rng):
+    """src/fmm/spheroidal_evaluator.hpp:24-29: compact direct part + FMM fast part."""
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 20000
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (4000, dim))
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    ev = pb.FmmGenericEvaluator(kind, pb.make_rbf(name, [1.0, 0.6], dim), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    ev.force_config(10, -1)
+    got = ev.evaluate()
+    ref = ofmm.direct(name, [1.0, 0.6], dim, kind, src, trg, w)
+    assert _relerr(got, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------
+# 6. edge cases
+# ---------------------------------------------------------------------------------------
+def test_empty_and_tiny_inputs(pb, rng):
+    odir, ofmm, _ = _oracle()
+    bbox = pb.Bbox(-np.ones(3), np.ones(3))
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), bbox)
+    # sigma = 0 pattern of SURVEY 3.1: zero sources -> zero output, zero targets -> empty output
+    ev.set_source_points(np.zeros((0, 3)))
+    ev.set_target_points(rng.uniform(-1, 1, (7, 3)))
+    ev.set_weights(np.zeros(0))
+    assert np.array_equal(ev.evaluate(), np.zeros(7))
+    ev.set_source_points(rng.uniform(-1, 1, (5, 3)))
+    ev.set_weights(rng.uniform(-1, 1, 5))
+    ev.set_target_points(np.zeros((0, 3)))
+    assert ev.evaluate().shape == (0,)
+    # one source, one target
+    ev.set_source_points(np.array([[0.1, 0.2, 0.3]]))
+    ev.set_weights(np.array([2.0]))
+    ev.set_target_points(np.array([[0.4, 0.2, 0.3]]))
+    np.testing.assert_allclose(ev.evaluate(), [-2.0 * 0.3], rtol=1e-14)
+    # size mismatch is an error, not an assert
+    from polatory_b200 import _lib
+    with pytest.raises(_lib.PolatoryB200Error):
+        ev.set_weights(np.zeros(3))
+
+
+def test_coincident_and_clustered_points(pb, rng):
+    """All sources in one leaf plus duplicated points: ragged leaves, P2P at d = 0."""
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 6000
+    src = np.concatenate([rng.uniform(-1, 1, (n // 2, dim)), 1e-3 * rng.standard_normal((n // 2, dim)) + 0.3])
+    src[10] = src[11]
+    trg = np.concatenate([src[:1000], rng.uniform(-1, 1, (1500, dim))])
+    w = rng.uniform(-1, 1, n)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("th3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    ev.force_config(10, -1)
+    got = ev.evaluate()
+    assert ev.config()["tree_height"] == 4
+    ref = ofmm.direct("th3", [1.0, 0.0], dim, 0, src, trg, w)
+    assert _relerr(got, ref) < 1e-7
+    ref_fmm = ofmm.fmm("th3", [1.0, 0.0], dim, 0, -np.ones(dim), np.ones(dim), src, trg, w, 10, -1, 0)
+    assert _relerr(got, ref_fmm) < 1e-10
+
+
+def test_device_resident_io_and_weight_update(pb, rng):
+    """Device pointers across the ABI (torch tensors), multipoles recomputed on set_weights."""
+    import torch
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 15000
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (9000, dim))
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(torch.from_numpy(src).cuda())
+    ev.set_target_points(torch.from_numpy(trg).cuda())
+    out = torch.empty(9000, dtype=torch.float64, device="cuda")
+    ev.force_config(8, -1)
+    for seed in (1, 2):
+        w = np.random.default_rng(seed).uniform(-1, 1, n)
+        ev.set_weights(torch.from_numpy(w).cuda())
+        ev.evaluate(out)
+        ref = ofmm.fmm("bh3", [1.0, 0.0], dim, 0, -np.ones(dim), np.ones(dim), src, trg, w, 8, -1, 0)
+        assert _relerr(out.cpu().numpy(), ref) < 1e-10
+    assert ev.launch_count() > 0
+    assert "m2l" in ev.phase_times()
+
+
+# ---------------------------------------------------------------------------------------
+# 7. Morton-range shards reassemble to the unsharded result
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_target_shards_sum_to_full(pb, world, rng):
+    dim, n = 3, 30000
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (20000, dim))
+    w = rng.uniform(-1, 1, n)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    full = ev.evaluate().copy()
+    total = np.zeros_like(full)
+    counts = np.zeros_like(full)
+    for r in range(world):
+        ev.set_target_shard(r, world)
+        part = ev.evaluate()
+        total += part
+        counts += part != 0.0
+    ev.set_target_shard(0, 1)
+    assert counts.max() <= 1  # disjoint shards
+    assert _relerr(total, full) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------
+# 8. BASELINE.json sizes, through size-independent properties
+# ---------------------------------------------------------------------------------------
+def test_full_size_linearity_and_sampled_direct(pb):
+    """Config #3 at full size (10^6 bh3 sources -> 10^7 grid targets): linearity in the weights
+    and a sampled comparison with the exact direct sum."""
+    import torch
+    odir, ofmm, _ = _oracle()
+    from polatory_b200 import workloads as wl
+    src, w1, trg, lo, hi = wl.c3_isosurface_field()
+    w2 = wl.uniform_weights(len(src), seed=7)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0, 0.0]), pb.Bbox(lo, hi))
+    ev.set_source_points(src)
+    d_trg = torch.from_numpy(trg).cuda()
+    ev.set_target_points(d_trg)
+    outs = []
+    for w in (w1, w2, w1 + 2.0 * w2):
+        ev.set_weights(w)
+        out = torch.empty(len(trg), dtype=torch.float64, device="cuda")
+        ev.evaluate(out)
+        outs.append(out)
+    assert ev.config() == {"tree_height": 8, "order": 6, "d": -1}
+    scale = float(outs[2].abs().max())
+    lin = float((outs[0] + 2.0 * outs[1] - outs[2]).abs().max())
+    assert lin < 1e-12 * scale
+    sub = np.random.default_rng(3).choice(len(trg), 256, replace=False)
+    ref = ofmm.direct("bh3", [1.0, 0.0], 3, 0, src, trg[sub], w1)
+    got = outs[0].cpu().numpy()[sub]
+    assert np.max(np.abs(got - ref)) < 2e-5 * np.max(np.abs(ref))  # order 6 (accuracy = infinity)
