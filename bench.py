@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--n-sources", type=int, default=N_SOURCES)
     ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--cpu-sample-layers", type=int, default=21,
                     help="x-layers of the target grid (central slab) the CPU arm evaluates per step")
     return ap.parse_args()
@@ -273,11 +274,14 @@ def main():
         ev.set_target_points(h_trg.numpy())
         ev.evaluate(h_out.numpy())
 
-    for _ in range(2):
-        step_host()
-    e2e_ms = timed(step_host, args.steps) / args.steps
-    e2e_value = world * n_trg / (e2e_ms * 1e-3) / 1e6
-    host_ok = bool(np.allclose(h_out.numpy()[:1000], d_out[:1000].cpu().numpy(), rtol=0, atol=0))
+    if args.no_e2e:
+        e2e_ms, e2e_value, host_ok = None, None, None
+    else:
+        for _ in range(2):
+            step_host()
+        e2e_ms = timed(step_host, args.steps) / args.steps
+        e2e_value = world * n_trg / (e2e_ms * 1e-3) / 1e6
+        host_ok = bool(np.allclose(h_out.numpy()[:1000], d_out[:1000].cpu().numpy(), rtol=0, atol=0))
 
     # ---- roofline of the dominant kernel (live CUDA-event time of the last timed step) ----
     peaks = {}

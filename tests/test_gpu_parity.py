@@ -53,7 +53,8 @@ def test_golden_direct_cases(pb):
         ev.set_target_points(g[key + "_trg"])
         ev.set_weights(g[key + "_w"])
         got = ev.evaluate()
-        assert ev.config()["tree_height"] == 0  # n_src * n_trg < 1024^2 -> full_direct
+        if name not in ("sph", "cub"):  # compact kernels run on a cell list instead (direct_evaluator.hpp:41-68)
+            assert ev.config()["tree_height"] == 0  # n_src * n_trg < 1024^2 -> full_direct
         ref = g[key + "_out"]
         if np.isnan(ref).any():
             assert (np.isnan(ref) == np.isnan(got)).all(), key

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Summarise gpurun_out ncu artefacts into profiles/ (tracked).
+  python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r01_x_launches.md
+  python tools/ncu_summary.py full gpurun_out/prof_top.ncu-rep profiles/r01_x_full.md
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct",
+]
+
+
+def launches(src, dst):
+    rows = list(csv.reader(open(src)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        name = re.sub(r"\(.*", "", r[ki])
+        name = re.sub(r"void |plt::|<unnamed>::|\(anonymous namespace\)::", "", name)[:80]
+        v = float(r[vi].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(r[ui], v)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list summary ({src}): gpu__time_duration.sum, --clock-control none\n\n")
+        f.write("Cold-cache, serialised per-launch times: compare SHARES, not absolutes.\n\n")
+        f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"| `{k}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / tot:.1f}% |\n")
+        f.write(f"\ntotal {tot:.1f} us over {sum(a[0] for a in agg.values())} launches\n")
+    print(open(dst).read())
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary ({src}), --clock-control none\n")
+        for r in rows[2:]:
+            f.write(f"\n## {r[hdr.index('Kernel Name')][:100]}\n\n| metric | unit | value |\n|---|---|---:|\n")
+            for w in WANT:
+                if w in hdr:
+                    i = hdr.index(w)
+                    f.write(f"| {w} | {units[i]} | {r[i]} |\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
