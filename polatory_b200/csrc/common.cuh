@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <utility>
+#include <vector>
 
 #include "../../include/polatory_b200.h"
 
@@ -100,6 +102,75 @@ class DevBuf {
   T* ptr_ = nullptr;
   size_t n_ = 0, cap_ = 0;
   cudaStream_t stream_ = nullptr;
+};
+
+// Grow-only bump arena for the temporaries of one evaluate(): after the first call with a given
+// problem shape the steady state performs no allocation at all (no cudaMalloc, no pool
+// traffic); reset() rewinds it.  Blocks are 256-byte aligned.  Growth adds a block; the next
+// reset() coalesces the blocks into one (the only place that synchronises the device).
+class Arena {
+ public:
+  Arena() = default;
+  Arena(const Arena&) = delete;
+  Arena& operator=(const Arena&) = delete;
+  ~Arena() {
+    for (auto& b : blocks_) cudaFree(b.ptr);
+  }
+  void reset() {
+    if (blocks_.size() > 1) {
+      size_t total = 0;
+      for (auto& b : blocks_) total += b.cap;
+      PLT_CUDA(cudaDeviceSynchronize());
+      for (auto& b : blocks_) cudaFree(b.ptr);
+      blocks_.clear();
+      add_block(total);
+    }
+    for (auto& b : blocks_) b.used = 0;
+    high_ = 0;
+  }
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t{255};
+    if (bytes == 0) bytes = 256;
+    for (auto& b : blocks_) {
+      if (b.used + bytes <= b.cap) {
+        T* p = reinterpret_cast<T*>(static_cast<char*>(b.ptr) + b.used);
+        b.used += bytes;
+        return p;
+      }
+    }
+    add_block(std::max(bytes, kMinBlock));
+    blocks_.back().used = bytes;
+    return static_cast<T*>(blocks_.back().ptr);
+  }
+  // Snapshot / restore of the bump pointers (nested temporaries, e.g. the accuracy search).
+  std::vector<size_t> mark() const {
+    std::vector<size_t> m;
+    for (auto& b : blocks_) m.push_back(b.used);
+    return m;
+  }
+  void rewind(const std::vector<size_t>& m) {
+    for (size_t i = 0; i < blocks_.size(); ++i) blocks_[i].used = i < m.size() ? m[i] : 0;
+  }
+  size_t capacity() const {
+    size_t t = 0;
+    for (auto& b : blocks_) t += b.cap;
+    return t;
+  }
+
+ private:
+  static constexpr size_t kMinBlock = size_t{64} << 20;
+  struct Block {
+    void* ptr;
+    size_t cap, used;
+  };
+  void add_block(size_t cap) {
+    void* p = nullptr;
+    PLT_CUDA(cudaMalloc(&p, cap));
+    blocks_.push_back(Block{p, cap, 0});
+  }
+  std::vector<Block> blocks_;
+  size_t high_ = 0;
 };
 
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }

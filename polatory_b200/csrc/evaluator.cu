@@ -6,6 +6,7 @@
 // (order, d) policy; everything below that line is device-resident and new.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -22,6 +23,7 @@
 #include "direct.cuh"
 #include "fmm_ops.cuh"
 #include "interp.hpp"
+#include "plan.cuh"
 #include "rbf_host.hpp"
 #include "tree.cuh"
 
@@ -56,19 +58,41 @@ __global__ void k_add(const double* __restrict__ a, int64_t n, double* __restric
   if (i < n) out[i] += a[i];
 }
 
-// Per-level compact-cell ranges covering the leaves [leaf_lo, leaf_hi) of a tree.
-__global__ void k_level_ranges(TreeView tr, int leaf_lo, int leaf_hi, int* __restrict__ lo, int* __restrict__ hi) {
+// Per-level compact-cell ranges covering the leaves [leaf_lo, leaf_hi) of a tree, and the
+// matching slot ranges of the plan's active-parent lists (children level l <-> parents l-1).
+__global__ void k_level_ranges(TreeView tr, PlanView pv, int leaf_lo, int leaf_hi, int* __restrict__ lo,
+                               int* __restrict__ hi, int* __restrict__ slot_lo, int* __restrict__ slot_hi) {
   int l = threadIdx.x;
   if (l >= tr.height) return;
   const int leaf = tr.height - 1;
   if (leaf_hi <= leaf_lo) {
     lo[l] = hi[l] = 0;
+    slot_lo[l] = slot_hi[l] = 0;
     return;
   }
   uint32_t k0 = tr.keys[tr.cell_off[leaf] + leaf_lo] >> (tr.dim * (leaf - l));
   uint32_t k1 = tr.keys[tr.cell_off[leaf] + leaf_hi - 1] >> (tr.dim * (leaf - l));
   lo[l] = tr.dense[tr.dense_off[l] + k0];
   hi[l] = tr.dense[tr.dense_off[l] + k1] + 1;
+  slot_lo[l] = slot_hi[l] = 0;
+  if (l >= 2) {
+    // parents of level l-1 in [plo, phi): slots of level l whose parent id falls in that range
+    const int plo = tr.dense[tr.dense_off[l - 1] + (k0 >> tr.dim)];
+    const int phi = tr.dense[tr.dense_off[l - 1] + (k1 >> tr.dim)] + 1;
+    const int b = pv.level_begin[l], e = pv.level_begin[l + 1];
+    int x = b, y = e;
+    while (x < y) {
+      int m = (x + y) >> 1;
+      if (pv.active[m] < plo) x = m + 1; else y = m;
+    }
+    slot_lo[l] = x;
+    y = e;
+    while (x < y) {
+      int m = (x + y) >> 1;
+      if (pv.active[m] < phi) x = m + 1; else y = m;
+    }
+    slot_hi[l] = x;
+  }
 }
 
 // First leaf whose point range starts at or after `point` (leaf-granular shard boundary).
@@ -159,6 +183,9 @@ struct plt_eval {
   bool have_weights = false;
 
   Tree src_tree, trg_tree;
+  Plan plan;           // interaction plan of (src_tree, target_tree()); rebuilt with either tree
+  Arena arena;         // temporaries of one evaluate()
+  DevBuf<double> stage;  // host -> device staging of caller points
   bool multipole_dirty = true;
   int up_order = 0, up_d = 0;  // configuration the cached multipoles were built with
   DevBuf<double> wt_sorted;    // [km][n_src] folded, sorted
@@ -259,13 +286,18 @@ struct plt_eval {
     for (int a = 0; a < dim; ++a) box.center[a] = lo[a] + 0.5 * (hi[a] - lo[a]);
   }
 
+  static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes attr{};
+    bool dev = cudaPointerGetAttributes(&attr, p) == cudaSuccess &&
+               (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    return dev;
+  }
+
   // Copy caller data (host or device pointer) in; host sources are fully consumed on return.
   void copy_in(void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
-    cudaPointerAttributes attr{};
-    bool dev = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
-               (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-    cudaGetLastError();
+    const bool dev = is_device_pointer(src);
     PLT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream));
     if (!dev) PLT_CUDA(cudaStreamSynchronize(stream));
   }
@@ -278,12 +310,17 @@ struct plt_eval {
       direct_part->set_points_impl(pts, n, source);
       fast_part->set_points_impl(pts, n, source);
     }
-    DevBuf<double> staged;
-    staged.alloc(static_cast<size_t>(n) * dim, stream);
-    copy_in(staged.get(), pts, sizeof(double) * n * dim);
+    const double* dev_pts = pts;
+    if (n > 0 && !is_device_pointer(pts)) {
+      stage.alloc(static_cast<size_t>(n) * dim, stream);
+      PLT_CUDA(cudaMemcpyAsync(stage.get(), pts, sizeof(double) * n * dim, cudaMemcpyHostToDevice, stream));
+      dev_pts = stage.get();
+    }
     DevBuf<double>& pos = source ? src_pos_c : trg_pos_c;
     pos.alloc(static_cast<size_t>(n) * dim, stream);
-    launch_transform_points(dim, aniso, staged.get(), n, pos.get(), stream, ctr);
+    launch_transform_points(dim, aniso, dev_pts, n, pos.get(), stream, ctr);
+    if (dev_pts != pts) PLT_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its host buffer
+    plan.reset();
     if (source) {
       n_src = n;
       src_tree.reset();
@@ -388,63 +425,70 @@ struct plt_eval {
   }
 
   // M2L + L2L + L2P + P2P for the target leaves [leaf_lo, leaf_hi) -> vt (SoA [kn][n_trg], sorted).
-  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const Tree& tt,
+  // vt must be zero on entry.
+  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const Tree& tt, const Plan& pl,
                 Interpolator& ip, double* vt, int leaf_lo, int leaf_hi, bool timed) {
     const int order = ip.host.order;
-    const int height = tt.height();
+    const int height = tt.height(), leaf = height - 1;
     const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
+    const int nc = 1 << dim, nn = dim == 1 ? 3 : (dim == 2 ? 9 : 27);
     TreeView sv = st.view(), tv = tt.view();
+    const PlanView pv = pl.view();
     if (leaf_hi <= leaf_lo) return;
 
-    // per-level compact ranges of the ancestors of the shard's leaves
-    std::vector<int> lo(height, 0), hi(height, 0);
-    if (leaf_lo == 0 && leaf_hi == tt.n_cells(height - 1)) {
-      for (int l = 0; l < height; ++l) hi[l] = tt.n_cells(l);
+    // per-level compact ranges of the ancestors of the shard's leaves + active-slot ranges
+    std::vector<int> lo(height, 0), hi(height, 0), slo(height, 0), shi(height, 0);
+    if (leaf_lo == 0 && leaf_hi == tt.n_cells(leaf)) {
+      for (int l = 0; l < height; ++l) {
+        hi[l] = tt.n_cells(l);
+        slo[l] = pv.level_begin[l];
+        shi[l] = pv.level_begin[l + 1];
+      }
     } else {
-      DevBuf<int> d_lo, d_hi;
-      d_lo.alloc(height, stream);
-      d_hi.alloc(height, stream);
-      PLT_LAUNCH(ctr, k_level_ranges, 1, 32, 0, stream, tv, leaf_lo, leaf_hi, d_lo.get(), d_hi.get());
-      PLT_CUDA(cudaMemcpyAsync(lo.data(), d_lo.get(), sizeof(int) * height, cudaMemcpyDeviceToHost, stream));
-      PLT_CUDA(cudaMemcpyAsync(hi.data(), d_hi.get(), sizeof(int) * height, cudaMemcpyDeviceToHost, stream));
+      int* d = arena.take<int>(4 * height);
+      PLT_LAUNCH(ctr, k_level_ranges, 1, 32, 0, stream, tv, pv, leaf_lo, leaf_hi, d, d + height, d + 2 * height,
+                 d + 3 * height);
+      std::vector<int> h(4 * height);
+      PLT_CUDA(cudaMemcpyAsync(h.data(), d, sizeof(int) * 4 * height, cudaMemcpyDeviceToHost, stream));
       PLT_CUDA(cudaStreamSynchronize(stream));
+      for (int l = 0; l < height; ++l) {
+        lo[l] = h[l];
+        hi[l] = h[height + l];
+        slo[l] = h[2 * height + l];
+        shi[l] = h[3 * height + l];
+      }
     }
 
-    DevBuf<double> L;
     if (height > 2) {
-      L.alloc(static_cast<size_t>(tt.total_cells()) * kn * P, stream);
-      L.zero(stream);
-      DevBuf<int> flags, active, d_count;
-      DevBuf<unsigned char> cub_tmp;
-      DevBuf<double2> Lhat;
-      d_count.alloc(1, stream);
-      const size_t per_parent = static_cast<size_t>(1 << dim) * kn * F;
-      const size_t budget = (size_t{2} << 30) / sizeof(double2);
+      // Can the last level run fused (leaf expansions in shared memory only)?
+      const size_t stages = 1 + (dim >= 2 ? 2 : 0) + (dim >= 3 ? 4 : 0) + 1;
+      static const bool no_fused = getenv("PLT_DEBUG_NO_FUSED") != nullptr;  // A/B switch for parity bisection
+      const bool fused = !no_fused && sizeof(double) * stages * P + 4096 + sizeof(int) * P <= 200 * 1024;
+      // Locals of the levels that are materialised: 2 .. leaf-1 (fused) or 2 .. leaf.
+      const size_t L_cells = fused ? tt.view().cell_off[leaf] : tt.total_cells();
+      double* L = nullptr;
+      if (leaf > 2 || !fused) {
+        L = arena.take<double>(std::max<size_t>(L_cells, 1) * kn * P);
+        PLT_CUDA(cudaMemsetAsync(L, 0, sizeof(double) * L_cells * kn * P, stream));
+      }
+      const size_t per_parent = static_cast<size_t>(nc) * kn * F;
+      const size_t budget = (size_t{8} << 30) / sizeof(double2);
       const int chunk_parents = static_cast<int>(std::max<size_t>(1, budget / per_parent));
+      int max_active = 0;
+      for (int l = 2; l < height; ++l) max_active = std::max(max_active, shi[l] - slo[l]);
+      double2* Lhat = arena.take<double2>(static_cast<size_t>(std::min(chunk_parents, std::max(max_active, 1))) * per_parent);
+      // compact M2L result of the leaf level (fused path), indexed by slot - level_begin[leaf]
+      double* Lc = nullptr;
+      const int n_leaf_active = pl.n_active(leaf);
+      if (fused) Lc = arena.take<double>(static_cast<size_t>(std::max(n_leaf_active, 1)) * nc * kn * P);
+
       for (int l = 2; l < height; ++l) {
-        const int np = hi[l - 1] - lo[l - 1];
-        if (np <= 0) continue;
-        if (timed) timer.begin("m2l_list", stream);
-        flags.alloc(tt.n_cells(l - 1), stream);
-        active.alloc(tt.n_cells(l - 1), stream);
-        launch_m2l_mark_active(dim, sv, tv, l, flags.get(), stream, ctr);
-        size_t tmp_bytes = 0;
-        cub::CountingInputIterator<int> iota(lo[l - 1]);
-        PLT_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.get() + lo[l - 1], active.get(),
-                                            d_count.get(), np, stream));
-        cub_tmp.alloc(tmp_bytes, stream);
-        PLT_CUDA(cub::DeviceSelect::Flagged(cub_tmp.get(), tmp_bytes, iota, flags.get() + lo[l - 1], active.get(),
-                                            d_count.get(), np, stream));
-        ctr.n += 1;
-        int n_active = 0;
-        PLT_CUDA(cudaMemcpyAsync(&n_active, d_count.get(), sizeof(int), cudaMemcpyDeviceToHost, stream));
-        PLT_CUDA(cudaStreamSynchronize(stream));
-        if (timed) timer.end(stream);
-        Lhat.alloc(static_cast<size_t>(std::min(chunk_parents, std::max(n_active, 1))) * per_parent, stream);
+        const int n_active = shi[l] - slo[l];
+        const bool compact_out = fused && l == leaf;
         for (int c0 = 0; c0 < n_active; c0 += chunk_parents) {
-          const int nc = std::min(chunk_parents, n_active - c0);
+          const int ncnk = std::min(chunk_parents, n_active - c0);
+          const size_t s0 = static_cast<size_t>(slo[l]) + c0;
           M2LArgs a{};
-          a.src = sv;
           a.trg = tv;
           a.level = l;
           a.order = order;
@@ -453,10 +497,13 @@ struct plt_eval {
           a.kn = kn;
           a.Mhat = Mhat_.get();
           a.Khat = ip.khat.get() + ip.khat_level_stride * (l - 2);
-          a.active = active.get() + c0;
-          a.n_active = nc;
-          a.Lhat = Lhat.get();
-          a.L = L.get();
+          a.active = pv.active + s0;
+          a.src_ids = pv.src_ids + s0 * nn * nc;
+          a.trg_mask = pv.trg_mask + s0;
+          a.n_active = ncnk;
+          a.Lhat = Lhat;
+          a.L = compact_out ? nullptr : L;
+          a.Lc = compact_out ? Lc + (s0 - pv.level_begin[leaf]) * nc * kn * P : nullptr;
           if (timed) timer.begin("m2l_hadamard", stream);
           launch_m2l_hadamard(a, stream, ctr);
           if (timed) timer.end(stream);
@@ -464,42 +511,47 @@ struct plt_eval {
           launch_m2l_idft(a, ip.dev, stream, ctr);
           if (timed) timer.end(stream);
         }
-        if (l > 2) {
+        if (l > 2 && !compact_out) {
           if (timed) timer.begin("l2l", stream);
-          launch_l2l(dim, kn, tv, l, ip.dev, L.get(), lo[l], hi[l], stream, ctr);
+          launch_l2l(dim, kn, tv, l, ip.dev, L, lo[l], hi[l], stream, ctr);
           if (timed) timer.end(stream);
         }
       }
-      if (timed) timer.begin("l2p", stream);
-      launch_l2p(dim, kn, tv, box, ip.dev, L.get(), vt, leaf_lo, leaf_hi, stream, ctr);
+      if (timed) timer.begin(fused ? "l2l_l2p_leaf" : "l2p", stream);
+      bool done = false;
+      if (fused)
+        done = launch_l2l_l2p_leaf(dim, kn, tv, box, ip.dev, leaf > 2 ? L : nullptr, Lc, pv.leaf_slot, vt, leaf_lo,
+                                   leaf_hi, lo[leaf - 1], hi[leaf - 1], stream, ctr);
+      if (!done) {
+        PLT_REQUIRE(!fused, "fused leaf pass rejected an order it was planned for");
+        launch_l2p(dim, kn, tv, box, ip.dev, L, vt, leaf_lo, leaf_hi, stream, ctr);
+      }
       if (timed) timer.end(stream);
     }
     if (timed) timer.begin("p2p", stream);
-    launch_p2p(kind, dim, rbf.k, sv, wt, tv, vt, symmetric, height > 2 ? 1 : 0, leaf_lo, leaf_hi, stream, ctr);
+    launch_p2p(kind, dim, rbf.k, sv, wt, tv, vt, pv.p2p_leaves, pv.n_p2p, leaf_lo, leaf_hi, stream, ctr);
     if (timed) timer.end(stream);
   }
 
   // Brute force in caller order: the tree_height == 0 branch.
   void brute_force(const double* spos, const double* w_c, int64_t ns, const double* tpos, int64_t nt,
                    double* out_caller) {
-    DevBuf<double> wt, vt, partial;
-    wt.alloc(static_cast<size_t>(km) * ns, stream);
-    vt.alloc(static_cast<size_t>(kn) * nt, stream);
-    launch_prepare_weights(kind, dim, aniso, w_c, nullptr, ns, wt.get(), stream, ctr);
+    double* wt = arena.take<double>(static_cast<size_t>(km) * ns);
+    double* vt = arena.take<double>(static_cast<size_t>(kn) * nt);
+    launch_prepare_weights(kind, dim, aniso, w_c, nullptr, ns, wt, stream, ctr);
     DirectArgs a{};
     a.k = rbf.k;
     a.spos = spos;
-    a.swt = wt.get();
+    a.swt = wt;
     a.ns = ns;
     a.tpos = tpos;
     a.nt = nt;
-    a.out = vt.get();
+    a.out = vt;
     a.n_chunks = (ns > 0 && nt > 0) ? direct_plan_chunks(ns, nt) : 1;
-    if (a.n_chunks > 1) partial.alloc(static_cast<size_t>(a.n_chunks) * kn * nt, stream);
-    a.partial = partial.get();
+    a.partial = a.n_chunks > 1 ? arena.take<double>(static_cast<size_t>(a.n_chunks) * kn * nt) : nullptr;
     a.symmetric = 0;
     launch_direct(kind, dim, a, stream, ctr);
-    launch_finish_outputs(kind, dim, aniso, vt.get(), nullptr, nt, 0, nt, out_caller, stream, ctr);
+    launch_finish_outputs(kind, dim, aniso, vt, nullptr, nt, 0, nt, out_caller, stream, ctr);
   }
 
   // src/fmm/fmm_accuracy_estimator.hpp:74-121.
@@ -527,65 +579,70 @@ struct plt_eval {
     std::vector<int> idx(n_src);
     std::iota(idx.begin(), idx.end(), 0);
     std::shuffle(idx.begin(), idx.end(), gen);
-    DevBuf<int> d_idx;
-    d_idx.alloc(nt, stream);
-    PLT_CUDA(cudaMemcpyAsync(d_idx.get(), idx.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, stream));
-    DevBuf<double> tpos;
-    tpos.alloc(static_cast<size_t>(dim) * nt, stream);
-    PLT_LAUNCH(ctr, k_gather_soa, ceil_div(nt, 256), 256, 0, stream, src_tree.pos(), n_src, d_idx.get(), nt, dim,
-               tpos.get());
+    const auto outer_mark = arena.mark();
+    int* d_idx = arena.take<int>(nt);
+    PLT_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, stream));
+    double* tpos = arena.take<double>(static_cast<size_t>(dim) * nt);
+    PLT_LAUNCH(ctr, k_gather_soa, ceil_div(nt, 256), 256, 0, stream, src_tree.pos(), n_src, d_idx, nt, dim, tpos);
     PLT_CUDA(cudaStreamSynchronize(stream));
     ensure_sorted_weights();
 
     // exact: brute force over the sorted sources with the folded sorted weights
-    DevBuf<double> exact_raw, approx_raw, partial;
-    exact_raw.alloc(static_cast<size_t>(kn) * nt, stream);
-    approx_raw.alloc(static_cast<size_t>(kn) * nt, stream);
+    double* exact_raw = arena.take<double>(static_cast<size_t>(kn) * nt);
+    double* approx_raw = arena.take<double>(static_cast<size_t>(kn) * nt);
+    double* exact = arena.take<double>(static_cast<size_t>(kn) * nt);
+    double* approx = arena.take<double>(static_cast<size_t>(kn) * nt);
     DirectArgs a{};
     a.k = rbf.k;
     a.spos = src_tree.pos();
     a.swt = wt_sorted.get();
     a.ns = n_src;
-    a.tpos = tpos.get();
+    a.tpos = tpos;
     a.nt = nt;
-    a.out = exact_raw.get();
+    a.out = exact_raw;
     a.n_chunks = direct_plan_chunks(n_src, nt);
-    if (a.n_chunks > 1) partial.alloc(static_cast<size_t>(a.n_chunks) * kn * nt, stream);
-    a.partial = partial.get();
+    a.partial = a.n_chunks > 1 ? arena.take<double>(static_cast<size_t>(a.n_chunks) * kn * nt) : nullptr;
     launch_direct(kind, dim, a, stream, ctr);
-    DevBuf<double> exact, approx;
-    exact.alloc(static_cast<size_t>(kn) * nt, stream);
-    approx.alloc(static_cast<size_t>(kn) * nt, stream);
-    launch_finish_outputs(kind, dim, aniso, exact_raw.get(), nullptr, nt, 0, nt, exact.get(), stream, ctr);
+    launch_finish_outputs(kind, dim, aniso, exact_raw, nullptr, nt, 0, nt, exact, stream, ctr);
 
     Tree sample_tree;
-    sample_tree.build(dim, height, box, tpos.get(), nt, stream, ctr);
-    DevBuf<unsigned long long> d_err;
-    d_err.alloc(1, stream);
+    sample_tree.build(dim, height, box, tpos, nt, stream, ctr);
+    Plan sample_plan;
+    sample_plan.build(src_tree, sample_tree, stream, ctr);
+    unsigned long long* d_err = arena.take<unsigned long long>(1);
     DevBuf<double> M_;
     DevBuf<double2> Mhat_;
-    for (int order = 8; order <= 20; order += 2) {
+    plt_config found{0, 0, kClassic};
+    for (int order = 8; order <= 20 && !found.order; order += 2) {
       const int min_d = order >= 12 ? 7 : kClassic;
       const int max_d = order >= 12 ? 9 : kClassic;
       for (int d = min_d; d <= max_d; ++d) {
+        const auto inner_mark = arena.mark();
         Interpolator& ip = interpolator(height, order, d);
         upward(src_tree, wt_sorted.get(), ip, M_, Mhat_, false);
-        downward(src_tree, wt_sorted.get(), Mhat_, sample_tree, ip, approx_raw.get(), 0,
+        PLT_CUDA(cudaMemsetAsync(approx_raw, 0, sizeof(double) * kn * nt, stream));
+        downward(src_tree, wt_sorted.get(), Mhat_, sample_tree, sample_plan, ip, approx_raw, 0,
                  sample_tree.n_cells(height - 1), false);
-        launch_finish_outputs(kind, dim, aniso, approx_raw.get(), sample_tree.perm(), nt, 0, nt, approx.get(),
-                              stream, ctr);
-        d_err.zero(stream);
-        PLT_LAUNCH(ctr, k_max_abs_diff, ceil_div(kn * nt, 256), 256, 0, stream, approx.get(), exact.get(), kn * nt,
-                   d_err.get());
+        launch_finish_outputs(kind, dim, aniso, approx_raw, sample_tree.perm(), nt, 0, nt, approx, stream, ctr);
+        PLT_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), stream));
+        PLT_LAUNCH(ctr, k_max_abs_diff, ceil_div(kn * nt, 256), 256, 0, stream, approx, exact, kn * nt, d_err);
         unsigned long long bits = 0;
-        PLT_CUDA(cudaMemcpyAsync(&bits, d_err.get(), sizeof(bits), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaMemcpyAsync(&bits, d_err, sizeof(bits), cudaMemcpyDeviceToHost, stream));
         PLT_CUDA(cudaStreamSynchronize(stream));
+        arena.rewind(inner_mark);
         double err_abs;
         std::memcpy(&err_abs, &bits, sizeof(double));
-        if (err_abs <= accuracy) return {height, order, d};
+        if (err_abs <= accuracy) {
+          found = {height, order, d};
+          break;
+        }
       }
     }
-    throw Error(PLT_ERR_ACCURACY, "failed to construct an evaluator that meets the desired accuracy");
+    PLT_CUDA(cudaStreamSynchronize(stream));
+    arena.rewind(outer_mark);
+    if (!found.order)
+      throw Error(PLT_ERR_ACCURACY, "failed to construct an evaluator that meets the desired accuracy");
+    return found;
   }
 
   // Compact-support kernels (cov_spherical, cov_cubic, spheroidal direct parts): the reference
@@ -604,17 +661,10 @@ struct plt_eval {
     PLT_REQUIRE(len == kn * nt, "output length must be kn * n_trg_points");
     PLT_REQUIRE(have_weights || n_src == 0, "set_weights must be called before evaluate");
     timer.reset();
-    DevBuf<double> out_dev;
-    cudaPointerAttributes attr{};
-    bool out_is_device = false;
-    if (out && cudaPointerGetAttributes(&attr, out) == cudaSuccess)
-      out_is_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
-    cudaGetLastError();
+    arena.reset();
+    const bool out_is_device = out && is_device_pointer(out);
     double* dst = out;
-    if (!out_is_device) {
-      out_dev.alloc(len, stream);
-      dst = out_dev.get();
-    }
+    if (!out_is_device) dst = arena.take<double>(std::max<int64_t>(len, 1));
     evaluate_device(dst);
     if (!out_is_device) {
       if (len) PLT_CUDA(cudaMemcpyAsync(out, dst, sizeof(double) * len, cudaMemcpyDeviceToHost, stream));
@@ -628,18 +678,17 @@ struct plt_eval {
     leaf_hi = n_leaf;
     if (shard_world <= 1) return;
     TreeView tv = tt.view();
-    DevBuf<int> d;
-    d.alloc(2, stream);
+    int* d = arena.take<int>(2);
     int bounds[2] = {0, n_leaf};
-    PLT_CUDA(cudaMemcpyAsync(d.get(), bounds, sizeof(bounds), cudaMemcpyHostToDevice, stream));
+    PLT_CUDA(cudaMemcpyAsync(d, bounds, sizeof(bounds), cudaMemcpyHostToDevice, stream));
     const int64_t n = tt.n();
     const int p0 = static_cast<int>(n * shard_rank / shard_world);
     const int p1 = static_cast<int>(n * (shard_rank + 1) / shard_world);
     if (shard_rank > 0)
-      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p0, d.get());
+      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p0, d);
     if (shard_rank + 1 < shard_world)
-      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p1, d.get() + 1);
-    PLT_CUDA(cudaMemcpyAsync(bounds, d.get(), sizeof(bounds), cudaMemcpyDeviceToHost, stream));
+      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p1, d + 1);
+    PLT_CUDA(cudaMemcpyAsync(bounds, d, sizeof(bounds), cudaMemcpyDeviceToHost, stream));
     PLT_CUDA(cudaStreamSynchronize(stream));
     leaf_lo = bounds[0];
     leaf_hi = bounds[1];
@@ -655,11 +704,12 @@ struct plt_eval {
       direct_part->shard_world = fast_part->shard_world = shard_world;
       direct_part->timer.reset();
       fast_part->timer.reset();
-      DevBuf<double> tmp;
-      tmp.alloc(len, stream);
+      direct_part->arena.reset();
+      fast_part->arena.reset();
+      double* tmp = arena.take<double>(std::max<int64_t>(len, 1));
       direct_part->evaluate_device(out);
-      fast_part->evaluate_device(tmp.get());
-      if (len) PLT_LAUNCH(ctr, k_add, ceil_div(len, 256), 256, 0, stream, tmp.get(), len, out);
+      fast_part->evaluate_device(tmp);
+      if (len) PLT_LAUNCH(ctr, k_add, ceil_div(len, 256), 256, 0, stream, tmp, len, out);
       config = fast_part->config;
       return;
     }
@@ -698,24 +748,31 @@ struct plt_eval {
       src_tree.build(dim, height, box, src_pos_c.get(), n_src, stream, ctr);
       wt_dirty = true;
       multipole_dirty = true;
+      plan.reset();
     }
-    if (!symmetric && (!trg_tree.built() || trg_tree.height() != height))
+    if (!symmetric && (!trg_tree.built() || trg_tree.height() != height)) {
       trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, stream, ctr);
+      plan.reset();
+    }
     ensure_sorted_weights();
     timer.end(stream);
     const Tree& tt = target_tree();
+    if (!plan.built()) {
+      timer.begin("plan", stream);
+      plan.build(src_tree, tt, stream, ctr);
+      timer.end(stream);
+    }
 
     int leaf_lo, leaf_hi;
     shard_leaves(tt, leaf_lo, leaf_hi);
 
-    DevBuf<double> vt;
-    vt.alloc(static_cast<size_t>(kn) * nt, stream);
-    vt.zero(stream);
+    double* vt = arena.take<double>(static_cast<size_t>(kn) * nt);
+    PLT_CUDA(cudaMemsetAsync(vt, 0, sizeof(double) * kn * nt, stream));
     if (compact) {
       config = {height, 0, kClassic};
       timer.begin("p2p", stream);
-      launch_p2p(kind, dim, rbf.k, src_tree.view(), wt_sorted.get(), tt.view(), vt.get(), symmetric, 0, leaf_lo,
-                 leaf_hi, stream, ctr);
+      launch_p2p(kind, dim, rbf.k, src_tree.view(), wt_sorted.get(), tt.view(), vt, plan.view().p2p_leaves,
+                 plan.n_p2p(), leaf_lo, leaf_hi, stream, ctr);
       timer.end(stream);
     } else {
       plt_config c = find_best_configuration(height);
@@ -726,7 +783,7 @@ struct plt_eval {
         up_order = c.order;
         up_d = c.d;
       }
-      downward(src_tree, wt_sorted.get(), Mhat, tt, ip, vt.get(), leaf_lo, leaf_hi, true);
+      downward(src_tree, wt_sorted.get(), Mhat, tt, plan, ip, vt, leaf_lo, leaf_hi, true);
       config = c;
     }
     timer.begin("finish", stream);
@@ -740,7 +797,7 @@ struct plt_eval {
       p_lo = b[0];
       p_hi = b[1];
     }
-    launch_finish_outputs(kind, dim, aniso, vt.get(), tt.perm(), nt, p_lo, p_hi, out, stream, ctr);
+    launch_finish_outputs(kind, dim, aniso, vt, tt.perm(), nt, p_lo, p_hi, out, stream, ctr);
     timer.end(stream);
   }
 };

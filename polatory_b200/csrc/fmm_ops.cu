@@ -9,6 +9,8 @@
 //   points : SoA [dim][n]; weights SoA [km][n]; raw outputs SoA [kn][n]
 #include "fmm_ops.cuh"
 
+#include <cstdlib>
+
 namespace plt {
 namespace {
 
@@ -339,6 +341,157 @@ __global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev 
 }
 
 // ------------------------------------------------------------------------------------
+// Fused last level of the downward pass (one CTA per parent cell of level leaf-1):
+//   L_child = L2L(L_parent) + Lc[slot][child]   (M2L result of the leaf level, if any)
+//   v_i     = L2P(L_child) for the points of the child
+// The leaf-level expansions (the largest array of the whole evaluation: 8 P bytes x kn per
+// leaf) live only in shared memory.  The per-axis L2L contractions of the first dim-1 axes are
+// shared between siblings: axis 0 gives 2 variants, axis 1 gives 4, the last axis is done per
+// child right before its L2P.  Same arithmetic, in the same order, as k_l2l + k_l2p.
+// ------------------------------------------------------------------------------------
+constexpr int kLeafThreads = 128;
+
+template <int DIM>
+__global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box box, InterpDev it, int kn,
+                                                               const double* __restrict__ L,
+                                                               const double* __restrict__ Lc,
+                                                               const int* __restrict__ leaf_slot,
+                                                               double* __restrict__ vt, int par_lo, int leaf_lo,
+                                                               int leaf_hi) {
+  extern __shared__ double sm[];
+  constexpr int NC = 1 << DIM;
+  constexpr int NW = kLeafThreads / 32;
+  const int p = it.order;
+  int P = 1;
+  for (int a = 0; a < DIM; ++a) P *= p;
+  double* s_t = sm;                        // [2][p][p]
+  double* s_beta = s_t + 2 * p * p;        // [p]
+  double* s_basis = s_beta + p;            // [NW][DIM][p]
+  double* s_inv = s_basis + NW * DIM * p;  // [NW][DIM]
+  double* lvl0 = s_inv + NW * DIM;         // [P]        parent
+  double* lvl1 = lvl0 + P;                 // [2][P]     after axis 0          (DIM >= 2)
+  double* lvl2 = lvl1 + (DIM >= 2 ? 2 * P : 0);  // [4][P] after axes 0, 1    (DIM == 3)
+  double* s_child = lvl2 + (DIM >= 3 ? 4 * P : 0);  // [P]
+  int* s_nidx = reinterpret_cast<int*>(s_child + P);  // [P] packed node indices
+  int* s_hit = s_nidx + P;                            // [NW][DIM]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int leaf = tr.height - 1, pl = leaf - 1;
+  const int pidx = par_lo + blockIdx.x;
+  const uint32_t pkey = tr.keys[tr.cell_off[pl] + pidx];
+  const int* dense_leaf = tr.dense + tr.dense_off[leaf];
+  const bool has_parent = L != nullptr;  // parent level >= 2
+  const int slot = leaf_slot ? leaf_slot[pidx] : -1;
+
+  for (int i = tid; i < 2 * p * p; i += kLeafThreads) s_t[i] = it.child[i];
+  for (int i = tid; i < p; i += kLeafThreads) s_beta[i] = it.beta[i];
+  for (int n = tid; n < P; n += kLeafThreads) {
+    int ni[DIM];
+    node_decode<DIM>(n, p, ni);
+    int packed = 0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) packed |= ni[a] << (8 * a);
+    s_nidx[n] = packed;
+  }
+  const double cw = box.width / static_cast<double>(1 << leaf);
+  const double inv_half = 1.0 / (0.5 * cw);
+  double* basis = s_basis + warp * DIM * p;
+  double* inv = s_inv + warp * DIM;
+  int* hit = s_hit + warp * DIM;
+
+  for (int b = 0; b < kn; ++b) {
+    __syncthreads();
+    if (has_parent) {
+      const double* Lp = L + (static_cast<size_t>(tr.cell_off[pl] + pidx) * kn + b) * P;
+      for (int n = tid; n < P; n += kLeafThreads) lvl0[n] = Lp[n];
+      __syncthreads();
+      // shared stages: axis a turns 2^a variants into 2^(a+1)
+      if constexpr (DIM >= 2) {
+        const double* in = lvl0;
+        double* out = lvl1;
+        int outer = 1, inner = P / p;
+#pragma unroll
+        for (int a = 0; a + 1 < DIM; ++a) {
+          const int nv = 2 << a;
+          for (int e = tid; e < nv * P; e += kLeafThreads) {
+            const int v = e / P, rem = e - v * P;
+            const int i = rem % inner, r = (rem / inner) % p, o = rem / (inner * p);
+            const double* src = in + static_cast<size_t>(v >> 1) * P + static_cast<size_t>(o) * p * inner + i;
+            const double* tm = s_t + (v & 1) * p * p;
+            double acc = 0.0;
+            for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q * inner];
+            out[e] = acc;
+          }
+          __syncthreads();
+          in = out;
+          out = lvl2;
+          outer *= p;
+          inner /= p;
+        }
+      }
+    }
+    const double* last_in = DIM == 1 ? lvl0 : (DIM == 2 ? lvl1 : lvl2);
+    for (int ch = 0; ch < NC; ++ch) {
+      const int cidx = dense_leaf[(pkey << DIM) | ch];
+      if (cidx < 0 || cidx < leaf_lo || cidx >= leaf_hi) continue;  // uniform across the CTA
+      // last axis -> this child's expansion
+      const double* add = slot >= 0 ? Lc + ((static_cast<size_t>(slot) * NC + ch) * kn + b) * P : nullptr;
+      for (int e = tid; e < P; e += kLeafThreads) {
+        double acc = 0.0;
+        if (has_parent) {
+          const int r = e % p, o = e / p;  // last axis: inner = 1
+          const double* src = last_in + static_cast<size_t>(ch >> 1) * P + static_cast<size_t>(o) * p;
+          const double* tm = s_t + (ch & 1) * p * p;
+          for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q];
+        }
+        // k_l2l accumulates the interpolated parent onto the M2L result: L_child = m2l + l2l
+        s_child[e] = add ? add[e] + acc : acc;
+      }
+      __syncthreads();
+      // L2P for the points of this child, one warp per point
+      double c[DIM], half;
+      cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
+      const int i0 = tr.leaf_start[cidx], i1 = tr.leaf_start[cidx + 1];
+      for (int i = i0 + warp; i < i1; i += NW) {
+        if (lane < DIM) hit[lane] = -1;
+        __syncwarp();
+        for (int e = lane; e < DIM * p; e += 32) {
+          const int a = e / p, k = e - a * p;
+          const double ca = a == 0 ? c[0] : (a == 1 ? c[DIM > 1 ? 1 : 0] : c[DIM > 2 ? 2 : 0]);
+          const double t = (tr.pos[a * tr.n + i] - ca) * inv_half;
+          const double dt = t - node_pos(k, p);
+          if (dt == 0.0) hit[a] = k;
+          basis[e] = s_beta[k] / dt;
+        }
+        __syncwarp();
+        if (lane < DIM) {
+          double sum = 0.0;
+          for (int k = 0; k < p; ++k) sum += basis[lane * p + k];
+          inv[lane] = 1.0 / sum;
+        }
+        __syncwarp();
+        for (int e = lane; e < DIM * p; e += 32) {
+          const int a = e / p, k = e - a * p;
+          basis[e] = hit[a] >= 0 ? (k == hit[a] ? 1.0 : 0.0) : basis[e] * inv[a];
+        }
+        __syncwarp();
+        double acc = 0.0;
+        for (int n = lane; n < P; n += 32) {
+          const int packed = s_nidx[n];
+          double s = 1.0;
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) s *= basis[a * p + ((packed >> (8 * a)) & 0xff)];
+          acc += s * s_child[n];
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) vt[b * tr.n + i] = acc;
+        __syncwarp();
+      }
+      __syncthreads();  // s_child is reused by the next child
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Small dense DFT stages (generic pointers: shared or global).
 //   out[o][k][i] = sum_n in[o][n][i] * W^(k n),   W = e^{-2 pi i / nf} (or its conjugate)
 // ------------------------------------------------------------------------------------
@@ -442,68 +595,30 @@ __global__ void __launch_bounds__(kBlock) k_m2hat(int first_cell, int n_cells, I
 // M2L, Fourier space.
 // ------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void k_m2l_mark_active(TreeView src, TreeView trg, int level, int* __restrict__ flags) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pl = level - 1;
-  if (i >= trg.n_cells[pl]) return;
-  int c[DIM];
-  morton_decode<DIM>(trg.keys[trg.cell_off[pl] + i], c);
-  const int nside = 1 << pl;
-  const int* sd = src.dense + src.dense_off[pl];
-  int nn = 1;
-  for (int a = 0; a < DIM; ++a) nn *= 3;
-  int found = 0;
-  for (int e = 0; e < nn && !found; ++e) {
-    int q[DIM], r = e;
-    bool ok = true;
-#pragma unroll
-    for (int a = DIM - 1; a >= 0; --a) {
-      q[a] = c[a] + (r % 3) - 1;
-      r /= 3;
-      ok = ok && q[a] >= 0 && q[a] < nside;
-    }
-    if (ok && sd[morton_encode<DIM>(q)] >= 0) found = 1;
-  }
-  flags[i] = found;
+struct M2LGeom {
+  static constexpr int NC = 1 << DIM;  // children per cell
+  static constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  static constexpr int NOFF = DIM == 1 ? 7 : (DIM == 2 ? 49 : 343);
+  static constexpr int CENTER = (NN - 1) / 2;
+};
+
+__device__ __forceinline__ void cfma(double2& acc, const double2& k, const double2& m) {
+  acc.x = fma(k.x, m.x, acc.x);
+  acc.x = fma(-k.y, m.y, acc.x);
+  acc.y = fma(k.x, m.y, acc.y);
+  acc.y = fma(k.y, m.x, acc.y);
 }
 
-// Hadamard accumulation, one CTA per active target parent, threads over frequencies.
+// Generic Hadamard accumulation (any kn x km), one CTA per active target parent, threads over
+// frequencies:
 //   Lhat[slot][ct][b][f] = sum_{cs in list(ct)} sum_a Khat[o(ct,cs)][b][a][f] * Mhat[cs][a][f]
 template <int DIM, int KN, int KM>
 __global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
-  constexpr int NC = 1 << DIM;        // children per cell
-  constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
-  constexpr int NOFF = DIM == 1 ? 7 : (DIM == 2 ? 49 : 343);
-  __shared__ int s_src[NN * NC];  // global compact id (within Mhat) of source child or -1
-  __shared__ int s_trg[NC];       // 1 if the target child exists
+  constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN;
+  __shared__ int s_src[NN * NC];  // Mhat cell index of the source child or -1
   const int slot = blockIdx.x;
-  const int pl = a.level - 1;
-  const int pidx = a.active[slot];
-  const uint32_t pkey = a.trg.keys[a.trg.cell_off[pl] + pidx];
-  int pc[DIM];
-  morton_decode<DIM>(pkey, pc);
-  const int nside_p = 1 << pl;
-  const int* sdense = a.src.dense + a.src.dense_off[a.level];
-  const int* tdense = a.trg.dense + a.trg.dense_off[a.level];
-  for (int e = threadIdx.x; e < NN * NC; e += blockDim.x) {
-    int nb = e / NC, ch = e % NC;
-    int q[DIM], r = nb;
-    bool ok = true;
-#pragma unroll
-    for (int d = DIM - 1; d >= 0; --d) {
-      q[d] = pc[d] + (r % 3) - 1;
-      r /= 3;
-      ok = ok && q[d] >= 0 && q[d] < nside_p;
-    }
-    int id = -1;
-    if (ok) {
-      uint32_t ck = (morton_encode<DIM>(q) << DIM) | ch;
-      int ci = sdense[ck];
-      if (ci >= 0) id = a.src.cell_off[a.level] + ci - a.src.cell_off[2];
-    }
-    s_src[e] = id;
-  }
-  for (int e = threadIdx.x; e < NC; e += blockDim.x) s_trg[e] = tdense[(pkey << DIM) | e] >= 0;
+  for (int e = threadIdx.x; e < NN * NC; e += blockDim.x) s_src[e] = a.src_ids[static_cast<size_t>(slot) * NN * NC + e];
+  const unsigned tmask = a.trg_mask[slot];
   __syncthreads();
 
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -513,6 +628,7 @@ __global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
 #pragma unroll
       for (int b = 0; b < KN; ++b) acc[c][b] = make_double2(0.0, 0.0);
     for (int nb = 0; nb < NN; ++nb) {
+      if (nb == M2LGeom<DIM>::CENTER) continue;
       int e3[DIM], r = nb;
 #pragma unroll
       for (int d = DIM - 1; d >= 0; --d) {
@@ -528,7 +644,7 @@ __global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
         for (int m = 0; m < KM; ++m) mh[m] = a.Mhat[(static_cast<size_t>(sid) * KM + m) * F + f];
 #pragma unroll
         for (int ct = 0; ct < NC; ++ct) {
-          if (!s_trg[ct]) continue;
+          if (!((tmask >> ct) & 1u)) continue;
           // offset o = source child coord - target child coord, per axis in [-3, 3]
           int oi = 0, far = 0;
 #pragma unroll
@@ -542,13 +658,7 @@ __global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
 #pragma unroll
           for (int b = 0; b < KN; ++b)
 #pragma unroll
-            for (int m = 0; m < KM; ++m) {
-              double2 kv = kh[static_cast<size_t>(b * KM + m) * F];
-              acc[ct][b].x = fma(kv.x, mh[m].x, acc[ct][b].x);
-              acc[ct][b].x = fma(-kv.y, mh[m].y, acc[ct][b].x);
-              acc[ct][b].y = fma(kv.x, mh[m].y, acc[ct][b].y);
-              acc[ct][b].y = fma(kv.y, mh[m].x, acc[ct][b].y);
-            }
+            for (int m = 0; m < KM; ++m) cfma(acc[ct][b], kh[static_cast<size_t>(b * KM + m) * F], mh[m]);
         }
       }
     }
@@ -557,6 +667,120 @@ __global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
 #pragma unroll
       for (int b = 0; b < KN; ++b)
         a.Lhat[((static_cast<size_t>(slot) * NC + ct) * KN + b) * F + f] = acc[ct][b];
+  }
+}
+
+// Scalar (kn = km = 1) Hadamard accumulation, the hot kernel of the far field.
+//
+// A CTA owns a tile of kHadTF = 32 consecutive frequencies and keeps the operator slice
+// Khat[all 7^dim offsets][tile] resident in shared memory (3-D: 343 x 32 x 16 B = 171.5 KiB),
+// then streams over its share of the active target parents, one parent per warp at a time:
+// lanes = the 32 frequencies of the tile, accumulators = the 2^dim target children (complex,
+// registers).  The parent's 3^dim x 2^dim source-id table is read with coalesced loads and
+// compacted with ballots, so the loop runs over *present* source cells only (surface clouds
+// fill a fifth of the table); their Mhat rows are fetched kHadG at a time (512 B per warp and
+// row, coalesced) before the arithmetic to keep several loads in flight per warp.  No CTA-wide
+// barrier inside the main loop.
+constexpr int kHadTF = 32;
+constexpr int kHadWarps = 16;
+constexpr int kHadG = 4;
+
+template <int DIM>
+__global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArgs a, int F, int n_ftiles) {
+  constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN, NOFF = M2LGeom<DIM>::NOFF;
+  constexpr int NE = NN * NC;              // entries of the source-id table
+  constexpr int NCH = (NE + 31) / 32;      // 32-entry chunks
+  extern __shared__ double2 sm2[];
+  double2* Ks = sm2;                                      // [NOFF][TF]
+  int2* s_meta = reinterpret_cast<int2*>(Ks + NOFF * kHadTF);  // [NE]: x = offset index base, y = far mask
+  const int ftile = blockIdx.x % n_ftiles, pslice = blockIdx.x / n_ftiles, n_pslices = gridDim.x / n_ftiles;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = ftile * kHadTF + lane;
+  const bool fok = f < F;
+
+  for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
+    const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
+    Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
+  }
+  for (int code = threadIdx.x; code < NE; code += blockDim.x) {
+    const int nb = code / NC, cs = code % NC;
+    int e3[DIM], r = nb;
+#pragma unroll
+    for (int d = DIM - 1; d >= 0; --d) {
+      e3[d] = (r % 3) - 1;
+      r /= 3;
+    }
+    int base = 0, mask = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) base = base * 7 + (2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) + 3);
+    for (int ct = 0; ct < NC; ++ct) {
+      bool far = false;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const int o = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) - ((ct >> (DIM - 1 - d)) & 1);
+        far = far || o > 1 || o < -1;
+      }
+      if (far) mask |= 1 << ct;
+    }
+    s_meta[code] = make_int2(base, mask);
+  }
+  __syncthreads();
+
+  // parents of this CTA: slot = pslice + n_pslices * (warp + kHadWarps * i)
+  for (int slot = pslice + n_pslices * warp; slot < a.n_active; slot += n_pslices * kHadWarps) {
+    const int* tab = a.src_ids + static_cast<size_t>(slot) * NE;
+    const int tmask = a.trg_mask[slot];
+    int sid_l[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int idx = c * 32 + lane;
+      sid_l[c] = idx < NE ? tab[idx] : -1;
+    }
+    double2 acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      unsigned m = __ballot_sync(0xffffffffu, sid_l[c] >= 0);
+      while (m) {
+        int code[kHadG], sid[kHadG];
+        double2 mh[kHadG];
+#pragma unroll
+        for (int g = 0; g < kHadG; ++g) {
+          if (m) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            code[g] = c * 32 + e;
+            sid[g] = __shfl_sync(0xffffffffu, sid_l[c], e);
+          } else {
+            code[g] = 0;
+            sid[g] = -1;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < kHadG; ++g)
+          mh[g] = (sid[g] >= 0 && fok) ? a.Mhat[static_cast<size_t>(sid[g]) * F + f] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int g = 0; g < kHadG; ++g) {
+          if (sid[g] < 0) continue;  // warp-uniform
+          const int2 meta = s_meta[code[g]];
+          const int fm = meta.y & tmask;
+          const double2* kp = Ks + meta.x * kHadTF + lane;
+#pragma unroll
+          for (int ct = 0; ct < NC; ++ct) {
+            int cto = 0;  // compile-time: sum_d ct_d 7^(DIM-1-d)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) cto = cto * 7 + ((ct >> (DIM - 1 - d)) & 1);
+            if ((fm >> ct) & 1) cfma(acc[ct], kp[-cto * kHadTF], mh[g]);
+          }
+        }
+      }
+    }
+    if (fok) {
+#pragma unroll
+      for (int ct = 0; ct < NC; ++ct)
+        if ((tmask >> ct) & 1) a.Lhat[(static_cast<size_t>(slot) * NC + ct) * F + f] = acc[ct];
+    }
   }
 }
 
@@ -581,12 +805,17 @@ __global__ void __launch_bounds__(kBlock) k_m2l_idft(M2LArgs a, InterpDev it, do
     const int b = w % a.kn;
     const int ct = (w / a.kn) % NC;
     const int slot = w / (a.kn * NC);
-    const int pidx = a.active[slot];
-    const uint32_t pkey = a.trg.keys[a.trg.cell_off[a.level - 1] + pidx];
-    const int cidx = a.trg.dense[a.trg.dense_off[a.level] + ((pkey << DIM) | ct)];
-    if (cidx < 0) continue;  // uniform across the CTA
+    if (!((a.trg_mask[slot] >> ct) & 1u)) continue;  // uniform across the CTA
     const double2* in0 = a.Lhat + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * F;
-    double* Lc = a.L + (static_cast<size_t>(a.trg.cell_off[a.level] + cidx) * a.kn + b) * P;
+    double* Lc;
+    if (a.L) {
+      const int pidx = a.active[slot];
+      const uint32_t pkey = a.trg.keys[a.trg.cell_off[a.level - 1] + pidx];
+      const int cidx = a.trg.dense[a.trg.dense_off[a.level] + ((pkey << DIM) | ct)];
+      Lc = a.L + (static_cast<size_t>(a.trg.cell_off[a.level] + cidx) * a.kn + b) * P;
+    } else {
+      Lc = a.Lc + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * P;
+    }
     if constexpr (DIM == 1) {
       idft_stage_c2r(in0, Lc, 1, p, s_tw, nf, false);
     } else {
@@ -761,6 +990,25 @@ void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const Inter
   if (dim == 3) PLT_LAUNCH(c, k_l2p<3>, n, kBlock, smem, s, tr, box, it, kn, L, vt, static_cast<int>(leaf_lo));
 }
 
+bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
+                         const double* Lc, const int* leaf_slot, double* vt, int64_t leaf_lo, int64_t leaf_hi,
+                         int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c) {
+  const int n = par_hi - par_lo;
+  if (n <= 0) return true;
+  const int p = it.order;
+  const size_t P = nodes_per_cell(p, dim);
+  const int nw = kLeafThreads / 32;
+  const size_t stages = 1 + (dim >= 2 ? 2 : 0) + (dim >= 3 ? 4 : 0) + 1;
+  const size_t smem = sizeof(double) * (2 * p * p + p + nw * dim * p + nw * dim + stages * P) +
+                      sizeof(int) * (P + nw * dim);
+  if (smem > kSmemCap || p > 255) return false;
+  const int lo = static_cast<int>(leaf_lo), hi = static_cast<int>(leaf_hi);
+  if (dim == 1) { smem_opt_in((const void*)k_l2l_l2p_leaf<1>, smem); PLT_LAUNCH(c, k_l2l_l2p_leaf<1>, n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt, par_lo, lo, hi); }
+  if (dim == 2) { smem_opt_in((const void*)k_l2l_l2p_leaf<2>, smem); PLT_LAUNCH(c, k_l2l_l2p_leaf<2>, n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt, par_lo, lo, hi); }
+  if (dim == 3) { smem_opt_in((const void*)k_l2l_l2p_leaf<3>, smem); PLT_LAUNCH(c, k_l2l_l2p_leaf<3>, n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt, par_lo, lo, hi); }
+  return true;
+}
+
 namespace {
 // Scratch policy for the DFT kernels: shared memory when the two complex stage buffers fit,
 // otherwise a per-CTA slice of a global scratch buffer (generic addressing, same code).
@@ -802,15 +1050,6 @@ void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, cons
   if (dim == 3) { smem_opt_in((const void*)k_m2hat<3>, d.smem); PLT_LAUNCH(c, k_m2hat<3>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
 }
 
-void launch_m2l_mark_active(int dim, const TreeView& src, const TreeView& trg, int level, int* flags,
-                            cudaStream_t s, LaunchCounter& c) {
-  const int n = trg.n_cells[level - 1];
-  if (n == 0) return;
-  if (dim == 1) PLT_LAUNCH(c, k_m2l_mark_active<1>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
-  if (dim == 2) PLT_LAUNCH(c, k_m2l_mark_active<2>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
-  if (dim == 3) PLT_LAUNCH(c, k_m2l_mark_active<3>, ceil_div(n, 256), 256, 0, s, src, trg, level, flags);
-}
-
 void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
                        cudaStream_t s, LaunchCounter& c) {
   for (int l = 2; l < trg.height; ++l) {
@@ -827,19 +1066,53 @@ void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsign
   if (dim == 3) PLT_LAUNCH(c, k_count_p2p<3>, ceil_div(n, 256), 256, 0, s, src, trg, counters);
 }
 
+namespace {
+// Parent slices per frequency tile: fill the 148 SMs with whole waves of one-CTA-per-SM.
+int hadamard_parent_slices(int n_ftiles, int n_batches) {
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ps = 1; ps <= 16 && ps <= std::max(1, n_batches); ++ps) {
+    const int total = n_ftiles * ps;
+    const double eff = static_cast<double>(total) / (static_cast<double>(ceil_div(total, kNumSM)) * kNumSM);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = ps;
+    }
+  }
+  return best;
+}
+
+template <int DIM>
+void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
+  constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
+  const int n_ftiles = ceil_div(F, kHadTF);
+  const int ps = hadamard_parent_slices(n_ftiles, ceil_div(a.n_active, kHadWarps));
+  const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * NN * NC;
+  smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM>, smem);
+  PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM>), n_ftiles * ps, kHadWarps * 32, smem, s, a, F, n_ftiles);
+}
+}  // namespace
+
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   if (a.n_active == 0) return;
   const int F = freqs_per_cell(a.order, a.dim);
+  static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
+  if (a.kn == 1 && a.km == 1 && !no_tiled) {
+    if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
+    if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
+    if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);
+    return;
+  }
   const int threads = F >= 256 ? 256 : ((F + 31) / 32 * 32);
 #define PLT_HAD(D, KN, KM) PLT_LAUNCH(c, (k_m2l_hadamard<D, KN, KM>), a.n_active, threads, 0, s, a, F)
   const int key = a.dim * 100 + a.kn * 10 + a.km;
   switch (key) {
     case 111: PLT_HAD(1, 1, 1); break;
     case 211: PLT_HAD(2, 1, 1); break;
+    case 311: PLT_HAD(3, 1, 1); break;
     case 212: PLT_HAD(2, 1, 2); break;
     case 221: PLT_HAD(2, 2, 1); break;
     case 222: PLT_HAD(2, 2, 2); break;
-    case 311: PLT_HAD(3, 1, 1); break;
     case 313: PLT_HAD(3, 1, 3); break;
     case 331: PLT_HAD(3, 3, 1); break;
     case 333: PLT_HAD(3, 3, 3); break;

@@ -58,19 +58,21 @@ void launch_tabulate_m2l(int kind, int dim, const RbfConst& k, const Box& box, i
                          double2* Khat_level, cudaStream_t s, LaunchCounter& c);
 
 struct M2LArgs {
-  TreeView src, trg;
+  TreeView trg;
   int level;             // target/source cell level (>= 2)
   int order, dim, km, kn;
   const double2* Mhat;   // all source cells, indexed by global compact id - cell_off[2]
   const double2* Khat;   // this level's operators
-  const int* active;     // compact ids (level-1 of the target tree) of active parents
+  // Slices of the plan (plan.cuh) for the chunk of active parents being processed:
+  const int* active;     // [n_active] compact ids (level-1 of the target tree)
+  const int* src_ids;    // [n_active][3^dim * 2^dim] Mhat cell index or -1
+  const unsigned char* trg_mask;  // [n_active] existing target children
   int n_active;
   double2* Lhat;         // scratch [n_active][2^dim][kn][F]
-  double* L;             // target locals, all levels, indexed by global compact id
+  double* L;             // target locals of the upper levels, indexed by global compact id (or null)
+  double* Lc;            // compact leaf-level output [n_active][2^dim][kn][P] (used when L == null)
 };
-// Marks target parents (level-1) that have any source cell in their 3^dim parent neighbourhood.
-void launch_m2l_mark_active(int dim, const TreeView& src, const TreeView& trg, int level, int* flags,
-                            cudaStream_t s, LaunchCounter& c);
+// Fourier-space accumulation over the M2L lists of the children of the active parents.
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
 // counters[0] += M2L pairs, [1] += target cells with a non-empty M2L list, [2] += P2P pairs.
 void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
@@ -82,9 +84,17 @@ void launch_l2l(int dim, int kn, const TreeView& tr, int child_level, const Inte
                 int cell_lo, int cell_hi, cudaStream_t s, LaunchCounter& c);
 void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
                 double* vt, int64_t lo, int64_t hi, cudaStream_t s, LaunchCounter& c);
-// Near field over the 3^dim adjacent source leaves; vt += ... (accumulate = 1) or vt = ...
+// Fused last level of the downward pass: for every parent of level leaf-1, L2L to its children
+// in shared memory (+ the children's own M2L result Lc, slot given by leaf_slot), then L2P.  The
+// leaf-level local expansions never touch HBM.  Returns false when the order is too large for
+// the shared-memory staging (caller falls back to launch_l2l + launch_l2p).
+bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
+                         const double* Lc, const int* leaf_slot, double* vt, int64_t leaf_lo, int64_t leaf_hi,
+                         int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c);
+// Near field over the 3^dim adjacent source leaves of the listed target leaves (ascending ids,
+// restricted to [lo, hi)); vt += ...
 void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const double* swt, const TreeView& trg,
-                double* vt, int symmetric, int accumulate, int64_t lo, int64_t hi, cudaStream_t s,
+                double* vt, const int* leaves, int n_leaves, int64_t lo, int64_t hi, cudaStream_t s,
                 LaunchCounter& c);
 
 }  // namespace plt

@@ -11,11 +11,15 @@ namespace {
 // include/polatory/fmm/kernel.hpp:71; list = build_p2p_interaction_list(src, trg, 1, mutual),
 // src/fmm/fmm_evaluator.hpp:95-97).
 //
-// One warp per target leaf.  Lanes own sources (32 at a time, coalesced loads of the
-// Morton-sorted SoA arrays); targets are processed in register groups of kTG, partial sums
-// stay in registers across all neighbour leaves and are reduced with warp shuffles once per
-// group.  The symmetric variant needs no special casing: the i == j pair evaluated at d = 0
-// is exactly the k(0,0) w_i self term of src/fmm/fmm_symmetric_evaluator.hpp:163-193.
+// One warp per *active* target leaf (plan.cuh: leaves with at least one non-empty adjacent
+// source leaf).  The sources of all adjacent leaves are addressed as one concatenated list
+// (27-entry prefix table per warp in shared memory, binary search per lane), so all 32 lanes
+// own a source even when single leaves hold only a handful of points; loads of the
+// Morton-sorted SoA arrays stay contiguous within a leaf.  Targets are processed in register
+// groups of kTG; partial sums stay in registers over the whole source list and are reduced
+// with warp shuffles once per group.  The symmetric variant needs no special casing: the
+// i == j pair evaluated at d = 0 is exactly the k(0,0) w_i self term of
+// src/fmm/fmm_symmetric_evaluator.hpp:163-193.
 // ------------------------------------------------------------------------------------
 constexpr int kP2PWarps = 4;
 constexpr int kTG = 8;
@@ -23,13 +27,17 @@ constexpr int kTG = 8;
 template <int FAM, int KIND, int DIM>
 __global__ void __launch_bounds__(kP2PWarps * 32)
 k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, double* __restrict__ vt,
-      int accumulate, int leaf_lo, int leaf_hi) {
+      const int* __restrict__ leaves, int n_leaves, int leaf_lo, int leaf_hi) {
   constexpr int KM = KindTraits<KIND, DIM>::km;
   constexpr int KN = KindTraits<KIND, DIM>::kn;
   constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
-  const int lane = threadIdx.x & 31;
-  const int cell = leaf_lo + blockIdx.x * kP2PWarps + (threadIdx.x >> 5);
-  if (cell >= leaf_hi) return;
+  __shared__ int s_start[kP2PWarps][32];   // first source point of neighbour nb
+  __shared__ int s_prefix[kP2PWarps][32];  // exclusive prefix of the neighbour sizes; [NN] = total
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int li = blockIdx.x * kP2PWarps + warp;
+  if (li >= n_leaves) return;
+  const int cell = leaves[li];
+  if (cell < leaf_lo || cell >= leaf_hi) return;
   const int leaf = trg.height - 1;
   const int nside = 1 << leaf;
   int tc[DIM];
@@ -37,47 +45,73 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
   const int t0 = trg.leaf_start[cell], t1 = trg.leaf_start[cell + 1];
   const int* sdense = src.dense + src.dense_off[leaf];
 
+  // neighbour table: lane nb < NN looks up its source leaf
+  int s0 = 0, cnt = 0;
+  if (lane < NN) {
+    int q[DIM], r = lane;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = tc[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (ok) {
+      const int sc = sdense[morton_encode<DIM>(q)];
+      if (sc >= 0) {
+        s0 = src.leaf_start[sc];
+        cnt = src.leaf_start[sc + 1] - s0;
+      }
+    }
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  s_start[warp][lane] = s0;
+  s_prefix[warp][lane] = incl - cnt;
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  __syncwarp();
+  const int* pre = s_prefix[warp];
+  const int* st = s_start[warp];
+
   for (int tb = t0; tb < t1; tb += kTG) {
     double tp[kTG][DIM];
     double v[kTG][KN];
 #pragma unroll
     for (int u = 0; u < kTG; ++u) {
-      int t = min(tb + u, t1 - 1);
+      const int t = min(tb + u, t1 - 1);
 #pragma unroll
       for (int a = 0; a < DIM; ++a) tp[u][a] = trg.pos[a * trg.n + t];
 #pragma unroll
       for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
     }
     const int nt = min(kTG, t1 - tb);
-    for (int nb = 0; nb < NN; ++nb) {
-      int q[DIM], r = nb;
-      bool ok = true;
+    for (int jb = 0; jb < total; jb += 32) {
+      const int jj = jb + lane;
+      if (jj < total) {
+        // neighbour holding concatenated index jj: last nb with prefix[nb] <= jj
+        int lo = 0, hi = NN - 1;
 #pragma unroll
-      for (int a = DIM - 1; a >= 0; --a) {
-        q[a] = tc[a] + (r % 3) - 1;
-        r /= 3;
-        ok = ok && q[a] >= 0 && q[a] < nside;
-      }
-      if (!ok) continue;
-      const int sc = sdense[morton_encode<DIM>(q)];
-      if (sc < 0) continue;
-      const int s0 = src.leaf_start[sc], s1 = src.leaf_start[sc + 1];
-      for (int sb = s0; sb < s1; sb += 32) {
-        const int j = sb + lane;
-        if (j < s1) {
-          double sp[DIM], w[KM];
+        for (int it = 0; it < 5; ++it) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (pre[mid] <= jj) lo = mid; else hi = mid - 1;
+        }
+        const int j = st[lo] + (jj - pre[lo]);
+        double sp[DIM], w[KM];
 #pragma unroll
-          for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
+        for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
 #pragma unroll
-          for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j];
+        for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j];
 #pragma unroll
-          for (int u = 0; u < kTG; ++u) {
-            if (u < nt) {
-              double d[DIM];
+        for (int u = 0; u < kTG; ++u) {
+          if (u < nt) {
+            double d[DIM];
 #pragma unroll
-              for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
-              pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
-            }
+            for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
+            pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
           }
         }
       }
@@ -88,10 +122,7 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
       for (int b = 0; b < KN; ++b) {
         double x = v[u][b];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && u < nt) {
-          double* dst = vt + b * trg.n + tb + u;
-          *dst = accumulate ? *dst + x : x;
-        }
+        if (lane == 0 && u < nt) vt[b * trg.n + tb + u] += x;
       }
     }
   }
@@ -210,14 +241,12 @@ __global__ void __launch_bounds__(128) k_tabulate_m2l(RbfConst k, double cell_w,
 }  // namespace
 
 void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const double* swt, const TreeView& trg,
-                double* vt, int symmetric, int accumulate, int64_t leaf_lo, int64_t leaf_hi, cudaStream_t s,
+                double* vt, const int* leaves, int n_leaves, int64_t leaf_lo, int64_t leaf_hi, cudaStream_t s,
                 LaunchCounter& c) {
-  (void)symmetric;
-  const int n = static_cast<int>(leaf_hi - leaf_lo);
-  if (n <= 0) return;
+  if (n_leaves <= 0 || leaf_hi <= leaf_lo) return;
   dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
-    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), ceil_div(n, kP2PWarps), kP2PWarps * 32, 0, s, k, src,
-               swt, trg, vt, accumulate, static_cast<int>(leaf_lo), static_cast<int>(leaf_hi));
+    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), ceil_div(n_leaves, kP2PWarps), kP2PWarps * 32, 0, s, k,
+               src, swt, trg, vt, leaves, n_leaves, static_cast<int>(leaf_lo), static_cast<int>(leaf_hi));
   });
 }
 

@@ -1,0 +1,219 @@
+// Device construction of the interaction plan (plan.cuh).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "plan.cuh"
+
+namespace plt {
+namespace {
+
+template <int DIM>
+struct Stencil {
+  static constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  static constexpr int NC = 1 << DIM;
+  static constexpr int CENTER = (NN - 1) / 2;
+};
+
+// flags[g - cell_off[1]] = 1 for every target cell g of levels 1 .. leaf-1 that has a source
+// cell among its 3^dim - 1 non-central same-level neighbours (its children then have a
+// non-empty M2L list; the central neighbour only contributes near-field pairs).
+template <int DIM>
+__global__ void k_plan_mark(TreeView src, TreeView trg, int* __restrict__ flags) {
+  const int leaf = trg.height - 1;
+  const int g = trg.cell_off[1] + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= trg.cell_off[leaf]) return;
+  int l = 1;
+  while (l + 1 < leaf && g >= trg.cell_off[l + 1]) ++l;
+  int c[DIM];
+  morton_decode<DIM>(trg.keys[g], c);
+  const int nside = 1 << l;
+  const int* sd = src.dense + src.dense_off[l];
+  int found = 0;
+  for (int e = 0; e < Stencil<DIM>::NN && !found; ++e) {
+    if (e == Stencil<DIM>::CENTER) continue;
+    int q[DIM], r = e;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = c[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (ok && sd[morton_encode<DIM>(q)] >= 0) found = 1;
+  }
+  flags[g - trg.cell_off[1]] = found;
+}
+
+template <int DIM>
+__global__ void k_plan_p2p_mark(TreeView src, TreeView trg, int* __restrict__ flags) {
+  const int leaf = trg.height - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= trg.n_cells[leaf]) return;
+  int c[DIM];
+  morton_decode<DIM>(trg.keys[trg.cell_off[leaf] + i], c);
+  const int nside = 1 << leaf;
+  const int* sd = src.dense + src.dense_off[leaf];
+  int found = 0;
+  for (int e = 0; e < Stencil<DIM>::NN && !found; ++e) {
+    int q[DIM], r = e;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = c[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (ok && sd[morton_encode<DIM>(q)] >= 0) found = 1;
+  }
+  flags[i] = found;
+}
+
+// counts: [0] n_active, [1] n_p2p, [2 + l] level_begin[l] for l = 0 .. height.
+__global__ void k_plan_bounds(TreeView trg, const int* __restrict__ raw, int* __restrict__ counts) {
+  const int l = threadIdx.x;
+  if (l > trg.height) return;
+  const int n = counts[0];
+  int v;
+  if (l < 2) {
+    v = 0;
+  } else if (l >= trg.height) {
+    v = n;
+  } else {
+    // first active entry whose parent level is >= l - 1
+    const int key = trg.cell_off[l - 1] - trg.cell_off[1];
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (raw[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    v = lo;
+  }
+  counts[2 + l] = v;
+}
+
+struct LevelBegin {
+  int v[25];
+};
+
+template <int DIM>
+__global__ void k_plan_fill(TreeView src, TreeView trg, const int* __restrict__ raw, LevelBegin lb, int n_active,
+                            int* __restrict__ active, int* __restrict__ src_ids,
+                            unsigned char* __restrict__ trg_mask, int* __restrict__ leaf_slot) {
+  constexpr int NN = Stencil<DIM>::NN, NC = Stencil<DIM>::NC;
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int slot = static_cast<int>(t / (NN * NC));
+  const int e = static_cast<int>(t % (NN * NC));
+  if (slot >= n_active) return;
+  int l = 2;  // level of the children
+  while (l + 1 < trg.height && slot >= lb.v[l + 1]) ++l;
+  const int pl = l - 1;
+  const int g = raw[slot] + trg.cell_off[1];
+  const int pidx = g - trg.cell_off[pl];
+  const uint32_t pkey = trg.keys[g];
+  int pc[DIM];
+  morton_decode<DIM>(pkey, pc);
+  const int nside_p = 1 << pl;
+  const int nb = e / NC, ch = e % NC;
+  int q[DIM], r = nb;
+  bool ok = true;
+#pragma unroll
+  for (int d = DIM - 1; d >= 0; --d) {
+    q[d] = pc[d] + (r % 3) - 1;
+    r /= 3;
+    ok = ok && q[d] >= 0 && q[d] < nside_p;
+  }
+  int id = -1;
+  if (ok) {
+    const uint32_t ck = (morton_encode<DIM>(q) << DIM) | ch;
+    const int ci = src.dense[src.dense_off[l] + ck];
+    if (ci >= 0) id = src.cell_off[l] + ci - src.cell_off[2];
+  }
+  src_ids[static_cast<size_t>(slot) * (NN * NC) + e] = id;
+  if (e == 0) {
+    active[slot] = pidx;
+    unsigned m = 0;
+    const int* td = trg.dense + trg.dense_off[l];
+    for (int c = 0; c < NC; ++c)
+      if (td[(pkey << DIM) | c] >= 0) m |= 1u << c;
+    trg_mask[slot] = static_cast<unsigned char>(m);
+    if (l == trg.height - 1) leaf_slot[pidx] = slot - lb.v[l];
+  }
+}
+
+}  // namespace
+
+void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCounter& ctr) {
+  const TreeView sv = src.view(), tv = trg.view();
+  PLT_REQUIRE(sv.height == tv.height && sv.dim == tv.dim, "source and target trees must have the same shape");
+  const int dim = tv.dim, height = tv.height, leaf = height - 1;
+  const int nn = dim == 1 ? 3 : (dim == 2 ? 9 : 27), nc = 1 << dim;
+  view_ = PlanView{};
+  counts_.alloc(2 + 25, stream);
+  counts_.zero(stream);
+
+  // ---- phase 1: flags + compaction (M2L parents of all levels at once; P2P leaves) ----
+  const int n_par = height > 2 ? tv.cell_off[leaf] - tv.cell_off[1] : 0;
+  size_t tmp_bytes = 0;
+  thrust::counting_iterator<int> iota(0);
+  if (n_par > 0) {
+    flags_.alloc(n_par, stream);
+    active_.alloc(2 * static_cast<size_t>(n_par), stream);  // [raw | level-local ids]
+    if (dim == 1) PLT_LAUNCH(ctr, k_plan_mark<1>, ceil_div(n_par, 256), 256, 0, stream, sv, tv, flags_.get());
+    if (dim == 2) PLT_LAUNCH(ctr, k_plan_mark<2>, ceil_div(n_par, 256), 256, 0, stream, sv, tv, flags_.get());
+    if (dim == 3) PLT_LAUNCH(ctr, k_plan_mark<3>, ceil_div(n_par, 256), 256, 0, stream, sv, tv, flags_.get());
+    PLT_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags_.get(), active_.get(), counts_.get(), n_par,
+                                        stream));
+    if (tmp_bytes > tmp_.size()) tmp_.alloc(tmp_bytes, stream);
+    PLT_CUDA(cub::DeviceSelect::Flagged(tmp_.get(), tmp_bytes, iota, flags_.get(), active_.get(), counts_.get(), n_par,
+                                        stream));
+    ctr.n += 1;
+  }
+  const int n_leaf = tv.n_cells[leaf];
+  p2p_flags_.alloc(n_leaf, stream);
+  p2p_leaves_.alloc(n_leaf, stream);
+  if (dim == 1) PLT_LAUNCH(ctr, k_plan_p2p_mark<1>, ceil_div(n_leaf, 256), 256, 0, stream, sv, tv, p2p_flags_.get());
+  if (dim == 2) PLT_LAUNCH(ctr, k_plan_p2p_mark<2>, ceil_div(n_leaf, 256), 256, 0, stream, sv, tv, p2p_flags_.get());
+  if (dim == 3) PLT_LAUNCH(ctr, k_plan_p2p_mark<3>, ceil_div(n_leaf, 256), 256, 0, stream, sv, tv, p2p_flags_.get());
+  PLT_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, p2p_flags_.get(), p2p_leaves_.get(), counts_.get() + 1,
+                                      n_leaf, stream));
+  if (tmp_bytes > tmp_.size()) tmp_.alloc(tmp_bytes, stream);
+  PLT_CUDA(cub::DeviceSelect::Flagged(tmp_.get(), tmp_bytes, iota, p2p_flags_.get(), p2p_leaves_.get(),
+                                      counts_.get() + 1, n_leaf, stream));
+  ctr.n += 1;
+  PLT_LAUNCH(ctr, k_plan_bounds, 1, 32, 0, stream, tv, active_.get(), counts_.get());
+
+  int host[2 + 25];
+  PLT_CUDA(cudaMemcpyAsync(host, counts_.get(), sizeof(host), cudaMemcpyDeviceToHost, stream));
+  PLT_CUDA(cudaStreamSynchronize(stream));  // the one synchronisation of the plan
+  const int n_active = host[0];
+  LevelBegin lb{};
+  for (int l = 0; l <= height; ++l) {
+    lb.v[l] = host[2 + l];
+    view_.level_begin[l] = host[2 + l];
+  }
+  view_.n_active = n_active;
+  view_.n_p2p = host[1];
+  view_.p2p_leaves = p2p_leaves_.get();
+
+  // ---- phase 2: resolve source ids, child masks and the leaf slot map ----
+  if (height > 2) {
+    leaf_slot_.alloc(tv.n_cells[leaf - 1], stream);
+    leaf_slot_.fill_byte(0xFF, stream);
+    src_ids_.alloc(static_cast<size_t>(std::max(n_active, 1)) * nn * nc, stream);
+    trg_mask_.alloc(std::max(n_active, 1), stream);
+    int* active_out = active_.get() + n_par;
+    if (n_active > 0) {
+      const int64_t threads = static_cast<int64_t>(n_active) * nn * nc;
+      if (dim == 1) PLT_LAUNCH(ctr, k_plan_fill<1>, ceil_div(threads, 256), 256, 0, stream, sv, tv, active_.get(), lb, n_active, active_out, src_ids_.get(), trg_mask_.get(), leaf_slot_.get());
+      if (dim == 2) PLT_LAUNCH(ctr, k_plan_fill<2>, ceil_div(threads, 256), 256, 0, stream, sv, tv, active_.get(), lb, n_active, active_out, src_ids_.get(), trg_mask_.get(), leaf_slot_.get());
+      if (dim == 3) PLT_LAUNCH(ctr, k_plan_fill<3>, ceil_div(threads, 256), 256, 0, stream, sv, tv, active_.get(), lb, n_active, active_out, src_ids_.get(), trg_mask_.get(), leaf_slot_.get());
+    }
+    view_.active = active_out;
+    view_.src_ids = src_ids_.get();
+    view_.trg_mask = trg_mask_.get();
+    view_.leaf_slot = leaf_slot_.get();
+  }
+  built_ = true;
+}
+
+}  // namespace plt

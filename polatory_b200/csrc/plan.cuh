@@ -1,0 +1,49 @@
+// Interaction plan of one (source tree, target tree) pair, built on the device.
+//
+// Replaces what the reference rebuilds on every evaluate() with
+//   scalfmm::list::sequential::build_m2l_interaction_list(src, trg, 1, 1)
+//   scalfmm::list::sequential::build_p2p_interaction_list(src, trg, 1, mutual)
+//   (src/fmm/fmm_evaluator.hpp:92-97, src/fmm/fmm_symmetric_evaluator.hpp:75-80).
+// The lists themselves are implicit (dense key -> cell maps, separation criterion 1); the
+// plan only compacts *which* target cells have work and resolves their source-cell ids once,
+// so that the M2L and P2P kernels run over dense work lists.  A plan stays valid as long as
+// both trees do: the matvec inside the Krylov solver builds it once per fit.
+#pragma once
+
+#include "common.cuh"
+#include "tree.cuh"
+
+namespace plt {
+
+// Device view, passed by value to kernels.
+struct PlanView {
+  // M2L: active target parents, grouped by the level of their children.
+  //   level l (2 <= l < height): slots [level_begin[l], level_begin[l + 1])
+  const int* active;             // [n_active] compact id of the parent at level l - 1 (target tree)
+  const int* src_ids;            // [n_active][3^dim * 2^dim] Mhat cell index (global id - cell_off[2]) or -1
+  const unsigned char* trg_mask; // [n_active] bit ct set <=> target child ct exists
+  const int* leaf_slot;          // [n_cells(leaf - 1)] slot - level_begin[leaf] of that parent, or -1
+  int level_begin[25];
+  int n_active;
+  // P2P: target leaves with at least one non-empty adjacent source leaf (ascending).
+  const int* p2p_leaves;
+  int n_p2p;
+};
+
+class Plan {
+ public:
+  void build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCounter& ctr);
+  bool built() const { return built_; }
+  void reset() { built_ = false; }
+  PlanView view() const { return view_; }
+  int n_active(int level) const { return view_.level_begin[level + 1] - view_.level_begin[level]; }
+  int n_p2p() const { return view_.n_p2p; }
+
+ private:
+  bool built_ = false;
+  PlanView view_{};
+  DevBuf<int> flags_, active_, src_ids_, leaf_slot_, p2p_flags_, p2p_leaves_, counts_;
+  DevBuf<unsigned char> trg_mask_, tmp_;
+};
+
+}  // namespace plt

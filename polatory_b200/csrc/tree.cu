@@ -121,10 +121,11 @@ void Tree::build(int dim, int height, const Box& box, const double* pos_caller, 
   dense_off_.assign(height + 1, 0);
   for (int l = 0; l < height; ++l) dense_off_[l + 1] = dense_off_[l] + (int64_t{1} << (dim * l));
   const int64_t total = dense_off_[height];
-  DevBuf<int64_t> d_off;
+  DevBuf<int64_t>& d_off = d_off_;
   d_off.alloc(height + 1, stream);
   PLT_CUDA(cudaMemcpyAsync(d_off.get(), dense_off_.data(), (height + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-  DevBuf<int> occ, scan;
+  DevBuf<int>& occ = occ_;
+  DevBuf<int>& scan = scan_;
   occ.alloc(total, stream);
   scan.alloc(total + 1, stream);
   occ.zero(stream);

@@ -126,6 +126,8 @@ class Tree {
   DevBuf<unsigned char> tmp_;
   DevBuf<uint32_t> key_tmp_;
   DevBuf<int> idx_tmp_;
+  DevBuf<int> occ_, scan_;
+  DevBuf<int64_t> d_off_;
   std::vector<int64_t> dense_off_;
   std::vector<int> cell_off_, n_cells_;
   int total_cells_ = 0;

@@ -91,7 +91,20 @@ def test_fmm_matches_cpu_restatement(pb, dim, n, name, params, kind, rng):
         cfg = ev.config()
         assert cfg["order"] == order and cfg["d"] == d and cfg["tree_height"] == ofmm.tree_height(dim, n)
         ref = ofmm.fmm(name, params, dim, kind, -np.ones(dim), np.ones(dim), src, trg, w, order, d, 0, a)
-        assert _relerr(got, ref) < 1e-10, (order, d, _relerr(got, ref))
+        # Order 6 (the evaluation default) agrees to rounding (~1e-14).  At order 12 two FP64
+        # implementations of the SAME discretisation differ by the rounding noise that the
+        # equispaced high-order interpolation amplifies: the oracle compiled with and without FMA
+        # contraction differs from itself by 1e-11..1e-10 on these inputs ("Parity").
+        # The bound there is 5e-10 plus "as accurate as the oracle against the exact sum".
+        tol = 1e-10 if order < 12 else 5e-10
+        assert _relerr(got, ref) < tol, (order, d, _relerr(got, ref))
+        if order >= 12:
+            sub = slice(0, 200)
+            exact = ofmm.direct(name, params, dim, kind, src, trg[sub], w, a)
+            kn = odir.kind_kn(kind, dim)
+            e_gpu = _relerr(got[:200 * kn], exact)
+            e_orc = _relerr(ref[:200 * kn], exact)
+            assert e_gpu < 1.5 * e_orc + 1e-12, (e_gpu, e_orc)
 
 
 # ---------------------------------------------------------------------------------------
@@ -303,7 +316,7 @@ def test_device_resident_io_and_weight_update(pb, rng):
         ref = ofmm.fmm("bh3", [1.0, 0.0], dim, 0, -np.ones(dim), np.ones(dim), src, trg, w, 8, -1, 0)
         assert _relerr(out.cpu().numpy(), ref) < 1e-10
     assert ev.launch_count() > 0
-    assert "m2l" in ev.phase_times()
+    assert "m2l_hadamard" in ev.phase_times()
 
 
 # ---------------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q --maxfail=12 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -5 | tee gpurun_out/smoke.log
 echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log
 if [ "${SKIP_REF:-0}" != "1" ]; then
