@@ -461,9 +461,8 @@ struct plt_eval {
 
     if (height > 2) {
       // Can the last level run fused (leaf expansions in shared memory only)?
-      const size_t stages = 1 + (dim >= 2 ? 2 : 0) + (dim >= 3 ? 4 : 0) + 1;
       static const bool no_fused = getenv("PLT_DEBUG_NO_FUSED") != nullptr;  // A/B switch for parity bisection
-      const bool fused = !no_fused && sizeof(double) * stages * P + 4096 + sizeof(int) * P <= 200 * 1024;
+      const bool fused = !no_fused && leaf_fused_supported(dim, order);
       // Locals of the levels that are materialised: 2 .. leaf-1 (fused) or 2 .. leaf.
       const size_t L_cells = fused ? tt.view().cell_off[leaf] : tt.total_cells();
       double* L = nullptr;

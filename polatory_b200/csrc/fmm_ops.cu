@@ -132,11 +132,11 @@ __device__ __forceinline__ void node_decode(int n, int order, int (&ni)[DIM]) {
 // ------------------------------------------------------------------------------------
 constexpr int kPointBatch = 32;
 
-template <int DIM>
+template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kBlock) k_p2m(TreeView tr, Box box, InterpDev it, int km,
                                                 const double* __restrict__ wt, double* __restrict__ M) {
   extern __shared__ double sm[];
-  const int p = it.order;
+  const int p = ORDER > 0 ? ORDER : it.order;
   double* s_beta = sm;                          // [p]
   double* s_basis = s_beta + p;                 // [batch][DIM][p]
   double* s_w = s_basis + kPointBatch * DIM * p;  // [batch][km]
@@ -207,11 +207,11 @@ __device__ __forceinline__ void axis_contract(const double* __restrict__ in, dou
 }
 
 // M2M: M_parent[m] = sum_children sum_n S_m^parent(y_n^child) M_child[n]   (CTA per parent cell)
-template <int DIM>
+template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kBlock) k_m2m(TreeView tr, int level, InterpDev it, int km,
                                                 double* __restrict__ M) {
   extern __shared__ double sm[];
-  const int p = it.order;
+  const int p = ORDER > 0 ? ORDER : it.order;
   int P = 1;
   for (int a = 0; a < DIM; ++a) P *= p;
   double* s_t = sm;               // [2][p][p]
@@ -254,11 +254,11 @@ __global__ void __launch_bounds__(kBlock) k_m2m(TreeView tr, int level, InterpDe
 }
 
 // L2L: L_child[n] += sum_m S_m^parent(x_n^child) L_parent[m]   (CTA per child cell)
-template <int DIM>
+template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kBlock) k_l2l(TreeView tr, int level, InterpDev it, int kn,
                                                 double* __restrict__ L, int cell_lo) {
   extern __shared__ double sm[];
-  const int p = it.order;
+  const int p = ORDER > 0 ? ORDER : it.order;
   int P = 1;
   for (int a = 0; a < DIM; ++a) P *= p;
   double* s_t = sm;
@@ -346,12 +346,20 @@ __global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev 
 //   v_i     = L2P(L_child) for the points of the child
 // The leaf-level expansions (the largest array of the whole evaluation: 8 P bytes x kn per
 // leaf) live only in shared memory.  The per-axis L2L contractions of the first dim-1 axes are
-// shared between siblings: axis 0 gives 2 variants, axis 1 gives 4, the last axis is done per
-// child right before its L2P.  Same arithmetic, in the same order, as k_l2l + k_l2p.
+// shared between siblings (axis 0 gives 2 variants, axis 1 gives 4), the last axis produces all
+// 2^dim children at once; then the points of the parent (contiguous in Morton order) are
+// evaluated, one warp per point, lanes over the nodes.  Four CTA barriers per parent.
+// Shared layout: [children 2^dim x P][last shared stage]; the parent and the first stage are
+// dead by the time the children are written and overlay the children area.
 // ------------------------------------------------------------------------------------
-constexpr int kLeafThreads = 128;
+constexpr int kLeafThreads = 256;
 
 template <int DIM>
+__host__ __device__ constexpr int leaf_stage_cells() {
+  return (1 << DIM) + (DIM == 1 ? 1 : (DIM == 2 ? 2 : 4));
+}
+
+template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box box, InterpDev it, int kn,
                                                                const double* __restrict__ L,
                                                                const double* __restrict__ Lc,
@@ -361,36 +369,44 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
   extern __shared__ double sm[];
   constexpr int NC = 1 << DIM;
   constexpr int NW = kLeafThreads / 32;
-  const int p = it.order;
+  const int p = ORDER > 0 ? ORDER : it.order;
   int P = 1;
   for (int a = 0; a < DIM; ++a) P *= p;
-  double* s_t = sm;                        // [2][p][p]
-  double* s_beta = s_t + 2 * p * p;        // [p]
-  double* s_basis = s_beta + p;            // [NW][DIM][p]
-  double* s_inv = s_basis + NW * DIM * p;  // [NW][DIM]
-  double* lvl0 = s_inv + NW * DIM;         // [P]        parent
-  double* lvl1 = lvl0 + P;                 // [2][P]     after axis 0          (DIM >= 2)
-  double* lvl2 = lvl1 + (DIM >= 2 ? 2 * P : 0);  // [4][P] after axes 0, 1    (DIM == 3)
-  double* s_child = lvl2 + (DIM >= 3 ? 4 * P : 0);  // [P]
-  int* s_nidx = reinterpret_cast<int*>(s_child + P);  // [P] packed node indices
-  int* s_hit = s_nidx + P;                            // [NW][DIM]
+  double* s_child = sm;                         // [NC][P]
+  double* s_last = s_child + NC * P;            // last shared stage: [1 | 2 | 4][P]
+  double* lvl0 = DIM == 1 ? s_last : s_child;   // parent
+  double* lvl1 = DIM == 2 ? s_last : s_child + P;  // after axis 0 (DIM >= 2)
+  double* s_t = s_last + (leaf_stage_cells<DIM>() - NC) * P;  // [2][p][p]
+  double* s_beta = s_t + 2 * p * p;             // [p]
+  double* s_basis = s_beta + p;                 // [NW][DIM][p]
+  double* s_inv = s_basis + NW * DIM * p;       // [NW][DIM]
+  int* s_hit = reinterpret_cast<int*>(s_inv + NW * DIM);  // [NW][DIM]
+  int* s_first = s_hit + NW * DIM;              // [NC] first point of the child (or -1)
+  int* s_pre = s_first + NC;                    // [NC + 1] prefix of the children's point counts
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int leaf = tr.height - 1, pl = leaf - 1;
   const int pidx = par_lo + blockIdx.x;
   const uint32_t pkey = tr.keys[tr.cell_off[pl] + pidx];
-  const int* dense_leaf = tr.dense + tr.dense_off[leaf];
   const bool has_parent = L != nullptr;  // parent level >= 2
   const int slot = leaf_slot ? leaf_slot[pidx] : -1;
 
   for (int i = tid; i < 2 * p * p; i += kLeafThreads) s_t[i] = it.child[i];
   for (int i = tid; i < p; i += kLeafThreads) s_beta[i] = it.beta[i];
-  for (int n = tid; n < P; n += kLeafThreads) {
-    int ni[DIM];
-    node_decode<DIM>(n, p, ni);
-    int packed = 0;
-#pragma unroll
-    for (int a = 0; a < DIM; ++a) packed |= ni[a] << (8 * a);
-    s_nidx[n] = packed;
+  if (tid == 0) {
+    const int* dense_leaf = tr.dense + tr.dense_off[leaf];
+    int run = 0;
+    for (int ch = 0; ch < NC; ++ch) {
+      const int cidx = dense_leaf[(pkey << DIM) | ch];
+      int first = -1, cnt = 0;
+      if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
+        first = tr.leaf_start[cidx];
+        cnt = tr.leaf_start[cidx + 1] - first;
+      }
+      s_first[ch] = first;
+      s_pre[ch] = run;
+      run += cnt;
+    }
+    s_pre[NC] = run;
   }
   const double cw = box.width / static_cast<double>(1 << leaf);
   const double inv_half = 1.0 / (0.5 * cw);
@@ -399,94 +415,100 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
   int* hit = s_hit + warp * DIM;
 
   for (int b = 0; b < kn; ++b) {
-    __syncthreads();
+    __syncthreads();  // tables ready / previous component done with the children
     if (has_parent) {
       const double* Lp = L + (static_cast<size_t>(tr.cell_off[pl] + pidx) * kn + b) * P;
       for (int n = tid; n < P; n += kLeafThreads) lvl0[n] = Lp[n];
       __syncthreads();
-      // shared stages: axis a turns 2^a variants into 2^(a+1)
       if constexpr (DIM >= 2) {
-        const double* in = lvl0;
+        // axis 0: parent -> 2 variants
+        const int inner = P / p;
         double* out = lvl1;
-        int outer = 1, inner = P / p;
-#pragma unroll
-        for (int a = 0; a + 1 < DIM; ++a) {
-          const int nv = 2 << a;
-          for (int e = tid; e < nv * P; e += kLeafThreads) {
-            const int v = e / P, rem = e - v * P;
-            const int i = rem % inner, r = (rem / inner) % p, o = rem / (inner * p);
-            const double* src = in + static_cast<size_t>(v >> 1) * P + static_cast<size_t>(o) * p * inner + i;
-            const double* tm = s_t + (v & 1) * p * p;
-            double acc = 0.0;
-            for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q * inner];
-            out[e] = acc;
-          }
-          __syncthreads();
-          in = out;
-          out = lvl2;
-          outer *= p;
-          inner /= p;
+        for (int e = tid; e < 2 * P; e += kLeafThreads) {
+          const int v = e / P, rem = e - v * P;
+          const int i = rem % inner, r = rem / inner;
+          const double* tm = s_t + v * p * p;
+          double acc = 0.0;
+          for (int q = 0; q < p; ++q) acc += tm[q * p + r] * lvl0[q * inner + i];
+          out[e] = acc;
         }
+        __syncthreads();
+      }
+      if constexpr (DIM == 3) {
+        // axis 1: 2 variants -> 4
+        const int inner = p;
+        for (int e = tid; e < 4 * P; e += kLeafThreads) {
+          const int v = e / P, rem = e - v * P;
+          const int i = rem % inner, r = (rem / inner) % p, o = rem / (inner * p);
+          const double* src = lvl1 + (v >> 1) * P + o * p * inner + i;
+          const double* tm = s_t + (v & 1) * p * p;
+          double acc = 0.0;
+          for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q * inner];
+          s_last[e] = acc;
+        }
+        __syncthreads();
       }
     }
-    const double* last_in = DIM == 1 ? lvl0 : (DIM == 2 ? lvl1 : lvl2);
-    for (int ch = 0; ch < NC; ++ch) {
-      const int cidx = dense_leaf[(pkey << DIM) | ch];
-      if (cidx < 0 || cidx < leaf_lo || cidx >= leaf_hi) continue;  // uniform across the CTA
-      // last axis -> this child's expansion
-      const double* add = slot >= 0 ? Lc + ((static_cast<size_t>(slot) * NC + ch) * kn + b) * P : nullptr;
-      for (int e = tid; e < P; e += kLeafThreads) {
-        double acc = 0.0;
-        if (has_parent) {
-          const int r = e % p, o = e / p;  // last axis: inner = 1
-          const double* src = last_in + static_cast<size_t>(ch >> 1) * P + static_cast<size_t>(o) * p;
-          const double* tm = s_t + (ch & 1) * p * p;
-          for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q];
-        }
-        // k_l2l accumulates the interpolated parent onto the M2L result: L_child = m2l + l2l
-        s_child[e] = add ? add[e] + acc : acc;
+    // last axis -> all children (k_l2l accumulates the interpolated parent onto the M2L result)
+    for (int e = tid; e < NC * P; e += kLeafThreads) {
+      const int ch = e / P, rem = e - ch * P;
+      if (s_first[ch] < 0) continue;
+      double acc = 0.0;
+      if (has_parent) {
+        const int r = rem % p, o = rem / p;
+        const double* src = s_last + (ch >> 1) * P + o * p;
+        const double* tm = s_t + (ch & 1) * p * p;
+        for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q];
       }
-      __syncthreads();
-      // L2P for the points of this child, one warp per point
+      if (slot >= 0) acc = Lc[((static_cast<size_t>(slot) * NC + ch) * kn + b) * P + rem] + acc;
+      s_child[e] = acc;
+    }
+    __syncthreads();
+    // L2P, one warp per point
+    const int total = s_pre[NC];
+    for (int k = warp; k < total; k += NW) {
+      int ch = 0;
+#pragma unroll
+      for (int c = 1; c < NC; ++c)
+        if (s_pre[c] <= k && s_first[c] >= 0) ch = c;
+      const int i = s_first[ch] + (k - s_pre[ch]);
       double c[DIM], half;
       cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
-      const int i0 = tr.leaf_start[cidx], i1 = tr.leaf_start[cidx + 1];
-      for (int i = i0 + warp; i < i1; i += NW) {
-        if (lane < DIM) hit[lane] = -1;
-        __syncwarp();
-        for (int e = lane; e < DIM * p; e += 32) {
-          const int a = e / p, k = e - a * p;
-          const double ca = a == 0 ? c[0] : (a == 1 ? c[DIM > 1 ? 1 : 0] : c[DIM > 2 ? 2 : 0]);
-          const double t = (tr.pos[a * tr.n + i] - ca) * inv_half;
-          const double dt = t - node_pos(k, p);
-          if (dt == 0.0) hit[a] = k;
-          basis[e] = s_beta[k] / dt;
-        }
-        __syncwarp();
-        if (lane < DIM) {
-          double sum = 0.0;
-          for (int k = 0; k < p; ++k) sum += basis[lane * p + k];
-          inv[lane] = 1.0 / sum;
-        }
-        __syncwarp();
-        for (int e = lane; e < DIM * p; e += 32) {
-          const int a = e / p, k = e - a * p;
-          basis[e] = hit[a] >= 0 ? (k == hit[a] ? 1.0 : 0.0) : basis[e] * inv[a];
-        }
-        __syncwarp();
-        double acc = 0.0;
-        for (int n = lane; n < P; n += 32) {
-          const int packed = s_nidx[n];
-          double s = 1.0;
-#pragma unroll
-          for (int a = 0; a < DIM; ++a) s *= basis[a * p + ((packed >> (8 * a)) & 0xff)];
-          acc += s * s_child[n];
-        }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) vt[b * tr.n + i] = acc;
-        __syncwarp();
+      if (lane < DIM) hit[lane] = -1;
+      __syncwarp();
+      for (int e = lane; e < DIM * p; e += 32) {
+        const int a = e / p, kk = e - a * p;
+        const double ca = a == 0 ? c[0] : (a == 1 ? c[DIM > 1 ? 1 : 0] : c[DIM > 2 ? 2 : 0]);
+        const double t = (tr.pos[a * tr.n + i] - ca) * inv_half;
+        const double dt = t - node_pos(kk, p);
+        if (dt == 0.0) hit[a] = kk;
+        basis[e] = s_beta[kk] / dt;
       }
-      __syncthreads();  // s_child is reused by the next child
+      __syncwarp();
+      if (lane < DIM) {
+        double sum = 0.0;
+        for (int kk = 0; kk < p; ++kk) sum += basis[lane * p + kk];
+        inv[lane] = 1.0 / sum;
+      }
+      __syncwarp();
+      for (int e = lane; e < DIM * p; e += 32) {
+        const int a = e / p, kk = e - a * p;
+        basis[e] = hit[a] >= 0 ? (kk == hit[a] ? 1.0 : 0.0) : basis[e] * inv[a];
+      }
+      __syncwarp();
+      const double* Lch = s_child + ch * P;
+      double acc = 0.0;
+      for (int n = lane; n < P; n += 32) {
+        int ni[DIM];
+        node_decode<DIM>(n, p, ni);
+        double s = 1.0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) s *= basis[a * p + ni[a]];
+        acc += s * Lch[n];
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) vt[b * tr.n + i] = acc;
+      __syncwarp();
     }
   }
 }
@@ -550,12 +572,12 @@ __device__ __forceinline__ void idft_stage_c2r(const double2* in, double* out, i
 
 // M -> Mhat for all cells of levels >= 2 (CTA grid-strides over cells).
 // Shared (or global scratch) buffers: real P, complex bufA, complex bufB.
-template <int DIM>
+template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kBlock) k_m2hat(int first_cell, int n_cells, InterpDev it, int km,
                                                   const double* __restrict__ M, double2* __restrict__ Mhat,
                                                   double2* gscratch, int scratch_elems) {
   extern __shared__ double2 sm2[];
-  const int p = it.order, nf = it.nf;
+  const int p = ORDER > 0 ? ORDER : it.order, nf = ORDER > 0 ? 2 * ORDER - 1 : it.nf;
   int P = 1, F = p;
   for (int a = 0; a < DIM; ++a) P *= p;
   for (int a = 0; a + 1 < DIM; ++a) F *= nf;
@@ -786,12 +808,12 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
 
 // Inverse DFT of the accumulated spectra, pruned to the order^dim nodes:  L[cell][b][:] = IDFT(Lhat)
 // One CTA per (slot, child, b).
-template <int DIM>
+template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kBlock) k_m2l_idft(M2LArgs a, InterpDev it, double2* gscratch,
                                                      int scratch_elems) {
   extern __shared__ double2 sm2[];
   constexpr int NC = 1 << DIM;
-  const int p = it.order, nf = it.nf;
+  const int p = ORDER > 0 ? ORDER : it.order, nf = ORDER > 0 ? 2 * ORDER - 1 : it.nf;
   int P = 1, F = p;
   for (int d = 0; d < DIM; ++d) P *= p;
   for (int d = 0; d + 1 < DIM; ++d) F *= nf;
@@ -917,6 +939,33 @@ size_t smem_opt_in(const void* fn, size_t bytes) {
 
 constexpr size_t kSmemCap = 200 * 1024;
 
+// (dim, order) -> template instance.  The orders of the two fixed policies of the reference
+// (accuracy = infinity -> 6, accuracy = 0 -> 12, src/fmm/fmm_accuracy_estimator.hpp:76-82) and the
+// first steps of the search are compiled with the order as a constant (index arithmetic without
+// integer divisions, unrolled contractions); any other order runs the generic instance (ORDER = 0).
+template <class F>
+void dispatch_dim_order(int dim, int order, F&& f) {
+  auto with_order = [&](auto dm) {
+    if constexpr (decltype(dm)::value == 1) {
+      f(dm, std::integral_constant<int, 0>{});
+    } else {
+      switch (order) {
+        case 6: f(dm, std::integral_constant<int, 6>{}); break;
+        case 8: f(dm, std::integral_constant<int, 8>{}); break;
+        case 10: f(dm, std::integral_constant<int, 10>{}); break;
+        case 12: f(dm, std::integral_constant<int, 12>{}); break;
+        default: f(dm, std::integral_constant<int, 0>{}); break;
+      }
+    }
+  };
+  switch (dim) {
+    case 1: with_order(std::integral_constant<int, 1>{}); break;
+    case 2: with_order(std::integral_constant<int, 2>{}); break;
+    case 3: with_order(std::integral_constant<int, 3>{}); break;
+    default: throw Error(PLT_ERR_INVALID, "dim must be 1, 2 or 3");
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -951,9 +1000,9 @@ void launch_p2m(int dim, int km, const TreeView& tr, const Box& box, const Inter
   const int n = tr.n_cells[leaf];
   if (n == 0) return;
   size_t smem = sizeof(double) * (it.order + kPointBatch * dim * it.order + kPointBatch * km);
-  if (dim == 1) PLT_LAUNCH(c, k_p2m<1>, n, kBlock, smem, s, tr, box, it, km, wt, M);
-  if (dim == 2) PLT_LAUNCH(c, k_p2m<2>, n, kBlock, smem, s, tr, box, it, km, wt, M);
-  if (dim == 3) PLT_LAUNCH(c, k_p2m<3>, n, kBlock, smem, s, tr, box, it, km, wt, M);
+  dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
+    PLT_LAUNCH(c, (k_p2m<dm.value, od.value>), n, kBlock, smem, s, tr, box, it, km, wt, M);
+  });
 }
 
 void launch_m2m(int dim, int km, const TreeView& tr, int level, const InterpDev& it, double* M, cudaStream_t s,
@@ -963,9 +1012,10 @@ void launch_m2m(int dim, int km, const TreeView& tr, int level, const InterpDev&
   const int P = nodes_per_cell(it.order, dim);
   size_t smem = sizeof(double) * (2 * it.order * it.order + 3 * static_cast<size_t>(P));
   PLT_REQUIRE(smem <= kSmemCap, "interpolation order too large for M2M shared-memory staging");
-  if (dim == 1) { smem_opt_in((const void*)k_m2m<1>, smem); PLT_LAUNCH(c, k_m2m<1>, n, kBlock, smem, s, tr, level, it, km, M); }
-  if (dim == 2) { smem_opt_in((const void*)k_m2m<2>, smem); PLT_LAUNCH(c, k_m2m<2>, n, kBlock, smem, s, tr, level, it, km, M); }
-  if (dim == 3) { smem_opt_in((const void*)k_m2m<3>, smem); PLT_LAUNCH(c, k_m2m<3>, n, kBlock, smem, s, tr, level, it, km, M); }
+  dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
+    smem_opt_in((const void*)k_m2m<dm.value, od.value>, smem);
+    PLT_LAUNCH(c, (k_m2m<dm.value, od.value>), n, kBlock, smem, s, tr, level, it, km, M);
+  });
 }
 
 void launch_l2l(int dim, int kn, const TreeView& tr, int level, const InterpDev& it, double* L, int cell_lo,
@@ -975,9 +1025,10 @@ void launch_l2l(int dim, int kn, const TreeView& tr, int level, const InterpDev&
   const int P = nodes_per_cell(it.order, dim);
   size_t smem = sizeof(double) * (2 * it.order * it.order + 2 * static_cast<size_t>(P));
   PLT_REQUIRE(smem <= kSmemCap, "interpolation order too large for L2L shared-memory staging");
-  if (dim == 1) { smem_opt_in((const void*)k_l2l<1>, smem); PLT_LAUNCH(c, k_l2l<1>, n, kBlock, smem, s, tr, level, it, kn, L, cell_lo); }
-  if (dim == 2) { smem_opt_in((const void*)k_l2l<2>, smem); PLT_LAUNCH(c, k_l2l<2>, n, kBlock, smem, s, tr, level, it, kn, L, cell_lo); }
-  if (dim == 3) { smem_opt_in((const void*)k_l2l<3>, smem); PLT_LAUNCH(c, k_l2l<3>, n, kBlock, smem, s, tr, level, it, kn, L, cell_lo); }
+  dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
+    smem_opt_in((const void*)k_l2l<dm.value, od.value>, smem);
+    PLT_LAUNCH(c, (k_l2l<dm.value, od.value>), n, kBlock, smem, s, tr, level, it, kn, L, cell_lo);
+  });
 }
 
 void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
@@ -995,19 +1046,26 @@ bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, co
                          int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c) {
   const int n = par_hi - par_lo;
   if (n <= 0) return true;
-  const int p = it.order;
-  const size_t P = nodes_per_cell(p, dim);
-  const int nw = kLeafThreads / 32;
-  const size_t stages = 1 + (dim >= 2 ? 2 : 0) + (dim >= 3 ? 4 : 0) + 1;
-  const size_t smem = sizeof(double) * (2 * p * p + p + nw * dim * p + nw * dim + stages * P) +
-                      sizeof(int) * (P + nw * dim);
-  if (smem > kSmemCap || p > 255) return false;
+  const size_t smem = leaf_fused_smem_bytes(dim, it.order);
+  if (smem > kSmemCap) return false;
   const int lo = static_cast<int>(leaf_lo), hi = static_cast<int>(leaf_hi);
-  if (dim == 1) { smem_opt_in((const void*)k_l2l_l2p_leaf<1>, smem); PLT_LAUNCH(c, k_l2l_l2p_leaf<1>, n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt, par_lo, lo, hi); }
-  if (dim == 2) { smem_opt_in((const void*)k_l2l_l2p_leaf<2>, smem); PLT_LAUNCH(c, k_l2l_l2p_leaf<2>, n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt, par_lo, lo, hi); }
-  if (dim == 3) { smem_opt_in((const void*)k_l2l_l2p_leaf<3>, smem); PLT_LAUNCH(c, k_l2l_l2p_leaf<3>, n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt, par_lo, lo, hi); }
+  dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
+    smem_opt_in((const void*)k_l2l_l2p_leaf<dm.value, od.value>, smem);
+    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt,
+               par_lo, lo, hi);
+  });
   return true;
 }
+
+size_t leaf_fused_smem_bytes(int dim, int order) {
+  const size_t P = nodes_per_cell(order, dim);
+  const int nw = kLeafThreads / 32, nc = 1 << dim;
+  const size_t cells = nc + (dim == 1 ? 1 : (dim == 2 ? 2 : 4));
+  return sizeof(double) * (cells * P + 2 * order * order + order + nw * dim * order + nw * dim) +
+         sizeof(int) * (nw * dim + nc + nc + 1);
+}
+
+bool leaf_fused_supported(int dim, int order) { return leaf_fused_smem_bytes(dim, order) <= kSmemCap; }
 
 namespace {
 // Scratch policy for the DFT kernels: shared memory when the two complex stage buffers fit,
@@ -1045,9 +1103,11 @@ void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, cons
   for (int l = 2; l < tr.height; ++l) n_cells += tr.n_cells[l];
   if (n_cells == 0) return;
   DftScratch d = plan_dft_scratch(it.order, dim, n_cells * km, s);
-  if (dim == 1) { smem_opt_in((const void*)k_m2hat<1>, d.smem); PLT_LAUNCH(c, k_m2hat<1>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
-  if (dim == 2) { smem_opt_in((const void*)k_m2hat<2>, d.smem); PLT_LAUNCH(c, k_m2hat<2>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
-  if (dim == 3) { smem_opt_in((const void*)k_m2hat<3>, d.smem); PLT_LAUNCH(c, k_m2hat<3>, d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(), d.elems); }
+  dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
+    smem_opt_in((const void*)k_m2hat<dm.value, od.value>, d.smem);
+    PLT_LAUNCH(c, (k_m2hat<dm.value, od.value>), d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(),
+               d.elems);
+  });
 }
 
 void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
@@ -1125,9 +1185,10 @@ void launch_m2l_idft(const M2LArgs& a, const InterpDev& it, cudaStream_t s, Laun
   if (a.n_active == 0) return;
   const int work = a.n_active * (1 << a.dim) * a.kn;
   DftScratch d = plan_dft_scratch(it.order, a.dim, work, s);
-  if (a.dim == 1) { smem_opt_in((const void*)k_m2l_idft<1>, d.smem); PLT_LAUNCH(c, k_m2l_idft<1>, d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems); }
-  if (a.dim == 2) { smem_opt_in((const void*)k_m2l_idft<2>, d.smem); PLT_LAUNCH(c, k_m2l_idft<2>, d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems); }
-  if (a.dim == 3) { smem_opt_in((const void*)k_m2l_idft<3>, d.smem); PLT_LAUNCH(c, k_m2l_idft<3>, d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems); }
+  dispatch_dim_order(a.dim, it.order, [&](auto dm, auto od) {
+    smem_opt_in((const void*)k_m2l_idft<dm.value, od.value>, d.smem);
+    PLT_LAUNCH(c, (k_m2l_idft<dm.value, od.value>), d.grid, kBlock, d.smem, s, a, it, d.buf.get(), d.elems);
+  });
 }
 
 }  // namespace plt

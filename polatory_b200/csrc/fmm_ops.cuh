@@ -91,6 +91,8 @@ void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const Inter
 bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
                          const double* Lc, const int* leaf_slot, double* vt, int64_t leaf_lo, int64_t leaf_hi,
                          int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c);
+size_t leaf_fused_smem_bytes(int dim, int order);
+bool leaf_fused_supported(int dim, int order);
 // Near field over the 3^dim adjacent source leaves of the listed target leaves (ascending ids,
 // restricted to [lo, hi)); vt += ...
 void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const double* swt, const TreeView& trg,
