@@ -379,7 +379,8 @@ struct plt_eval {
       PLT_CUDA(cudaMemcpyAsync(ip->child.get(), h.child.data(), sizeof(double) * h.child.size(), cudaMemcpyHostToDevice, stream));
       PLT_CUDA(cudaMemcpyAsync(ip->tw.get(), h.tw.data(), sizeof(double2) * h.nf, cudaMemcpyHostToDevice, stream));
       PLT_CUDA(cudaStreamSynchronize(stream));  // host tables are about to go out of scope of the copy
-      ip->dev = InterpDev{order, h.nf, ip->beta.get(), ip->child.get(), ip->tw.get()};
+      ip->dev = InterpDev{order, h.nf, ip->beta.get(), ip->child.get(), ip->tw.get(),
+                          h.tw.data(), h.child.data(), h.beta.data()};
       const size_t F = freqs_per_cell(order, dim);
       ip->khat_level_stride = static_cast<size_t>(ipow(7, dim)) * kn * km * F;
       const int n_levels = std::max(0, height - 2);

@@ -345,22 +345,72 @@ __global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev 
 //   L_child = L2L(L_parent) + Lc[slot][child]   (M2L result of the leaf level, if any)
 //   v_i     = L2P(L_child) for the points of the child
 // The leaf-level expansions (the largest array of the whole evaluation: 8 P bytes x kn per
-// leaf) live only in shared memory.  The per-axis L2L contractions of the first dim-1 axes are
-// shared between siblings (axis 0 gives 2 variants, axis 1 gives 4), the last axis produces all
-// 2^dim children at once; then the points of the parent (contiguous in Morton order) are
-// evaluated, one warp per point, lanes over the nodes.  Four CTA barriers per parent.
+// leaf) live only in shared memory.
+//   * L2L: per-axis contractions, register-blocked by columns (a thread loads the p inputs of a
+//     column and produces its p outputs; the transfer matrices are kernel-parameter constants).
+//     The first dim-1 axes are shared between siblings (axis 0: 2 variants, axis 1: 4), the last
+//     axis produces all 2^dim children.
+//   * L2P: warp <-> child, lane <-> point; the lane builds its 1-D bases in registers and
+//     contracts the child's tensor axis by axis (p^dim + p^(dim-1) + ... FMAs), every lane of the
+//     warp reading the same expansion entries (shared-memory broadcast).
+//     The barycentric basis is evaluated in product form,
+//       S_m(t) = beta_m prod_{j != m}(t - t_j) / sum_i beta_i prod_{j != i}(t - t_j),
+//     algebraically the quotient form of interp.hpp (both numerator and denominator multiplied
+//     by prod_j (t - t_j)) without its divisions and without the t == t_m special case.
 // Shared layout: [children 2^dim x P][last shared stage]; the parent and the first stage are
 // dead by the time the children are written and overlay the children area.
 // ------------------------------------------------------------------------------------
 constexpr int kLeafThreads = 256;
+constexpr int kLeafMaxOrder = 12;
+
+struct LeafTables {
+  double child[2 * kLeafMaxOrder * kLeafMaxOrder];  // [2][p][p]
+  double beta[kLeafMaxOrder];
+};
 
 template <int DIM>
 __host__ __device__ constexpr int leaf_stage_cells() {
   return (1 << DIM) + (DIM == 1 ? 1 : (DIM == 2 ? 2 : 4));
 }
 
+// out[r * stride] = sum_q T[q][r] in[q * stride]   (child node r <- parent node q)
+template <int p>
+__device__ __forceinline__ void leaf_contract_col(const double* __restrict__ tm, const double* in, int stride,
+                                                  double* out) {
+  double x[p];
+#pragma unroll
+  for (int q = 0; q < p; ++q) x[q] = in[q * stride];
+#pragma unroll
+  for (int r = 0; r < p; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < p; ++q) acc += tm[q * p + r] * x[q];
+    out[r * stride] = acc;
+  }
+}
+
+template <int p>
+__device__ __forceinline__ void product_basis(const double* __restrict__ beta, double t, double (&s)[p]) {
+  double d[p], pre[p];
+#pragma unroll
+  for (int m = 0; m < p; ++m) d[m] = t - (-1.0 + 2.0 * m / (p - 1));
+  pre[0] = 1.0;
+#pragma unroll
+  for (int m = 1; m < p; ++m) pre[m] = pre[m - 1] * d[m - 1];
+  double suf = 1.0, sum = 0.0;
+#pragma unroll
+  for (int m = p - 1; m >= 0; --m) {
+    s[m] = beta[m] * (pre[m] * suf);
+    sum += s[m];
+    suf *= d[m];
+  }
+  const double inv = 1.0 / sum;
+#pragma unroll
+  for (int m = 0; m < p; ++m) s[m] *= inv;
+}
+
 template <int DIM, int ORDER>
-__global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box box, InterpDev it, int kn,
+__global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box box, LeafTables tb, int kn,
                                                                const double* __restrict__ L,
                                                                const double* __restrict__ Lc,
                                                                const int* __restrict__ leaf_slot,
@@ -369,20 +419,15 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
   extern __shared__ double sm[];
   constexpr int NC = 1 << DIM;
   constexpr int NW = kLeafThreads / 32;
-  const int p = ORDER > 0 ? ORDER : it.order;
-  int P = 1;
-  for (int a = 0; a < DIM; ++a) P *= p;
+  constexpr int p = ORDER;
+  constexpr int P = DIM == 1 ? p : (DIM == 2 ? p * p : p * p * p);
+  constexpr int PC = P / p;  // columns per axis
   double* s_child = sm;                         // [NC][P]
   double* s_last = s_child + NC * P;            // last shared stage: [1 | 2 | 4][P]
   double* lvl0 = DIM == 1 ? s_last : s_child;   // parent
   double* lvl1 = DIM == 2 ? s_last : s_child + P;  // after axis 0 (DIM >= 2)
-  double* s_t = s_last + (leaf_stage_cells<DIM>() - NC) * P;  // [2][p][p]
-  double* s_beta = s_t + 2 * p * p;             // [p]
-  double* s_basis = s_beta + p;                 // [NW][DIM][p]
-  double* s_inv = s_basis + NW * DIM * p;       // [NW][DIM]
-  int* s_hit = reinterpret_cast<int*>(s_inv + NW * DIM);  // [NW][DIM]
-  int* s_first = s_hit + NW * DIM;              // [NC] first point of the child (or -1)
-  int* s_pre = s_first + NC;                    // [NC + 1] prefix of the children's point counts
+  __shared__ int s_first[NC];  // first point of the child, or -1
+  __shared__ int s_count[NC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int leaf = tr.height - 1, pl = leaf - 1;
   const int pidx = par_lo + blockIdx.x;
@@ -390,29 +435,16 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
   const bool has_parent = L != nullptr;  // parent level >= 2
   const int slot = leaf_slot ? leaf_slot[pidx] : -1;
 
-  for (int i = tid; i < 2 * p * p; i += kLeafThreads) s_t[i] = it.child[i];
-  for (int i = tid; i < p; i += kLeafThreads) s_beta[i] = it.beta[i];
-  if (tid == 0) {
-    const int* dense_leaf = tr.dense + tr.dense_off[leaf];
-    int run = 0;
-    for (int ch = 0; ch < NC; ++ch) {
-      const int cidx = dense_leaf[(pkey << DIM) | ch];
-      int first = -1, cnt = 0;
-      if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
-        first = tr.leaf_start[cidx];
-        cnt = tr.leaf_start[cidx + 1] - first;
-      }
-      s_first[ch] = first;
-      s_pre[ch] = run;
-      run += cnt;
+  if (tid < NC) {
+    const int cidx = tr.dense[tr.dense_off[leaf] + ((pkey << DIM) | tid)];
+    int first = -1, cnt = 0;
+    if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
+      first = tr.leaf_start[cidx];
+      cnt = tr.leaf_start[cidx + 1] - first;
     }
-    s_pre[NC] = run;
+    s_first[tid] = first;
+    s_count[tid] = cnt;
   }
-  const double cw = box.width / static_cast<double>(1 << leaf);
-  const double inv_half = 1.0 / (0.5 * cw);
-  double* basis = s_basis + warp * DIM * p;
-  double* inv = s_inv + warp * DIM;
-  int* hit = s_hit + warp * DIM;
 
   for (int b = 0; b < kn; ++b) {
     __syncthreads();  // tables ready / previous component done with the children
@@ -421,94 +453,88 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
       for (int n = tid; n < P; n += kLeafThreads) lvl0[n] = Lp[n];
       __syncthreads();
       if constexpr (DIM >= 2) {
-        // axis 0: parent -> 2 variants
-        const int inner = P / p;
-        double* out = lvl1;
-        for (int e = tid; e < 2 * P; e += kLeafThreads) {
-          const int v = e / P, rem = e - v * P;
-          const int i = rem % inner, r = rem / inner;
-          const double* tm = s_t + v * p * p;
-          double acc = 0.0;
-          for (int q = 0; q < p; ++q) acc += tm[q * p + r] * lvl0[q * inner + i];
-          out[e] = acc;
+        // axis 0 (stride P / p): parent -> 2 variants
+        for (int item = tid; item < 2 * PC; item += kLeafThreads) {
+          const int v = item / PC, col = item - v * PC;
+          leaf_contract_col<p>(tb.child + v * p * p, lvl0 + col, PC, lvl1 + v * P + col);
         }
         __syncthreads();
       }
       if constexpr (DIM == 3) {
-        // axis 1: 2 variants -> 4
-        const int inner = p;
-        for (int e = tid; e < 4 * P; e += kLeafThreads) {
-          const int v = e / P, rem = e - v * P;
-          const int i = rem % inner, r = (rem / inner) % p, o = rem / (inner * p);
-          const double* src = lvl1 + (v >> 1) * P + o * p * inner + i;
-          const double* tm = s_t + (v & 1) * p * p;
-          double acc = 0.0;
-          for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q * inner];
-          s_last[e] = acc;
+        // axis 1 (stride p): 2 variants -> 4.  column = (i, k)
+        for (int item = tid; item < 4 * PC; item += kLeafThreads) {
+          const int v = item / PC, col = item - v * PC;
+          const int i = col / p, k = col - i * p;
+          leaf_contract_col<p>(tb.child + (v & 1) * p * p, lvl1 + (v >> 1) * P + i * p * p + k, p,
+                               s_last + v * P + i * p * p + k);
         }
         __syncthreads();
       }
     }
-    // last axis -> all children (k_l2l accumulates the interpolated parent onto the M2L result)
-    for (int e = tid; e < NC * P; e += kLeafThreads) {
-      const int ch = e / P, rem = e - ch * P;
+    // last axis (stride 1) -> all children; k_l2l accumulates the parent onto the M2L result
+    for (int item = tid; item < NC * PC; item += kLeafThreads) {
+      const int ch = item / PC, col = item - ch * PC;
       if (s_first[ch] < 0) continue;
-      double acc = 0.0;
+      double* out = s_child + ch * P + col * p;
       if (has_parent) {
-        const int r = rem % p, o = rem / p;
-        const double* src = s_last + (ch >> 1) * P + o * p;
-        const double* tm = s_t + (ch & 1) * p * p;
-        for (int q = 0; q < p; ++q) acc += tm[q * p + r] * src[q];
+        leaf_contract_col<p>(tb.child + (ch & 1) * p * p, s_last + (ch >> 1) * P + col * p, 1, out);
+      } else {
+#pragma unroll
+        for (int r = 0; r < p; ++r) out[r] = 0.0;
       }
-      if (slot >= 0) acc = Lc[((static_cast<size_t>(slot) * NC + ch) * kn + b) * P + rem] + acc;
-      s_child[e] = acc;
+      if (slot >= 0) {
+        const double* add = Lc + ((static_cast<size_t>(slot) * NC + ch) * kn + b) * P + col * p;
+#pragma unroll
+        for (int r = 0; r < p; ++r) out[r] = add[r] + out[r];
+      }
     }
     __syncthreads();
-    // L2P, one warp per point
-    const int total = s_pre[NC];
-    for (int k = warp; k < total; k += NW) {
-      int ch = 0;
-#pragma unroll
-      for (int c = 1; c < NC; ++c)
-        if (s_pre[c] <= k && s_first[c] >= 0) ch = c;
-      const int i = s_first[ch] + (k - s_pre[ch]);
+    // L2P: warp <-> child, lane <-> point
+    for (int ch = warp; ch < NC; ch += NW) {
+      const int first = s_first[ch], cnt = s_count[ch];
+      if (first < 0) continue;
       double c[DIM], half;
       cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
-      if (lane < DIM) hit[lane] = -1;
-      __syncwarp();
-      for (int e = lane; e < DIM * p; e += 32) {
-        const int a = e / p, kk = e - a * p;
-        const double ca = a == 0 ? c[0] : (a == 1 ? c[DIM > 1 ? 1 : 0] : c[DIM > 2 ? 2 : 0]);
-        const double t = (tr.pos[a * tr.n + i] - ca) * inv_half;
-        const double dt = t - node_pos(kk, p);
-        if (dt == 0.0) hit[a] = kk;
-        basis[e] = s_beta[kk] / dt;
-      }
-      __syncwarp();
-      if (lane < DIM) {
-        double sum = 0.0;
-        for (int kk = 0; kk < p; ++kk) sum += basis[lane * p + kk];
-        inv[lane] = 1.0 / sum;
-      }
-      __syncwarp();
-      for (int e = lane; e < DIM * p; e += 32) {
-        const int a = e / p, kk = e - a * p;
-        basis[e] = hit[a] >= 0 ? (kk == hit[a] ? 1.0 : 0.0) : basis[e] * inv[a];
-      }
-      __syncwarp();
+      const double inv_half = 1.0 / half;
       const double* Lch = s_child + ch * P;
-      double acc = 0.0;
-      for (int n = lane; n < P; n += 32) {
-        int ni[DIM];
-        node_decode<DIM>(n, p, ni);
-        double s = 1.0;
+      for (int j = lane; j < cnt; j += 32) {
+        const int i = first + j;
+        double bs[DIM][p];
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) s *= basis[a * p + ni[a]];
-        acc += s * Lch[n];
+        for (int a = 0; a < DIM; ++a)
+          product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
+        double v = 0.0;
+        if constexpr (DIM == 1) {
+#pragma unroll
+          for (int k = 0; k < p; ++k) v = fma(bs[0][k], Lch[k], v);
+        } else if constexpr (DIM == 2) {
+#pragma unroll
+          for (int i0 = 0; i0 < p; ++i0) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < p; ++k) r = fma(bs[1][k], Lch[i0 * p + k], r);
+            v = fma(bs[0][i0], r, v);
+          }
+        } else {
+#pragma unroll 1
+          for (int i0 = 0; i0 < p; ++i0) {
+            double ri = 0.0;
+#pragma unroll
+            for (int i1 = 0; i1 < p; ++i1) {
+              double r = 0.0;
+#pragma unroll
+              for (int k = 0; k < p; ++k) r = fma(bs[2][k], Lch[(i0 * p + i1) * p + k], r);
+              ri = fma(bs[1][i1], r, ri);
+            }
+            double b0 = bs[0][0];  // register select instead of a dynamically indexed array
+#pragma unroll
+            for (int m = 1; m < p; ++m)
+              if (i0 == m) b0 = bs[0][m];
+            v = fma(b0, ri, v);
+          }
+        }
+        vt[b * tr.n + i] = v;
       }
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) vt[b * tr.n + i] = acc;
-      __syncwarp();
     }
   }
 }
@@ -859,6 +885,120 @@ __global__ void __launch_bounds__(kBlock) k_m2l_idft(M2LArgs a, InterpDev it, do
   }
 }
 
+// Register-blocked 3-D inverse DFT (orders compiled in).  Every thread owns one *column* of a
+// stage: it loads the column's nf (or p) inputs once into registers and produces all p outputs,
+// with the twiddles as kernel-parameter constants (constant-bank operands of the DFMAs), so the
+// shared-memory traffic is one read and one write per element and stage instead of two reads
+// per complex multiply-add.  A CTA transforms NB cells at a time.
+struct TwTable {
+  double2 w[2 * 12 - 1];  // forward twiddles (cos, -sin) of length nf = 2 * order - 1, order <= 12
+};
+
+template <int ORDER, int NB>
+__global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
+  constexpr int DIM = 3, NC = 8, p = ORDER, nf = 2 * ORDER - 1;
+  constexpr int P = p * p * p, F = nf * nf * p, YN = p * nf * p;
+  extern __shared__ double2 sm2[];
+  double2* Y = sm2;            // [NB][p][nf][p]
+  double2* Z = Y + NB * YN;    // [NB][p][p][p]
+  __shared__ const double2* s_in[NB];
+  __shared__ double* s_out[NB];
+  const int total = a.n_active * NC * a.kn;
+  const int w0 = blockIdx.x * NB;
+  if (threadIdx.x < NB) {
+    const int w = w0 + threadIdx.x;
+    const double2* in = nullptr;
+    double* out = nullptr;
+    if (w < total) {
+      const int b = w % a.kn;
+      const int ct = (w / a.kn) % NC;
+      const int slot = w / (a.kn * NC);
+      if ((a.trg_mask[slot] >> ct) & 1u) {
+        in = a.Lhat + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * F;
+        if (a.L) {
+          const int pidx = a.active[slot];
+          const uint32_t pkey = a.trg.keys[a.trg.cell_off[a.level - 1] + pidx];
+          const int cidx = a.trg.dense[a.trg.dense_off[a.level] + ((pkey << DIM) | ct)];
+          out = a.L + (static_cast<size_t>(a.trg.cell_off[a.level] + cidx) * a.kn + b) * P;
+        } else {
+          out = a.Lc + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * P;
+        }
+      }
+    }
+    s_in[threadIdx.x] = in;
+    s_out[threadIdx.x] = out;
+  }
+  __syncthreads();
+  // stage A: axis 0, nf -> p.  column = (f1, f2)
+  for (int item = threadIdx.x; item < NB * nf * p; item += blockDim.x) {
+    const int c = item / (nf * p), col = item % (nf * p);
+    const double2* in = s_in[c];
+    if (!in) continue;
+    double2 x[nf];
+#pragma unroll
+    for (int f = 0; f < nf; ++f) x[f] = in[f * (nf * p) + col];
+#pragma unroll
+    for (int m = 0; m < p; ++m) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int f = 0; f < nf; ++f) {
+        const double2 t = tw.w[(m * f) % nf];  // conj: e^{+i theta}
+        re = fma(x[f].x, t.x, re);
+        re = fma(x[f].y, t.y, re);
+        im = fma(x[f].y, t.x, im);
+        im = fma(-x[f].x, t.y, im);
+      }
+      Y[c * YN + m * (nf * p) + col] = make_double2(re, im);
+    }
+  }
+  __syncthreads();
+  // stage B: axis 1, nf -> p.  column = (m0, f2)
+  for (int item = threadIdx.x; item < NB * p * p; item += blockDim.x) {
+    const int c = item / (p * p), col = item % (p * p);
+    if (!s_in[c]) continue;
+    const int m0 = col / p, f2 = col % p;
+    const double2* yin = Y + c * YN + m0 * (nf * p) + f2;
+    double2 x[nf];
+#pragma unroll
+    for (int f = 0; f < nf; ++f) x[f] = yin[f * p];
+#pragma unroll
+    for (int m = 0; m < p; ++m) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int f = 0; f < nf; ++f) {
+        const double2 t = tw.w[(m * f) % nf];
+        re = fma(x[f].x, t.x, re);
+        re = fma(x[f].y, t.y, re);
+        im = fma(x[f].y, t.x, im);
+        im = fma(-x[f].x, t.y, im);
+      }
+      Z[c * P + (m0 * p + m) * p + f2] = make_double2(re, im);
+    }
+  }
+  __syncthreads();
+  // stage C: axis 2, half spectrum -> real.  column = (m0, m1)
+  for (int item = threadIdx.x; item < NB * p * p; item += blockDim.x) {
+    const int c = item / (p * p), col = item % (p * p);
+    double* out = s_out[c];
+    if (!out) continue;
+    const double2* zin = Z + c * P + col * p;
+    double2 x[p];
+#pragma unroll
+    for (int k = 0; k < p; ++k) x[k] = zin[k];
+#pragma unroll
+    for (int m = 0; m < p; ++m) {
+      double acc = x[0].x;
+#pragma unroll
+      for (int k = 1; k < p; ++k) {
+        const double2 t = tw.w[(k * m) % nf];
+        acc = fma(2.0 * x[k].x, t.x, acc);
+        acc = fma(2.0 * x[k].y, t.y, acc);
+      }
+      out[col * p + m] = acc;
+    }
+  }
+}
+
 // Work counters for the roofline figures (not on the timed path): M2L pairs and target cells
 // with a non-empty list at one level; P2P pairs at the leaves.
 template <int DIM>
@@ -931,13 +1071,17 @@ __global__ void k_count_p2p(TreeView src, TreeView trg, unsigned long long* __re
 }
 
 size_t smem_opt_in(const void* fn, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 40 * 1024) {  // static shared memory counts towards the 48 KiB default limit
     PLT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
   }
   return bytes;
 }
 
 constexpr size_t kSmemCap = 200 * 1024;
+
+struct InterpTablesView {
+  const double* tw;  // host copy of the forward twiddles [nf][2]
+};
 
 // (dim, order) -> template instance.  The orders of the two fixed policies of the reference
 // (accuracy = infinity -> 6, accuracy = 0 -> 12, src/fmm/fmm_accuracy_estimator.hpp:76-82) and the
@@ -1041,17 +1185,42 @@ void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const Inter
   if (dim == 3) PLT_LAUNCH(c, k_l2p<3>, n, kBlock, smem, s, tr, box, it, kn, L, vt, static_cast<int>(leaf_lo));
 }
 
+namespace {
+template <class F>
+void dispatch_leaf(int dim, int order, F&& f) {
+  auto with_order = [&](auto dm) {
+    switch (order) {
+      case 6: f(dm, std::integral_constant<int, 6>{}); break;
+      case 8: f(dm, std::integral_constant<int, 8>{}); break;
+      case 10: f(dm, std::integral_constant<int, 10>{}); break;
+      case 12: f(dm, std::integral_constant<int, 12>{}); break;
+      default: throw Error(PLT_ERR_INVALID, "fused leaf pass: order not compiled in");
+    }
+  };
+  switch (dim) {
+    case 1: with_order(std::integral_constant<int, 1>{}); break;
+    case 2: with_order(std::integral_constant<int, 2>{}); break;
+    case 3: with_order(std::integral_constant<int, 3>{}); break;
+    default: throw Error(PLT_ERR_INVALID, "dim must be 1, 2 or 3");
+  }
+}
+}  // namespace
+
 bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
                          const double* Lc, const int* leaf_slot, double* vt, int64_t leaf_lo, int64_t leaf_hi,
                          int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c) {
   const int n = par_hi - par_lo;
   if (n <= 0) return true;
+  if (!leaf_fused_supported(dim, it.order) || !it.host_child || !it.host_beta) return false;
   const size_t smem = leaf_fused_smem_bytes(dim, it.order);
-  if (smem > kSmemCap) return false;
+  LeafTables tb{};
+  const int p = it.order;
+  for (int i = 0; i < 2 * p * p; ++i) tb.child[i] = it.host_child[i];
+  for (int i = 0; i < p; ++i) tb.beta[i] = it.host_beta[i];
   const int lo = static_cast<int>(leaf_lo), hi = static_cast<int>(leaf_hi);
-  dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
+  dispatch_leaf(dim, it.order, [&](auto dm, auto od) {
     smem_opt_in((const void*)k_l2l_l2p_leaf<dm.value, od.value>, smem);
-    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, kLeafThreads, smem, s, tr, box, it, kn, L, Lc, leaf_slot, vt,
+    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, kLeafThreads, smem, s, tr, box, tb, kn, L, Lc, leaf_slot, vt,
                par_lo, lo, hi);
   });
   return true;
@@ -1059,13 +1228,15 @@ bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, co
 
 size_t leaf_fused_smem_bytes(int dim, int order) {
   const size_t P = nodes_per_cell(order, dim);
-  const int nw = kLeafThreads / 32, nc = 1 << dim;
+  const int nc = 1 << dim;
   const size_t cells = nc + (dim == 1 ? 1 : (dim == 2 ? 2 : 4));
-  return sizeof(double) * (cells * P + 2 * order * order + order + nw * dim * order + nw * dim) +
-         sizeof(int) * (nw * dim + nc + nc + 1);
+  return sizeof(double) * cells * P;
 }
 
-bool leaf_fused_supported(int dim, int order) { return leaf_fused_smem_bytes(dim, order) <= kSmemCap; }
+bool leaf_fused_supported(int dim, int order) {
+  const bool compiled = order == 6 || order == 8 || order == 10 || order == 12;
+  return compiled && leaf_fused_smem_bytes(dim, order) <= kSmemCap;
+}
 
 namespace {
 // Scratch policy for the DFT kernels: shared memory when the two complex stage buffers fit,
@@ -1181,8 +1352,32 @@ void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
 #undef PLT_HAD
 }
 
+namespace {
+template <int ORDER, int NB>
+void launch_idft3(const M2LArgs& a, const InterpTablesView& tv, cudaStream_t s, LaunchCounter& c) {
+  constexpr int p = ORDER, nf = 2 * ORDER - 1;
+  TwTable tw{};
+  for (int i = 0; i < nf; ++i) tw.w[i] = make_double2(tv.tw[2 * i], tv.tw[2 * i + 1]);
+  const size_t smem = sizeof(double2) * NB * (p * nf * p + p * p * p);
+  smem_opt_in((const void*)k_m2l_idft3<ORDER, NB>, smem);
+  const int total = a.n_active * 8 * a.kn;
+  PLT_LAUNCH(c, (k_m2l_idft3<ORDER, NB>), ceil_div(total, NB), 256, smem, s, a, tw);
+}
+}  // namespace
+
 void launch_m2l_idft(const M2LArgs& a, const InterpDev& it, cudaStream_t s, LaunchCounter& c) {
   if (a.n_active == 0) return;
+  static const bool no_reg = getenv("PLT_DEBUG_NO_REGDFT") != nullptr;  // A/B switch for parity bisection
+  if (a.dim == 3 && it.host_tw && !no_reg) {
+    const InterpTablesView tv{it.host_tw};
+    switch (it.order) {
+      case 6: launch_idft3<6, 4>(a, tv, s, c); return;
+      case 8: launch_idft3<8, 2>(a, tv, s, c); return;
+      case 10: launch_idft3<10, 1>(a, tv, s, c); return;
+      case 12: launch_idft3<12, 1>(a, tv, s, c); return;
+      default: break;
+    }
+  }
   const int work = a.n_active * (1 << a.dim) * a.kn;
   DftScratch d = plan_dft_scratch(it.order, a.dim, work, s);
   dispatch_dim_order(a.dim, it.order, [&](auto dm, auto od) {

@@ -21,6 +21,11 @@ struct InterpDev {
   const double* beta;    // [order]
   const double* child;   // [2][order][order]
   const double2* tw;     // [nf] forward twiddles (cos, -sin)
+  // Host copies (owned by the Interpolator) for kernels that take the tables as by-value
+  // kernel parameters (constant bank): twiddles [nf][2], child [2][order][order], beta [order].
+  const double* host_tw = nullptr;
+  const double* host_child = nullptr;
+  const double* host_beta = nullptr;
 };
 
 inline int ipow(int b, int e) {
