@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev 
 // Shared layout: [children 2^dim x P][last shared stage]; the parent and the first stage are
 // dead by the time the children are written and overlay the children area.
 // ------------------------------------------------------------------------------------
-constexpr int kLeafThreads = 256;
+constexpr int kLeafThreads = 128;
 constexpr int kLeafMaxOrder = 12;
 
 struct LeafTables {
@@ -410,7 +410,7 @@ __device__ __forceinline__ void product_basis(const double* __restrict__ beta, d
 }
 
 template <int DIM, int ORDER>
-__global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box box, LeafTables tb, int kn,
+__global__ void __launch_bounds__(kLeafThreads, ORDER <= 6 ? 6 : 4) k_l2l_l2p_leaf(TreeView tr, Box box, LeafTables tb, int kn,
                                                                const double* __restrict__ L,
                                                                const double* __restrict__ Lc,
                                                                const int* __restrict__ leaf_slot,
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
       }
     }
     __syncthreads();
-    // L2P: warp <-> child, lane <-> point
+    // L2P: warp <-> child
     for (int ch = warp; ch < NC; ch += NW) {
       const int first = s_first[ch], cnt = s_count[ch];
       if (first < 0) continue;
@@ -497,43 +497,61 @@ __global__ void __launch_bounds__(kLeafThreads) k_l2l_l2p_leaf(TreeView tr, Box 
       cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
       const double inv_half = 1.0 / half;
       const double* Lch = s_child + ch * P;
-      for (int j = lane; j < cnt; j += 32) {
-        const int i = first + j;
-        double bs[DIM][p];
+      if constexpr (DIM == 3) {
+        // p lanes per point (lane <-> slab i0 of the tensor), 32 / p points per pass: leaves hold
+        // only a few points, so the lanes are spent on the contraction instead of on more points.
+        constexpr int PP = 32 / p;
+        const int sub = lane / p, i0 = lane - sub * p;
+        for (int j0 = 0; j0 < cnt; j0 += PP) {
+          const int j = j0 + sub;
+          const bool act = sub < PP && j < cnt;
+          const int i = first + (act ? j : 0);
+          double bs[DIM][p];
 #pragma unroll
-        for (int a = 0; a < DIM; ++a)
-          product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
-        double v = 0.0;
-        if constexpr (DIM == 1) {
+          for (int a = 0; a < DIM; ++a)
+            product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
+          double b0 = bs[0][0];  // register select instead of a dynamically indexed array
 #pragma unroll
-          for (int k = 0; k < p; ++k) v = fma(bs[0][k], Lch[k], v);
-        } else if constexpr (DIM == 2) {
+          for (int m = 1; m < p; ++m)
+            if (i0 == m) b0 = bs[0][m];
+          const double* Ls = Lch + i0 * p * p;
+          double ri = 0.0;
 #pragma unroll
-          for (int i0 = 0; i0 < p; ++i0) {
+          for (int i1 = 0; i1 < p; ++i1) {
             double r = 0.0;
 #pragma unroll
-            for (int k = 0; k < p; ++k) r = fma(bs[1][k], Lch[i0 * p + k], r);
-            v = fma(bs[0][i0], r, v);
+            for (int k = 0; k < p; ++k) r = fma(bs[2][k], Ls[i1 * p + k], r);
+            ri = fma(bs[1][i1], r, ri);
           }
-        } else {
-#pragma unroll 1
-          for (int i0 = 0; i0 < p; ++i0) {
-            double ri = 0.0;
+          double v = b0 * ri;
+          // sum over the p lanes of the point; the group's first lane ends up with the total
+          double tot = v;
 #pragma unroll
-            for (int i1 = 0; i1 < p; ++i1) {
+          for (int m = 1; m < p; ++m) tot += __shfl_down_sync(0xffffffffu, v, m);
+          if (act && i0 == 0) vt[b * tr.n + i] = tot;
+        }
+      } else {
+        for (int j = lane; j < cnt; j += 32) {
+          const int i = first + j;
+          double bs[DIM][p];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a)
+            product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
+          double v = 0.0;
+          if constexpr (DIM == 1) {
+#pragma unroll
+            for (int k = 0; k < p; ++k) v = fma(bs[0][k], Lch[k], v);
+          } else {
+#pragma unroll
+            for (int i0 = 0; i0 < p; ++i0) {
               double r = 0.0;
 #pragma unroll
-              for (int k = 0; k < p; ++k) r = fma(bs[2][k], Lch[(i0 * p + i1) * p + k], r);
-              ri = fma(bs[1][i1], r, ri);
+              for (int k = 0; k < p; ++k) r = fma(bs[1][k], Lch[i0 * p + k], r);
+              v = fma(bs[0][i0], r, v);
             }
-            double b0 = bs[0][0];  // register select instead of a dynamically indexed array
-#pragma unroll
-            for (int m = 1; m < p; ++m)
-              if (i0 == m) b0 = bs[0][m];
-            v = fma(b0, ri, v);
           }
+          vt[b * tr.n + i] = v;
         }
-        vt[b * tr.n + i] = v;
       }
     }
   }
@@ -741,6 +759,7 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
   extern __shared__ double2 sm2[];
   double2* Ks = sm2;                                      // [NOFF][TF]
   int2* s_meta = reinterpret_cast<int2*>(Ks + NOFF * kHadTF);  // [NE]: x = offset index base, y = far mask
+  int2* s_list = s_meta + NE;                                   // [warps][NE]: (Mhat row, code) of present sources
   const int ftile = blockIdx.x % n_ftiles, pslice = blockIdx.x / n_ftiles, n_pslices = gridDim.x / n_ftiles;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f = ftile * kHadTF + lane;
@@ -775,54 +794,60 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
   __syncthreads();
 
   // parents of this CTA: slot = pslice + n_pslices * (warp + kHadWarps * i)
+  int2* list = s_list + warp * NE;
   for (int slot = pslice + n_pslices * warp; slot < a.n_active; slot += n_pslices * kHadWarps) {
     const int* tab = a.src_ids + static_cast<size_t>(slot) * NE;
     const int tmask = a.trg_mask[slot];
-    int sid_l[NCH];
+    // compact the present source cells that have a far target child: list of (Mhat row, code)
+    int n = 0;
+    __syncwarp();  // previous parent done with the list
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int idx = c * 32 + lane;
-      sid_l[c] = idx < NE ? tab[idx] : -1;
+      const int sid = idx < NE ? tab[idx] : -1;
+      const bool pres = sid >= 0 && (s_meta[idx].y & tmask) != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, pres);
+      if (pres) list[n + __popc(m & ((1u << lane) - 1u))] = make_int2(sid, idx);
+      n += __popc(m);
     }
+    __syncwarp();
     double2 acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
+
+    // software pipeline over groups of kHadG entries: the Mhat rows of the next group are in
+    // flight while the current group is multiplied
+    auto load = [&](double2 (&mh)[kHadG], int base) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      unsigned m = __ballot_sync(0xffffffffu, sid_l[c] >= 0);
-      while (m) {
-        int code[kHadG], sid[kHadG];
-        double2 mh[kHadG];
+      for (int g = 0; g < kHadG; ++g) {
+        const int e = base + g;
+        mh[g] = (e < n && fok) ? a.Mhat[static_cast<size_t>(list[e].x) * F + f] : make_double2(0.0, 0.0);
+      }
+    };
+    auto compute = [&](const double2 (&mh)[kHadG], int base) {
 #pragma unroll
-        for (int g = 0; g < kHadG; ++g) {
-          if (m) {
-            const int e = __ffs(m) - 1;
-            m &= m - 1;
-            code[g] = c * 32 + e;
-            sid[g] = __shfl_sync(0xffffffffu, sid_l[c], e);
-          } else {
-            code[g] = 0;
-            sid[g] = -1;
-          }
-        }
+      for (int g = 0; g < kHadG; ++g) {
+        const int e = base + g;
+        if (e >= n) break;  // warp-uniform
+        const int2 meta = s_meta[list[e].y];
+        const int fm = meta.y & tmask;
+        const double2* kp = Ks + meta.x * kHadTF + lane;
 #pragma unroll
-        for (int g = 0; g < kHadG; ++g)
-          mh[g] = (sid[g] >= 0 && fok) ? a.Mhat[static_cast<size_t>(sid[g]) * F + f] : make_double2(0.0, 0.0);
+        for (int ct = 0; ct < NC; ++ct) {
+          int cto = 0;  // compile-time: sum_d ct_d 7^(DIM-1-d)
 #pragma unroll
-        for (int g = 0; g < kHadG; ++g) {
-          if (sid[g] < 0) continue;  // warp-uniform
-          const int2 meta = s_meta[code[g]];
-          const int fm = meta.y & tmask;
-          const double2* kp = Ks + meta.x * kHadTF + lane;
-#pragma unroll
-          for (int ct = 0; ct < NC; ++ct) {
-            int cto = 0;  // compile-time: sum_d ct_d 7^(DIM-1-d)
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) cto = cto * 7 + ((ct >> (DIM - 1 - d)) & 1);
-            if ((fm >> ct) & 1) cfma(acc[ct], kp[-cto * kHadTF], mh[g]);
-          }
+          for (int d = 0; d < DIM; ++d) cto = cto * 7 + ((ct >> (DIM - 1 - d)) & 1);
+          if ((fm >> ct) & 1) cfma(acc[ct], kp[-cto * kHadTF], mh[g]);
         }
       }
+    };
+    double2 mhA[kHadG], mhB[kHadG];
+    load(mhA, 0);
+    for (int g0 = 0; g0 < n; g0 += 2 * kHadG) {
+      load(mhB, g0 + kHadG);
+      compute(mhA, g0);
+      load(mhA, g0 + 2 * kHadG);
+      compute(mhB, g0 + kHadG);
     }
     if (fok) {
 #pragma unroll
@@ -1318,7 +1343,7 @@ void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounte
   constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
   const int n_ftiles = ceil_div(F, kHadTF);
   const int ps = hadamard_parent_slices(n_ftiles, ceil_div(a.n_active, kHadWarps));
-  const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * NN * NC;
+  const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * NN * NC * (1 + kHadWarps);
   smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM>, smem);
   PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM>), n_ftiles * ps, kHadWarps * 32, smem, s, a, F, n_ftiles);
 }
