@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
-    ap.add_argument("--cpu-sample-layers", type=int, default=21,
-                    help="x-layers of the target grid (central slab) the CPU arm evaluates per step")
+    ap.add_argument("--cpu-sample-layers", type=int, default=216,
+                    help="x-layers of the target grid (central slab) the CPU arm evaluates per step "
+                         "(default: all of them, ~10 s of CPU work on 16 cores)")
     return ap.parse_args()
 
 
@@ -333,8 +334,19 @@ def main():
         dist.destroy_process_group()
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per step of a kernel from this round's `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py traffic); None when not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(kernel, {}).get("dram_bytes_per_step")
+    except Exception:
+        return None
+
+
 def roofline_for(name, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, ev):
-    """Algorithmic work of the dominant kernel / its CUDA-event time."""
+    """Algorithmic work of the dominant kernel / its CUDA-event time
+    (sum over the kernel's launches of one step, events on the launching stream)."""
     if not name:
         return None
     ms = phases[name]
@@ -347,7 +359,7 @@ def roofline_for(name, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, 
         flops = 8.0 * F * stats["m2l_pairs"]  # one complex multiply-add per frequency and pair
         ach = flops / (ms * 1e-3) / 1e12
         out.update({"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                    "frac": ach / fp64_peak if fp64_peak else None, "traffic": measured_traffic("m2l_hadamard"),
                     "peak_source": "DFMA-chain microbenchmark in this run (plt_measure_fp64_peak)",
                     "algorithmic": f"8 flop x F={F} frequencies x {stats['m2l_pairs']} M2L pairs"})
     elif name == "m2l_idft" and stats.get("m2l_target_cells"):

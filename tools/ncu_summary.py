@@ -67,5 +67,27 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst):
+    """profiles/traffic.json: DRAM read+write bytes per bench step of the Hadamard M2L launches in a
+    `--set full` capture that holds exactly one step's launches of that kernel (one per level)."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n, ms = 0.0, 0, 0.0
+    for r in rows[2:]:
+        if "hadamard" not in r[hdr.index("Kernel Name")]:
+            continue
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        ms += float(r[hdr.index("gpu__time_duration.sum")])
+        n += 1
+    json.dump({"m2l_hadamard": {"dram_bytes_per_step": tot, "launches": n, "ncu_ms": ms, "source": src}},
+              open(dst, "w"), indent=1)
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
