@@ -360,7 +360,9 @@ __global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev 
 // Shared layout: [children 2^dim x P][last shared stage]; the parent and the first stage are
 // dead by the time the children are written and overlay the children area.
 // ------------------------------------------------------------------------------------
-constexpr int kLeafThreads = 128;
+// Threads per CTA by order: the shared-memory footprint (12 P doubles in 3-D) allows one resident CTA
+// per SM from order 10 on, so the CTA itself has to bring the warps.
+__host__ __device__ constexpr int leaf_threads(int order) { return order >= 10 ? 512 : (order >= 8 ? 256 : 128); }
 constexpr int kLeafMaxOrder = 12;
 
 struct LeafTables {
@@ -410,7 +412,7 @@ __device__ __forceinline__ void product_basis(const double* __restrict__ beta, d
 }
 
 template <int DIM, int ORDER>
-__global__ void __launch_bounds__(kLeafThreads, ORDER <= 6 ? 6 : 4) k_l2l_l2p_leaf(TreeView tr, Box box, LeafTables tb, int kn,
+__global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <= 8 ? 2 : 1)) k_l2l_l2p_leaf(TreeView tr, Box box, LeafTables tb, int kn,
                                                                const double* __restrict__ L,
                                                                const double* __restrict__ Lc,
                                                                const int* __restrict__ leaf_slot,
@@ -418,12 +420,17 @@ __global__ void __launch_bounds__(kLeafThreads, ORDER <= 6 ? 6 : 4) k_l2l_l2p_le
                                                                int leaf_hi) {
   extern __shared__ double sm[];
   constexpr int NC = 1 << DIM;
+  constexpr int kLeafThreads = leaf_threads(ORDER);
   constexpr int NW = kLeafThreads / 32;
   constexpr int p = ORDER;
   constexpr int P = DIM == 1 ? p : (DIM == 2 ? p * p : p * p * p);
   constexpr int PC = P / p;  // columns per axis
-  double* s_child = sm;                         // [NC][P]
-  double* s_last = s_child + NC * P;            // last shared stage: [1 | 2 | 4][P]
+  // 3-D: the L2P lanes of a point read p different i0-slabs of the child at once; a slab stride of
+  // p^2 doubles maps them all to the same bank (p even), p^2 + 1 spreads them over p banks.
+  constexpr int S = DIM == 3 ? p * p + 1 : PC;  // stride of the leading index of a child
+  constexpr int PS = DIM == 3 ? p * S : P;      // stride between children
+  double* s_child = sm;                         // [NC][PS]
+  double* s_last = s_child + NC * PS;           // last shared stage: [1 | 2 | 4][P]
   double* lvl0 = DIM == 1 ? s_last : s_child;   // parent
   double* lvl1 = DIM == 2 ? s_last : s_child + P;  // after axis 0 (DIM >= 2)
   __shared__ int s_first[NC];  // first point of the child, or -1
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(kLeafThreads, ORDER <= 6 ? 6 : 4) k_l2l_l2p_le
     for (int item = tid; item < NC * PC; item += kLeafThreads) {
       const int ch = item / PC, col = item - ch * PC;
       if (s_first[ch] < 0) continue;
-      double* out = s_child + ch * P + col * p;
+      double* out = s_child + ch * PS + (DIM == 3 ? (col / p) * S + (col % p) * p : col * p);
       if (has_parent) {
         leaf_contract_col<p>(tb.child + (ch & 1) * p * p, s_last + (ch >> 1) * P + col * p, 1, out);
       } else {
@@ -489,48 +496,65 @@ __global__ void __launch_bounds__(kLeafThreads, ORDER <= 6 ? 6 : 4) k_l2l_l2p_le
       }
     }
     __syncthreads();
-    // L2P: warp <-> child
-    for (int ch = warp; ch < NC; ch += NW) {
-      const int first = s_first[ch], cnt = s_count[ch];
-      if (first < 0) continue;
-      double c[DIM], half;
-      cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
-      const double inv_half = 1.0 / half;
-      const double* Lch = s_child + ch * P;
-      if constexpr (DIM == 3) {
-        // p lanes per point (lane <-> slab i0 of the tensor), 32 / p points per pass: leaves hold
-        // only a few points, so the lanes are spent on the contraction instead of on more points.
-        constexpr int PP = 32 / p;
-        const int sub = lane / p, i0 = lane - sub * p;
-        for (int j0 = 0; j0 < cnt; j0 += PP) {
-          const int j = j0 + sub;
-          const bool act = sub < PP && j < cnt;
-          const int i = first + (act ? j : 0);
-          double bs[DIM][p];
+    // L2P
+    if constexpr (DIM == 3) {
+      // p lanes per point (lane <-> slab i0 of the child's tensor), PP = 32 / p points per warp pass;
+      // the (child, point group) passes of the whole parent are dealt round-robin to the warps.
+      constexpr int PP = 32 / p;
+      const int sub = lane / p, i0 = lane - sub * p;
+      int pre[NC + 1];
+      pre[0] = 0;
 #pragma unroll
-          for (int a = 0; a < DIM; ++a)
-            product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
-          double b0 = bs[0][0];  // register select instead of a dynamically indexed array
+      for (int c = 0; c < NC; ++c) pre[c + 1] = pre[c] + (s_first[c] >= 0 ? (s_count[c] + PP - 1) / PP : 0);
+      for (int g = warp; g < pre[NC]; g += NW) {
+        int ch = 0;
 #pragma unroll
-          for (int m = 1; m < p; ++m)
-            if (i0 == m) b0 = bs[0][m];
-          const double* Ls = Lch + i0 * p * p;
-          double ri = 0.0;
+        for (int c = 1; c < NC; ++c)
+          if (g >= pre[c]) ch = c;
+        int gbase = 0;
 #pragma unroll
-          for (int i1 = 0; i1 < p; ++i1) {
-            double r = 0.0;
+        for (int c = 0; c < NC; ++c)
+          if (c == ch) gbase = pre[c];
+        const int first = s_first[ch], cnt = s_count[ch];
+        double c[DIM], half;
+        cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
+        const double inv_half = 1.0 / half;
+        const double* Lch = s_child + ch * PS;
+        const int j = (g - gbase) * PP + sub;
+        const bool act = sub < PP && j < cnt;
+        const int i = first + (act ? j : 0);
+        double bs[DIM][p];
 #pragma unroll
-            for (int k = 0; k < p; ++k) r = fma(bs[2][k], Ls[i1 * p + k], r);
-            ri = fma(bs[1][i1], r, ri);
-          }
-          double v = b0 * ri;
-          // sum over the p lanes of the point; the group's first lane ends up with the total
-          double tot = v;
+        for (int a = 0; a < DIM; ++a)
+          product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
+        double b0 = bs[0][0];  // register select instead of a dynamically indexed array
 #pragma unroll
-          for (int m = 1; m < p; ++m) tot += __shfl_down_sync(0xffffffffu, v, m);
-          if (act && i0 == 0) vt[b * tr.n + i] = tot;
+        for (int m = 1; m < p; ++m)
+          if (i0 == m) b0 = bs[0][m];
+        const double* Ls = Lch + i0 * S;
+        double ri = 0.0;
+#pragma unroll
+        for (int i1 = 0; i1 < p; ++i1) {
+          double r = 0.0;
+#pragma unroll
+          for (int k = 0; k < p; ++k) r = fma(bs[2][k], Ls[i1 * p + k], r);
+          ri = fma(bs[1][i1], r, ri);
         }
-      } else {
+        const double v = b0 * ri;
+        // sum over the p lanes of the point; the group's first lane ends up with the total
+        double tot = v;
+#pragma unroll
+        for (int m = 1; m < p; ++m) tot += __shfl_down_sync(0xffffffffu, v, m);
+        if (act && i0 == 0) vt[b * tr.n + i] = tot;
+      }
+    } else {
+      for (int ch = warp; ch < NC; ch += NW) {
+        const int first = s_first[ch], cnt = s_count[ch];
+        if (first < 0) continue;
+        double c[DIM], half;
+        cell_center<DIM>(box, leaf, (pkey << DIM) | ch, c, half);
+        const double inv_half = 1.0 / half;
+        const double* Lch = s_child + ch * P;
         for (int j = lane; j < cnt; j += 32) {
           const int i = first + j;
           double bs[DIM][p];
@@ -1024,6 +1048,89 @@ __global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
   }
 }
 
+// Register-blocked 3-D forward DFT of the multipoles (the mirror image of k_m2l_idft3):
+//   stage A: axis 2, p real -> p complex (half spectrum);  B: axis 1, p -> nf;  C: axis 0, p -> nf.
+// Zero padding from p to nf points is implicit (only p inputs per column are read).
+template <int ORDER, int NB>
+__global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int km, const double* __restrict__ M,
+                                                double2* __restrict__ Mhat, TwTable tw) {
+  constexpr int p = ORDER, nf = 2 * ORDER - 1;
+  constexpr int P = p * p * p, F = nf * nf * p, YN = p * nf * p;
+  extern __shared__ double2 sm2[];
+  double2* Y1 = sm2;            // [NB][p][p][p]   (n0, n1, k2)
+  double2* Y2 = Y1 + NB * P;    // [NB][p][nf][p]  (n0, k1, k2)
+  const int total = n_cells * km;
+  const int w0 = blockIdx.x * NB;
+  const int nb = min(NB, total - w0);
+  const double* Mc = M + static_cast<size_t>(first_cell) * km * P + static_cast<size_t>(w0) * P;
+  double2* out = Mhat + static_cast<size_t>(w0) * F;
+  // stage A: column = (n0, n1)
+  for (int item = threadIdx.x; item < nb * p * p; item += blockDim.x) {
+    const int c = item / (p * p), col = item % (p * p);
+    const double* in = Mc + static_cast<size_t>(c) * P + col * p;
+    double x[p];
+#pragma unroll
+    for (int n = 0; n < p; ++n) x[n] = in[n];
+#pragma unroll
+    for (int k = 0; k < p; ++k) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int n = 0; n < p; ++n) {
+        const double2 t = tw.w[(k * n) % nf];
+        re = fma(x[n], t.x, re);
+        im = fma(x[n], t.y, im);
+      }
+      Y1[c * P + col * p + k] = make_double2(re, im);
+    }
+  }
+  __syncthreads();
+  // stage B: column = (n0, k2), stride p
+  for (int item = threadIdx.x; item < nb * p * p; item += blockDim.x) {
+    const int c = item / (p * p), col = item % (p * p);
+    const int n0 = col / p, k2 = col % p;
+    const double2* in = Y1 + c * P + n0 * p * p + k2;
+    double2 x[p];
+#pragma unroll
+    for (int n = 0; n < p; ++n) x[n] = in[n * p];
+#pragma unroll
+    for (int k = 0; k < nf; ++k) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int n = 0; n < p; ++n) {
+        const double2 t = tw.w[(k * n) % nf];
+        re = fma(x[n].x, t.x, re);
+        re = fma(-x[n].y, t.y, re);
+        im = fma(x[n].x, t.y, im);
+        im = fma(x[n].y, t.x, im);
+      }
+      Y2[c * YN + (n0 * nf + k) * p + k2] = make_double2(re, im);
+    }
+  }
+  __syncthreads();
+  // stage C: column = (k1, k2), stride nf * p
+  for (int item = threadIdx.x; item < nb * nf * p; item += blockDim.x) {
+    const int c = item / (nf * p), col = item % (nf * p);
+    const double2* in = Y2 + c * YN + col;
+    double2 x[p];
+#pragma unroll
+    for (int n = 0; n < p; ++n) x[n] = in[n * (nf * p)];
+    double2* o = out + static_cast<size_t>(c) * F + col;
+#pragma unroll
+    for (int k = 0; k < nf; ++k) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int n = 0; n < p; ++n) {
+        const double2 t = tw.w[(k * n) % nf];
+        re = fma(x[n].x, t.x, re);
+        re = fma(-x[n].y, t.y, re);
+        im = fma(x[n].x, t.y, im);
+        im = fma(x[n].y, t.x, im);
+      }
+      o[static_cast<size_t>(k) * (nf * p)] = make_double2(re, im);
+    }
+  }
+}
+
 // Work counters for the roofline figures (not on the timed path): M2L pairs and target cells
 // with a non-empty list at one level; P2P pairs at the leaves.
 template <int DIM>
@@ -1245,7 +1352,7 @@ bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, co
   const int lo = static_cast<int>(leaf_lo), hi = static_cast<int>(leaf_hi);
   dispatch_leaf(dim, it.order, [&](auto dm, auto od) {
     smem_opt_in((const void*)k_l2l_l2p_leaf<dm.value, od.value>, smem);
-    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, kLeafThreads, smem, s, tr, box, tb, kn, L, Lc, leaf_slot, vt,
+    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, leaf_threads(od.value), smem, s, tr, box, tb, kn, L, Lc, leaf_slot, vt,
                par_lo, lo, hi);
   });
   return true;
@@ -1253,9 +1360,10 @@ bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, co
 
 size_t leaf_fused_smem_bytes(int dim, int order) {
   const size_t P = nodes_per_cell(order, dim);
-  const int nc = 1 << dim;
-  const size_t cells = nc + (dim == 1 ? 1 : (dim == 2 ? 2 : 4));
-  return sizeof(double) * cells * P;
+  const size_t nc = size_t{1} << dim;
+  const size_t PS = dim == 3 ? static_cast<size_t>(order) * (order * order + 1) : P;  // padded child stride
+  const size_t last = dim == 1 ? 1 : (dim == 2 ? 2 : 4);
+  return sizeof(double) * (nc * PS + last * P);
 }
 
 bool leaf_fused_supported(int dim, int order) {
@@ -1291,6 +1399,19 @@ DftScratch plan_dft_scratch(int order, int dim, int work_items, cudaStream_t s) 
 }
 }  // namespace
 
+namespace {
+template <int ORDER, int NB>
+void launch_m2hat3(int first, int n_cells, int km, const double* tw_host, const double* M, double2* Mhat,
+                   cudaStream_t s, LaunchCounter& c) {
+  constexpr int p = ORDER, nf = 2 * ORDER - 1;
+  TwTable tw{};
+  for (int i = 0; i < nf; ++i) tw.w[i] = make_double2(tw_host[2 * i], tw_host[2 * i + 1]);
+  const size_t smem = sizeof(double2) * NB * (p * p * p + p * nf * p);
+  smem_opt_in((const void*)k_m2hat3<ORDER, NB>, smem);
+  PLT_LAUNCH(c, (k_m2hat3<ORDER, NB>), ceil_div(n_cells * km, NB), 256, smem, s, first, n_cells, km, M, Mhat, tw);
+}
+}  // namespace
+
 void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, const double* M, double2* Mhat,
                   cudaStream_t s, LaunchCounter& c) {
   if (tr.height <= 2) return;
@@ -1298,6 +1419,16 @@ void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, cons
   int n_cells = 0;
   for (int l = 2; l < tr.height; ++l) n_cells += tr.n_cells[l];
   if (n_cells == 0) return;
+  static const bool no_reg = getenv("PLT_DEBUG_NO_REGDFT") != nullptr;  // A/B switch for parity bisection
+  if (dim == 3 && it.host_tw && !no_reg) {
+    switch (it.order) {
+      case 6: launch_m2hat3<6, 4>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
+      case 8: launch_m2hat3<8, 2>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
+      case 10: launch_m2hat3<10, 1>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
+      case 12: launch_m2hat3<12, 1>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
+      default: break;
+    }
+  }
   DftScratch d = plan_dft_scratch(it.order, dim, n_cells * km, s);
   dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
     smem_opt_in((const void*)k_m2hat<dm.value, od.value>, d.smem);

@@ -25,7 +25,7 @@ constexpr int kP2PWarps = 4;
 constexpr int kTG = 8;
 
 template <int FAM, int KIND, int DIM>
-__global__ void __launch_bounds__(kP2PWarps * 32)
+__global__ void __launch_bounds__(kP2PWarps * 32, KIND == KIND_K ? 6 : 4)
 k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, double* __restrict__ vt,
       const int* __restrict__ leaves, int n_leaves, int leaf_lo, int leaf_hi) {
   constexpr int KM = KindTraits<KIND, DIM>::km;
@@ -105,13 +105,24 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
         for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
 #pragma unroll
         for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j];
+        if (nt == kTG) {
+          // full group: branch-free, the kTG independent pair evaluations interleave
 #pragma unroll
-        for (int u = 0; u < kTG; ++u) {
-          if (u < nt) {
+          for (int u = 0; u < kTG; ++u) {
             double d[DIM];
 #pragma unroll
             for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
             pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < kTG; ++u) {
+            if (u < nt) {
+              double d[DIM];
+#pragma unroll
+              for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
+              pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
+            }
           }
         }
       }
