@@ -127,6 +127,16 @@ int plt_eval_set_stream(plt_eval* h, void* cuda_stream);
  * begin = 0, end = -1 restores the full range. */
 int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size);
 
+/* Multi-GPU matvec support: the permutation of the target tree, perm[i] =
+ * caller index of the i-th point in Morton order (the order target shards are cut in), and
+ * the sorted-order point range [begin, end) of the current target shard (cuts are moved to
+ * leaf boundaries).  A caller that feeds its points already in this order gets an identity
+ * permutation (the sort is stable), so each rank's shard is a contiguous slice of the
+ * Krylov vectors.  Both build the tree(s) if needed; on the brute-force branch (no tree) the
+ * permutation is the identity and rank 0 owns everything. */
+int plt_eval_get_permutation(plt_eval* h, int32_t* perm, int64_t n);
+int plt_eval_get_target_shard_range(plt_eval* h, int64_t* begin, int64_t* end);
+
 /* Per-phase device time of the last evaluate() in milliseconds (CUDA events on the
  * handle's stream).  names/ms: arrays of capacity cap; returns the number of phases. */
 int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap);
@@ -146,6 +156,41 @@ const char* plt_last_error(plt_eval* h);
 /* FP64 FMA peak of the current device, measured with a DFMA-chain microbenchmark (TFLOP/s);
  * the denominator of the FP64 roofline. */
 int plt_measure_fp64_peak(double* tflops);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident flexible GMRES: replaces krylov::Fgmres
+ *   include/polatory/krylov/gmres_base.hpp:11-91, src/krylov/gmres_base.cpp:7-85,
+ *   src/krylov/gmres.cpp:9-50, src/krylov/fgmres.cpp:8-28
+ * as driven by interpolation::Solver::solve (include/polatory/interpolation/solver.hpp:99-139).
+ * Vectors stay in HBM; the operator / right preconditioner are callbacks receiving DEVICE
+ * pointers of length n_local that must issue their work on the solver's stream and return 0.
+ * With sharded vectors (one rank per GPU) the `allreduce` callback sums `count` doubles of a
+ * DEVICE buffer in place across ranks (NCCL), which reduces the Krylov dot products.
+ * ------------------------------------------------------------------------------------- */
+typedef struct plt_fgmres plt_fgmres;
+typedef int (*plt_linop_fn)(void* ctx, const double* x_dev, double* y_dev);
+typedef int (*plt_allreduce_fn)(void* ctx, double* buf_dev, int count);
+
+/* Fgmres(op, rhs, max_iter): n_local = local vector length, max_iter = maximum iterations
+ * (no restart, as the reference). */
+int plt_fgmres_create(int64_t n_local, int max_iter, plt_fgmres** out);
+void plt_fgmres_destroy(plt_fgmres* h);
+int plt_fgmres_set_operator(plt_fgmres* h, plt_linop_fn op, void* ctx);
+/* set_right_preconditioner (gmres_base.cpp:33-37); NULL = identity.  Before setup(). */
+int plt_fgmres_set_right_preconditioner(plt_fgmres* h, plt_linop_fn pc, void* ctx);
+int plt_fgmres_set_allreduce(plt_fgmres* h, plt_allreduce_fn fn, void* ctx);
+int plt_fgmres_set_stream(plt_fgmres* h, void* cuda_stream);
+/* set_initial_solution + setup (gmres_base.cpp:27-31,39-51): rhs, x0 host or device pointers
+ * (x0 NULL = zero). */
+int plt_fgmres_setup(plt_fgmres* h, const double* rhs, const double* x0);
+/* iterate_process (gmres.cpp:9-50): one Arnoldi step + Givens update; one host sync. */
+int plt_fgmres_iterate(plt_fgmres* h);
+/* solution_vector (fgmres.cpp:8-26): x = x0 + Z y; x host or device pointer. */
+int plt_fgmres_solution(plt_fgmres* h, double* x);
+/* iteration_count / absolute_residual / relative_residual (gmres_base.cpp:7-15). */
+int plt_fgmres_status(plt_fgmres* h, int* iteration_count, double* absolute_residual, double* relative_residual);
+int64_t plt_fgmres_launch_count(plt_fgmres* h);
+const char* plt_fgmres_last_error(plt_fgmres* h);
 
 /* Library/ABI version and a device probe (returns PLT_ERR_CUDA without a usable GPU). */
 int plt_version(void);

@@ -9,6 +9,9 @@ from .fmm import (Bbox, FmmGenericEvaluator, FmmGenericSymmetricEvaluator, KIND_
                   make_fmm_hessian_symmetric_evaluator, make_fmm_symmetric_evaluator)
 from .rbf import Rbf, make_rbf
 
+# krylov.Fgmres / operator.Operator (the device Krylov driver and the RBF matvec)
+# import torch lazily: `from polatory_b200 import krylov, operator`.
+
 __all__ = [
     "Bbox", "FmmGenericEvaluator", "FmmGenericSymmetricEvaluator", "KIND_K", "KIND_F", "KIND_FT", "KIND_H",
     "kClassic", "make_fmm_evaluator", "make_fmm_gradient_evaluator", "make_fmm_gradient_transpose_evaluator",

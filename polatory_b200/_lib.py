@@ -38,15 +38,34 @@ SYMBOLS = [
     ("plt_eval_get_config", ctypes.c_int, [_vp, ctypes.POINTER(PltConfig)]),
     ("plt_eval_set_stream", ctypes.c_int, [_vp, _vp]),
     ("plt_eval_set_target_shard", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    ("plt_eval_get_permutation", ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
+    ("plt_eval_get_target_shard_range", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64),
+                                                       ctypes.POINTER(ctypes.c_int64)]),
     ("plt_eval_phase_times", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), _c_double_p, ctypes.c_int]),
     ("plt_eval_work_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                            ctypes.POINTER(ctypes.c_int64)]),
     ("plt_eval_launch_count", ctypes.c_int64, [_vp]),
     ("plt_last_error", ctypes.c_char_p, [_vp]),
     ("plt_measure_fp64_peak", ctypes.c_int, [_c_double_p]),
+    ("plt_fgmres_create", ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("plt_fgmres_destroy", None, [_vp]),
+    ("plt_fgmres_set_operator", ctypes.c_int, [_vp, _vp, _vp]),
+    ("plt_fgmres_set_right_preconditioner", ctypes.c_int, [_vp, _vp, _vp]),
+    ("plt_fgmres_set_allreduce", ctypes.c_int, [_vp, _vp, _vp]),
+    ("plt_fgmres_set_stream", ctypes.c_int, [_vp, _vp]),
+    ("plt_fgmres_setup", ctypes.c_int, [_vp, _vp, _vp]),
+    ("plt_fgmres_iterate", ctypes.c_int, [_vp]),
+    ("plt_fgmres_solution", ctypes.c_int, [_vp, _vp]),
+    ("plt_fgmres_status", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), _c_double_p, _c_double_p]),
+    ("plt_fgmres_launch_count", ctypes.c_int64, [_vp]),
+    ("plt_fgmres_last_error", ctypes.c_char_p, [_vp]),
     ("plt_version", ctypes.c_int, []),
     ("plt_device_check", ctypes.c_int, []),
 ]
+
+# Callback types of the Krylov solver (include/polatory_b200.h: plt_linop_fn, plt_allreduce_fn).
+LINOP_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _vp)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_int)
 
 _lib = None
 

@@ -672,26 +672,112 @@ struct plt_eval {
     }
   }
 
-  void shard_leaves(const Tree& tt, int& leaf_lo, int& leaf_hi) {
+  // Leaf range [leaf_lo, leaf_hi) and sorted point range [p_lo, p_hi) of the current target shard.
+  // Cached per (target tree build, rank, world): the steady-state sharded matvec has no extra sync.
+  struct ShardBounds {
+    int rank = -1, world = 0;
+    int leaf_lo = 0, leaf_hi = 0, p_lo = 0, p_hi = 0;
+    bool valid = false;
+  } shard_cache;
+
+  void shard_leaves(const Tree& tt, int& leaf_lo, int& leaf_hi, int& p_lo, int& p_hi) {
     const int n_leaf = tt.n_cells(tt.height() - 1);
     leaf_lo = 0;
     leaf_hi = n_leaf;
+    p_lo = 0;
+    p_hi = static_cast<int>(tt.n());
     if (shard_world <= 1) return;
-    TreeView tv = tt.view();
-    int* d = arena.take<int>(2);
-    int bounds[2] = {0, n_leaf};
-    PLT_CUDA(cudaMemcpyAsync(d, bounds, sizeof(bounds), cudaMemcpyHostToDevice, stream));
-    const int64_t n = tt.n();
-    const int p0 = static_cast<int>(n * shard_rank / shard_world);
-    const int p1 = static_cast<int>(n * (shard_rank + 1) / shard_world);
-    if (shard_rank > 0)
-      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p0, d);
-    if (shard_rank + 1 < shard_world)
-      PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p1, d + 1);
-    PLT_CUDA(cudaMemcpyAsync(bounds, d, sizeof(bounds), cudaMemcpyDeviceToHost, stream));
+    if (!(shard_cache.valid && shard_cache.rank == shard_rank && shard_cache.world == shard_world)) {
+      TreeView tv = tt.view();
+      DevBuf<int> dbuf;
+      dbuf.alloc(4, stream);
+      int* d = dbuf.get();
+      int bounds[4] = {0, n_leaf, 0, 0};
+      PLT_CUDA(cudaMemcpyAsync(d, bounds, sizeof(bounds), cudaMemcpyHostToDevice, stream));
+      const int64_t n = tt.n();
+      const int p0 = static_cast<int>(n * shard_rank / shard_world);
+      const int p1 = static_cast<int>(n * (shard_rank + 1) / shard_world);
+      if (shard_rank > 0)
+        PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p0, d);
+      if (shard_rank + 1 < shard_world)
+        PLT_LAUNCH(ctr, k_find_leaf, ceil_div(n_leaf + 1, 256), 256, 0, stream, tv.leaf_start, n_leaf, p1, d + 1);
+      PLT_CUDA(cudaMemcpyAsync(bounds, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+      PLT_CUDA(cudaMemcpyAsync(&bounds[2], tv.leaf_start + bounds[0], sizeof(int), cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaMemcpyAsync(&bounds[3], tv.leaf_start + bounds[1], sizeof(int), cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+      shard_cache = ShardBounds{shard_rank, shard_world, bounds[0], bounds[1], bounds[2], bounds[3], true};
+    }
+    leaf_lo = shard_cache.leaf_lo;
+    leaf_hi = shard_cache.leaf_hi;
+    p_lo = shard_cache.p_lo;
+    p_hi = shard_cache.p_hi;
+  }
+
+  // True when evaluate() takes the brute-force branch (no tree).
+  bool brute_force_branch() const {
+    const bool compact = std::isfinite(rbf.support_radius);
+    const int64_t nt = targets();
+    const bool small = symmetric ? n_src < 1024 : n_src * nt < int64_t{1024} * 1024;
+    return (small && !compact && force_height == 0) || (compact && compact_height() <= 2 && shard_world == 1);
+  }
+
+  // Builds the source / target trees of the FMM (or compact) branch if they are not current.
+  void ensure_trees() {
+    const bool compact = std::isfinite(rbf.support_radius);
+    const int64_t nt = targets();
+    int height = compact ? compact_height()
+                         : fmm_tree_height(dim, symmetric ? n_src : std::max(n_src, nt));
+    if (force_height > 0) height = force_height;
+    if (!src_tree.built() || src_tree.height() != height) {
+      src_tree.build(dim, height, box, src_pos_c.get(), n_src, stream, ctr);
+      wt_dirty = true;
+      multipole_dirty = true;
+      plan.reset();
+      if (symmetric) shard_cache.valid = false;
+    }
+    if (!symmetric && (!trg_tree.built() || trg_tree.height() != height)) {
+      trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, stream, ctr);
+      plan.reset();
+      shard_cache.valid = false;
+    }
+  }
+
+  void get_permutation(int32_t* perm, int64_t n) {
+    plt_eval* e = fast_part ? fast_part.get() : this;
+    const int64_t nt = e->targets();
+    PLT_REQUIRE(n == nt, "get_permutation: length must be the number of target points");
+    if (nt == 0) return;
+    if (e->n_src == 0 || e->brute_force_branch()) {
+      std::vector<int32_t> id(nt);
+      for (int64_t i = 0; i < nt; ++i) id[i] = static_cast<int32_t>(i);
+      PLT_CUDA(cudaMemcpyAsync(perm, id.data(), sizeof(int32_t) * nt, cudaMemcpyDefault, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+      return;
+    }
+    e->stream = stream;
+    e->ensure_trees();
+    PLT_CUDA(cudaMemcpyAsync(perm, e->target_tree().perm(), sizeof(int32_t) * nt, cudaMemcpyDefault, stream));
     PLT_CUDA(cudaStreamSynchronize(stream));
-    leaf_lo = bounds[0];
-    leaf_hi = bounds[1];
+  }
+
+  void get_shard_range(int64_t* begin, int64_t* end) {
+    plt_eval* e = fast_part ? fast_part.get() : this;
+    const int64_t nt = e->targets();
+    if (nt == 0 || e->n_src == 0 || e->brute_force_branch()) {
+      // not sharded: rank 0 computes everything (see evaluate_device)
+      *begin = 0;
+      *end = (shard_world <= 1 || shard_rank == 0) ? nt : 0;
+      return;
+    }
+    e->stream = stream;
+    e->shard_rank = shard_rank;
+    e->shard_world = shard_world;
+    e->ensure_trees();
+    int leaf_lo, leaf_hi, p_lo, p_hi;
+    e->shard_leaves(e->target_tree(), leaf_lo, leaf_hi, p_lo, p_hi);
+    *begin = p_lo;
+    *end = p_hi;
   }
 
   void evaluate_device(double* out) {
@@ -739,21 +825,9 @@ struct plt_eval {
       return;
     }
 
-    int height = compact ? compact_height()
-                         : fmm_tree_height(dim, symmetric ? n_src : std::max(n_src, nt));
-    if (force_height > 0) height = force_height;
-
     timer.begin("tree", stream);
-    if (!src_tree.built() || src_tree.height() != height) {
-      src_tree.build(dim, height, box, src_pos_c.get(), n_src, stream, ctr);
-      wt_dirty = true;
-      multipole_dirty = true;
-      plan.reset();
-    }
-    if (!symmetric && (!trg_tree.built() || trg_tree.height() != height)) {
-      trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, stream, ctr);
-      plan.reset();
-    }
+    ensure_trees();
+    const int height = src_tree.height();
     ensure_sorted_weights();
     timer.end(stream);
     const Tree& tt = target_tree();
@@ -763,8 +837,8 @@ struct plt_eval {
       timer.end(stream);
     }
 
-    int leaf_lo, leaf_hi;
-    shard_leaves(tt, leaf_lo, leaf_hi);
+    int leaf_lo, leaf_hi, p_lo, p_hi;
+    shard_leaves(tt, leaf_lo, leaf_hi, p_lo, p_hi);
 
     double* vt = arena.take<double>(static_cast<size_t>(kn) * nt);
     PLT_CUDA(cudaMemsetAsync(vt, 0, sizeof(double) * kn * nt, stream));
@@ -787,16 +861,6 @@ struct plt_eval {
       config = c;
     }
     timer.begin("finish", stream);
-    TreeView tv = tt.view();
-    int p_lo = 0, p_hi = static_cast<int>(nt);
-    if (shard_world > 1) {
-      int b[2];
-      PLT_CUDA(cudaMemcpyAsync(&b[0], tv.leaf_start + leaf_lo, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      PLT_CUDA(cudaMemcpyAsync(&b[1], tv.leaf_start + leaf_hi, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      PLT_CUDA(cudaStreamSynchronize(stream));
-      p_lo = b[0];
-      p_hi = b[1];
-    }
     launch_finish_outputs(kind, dim, aniso, vt, tt.perm(), nt, p_lo, p_hi, out, stream, ctr);
     timer.end(stream);
   }
@@ -927,6 +991,20 @@ int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size) {
     PLT_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad shard");
     h->shard_rank = rank;
     h->shard_world = world_size;
+  });
+}
+
+int plt_eval_get_permutation(plt_eval* h, int32_t* perm, int64_t n) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(perm != nullptr, "null output");
+    h->get_permutation(perm, n);
+  });
+}
+
+int plt_eval_get_target_shard_range(plt_eval* h, int64_t* begin, int64_t* end) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(begin && end, "null output");
+    h->get_shard_range(begin, end);
   });
 }
 

@@ -783,16 +783,9 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
   extern __shared__ double2 sm2[];
   double2* Ks = sm2;                                      // [NOFF][TF]
   int2* s_meta = reinterpret_cast<int2*>(Ks + NOFF * kHadTF);  // [NE]: x = offset index base, y = far mask
-  int2* s_list = s_meta + NE;                                   // [warps][NE]: (Mhat row, code) of present sources
-  const int ftile = blockIdx.x % n_ftiles, pslice = blockIdx.x / n_ftiles, n_pslices = gridDim.x / n_ftiles;
+  int2* s_list = s_meta + NE;                                   // [warps][NE]: (Mhat row, base | far mask << 16)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f = ftile * kHadTF + lane;
-  const bool fok = f < F;
 
-  for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
-    const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
-    Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
-  }
   for (int code = threadIdx.x; code < NE; code += blockDim.x) {
     const int nb = code / NC, cs = code % NC;
     int e3[DIM], r = nb;
@@ -815,63 +808,296 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
     }
     s_meta[code] = make_int2(base, mask);
   }
+
+  // Balanced persistent schedule: the n_ftiles x n_active (frequency tile, parent) items, tile-major,
+  // are cut into gridDim.x equal contiguous ranges; a range spans at most a few tiles, and the CTA
+  // re-stages the operator slice when it crosses a tile boundary.
+  const long long n_items = static_cast<long long>(n_ftiles) * a.n_active;
+  const long long q_lo = n_items * blockIdx.x / gridDim.x, q_hi = n_items * (blockIdx.x + 1) / gridDim.x;
+  int2* list = s_list + warp * NE;
+  for (long long q0 = q_lo; q0 < q_hi;) {
+    const int ftile = static_cast<int>(q0 / a.n_active);
+    const int slot_lo = static_cast<int>(q0 - static_cast<long long>(ftile) * a.n_active);
+    const long long seg_end = min(q_hi, static_cast<long long>(ftile + 1) * a.n_active);
+    const int slot_hi = slot_lo + static_cast<int>(seg_end - q0);
+    q0 = seg_end;
+    const int f = ftile * kHadTF + lane;
+    const bool fok = f < F;
+    __syncthreads();  // previous tile's operators no longer in use (and s_meta written)
+    for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
+      const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
+      Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    for (int slot = slot_lo + warp; slot < slot_hi; slot += kHadWarps) {
+      const int* tab = a.src_ids + static_cast<size_t>(slot) * NE;
+      const int tmask = a.trg_mask[slot];
+      // compact the present source cells that have a far target child
+      int n = 0;
+      __syncwarp();  // previous parent done with the list
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int idx = c * 32 + lane;
+        const int sid = idx < NE ? tab[idx] : -1;
+        int2 meta = make_int2(0, 0);
+        if (idx < NE) meta = s_meta[idx];
+        const int fm = meta.y & tmask;
+        const bool pres = sid >= 0 && fm != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, pres);
+        if (pres) list[n + __popc(m & ((1u << lane) - 1u))] = make_int2(sid, meta.x | (fm << 16));
+        n += __popc(m);
+      }
+      __syncwarp();
+      double2 acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
+
+      // software pipeline over groups of kHadG entries: the Mhat rows of the next group are in
+      // flight while the current group is multiplied
+      auto load = [&](double2 (&mh)[kHadG], int (&pk)[kHadG], int base) {
+#pragma unroll
+        for (int g = 0; g < kHadG; ++g) {
+          const int e = base + g;
+          int2 le = make_int2(0, 0);
+          if (e < n) le = list[e];
+          pk[g] = le.y;
+          mh[g] = (e < n && fok) ? a.Mhat[static_cast<size_t>(le.x) * F + f] : make_double2(0.0, 0.0);
+        }
+      };
+      auto compute = [&](const double2 (&mh)[kHadG], const int (&pk)[kHadG], int base) {
+#pragma unroll
+        for (int g = 0; g < kHadG; ++g) {
+          if (base + g >= n) break;  // warp-uniform
+          const int fm = pk[g] >> 16;
+          const double2* kp = Ks + (pk[g] & 0xffff) * kHadTF + lane;
+#pragma unroll
+          for (int ct = 0; ct < NC; ++ct) {
+            int cto = 0;  // compile-time: sum_d ct_d 7^(DIM-1-d)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) cto = cto * 7 + ((ct >> (DIM - 1 - d)) & 1);
+            if ((fm >> ct) & 1) cfma(acc[ct], kp[-cto * kHadTF], mh[g]);
+          }
+        }
+      };
+      double2 mhA[kHadG], mhB[kHadG];
+      int pkA[kHadG], pkB[kHadG];
+      load(mhA, pkA, 0);
+      for (int g0 = 0; g0 < n; g0 += 2 * kHadG) {
+        load(mhB, pkB, g0 + kHadG);
+        compute(mhA, pkA, g0);
+        load(mhA, pkA, g0 + 2 * kHadG);
+        compute(mhB, pkB, g0 + kHadG);
+      }
+      if (fok) {
+#pragma unroll
+        for (int ct = 0; ct < NC; ++ct)
+          if ((tmask >> ct) & 1) a.Lhat[(static_cast<size_t>(slot) * NC + ct) * F + f] = acc[ct];
+      }
+    }
+  }
+}
+
+// Source-parent-blocked variant of the scalar Hadamard accumulation.
+//
+// The tiled kernel above needs one 16-byte operator value from shared memory per complex FMA,
+// which saturates the 128 B/clk shared-memory pipe at half the DFMA rate.  Here the inner loop
+// runs over whole *source parents* (the 3^dim - 1 neighbours of the target parent): the
+// 2^dim x 2^dim (source child e, target child i) pairs of one source parent only touch the
+// 3^dim offsets  o = 2 d + delta,  delta = e - i in {-1, 0, 1}^dim,  so each operator value is
+// loaded once and used for every present pair with that delta (up to 2^dim, 2.5 on average for
+// a full block).  Lanes are still the 32 frequencies of the tile; the 2^dim source spectra of
+// the block and the 2^dim target accumulators live in registers; all guards are warp-uniform.
+template <int DIM>
+struct HadDelta {
+  static constexpr int NC = 1 << DIM;
+  static constexpr int ND = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  // bit (e * NC + i) set <=> e - i == delta (component-wise); delta index di in base 3, axis 0 most significant
+  static constexpr unsigned long long mask(int di) {
+    int dl[3] = {0, 0, 0};
+    for (int a = DIM - 1; a >= 0; --a) {
+      dl[a] = di % 3 - 1;
+      di /= 3;
+    }
+    unsigned long long m = 0;
+    for (int e = 0; e < NC; ++e)
+      for (int i = 0; i < NC; ++i) {
+        bool ok = true;
+        for (int a = 0; a < DIM; ++a) ok = ok && (((e >> (DIM - 1 - a)) & 1) - ((i >> (DIM - 1 - a)) & 1) == dl[a]);
+        if (ok) m |= 1ull << (e * NC + i);
+      }
+    return m;
+  }
+  static constexpr int koff(int di) {  // sum_a delta_a 7^(DIM-1-a)
+    int dl[3] = {0, 0, 0};
+    for (int a = DIM - 1; a >= 0; --a) {
+      dl[a] = di % 3 - 1;
+      di /= 3;
+    }
+    int o = 0;
+    for (int a = 0; a < DIM; ++a) o = o * 7 + dl[a];
+    return o;
+  }
+};
+
+template <int DIM, int DI, int E, int I>
+__device__ __forceinline__ void had_pair(double2 (&acc)[1 << DIM], const double2 (&mh)[1 << DIM], const double2& k,
+                                         unsigned long long pm) {
+  constexpr int NC = 1 << DIM;
+  if constexpr ((HadDelta<DIM>::mask(DI) >> (E * NC + I)) & 1ull) {
+    if ((pm >> (E * NC + I)) & 1ull) cfma(acc[I], k, mh[E]);
+  }
+}
+
+template <int DIM, int DI, int E>
+__device__ __forceinline__ void had_pairs_e(double2 (&acc)[1 << DIM], const double2 (&mh)[1 << DIM], const double2& k,
+                                            unsigned long long pm) {
+  // for a given (delta, e) there is at most one target child i = e - delta
+  had_pair<DIM, DI, E, 0>(acc, mh, k, pm);
+  if constexpr (DIM >= 1) had_pair<DIM, DI, E, 1>(acc, mh, k, pm);
+  if constexpr (DIM >= 2) {
+    had_pair<DIM, DI, E, 2>(acc, mh, k, pm);
+    had_pair<DIM, DI, E, 3>(acc, mh, k, pm);
+  }
+  if constexpr (DIM >= 3) {
+    had_pair<DIM, DI, E, 4>(acc, mh, k, pm);
+    had_pair<DIM, DI, E, 5>(acc, mh, k, pm);
+    had_pair<DIM, DI, E, 6>(acc, mh, k, pm);
+    had_pair<DIM, DI, E, 7>(acc, mh, k, pm);
+  }
+}
+
+template <int DIM, int DI>
+__device__ __forceinline__ void had_delta(double2 (&acc)[1 << DIM], const double2 (&mh)[1 << DIM], const double2* kp,
+                                          unsigned long long pm) {
+  constexpr unsigned long long DM = HadDelta<DIM>::mask(DI);
+  if (pm & DM) {
+    const double2 k = kp[HadDelta<DIM>::koff(DI) * kHadTF];
+    had_pairs_e<DIM, DI, 0>(acc, mh, k, pm);
+    had_pairs_e<DIM, DI, 1>(acc, mh, k, pm);
+    if constexpr (DIM >= 2) {
+      had_pairs_e<DIM, DI, 2>(acc, mh, k, pm);
+      had_pairs_e<DIM, DI, 3>(acc, mh, k, pm);
+    }
+    if constexpr (DIM >= 3) {
+      had_pairs_e<DIM, DI, 4>(acc, mh, k, pm);
+      had_pairs_e<DIM, DI, 5>(acc, mh, k, pm);
+      had_pairs_e<DIM, DI, 6>(acc, mh, k, pm);
+      had_pairs_e<DIM, DI, 7>(acc, mh, k, pm);
+    }
+  }
+  if constexpr (DI + 1 < HadDelta<DIM>::ND) had_delta<DIM, DI + 1>(acc, mh, kp, pm);
+}
+
+template <int DIM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_m2l_hadamard_blocked(M2LArgs a, int F, int n_ftiles) {
+  constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN, NOFF = M2LGeom<DIM>::NOFF;
+  constexpr int NE = NN * NC;              // entries of the source-id table
+  constexpr int NCH = (NE + 31) / 32;      // 32-entry chunks
+  constexpr int NEP = NCH * 32;            // padded
+  extern __shared__ double2 sm2[];
+  double2* Ks = sm2;                                                        // [NOFF][TF]
+  unsigned long long* s_pm = reinterpret_cast<unsigned long long*>(Ks + NOFF * kHadTF);  // [warps][32]
+  int* s_ids = reinterpret_cast<int*>(s_pm + WARPS * 32);                  // [warps][NEP]
+  int* s_kbase = s_ids + WARPS * NEP;                                       // [32] operator row of (nb, delta = 0)
+  unsigned char* s_far = reinterpret_cast<unsigned char*>(s_kbase + 32);    // [NEP] far mask over target children
+  unsigned char* s_bits = s_far + NEP;                                      // [warps][NEP]
+  unsigned char* s_list = s_bits + WARPS * NEP;                             // [warps][32]
+  const int ftile = blockIdx.x % n_ftiles, pslice = blockIdx.x / n_ftiles, n_pslices = gridDim.x / n_ftiles;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = ftile * kHadTF + lane;
+  const bool fok = f < F;
+
+  for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
+    const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
+    Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
+  }
+  for (int code = threadIdx.x; code < NEP; code += blockDim.x) {
+    int mask = 0;
+    if (code < NE) {
+      const int nb = code / NC, cs = code % NC;
+      int e3[DIM], r = nb;
+#pragma unroll
+      for (int d = DIM - 1; d >= 0; --d) {
+        e3[d] = (r % 3) - 1;
+        r /= 3;
+      }
+      for (int ct = 0; ct < NC; ++ct) {
+        bool far = false;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          const int o = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) - ((ct >> (DIM - 1 - d)) & 1);
+          far = far || o > 1 || o < -1;
+        }
+        if (far) mask |= 1 << ct;
+      }
+      if (cs == 0) {
+        int base = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) base = base * 7 + (2 * e3[d] + 3);
+        s_kbase[nb] = base;
+      }
+    }
+    s_far[code] = static_cast<unsigned char>(mask);
+  }
   __syncthreads();
 
-  // parents of this CTA: slot = pslice + n_pslices * (warp + kHadWarps * i)
-  int2* list = s_list + warp * NE;
-  for (int slot = pslice + n_pslices * warp; slot < a.n_active; slot += n_pslices * kHadWarps) {
+  int* ids = s_ids + warp * NEP;
+  unsigned char* bits = s_bits + warp * NEP;
+  unsigned long long* pms = s_pm + warp * 32;
+  unsigned char* list = s_list + warp * 32;
+  for (int slot = pslice + n_pslices * warp; slot < a.n_active; slot += n_pslices * WARPS) {
     const int* tab = a.src_ids + static_cast<size_t>(slot) * NE;
     const int tmask = a.trg_mask[slot];
-    // compact the present source cells that have a far target child: list of (Mhat row, code)
-    int n = 0;
-    __syncwarp();  // previous parent done with the list
+    __syncwarp();  // previous parent done with the per-warp tables
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int idx = c * 32 + lane;
       const int sid = idx < NE ? tab[idx] : -1;
-      const bool pres = sid >= 0 && (s_meta[idx].y & tmask) != 0;
-      const unsigned m = __ballot_sync(0xffffffffu, pres);
-      if (pres) list[n + __popc(m & ((1u << lane) - 1u))] = make_int2(sid, idx);
-      n += __popc(m);
+      ids[idx] = sid;
+      bits[idx] = sid >= 0 ? static_cast<unsigned char>(s_far[idx] & tmask) : static_cast<unsigned char>(0);
     }
     __syncwarp();
+    // pair mask of source parent nb = lane: bit (e * NC + i) <=> source child e present, target child i present, far
+    unsigned long long pm = 0;
+    if (lane < NN) {
+#pragma unroll
+      for (int e = 0; e < NC; ++e) pm |= static_cast<unsigned long long>(bits[lane * NC + e]) << (e * NC);
+    }
+    pms[lane] = pm;
+    const unsigned bal = __ballot_sync(0xffffffffu, pm != 0ull);
+    if (pm != 0ull) list[__popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned char>(lane);
+    const int n = __popc(bal);
+    __syncwarp();
+
     double2 acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
 
-    // software pipeline over groups of kHadG entries: the Mhat rows of the next group are in
-    // flight while the current group is multiplied
-    auto load = [&](double2 (&mh)[kHadG], int base) {
+    auto load = [&](double2 (&mh)[NC], int k) {
+      if (k < n) {
+        const int nb = list[k];
+        const unsigned long long q = pms[nb];
 #pragma unroll
-      for (int g = 0; g < kHadG; ++g) {
-        const int e = base + g;
-        mh[g] = (e < n && fok) ? a.Mhat[static_cast<size_t>(list[e].x) * F + f] : make_double2(0.0, 0.0);
-      }
-    };
-    auto compute = [&](const double2 (&mh)[kHadG], int base) {
-#pragma unroll
-      for (int g = 0; g < kHadG; ++g) {
-        const int e = base + g;
-        if (e >= n) break;  // warp-uniform
-        const int2 meta = s_meta[list[e].y];
-        const int fm = meta.y & tmask;
-        const double2* kp = Ks + meta.x * kHadTF + lane;
-#pragma unroll
-        for (int ct = 0; ct < NC; ++ct) {
-          int cto = 0;  // compile-time: sum_d ct_d 7^(DIM-1-d)
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) cto = cto * 7 + ((ct >> (DIM - 1 - d)) & 1);
-          if ((fm >> ct) & 1) cfma(acc[ct], kp[-cto * kHadTF], mh[g]);
+        for (int e = 0; e < NC; ++e) {
+          const bool on = ((q >> (e * NC)) & ((1ull << NC) - 1ull)) != 0ull;
+          mh[e] = (on && fok) ? a.Mhat[static_cast<size_t>(ids[nb * NC + e]) * F + f] : make_double2(0.0, 0.0);
         }
       }
     };
-    double2 mhA[kHadG], mhB[kHadG];
+    auto compute = [&](const double2 (&mh)[NC], int k) {
+      if (k < n) {
+        const int nb = list[k];
+        had_delta<DIM, 0>(acc, mh, Ks + s_kbase[nb] * kHadTF + lane, pms[nb]);
+      }
+    };
+    double2 mhA[NC], mhB[NC];
     load(mhA, 0);
-    for (int g0 = 0; g0 < n; g0 += 2 * kHadG) {
-      load(mhB, g0 + kHadG);
-      compute(mhA, g0);
-      load(mhA, g0 + 2 * kHadG);
-      compute(mhB, g0 + kHadG);
+    for (int k = 0; k < n; k += 2) {
+      load(mhB, k + 1);
+      compute(mhA, k);
+      load(mhA, k + 2);
+      compute(mhB, k + 1);
     }
     if (fok) {
 #pragma unroll
@@ -1473,10 +1699,26 @@ template <int DIM>
 void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
   constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
   const int n_ftiles = ceil_div(F, kHadTF);
-  const int ps = hadamard_parent_slices(n_ftiles, ceil_div(a.n_active, kHadWarps));
+  // one persistent CTA per SM; fewer when there is not a warp-round of parents per CTA
+  const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(a.n_active, kHadWarps);
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
   const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * NN * NC * (1 + kHadWarps);
   smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM>, smem);
-  PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM>), n_ftiles * ps, kHadWarps * 32, smem, s, a, F, n_ftiles);
+  PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM>), grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
+}
+}  // namespace
+
+namespace {
+template <int DIM, int WARPS>
+void launch_hadamard_blocked(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
+  constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
+  constexpr int NEP = (NN * NC + 31) / 32 * 32;
+  const int n_ftiles = ceil_div(F, kHadTF);
+  const int ps = hadamard_parent_slices(n_ftiles, ceil_div(a.n_active, WARPS));
+  const size_t smem = sizeof(double2) * NOFF * kHadTF + static_cast<size_t>(WARPS) * (32 * 8 + NEP * 4 + NEP + 32) +
+                      32 * 4 + NEP;
+  smem_opt_in((const void*)k_m2l_hadamard_blocked<DIM, WARPS>, smem);
+  PLT_LAUNCH(c, (k_m2l_hadamard_blocked<DIM, WARPS>), n_ftiles * ps, WARPS * 32, smem, s, a, F, n_ftiles);
 }
 }  // namespace
 
@@ -1484,10 +1726,24 @@ void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   if (a.n_active == 0) return;
   const int F = freqs_per_cell(a.order, a.dim);
   static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
+  // PLT_HAD_VARIANT: 0 = frequency-tiled per-pair kernel, 8 / 12 / 16 = source-parent-blocked kernel with that many warps
+  static const int variant = getenv("PLT_HAD_VARIANT") ? atoi(getenv("PLT_HAD_VARIANT")) : 0;
   if (a.kn == 1 && a.km == 1 && !no_tiled) {
-    if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
-    if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
-    if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);
+    if (variant == 0) {
+      if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
+      if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
+      if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);
+    } else if (a.dim == 1) {
+      launch_hadamard_blocked<1, 16>(a, F, s, c);
+    } else if (a.dim == 2) {
+      launch_hadamard_blocked<2, 16>(a, F, s, c);
+    } else if (variant == 8) {
+      launch_hadamard_blocked<3, 8>(a, F, s, c);
+    } else if (variant == 12) {
+      launch_hadamard_blocked<3, 12>(a, F, s, c);
+    } else {
+      launch_hadamard_blocked<3, 16>(a, F, s, c);
+    }
     return;
   }
   const int threads = F >= 256 ? 256 : ((F + 31) / 32 * 32);

@@ -127,6 +127,19 @@ class _EvaluatorBase:
     def set_target_shard(self, rank, world_size):
         _lib.check(self._h, self._lib.plt_eval_set_target_shard(self._h, int(rank), int(world_size)))
 
+    def permutation(self):
+        """perm[i] = caller index of the i-th target point in Morton order (builds the tree)."""
+        n = self._n_src if self._symmetric else self._n_trg
+        perm = np.empty(n, dtype=np.int32)
+        _lib.check(self._h, self._lib.plt_eval_get_permutation(self._h, ctypes.c_void_p(perm.ctypes.data), n))
+        return perm
+
+    def target_shard_range(self):
+        """Sorted-order point range [begin, end) of the current target shard."""
+        b, e = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._h, self._lib.plt_eval_get_target_shard_range(self._h, ctypes.byref(b), ctypes.byref(e)))
+        return b.value, e.value
+
     def phase_times(self):
         cap = 32
         names = (ctypes.c_char_p * cap)()

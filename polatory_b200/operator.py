@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's RBF operator (the Krylov matvec) over the device evaluators.
+
+  interpolation::Operator<Dim>   include/polatory/interpolation/operator.hpp:18-127
+  polynomial::MonomialBasis      include/polatory/polynomial/monomial_basis.hpp:24-330
+  interpolation::Solver::solve   include/polatory/interpolation/solver.hpp:75-142 (the loop only)
+
+The operator is the saddle-point matrix
+    [ A + nugget I   F    P_mu    ]
+    [ F^T            H    P_sigma ]      A, F, F^T, H = the four evaluator kinds per RBF
+    [ P^T                 0       ]
+applied to CUDA vectors: every FMM evaluation reads and writes HBM directly (zero-copy across
+the C ABI); torch is used for the vector plumbing and the skinny polynomial products only.
+
+Multi-GPU (`group` given, one rank per GPU): points are put in the Morton order of
+the symmetric evaluator's tree, rank r owns the contiguous range `[lo, hi)` of its target shard
+and the Krylov vectors are sharded accordingly (the `l` polynomial coefficients live on the last
+rank).  One matvec = one all_reduce that assembles the full weight vector from the shards (the
+"all-gather of the weights" -- NCCL over NVLink), the upward pass on every rank, and the
+downward pass + near field of the rank's own leaves.  Gradient data (sigma > 0) is supported on
+one GPU only in this round.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import fmm
+
+
+class Model:
+    """What Operator needs from polatory::Model (include/polatory/model.hpp): the RBFs, the
+    polynomial degree (-1 = none) and the nugget."""
+
+    def __init__(self, rbfs, poly_degree=-1, nugget=0.0):
+        self.rbfs = list(rbfs) if isinstance(rbfs, (list, tuple)) else [rbfs]
+        self.dim = self.rbfs[0].dim
+        self.poly_degree = int(poly_degree)
+        self.nugget = float(nugget)
+
+    def poly_basis_size(self):
+        # polynomial_basis_base.hpp: C(dim + degree, degree)
+        d, k = self.dim, self.poly_degree
+        if k < 0:
+            return 0
+        from math import comb
+        return comb(d + k, k)
+
+
+def monomial_basis(dim, degree, points, grad_points=None):
+    """MonomialBasis<Dim>::evaluate(points, grad_points): (mu + dim*sigma) x l matrix; value rows
+    first, then `dim` derivative rows per gradient point (monomial_basis.hpp:31-330).  Column
+    order: 1 | x y z | x^2 xy xz y^2 yz z^2 (the dim-restricted prefix of it)."""
+    points = np.asarray(points, dtype=np.float64).reshape(-1, dim)
+    gp = np.zeros((0, dim)) if grad_points is None else np.asarray(grad_points, dtype=np.float64).reshape(-1, dim)
+    mu, sigma = len(points), len(gp)
+    exps = [tuple([0] * dim)]
+    if degree >= 1:
+        exps += [tuple(1 if a == b else 0 for b in range(dim)) for a in range(dim)]
+    if degree >= 2:
+        for a in range(dim):
+            for b in range(a, dim):
+                e = [0] * dim
+                e[a] += 1
+                e[b] += 1
+                exps.append(tuple(e))
+    if degree < 0:
+        exps = []
+    out = np.zeros((mu + dim * sigma, len(exps)))
+    for c, e in enumerate(exps):
+        col = np.ones(mu)
+        for a in range(dim):
+            col = col * points[:, a] ** e[a]
+        out[:mu, c] = col
+        for k in range(dim):  # d/dx_k of the monomial at the gradient points
+            if e[k] == 0:
+                continue
+            col = np.full(sigma, float(e[k]))
+            for a in range(dim):
+                p = e[a] - (1 if a == k else 0)
+                col = col * gp[:, a] ** p
+            out[mu + k:mu + dim * sigma:dim, c] = col
+    return out
+
+
+class Operator:
+    """interpolation::Operator: `set_points`, `size()`, `__call__(weights)`; plus `apply(x, y)` on
+    CUDA tensors for the device Krylov solver."""
+
+    def __init__(self, model, bbox, accuracy=float("inf"), grad_accuracy=float("inf"), group=None, device=None):
+        import torch
+        self._torch = torch
+        self.model = model
+        self.dim = model.dim
+        self.l = model.poly_basis_size()
+        self.accuracy = accuracy
+        self.grad_accuracy = grad_accuracy
+        self.group = group
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.rank, self.world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+            self._dist = dist
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        # operator.hpp:44-49
+        self.a = [fmm.make_fmm_symmetric_evaluator(r, bbox) for r in model.rbfs]
+        self.f = [fmm.make_fmm_gradient_evaluator(r, bbox) for r in model.rbfs]
+        self.ft = [fmm.make_fmm_gradient_transpose_evaluator(r, bbox) for r in model.rbfs]
+        self.h = [fmm.make_fmm_hessian_symmetric_evaluator(r, bbox) for r in model.rbfs]
+        self.mu = self.sigma = 0
+        self.lo, self.hi = 0, 0
+        self.perm = None
+        self.p = None
+
+    # -- operator.hpp:83-107 -----------------------------------------------------------
+    def set_points(self, points, grad_points=None):
+        torch = self._torch
+        dim = self.dim
+        points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, dim)
+        gp = np.zeros((0, dim)) if grad_points is None else \
+            np.ascontiguousarray(grad_points, dtype=np.float64).reshape(-1, dim)
+        self.mu, self.sigma = len(points), len(gp)
+        n_rbf = len(self.a)
+        acc = (self.accuracy / 2.0 if self.sigma > 0 else self.accuracy) / n_rbf
+        gacc = (self.grad_accuracy / 2.0 if self.sigma > 0 else self.grad_accuracy) / n_rbf
+        if self.world > 1:
+            if self.sigma > 0:
+                raise NotImplementedError("sharded operator: gradient data is single-GPU only in this round")
+            # Morton order of the symmetric evaluator's tree = the order shards are cut in
+            self.a[0].set_points(points)
+            self.perm = self.a[0].permutation()
+            points = np.ascontiguousarray(points[self.perm])
+        else:
+            self.perm = np.arange(self.mu)
+        self._points = points
+        for i in range(n_rbf):
+            self.a[i].set_points(points)
+            self.a[i].set_accuracy(acc)
+            if self.sigma > 0:
+                self.f[i].set_source_points(gp)
+                self.f[i].set_target_points(points)
+                self.ft[i].set_source_points(points)
+                self.ft[i].set_target_points(gp)
+                self.h[i].set_points(gp)
+                self.f[i].set_accuracy(acc)
+                self.ft[i].set_accuracy(gacc)
+                self.h[i].set_accuracy(gacc)
+        self.lo, self.hi = 0, self.mu
+        if self.world > 1:
+            for i in range(n_rbf):
+                self.a[i].set_target_shard(self.rank, self.world)
+            self.lo, self.hi = self.a[0].target_shard_range()
+            for i in range(1, n_rbf):
+                assert self.a[i].target_shard_range() == (self.lo, self.hi)
+        if self.l > 0:
+            p = monomial_basis(dim, self.model.poly_degree, points, gp)
+            self.p = torch.from_numpy(p).to(self.device)
+        m = self.mu + dim * self.sigma
+        self._full = torch.zeros(m + self.l, dtype=torch.float64, device=self.device)
+        self._tmp_mu = torch.empty(self.mu, dtype=torch.float64, device=self.device)
+        self._res_mu = torch.empty(self.mu, dtype=torch.float64, device=self.device)
+        self._tmp_sg = torch.empty(dim * self.sigma, dtype=torch.float64, device=self.device)
+
+    def size(self):
+        """Global size mu + dim*sigma + l (operator.hpp:109)."""
+        return self.mu + self.dim * self.sigma + self.l
+
+    def local_size(self):
+        """Length of this rank's shard of a Krylov vector."""
+        if self.world == 1:
+            return self.size()
+        return (self.hi - self.lo) + (self.l if self.rank == self.world - 1 else 0)
+
+    # -- shard <-> global (caller order) ---------------------------------------------------
+    def scatter(self, global_vec):
+        """This rank's shard of a global caller-order vector (numpy or tensor)."""
+        torch = self._torch
+        g = torch.as_tensor(global_vec, dtype=torch.float64).to(self.device)
+        if self.world == 1:
+            return g.clone()
+        perm = torch.from_numpy(self.perm[self.lo:self.hi].astype(np.int64)).to(self.device)
+        parts = [g[perm]]
+        if self.rank == self.world - 1:
+            parts.append(g[self.mu:])
+        return torch.cat(parts)
+
+    def gather(self, local_vec):
+        """Global caller-order vector from the shards (one all_reduce)."""
+        torch = self._torch
+        if self.world == 1:
+            return local_vec.clone()
+        full = self._assemble(local_vec).clone()
+        out = torch.empty_like(full)
+        out[torch.from_numpy(self.perm.astype(np.int64)).to(self.device)] = full[:self.mu]
+        out[self.mu:] = full[self.mu:]
+        return out
+
+    def _assemble(self, x_local):
+        """Full (Morton-order) vector on every rank from the shards: the weight all-gather."""
+        full = self._full
+        full.zero_()
+        nloc = self.hi - self.lo
+        full[self.lo:self.hi] = x_local[:nloc]
+        if self.rank == self.world - 1 and self.l:
+            full[self.mu:] = x_local[nloc:]
+        self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
+        return full
+
+    # -- operator.hpp:52-81 ------------------------------------------------------------------
+    def apply(self, x, y):
+        mu, ds, l = self.mu, self.dim * self.sigma, self.l
+        m = mu + ds
+        if self.world == 1:
+            full, out = x, y
+        else:
+            full, out = self._assemble(x), None
+        w_mu, w_sg = full[:mu], full[mu:m]
+        acc_mu = self._tmp_mu
+        # y.head(mu) = nugget * w.head(mu) + sum_i (A_i w_mu + F_i w_sigma)
+        res_mu = out[:mu] if out is not None else self._res_mu
+        res_sg = out[mu:m] if out is not None else None
+        for i in range(len(self.a)):
+            self.a[i].set_weights(w_mu)
+            if i == 0:
+                self.a[i].evaluate(res_mu)
+            else:
+                self.a[i].evaluate(acc_mu)
+                res_mu += acc_mu
+            if ds:
+                self.f[i].set_weights(w_sg)
+                self.f[i].evaluate(acc_mu)
+                res_mu += acc_mu
+                self.ft[i].set_weights(w_mu)
+                self.ft[i].evaluate(res_sg if i == 0 else self._tmp_sg)
+                if i > 0:
+                    res_sg += self._tmp_sg
+                self.h[i].set_weights(w_sg)
+                self.h[i].evaluate(self._tmp_sg)
+                res_sg += self._tmp_sg
+        if self.model.nugget != 0.0:
+            if self.world == 1:
+                res_mu.add_(w_mu, alpha=self.model.nugget)
+            else:
+                res_mu[self.lo:self.hi].add_(w_mu[self.lo:self.hi], alpha=self.model.nugget)
+        if self.world == 1:
+            if l:
+                y[:m] += self.p @ x[m:]
+                y[m:] = self.p.T @ x[:m]
+            return y
+        nloc = self.hi - self.lo
+        y[:nloc] = res_mu[self.lo:self.hi]
+        if l:
+            y[:nloc] += self.p[self.lo:self.hi] @ full[m:]
+            if self.rank == self.world - 1:
+                y[nloc:] = self.p.T @ full[:m]
+        return y
+
+    def __call__(self, weights):
+        torch = self._torch
+        x = torch.as_tensor(weights, dtype=torch.float64).to(self.device)
+        y = torch.empty_like(x)
+        self.apply(x, y)
+        return y
+
+
+def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=None):
+    """The loop of interpolation::Solver::solve (solver.hpp:99-139) on the device: FGMRES with an
+    optional right preconditioner over `op`; `values` is this rank's shard of the right-hand side
+    (without the `l` zeros, which are appended here).  Convergence: max-norm of the true residual
+    <= tolerance, checked with one extra matvec once the solver's own 2-norm estimate allows it
+    (the reference's sampled ResidualEvaluator, SURVEY.md 8f-4, is not built).
+    Returns (weights shard, iteration count)."""
+    import torch
+    from .krylov import Fgmres
+    dev = op.device
+    values = torch.as_tensor(values, dtype=torch.float64).to(dev)
+    n_tail = op.local_size() - values.numel()
+    rhs = torch.cat([values, torch.zeros(n_tail, dtype=torch.float64, device=dev)])
+    solver = Fgmres(op, rhs, max_iter, group=op.group)
+    if initial_weights is not None:
+        solver.set_initial_solution(initial_weights)
+    if preconditioner is not None:
+        solver.set_right_preconditioner(preconditioner)
+    solver.setup()
+    weights = solver.solution_vector()
+    if solver.relative_residual() == 0.0:
+        return weights, 0
+    n_glob = op.size()
+    fit = torch.empty_like(rhs)
+    while True:
+        weights = solver.solution_vector()
+        if solver.absolute_residual() <= tolerance * np.sqrt(n_glob):
+            op.apply(weights, fit)
+            res = (fit[:values.numel()] - values).abs().max() if values.numel() else torch.zeros((), device=dev)
+            if op.group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(res, op=dist.ReduceOp.MAX, group=op.group)
+            if float(res) <= tolerance:
+                return weights, solver.iteration_count()
+        if solver.iteration_count() == solver.max_iterations():
+            raise RuntimeError("reached the maximum number of iterations")  # solver.hpp:132-134
+        solver.iterate_process()
