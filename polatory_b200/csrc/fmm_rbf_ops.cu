@@ -27,22 +27,34 @@ constexpr int kTG = 8;
 template <int FAM, int KIND, int DIM>
 __global__ void __launch_bounds__(kP2PWarps * 32, KIND == KIND_K ? 6 : 4)
 k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, double* __restrict__ vt,
-      const int* __restrict__ leaves, int n_leaves, int leaf_lo, int leaf_hi) {
+      const int* __restrict__ leaves, int n_leaves, int leaf_lo, int leaf_hi, int* __restrict__ queue,
+      int n_split) {
   constexpr int KM = KindTraits<KIND, DIM>::km;
   constexpr int KN = KindTraits<KIND, DIM>::kn;
   constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
   __shared__ int s_start[kP2PWarps][32];   // first source point of neighbour nb
   __shared__ int s_prefix[kP2PWarps][32];  // exclusive prefix of the neighbour sizes; [NN] = total
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int li = blockIdx.x * kP2PWarps + warp;
-  if (li >= n_leaves) return;
+  // Persistent warps pull target leaves from a global queue: leaf populations of surface clouds
+  // vary by an order of magnitude, and a static leaf -> warp map left a third of the resident
+  // warp slots idle (ncu: 15.6 of 24 warps active per SM).
+  // A queue item is (leaf, split): the target groups of a heavy leaf are dealt round-robin to
+  // n_split items so that a few hundred-point leaves (volume clouds under anisotropy) do not
+  // serialise on one warp each.
+  for (;;) {
+  int qi = 0;
+  if (lane == 0) qi = atomicAdd(queue, 1);
+  qi = __shfl_sync(0xffffffffu, qi, 0);
+  const int li = qi / n_split, split = qi - li * n_split;
+  if (li >= n_leaves) break;
   const int cell = leaves[li];
-  if (cell < leaf_lo || cell >= leaf_hi) return;
+  if (cell < leaf_lo || cell >= leaf_hi) continue;
   const int leaf = trg.height - 1;
   const int nside = 1 << leaf;
   int tc[DIM];
   morton_decode<DIM>(trg.keys[trg.cell_off[leaf] + cell], tc);
   const int t0 = trg.leaf_start[cell], t1 = trg.leaf_start[cell + 1];
+  if (t0 + split * kTG >= t1) continue;
   const int* sdense = src.dense + src.dense_off[leaf];
 
   // neighbour table: lane nb < NN looks up its source leaf
@@ -70,6 +82,7 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
     int v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
+  __syncwarp();  // previous leaf done with the tables
   s_start[warp][lane] = s0;
   s_prefix[warp][lane] = incl - cnt;
   const int total = __shfl_sync(0xffffffffu, incl, 31);
@@ -77,7 +90,7 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
   const int* pre = s_prefix[warp];
   const int* st = s_start[warp];
 
-  for (int tb = t0; tb < t1; tb += kTG) {
+  for (int tb = t0 + split * kTG; tb < t1; tb += n_split * kTG) {
     double tp[kTG][DIM];
     double v[kTG][KN];
 #pragma unroll
@@ -136,6 +149,7 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
         if (lane == 0 && u < nt) vt[b * trg.n + tb + u] += x;
       }
     }
+  }
   }
 }
 
@@ -255,9 +269,17 @@ void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const
                 double* vt, const int* leaves, int n_leaves, int64_t leaf_lo, int64_t leaf_hi, cudaStream_t s,
                 LaunchCounter& c) {
   if (n_leaves <= 0 || leaf_hi <= leaf_lo) return;
+  DevBuf<int> queue;  // stream-ordered pool allocation: no synchronisation
+  queue.alloc(1, s);
+  queue.zero(s);
+  // heavy leaves (more than ~64 targets on average) are split across several queue items
+  const int64_t avg_targets = trg.n / std::max(1, trg.n_cells[trg.height - 1]);
+  const int n_split = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(16, avg_targets / 32)));
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(static_cast<int64_t>(n_leaves) * n_split, kP2PWarps),
+                                                      kNumSM * 8));
   dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
-    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), ceil_div(n_leaves, kP2PWarps), kP2PWarps * 32, 0, s, k,
-               src, swt, trg, vt, leaves, n_leaves, static_cast<int>(leaf_lo), static_cast<int>(leaf_hi));
+    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), grid, kP2PWarps * 32, 0, s, k, src, swt, trg, vt, leaves,
+               n_leaves, static_cast<int>(leaf_lo), static_cast<int>(leaf_hi), queue.get(), n_split);
   });
 }
 

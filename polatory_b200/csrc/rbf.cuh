@@ -66,6 +66,33 @@ __device__ __forceinline__ double ipow_odd(double q, double q2, int n) {
   return r;
 }
 
+// 1/sqrt(x) for normal x > 0: MUFU.RSQ64H seed (relative error ~2^-21) + one third-order
+// correction y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2  -> error ~e^3 < 2^-60, i.e. correctly
+// rounded to within the last ulp or two.  Branch-free, 5 FP64-pipe instructions; CUDA's
+// rsqrt(double) costs ~10 plus an integer special-case prologue, which made the bh3 pair loop
+// issue-bound at 37 % FP64-pipe utilisation (profiles/r01_f_p2p_full.md).
+__device__ __forceinline__ double rsqrt_seed(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  const double y = rsqrt_seed(x);
+  const double xy = x * y;
+  const double e = fma(-xy, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+// sqrt(x) for x >= 0 (returns 0 at 0): same seed, corrected as xy (1 + e p).
+__device__ __forceinline__ double sqrt_fast(double x) {
+  const double xc = x + 1e-300;  // keeps the seed finite at x == 0; sqrt(1e-300) = 1e-150 ~ 0
+  const double y = rsqrt_seed(xc);
+  const double xy = xc * y;
+  const double e = fma(-xy, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(xy * e, p, xy);
+}
+
 // Radial scalars.  NEED selects which outputs are computed (others untouched).
 template <int FAM, int NEED>
 __device__ __forceinline__ void rbf_radial(const RbfConst& k, double r2, double& phi, double& g,
@@ -74,15 +101,23 @@ __device__ __forceinline__ void rbf_radial(const RbfConst& k, double r2, double&
     // phi = -s rho, g = -s / rho, gh = +s / rho^3; zero gradient/Hessian at rho == 0
     // (polyharmonic_odd.hpp:32-67, K = 1, kSign = -1).
     double rho2 = r2 + k.c[1];
-    double inv = rho2 > 0.0 ? rsqrt(rho2) : 0.0;
-    if constexpr (NEED == NEED_PHI) phi = -k.c[0] * (rho2 * inv);
-    if constexpr (NEED >= NEED_G) g = -k.c[0] * inv;
-    if constexpr (NEED == NEED_G_GH) gh = k.c[0] * inv * inv * inv;
+    if constexpr (NEED == NEED_PHI) {
+      phi = -k.c[0] * sqrt_fast(rho2);
+    } else {
+      double inv = rho2 > 0.0 ? rsqrt_fast(rho2 + 1e-300) : 0.0;
+      g = -k.c[0] * inv;
+      if constexpr (NEED == NEED_G_GH) gh = k.c[0] * inv * inv * inv;
+    }
   } else if constexpr (FAM == FAM_TH3) {
     // phi = s rho^3, g = 3 s rho, gh = 3 s / rho (K = 3, kSign = +1).
     double rho2 = r2 + k.c[1];
-    double inv = rho2 > 0.0 ? rsqrt(rho2) : 0.0;
-    double rho = rho2 * inv;
+    double inv = 0.0, rho;
+    if constexpr (NEED == NEED_PHI) {
+      rho = sqrt_fast(rho2);
+    } else {
+      inv = rho2 > 0.0 ? rsqrt_fast(rho2 + 1e-300) : 0.0;
+      rho = rho2 * inv;
+    }
     if constexpr (NEED == NEED_PHI) phi = k.c[0] * rho2 * rho;
     if constexpr (NEED >= NEED_G) g = 3.0 * k.c[0] * rho;
     if constexpr (NEED == NEED_G_GH) gh = 3.0 * k.c[0] * inv;
