@@ -775,7 +775,7 @@ constexpr int kHadTF = 32;
 constexpr int kHadWarps = 16;
 constexpr int kHadG = 4;
 
-template <int DIM>
+template <int DIM, bool VEC>
 __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArgs a, int F, int n_ftiles) {
   constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN, NOFF = M2LGeom<DIM>::NOFF;
   constexpr int NE = NN * NC;              // entries of the source-id table
@@ -823,10 +823,15 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
     q0 = seg_end;
     const int f = ftile * kHadTF + lane;
     const bool fok = f < F;
-    __syncthreads();  // previous tile's operators no longer in use (and s_meta written)
+    // Vector kinds (kn x km > 1): one (b, a) component pair at a time with its own operator slice;
+    // the partial sums over a are carried through Lhat by the warp that owns the parent.
+    const int kn = VEC ? a.kn : 1, km = VEC ? a.km : 1;  // scalar instantiation: compile-time 1 x 1
+    for (int comp = 0; comp < kn * km; ++comp) {
+    const int cb = comp / km, ca = comp - cb * km;
+    __syncthreads();  // previous operator slice no longer in use (and s_meta written)
     for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
       const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
-      Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
+      Ks[e] = ff < F ? a.Khat[(static_cast<size_t>(oi) * kn * km + comp) * F + ff] : make_double2(0.0, 0.0);
     }
     __syncthreads();
 
@@ -851,7 +856,10 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
       __syncwarp();
       double2 acc[NC];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
+      for (int c = 0; c < NC; ++c) {
+        acc[c] = make_double2(0.0, 0.0);
+        if (VEC && ca > 0 && fok && ((tmask >> c) & 1)) acc[c] = a.Lhat[((static_cast<size_t>(slot) * NC + c) * kn + cb) * F + f];
+      }
 
       // software pipeline over groups of kHadG entries: the Mhat rows of the next group are in
       // flight while the current group is multiplied
@@ -862,7 +870,7 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
           int2 le = make_int2(0, 0);
           if (e < n) le = list[e];
           pk[g] = le.y;
-          mh[g] = (e < n && fok) ? a.Mhat[static_cast<size_t>(le.x) * F + f] : make_double2(0.0, 0.0);
+          mh[g] = (e < n && fok) ? a.Mhat[(static_cast<size_t>(le.x) * km + ca) * F + f] : make_double2(0.0, 0.0);
         }
       };
       auto compute = [&](const double2 (&mh)[kHadG], const int (&pk)[kHadG], int base) {
@@ -892,8 +900,9 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
       if (fok) {
 #pragma unroll
         for (int ct = 0; ct < NC; ++ct)
-          if ((tmask >> ct) & 1) a.Lhat[(static_cast<size_t>(slot) * NC + ct) * F + f] = acc[ct];
+          if ((tmask >> ct) & 1) a.Lhat[((static_cast<size_t>(slot) * NC + ct) * kn + cb) * F + f] = acc[ct];
       }
+    }
     }
   }
 }
@@ -1703,8 +1712,13 @@ void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounte
   const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(a.n_active, kHadWarps);
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
   const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * NN * NC * (1 + kHadWarps);
-  smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM>, smem);
-  PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM>), grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
+  if (a.kn * a.km == 1) {
+    smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM, false>, smem);
+    PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM, false>), grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
+  } else {
+    smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM, true>, smem);
+    PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM, true>), grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
+  }
 }
 }  // namespace
 
@@ -1728,6 +1742,12 @@ void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
   // PLT_HAD_VARIANT: 0 = frequency-tiled per-pair kernel, 8 / 12 / 16 = source-parent-blocked kernel with that many warps
   static const int variant = getenv("PLT_HAD_VARIANT") ? atoi(getenv("PLT_HAD_VARIANT")) : 0;
+  if (!no_tiled && variant == 0) {
+    if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
+    if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
+    if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);
+    return;
+  }
   if (a.kn == 1 && a.km == 1 && !no_tiled) {
     if (variant == 0) {
       if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
