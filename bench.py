@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-fit", action="store_true", help="skip the auxiliary config #2 FGMRES-iteration timing")
     ap.add_argument("--cpu-sample-layers", type=int, default=216,
                     help="x-layers of the target grid (central slab) the CPU arm evaluates per step "
                          "(default: all of them, ~10 s of CPU work on 16 cores)")
@@ -314,6 +315,9 @@ def main():
         "fp64_peak_tflops_measured": fp64_peak,
     }
 
+    if world == 1 and not args.no_fit:
+        line["fit"] = fit_iteration_timing(src, dev)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub, height, desc = cpu_sample(args, src, w, trg, lo, hi)
         order, d = cfg["order"], cfg["d"]
@@ -332,6 +336,43 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def fit_iteration_timing(points, dev, iters=12):
+    """Auxiliary figure for the second half of BASELINE.json's metric (the 1M-point fit): device time
+    of one FGMRES iteration (FMM matvec at accuracy 0 -> order 12 / d 8, Arnoldi, Givens) on the
+    config #2 centres.  The RAS preconditioner is not built, so this is a
+    per-iteration cost, not a fit wall-time."""
+    import torch
+    import polatory_b200 as pb
+    from polatory_b200.krylov import Fgmres
+    from polatory_b200.operator import Model, Operator
+    n = len(points)
+    model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.0)
+    op = Operator(model, pb.Bbox(points.min(axis=0), points.max(axis=0)), accuracy=0.0)
+    op.set_points(points)
+    rhs = torch.zeros(op.size(), dtype=torch.float64, device=dev)
+    third = (n + 2) // 3
+    rhs[third:2 * third] = 1e-2   # SDF offsets (+d, -d) as the right-hand side
+    rhs[2 * third:n] = -1e-2
+    solver = Fgmres(op, rhs, iters + 3)
+    solver.setup()
+    for _ in range(3):
+        solver.iterate_process()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        solver.iterate_process()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    ph = op.a[0].phase_times()
+    return {"workload": f"config #2 matvec inside FGMRES: {n} bh3 centres, degree 0, accuracy 0",
+            "config": op.a[0].config(), "fgmres_ms_per_iteration": ms, "matvec_ms": float(sum(ph.values())),
+            "iterations_timed": iters, "krylov_dim_at_end": solver.iteration_count(),
+            "preconditioner": "none (RAS not built): per-iteration cost only",
+            "matvec_phases_ms": {k: round(v, 4) for k, v in ph.items()}}
 
 
 def measured_traffic(kernel):

@@ -18,12 +18,12 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
 if [ "${SKIP_LAUNCHES:-0}" != "1" ]; then
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launches.log 2>&1
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-fit > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log | cut -c1-300
 fi
 echo "== ncu full: ${NCU_KERNEL:=k_m2l_hadamard}"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL} -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -f -o gpurun_out/prof_${NCU_TAG:-top} \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-fit > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 fi
 ls -la gpurun_out
