@@ -907,380 +907,6 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
   }
 }
 
-// Parent-paired variant of the scalar kernel: a warp accumulates TWO consecutive active parents at
-// once.  An operator value loaded from shared memory is then used for both parents whenever the
-// same relative source position is occupied for both (neighbouring parents of a surface cloud
-// share ~60 % of their occupied positions), which is the only operand reuse the sparsity of the
-// source table leaves: the kernel above is bound by the 128 B/clk shared-memory pipe at one
-// 16-byte operator value per complex FMA (tools/ubench/kpath.cu: 4.0 SM-cycles per warp-level
-// LDS.128 against 2.06 for the four DFMAs).  Entries are compacted over the UNION of the two
-// source tables and classified (both / first only / second only) so that every branch is
-// warp-uniform and no predicated-off DFMA is issued for an absent parent.
-constexpr int kPairG = 2;
-
-template <int DIM, int MODE>  // MODE 1: parent A only, 2: parent B only, 3: both
-__device__ __forceinline__ void had_pair_entry(double2 (&accA)[1 << DIM], double2 (&accB)[1 << DIM], const double2* kp,
-                                               int fmA, int fmB, const double2& mA, const double2& mB) {
-  constexpr int NC = 1 << DIM;
-#pragma unroll
-  for (int ct = 0; ct < NC; ++ct) {
-    int cto = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) cto = cto * 7 + ((ct >> (DIM - 1 - d)) & 1);
-    if (MODE == 1) {
-      if ((fmA >> ct) & 1) cfma(accA[ct], kp[-cto * kHadTF], mA);
-    } else if (MODE == 2) {
-      if ((fmB >> ct) & 1) cfma(accB[ct], kp[-cto * kHadTF], mB);
-    } else {
-      if (((fmA | fmB) >> ct) & 1) {
-        const double2 k = kp[-cto * kHadTF];
-        if ((fmA >> ct) & 1) cfma(accA[ct], k, mA);
-        if ((fmB >> ct) & 1) cfma(accB[ct], k, mB);
-      }
-    }
-  }
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_paired(M2LArgs a, int F, int n_ftiles) {
-  constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN, NOFF = M2LGeom<DIM>::NOFF;
-  constexpr int NE = NN * NC;
-  constexpr int NCH = (NE + 31) / 32;
-  extern __shared__ double2 sm2[];
-  double2* Ks = sm2;                                           // [NOFF][TF]
-  int2* s_meta = reinterpret_cast<int2*>(Ks + NOFF * kHadTF);  // [NE]: x = offset index base, y = far mask
-  int4* s_list = reinterpret_cast<int4*>(s_meta + NE + (NE & 1));  // [warps][NE]: (row A, row B, base | fmA << 16 | fmB << 24, -)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  for (int code = threadIdx.x; code < NE; code += blockDim.x) {
-    const int nb = code / NC, cs = code % NC;
-    int e3[DIM], r = nb;
-#pragma unroll
-    for (int d = DIM - 1; d >= 0; --d) {
-      e3[d] = (r % 3) - 1;
-      r /= 3;
-    }
-    int base = 0, mask = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) base = base * 7 + (2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) + 3);
-    for (int ct = 0; ct < NC; ++ct) {
-      bool far = false;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        const int o = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) - ((ct >> (DIM - 1 - d)) & 1);
-        far = far || o > 1 || o < -1;
-      }
-      if (far) mask |= 1 << ct;
-    }
-    s_meta[code] = make_int2(base, mask);
-  }
-
-  const int n_pairs = (a.n_active + 1) / 2;
-  const long long n_items = static_cast<long long>(n_ftiles) * n_pairs;
-  const long long q_lo = n_items * blockIdx.x / gridDim.x, q_hi = n_items * (blockIdx.x + 1) / gridDim.x;
-  int4* list = s_list + warp * (NE - NC);  // the central neighbour never has a far pair
-  for (long long q0 = q_lo; q0 < q_hi;) {
-    const int ftile = static_cast<int>(q0 / n_pairs);
-    const int pair_lo = static_cast<int>(q0 - static_cast<long long>(ftile) * n_pairs);
-    const long long seg_end = min(q_hi, static_cast<long long>(ftile + 1) * n_pairs);
-    const int pair_hi = pair_lo + static_cast<int>(seg_end - q0);
-    q0 = seg_end;
-    const int f = ftile * kHadTF + lane;
-    const bool fok = f < F;
-    __syncthreads();
-    for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
-      const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
-      Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-
-    for (int pr = pair_lo + warp; pr < pair_hi; pr += kHadWarps) {
-      const int slotA = 2 * pr, slotB = 2 * pr + 1;
-      const bool hasB = slotB < a.n_active;
-      const int* tabA = a.src_ids + static_cast<size_t>(slotA) * NE;
-      const int* tabB = a.src_ids + static_cast<size_t>(hasB ? slotB : slotA) * NE;
-      const int tmA = a.trg_mask[slotA];
-      const int tmB = hasB ? a.trg_mask[slotB] : 0;
-      int n = 0;
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int idx = c * 32 + lane;
-        int sA = -1, sB = -1;
-        int2 meta = make_int2(0, 0);
-        if (idx < NE) {
-          sA = tabA[idx];
-          sB = tabB[idx];
-          meta = s_meta[idx];
-        }
-        const int fmA = sA >= 0 ? (meta.y & tmA) : 0;
-        const int fmB = sB >= 0 ? (meta.y & tmB) : 0;
-        const bool pres = (fmA | fmB) != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, pres);
-        if (pres) list[n + __popc(m & ((1u << lane) - 1u))] = make_int4(sA, sB, meta.x | (fmA << 16) | (fmB << 24), 0);
-        n += __popc(m);
-      }
-      __syncwarp();
-      double2 accA[NC], accB[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) accA[c] = accB[c] = make_double2(0.0, 0.0);
-
-      auto load = [&](double2 (&mA)[kPairG], double2 (&mB)[kPairG], int (&pk)[kPairG], int base) {
-#pragma unroll
-        for (int g = 0; g < kPairG; ++g) {
-          const int e = base + g;
-          int4 le = make_int4(0, 0, 0, 0);
-          if (e < n) le = list[e];
-          pk[g] = le.z;
-          const bool onA = ((le.z >> 16) & 0xff) != 0, onB = ((le.z >> 24) & 0xff) != 0;
-          mA[g] = (onA && fok) ? a.Mhat[static_cast<size_t>(le.x) * F + f] : make_double2(0.0, 0.0);
-          mB[g] = (onB && fok) ? a.Mhat[static_cast<size_t>(le.y) * F + f] : make_double2(0.0, 0.0);
-        }
-      };
-      auto compute = [&](const double2 (&mA)[kPairG], const double2 (&mB)[kPairG], const int (&pk)[kPairG], int base) {
-#pragma unroll
-        for (int g = 0; g < kPairG; ++g) {
-          if (base + g >= n) break;  // warp-uniform
-          const int fmA = (pk[g] >> 16) & 0xff, fmB = (pk[g] >> 24) & 0xff;
-          const double2* kp = Ks + (pk[g] & 0xffff) * kHadTF + lane;
-          if (fmA != 0 && fmB != 0) {
-            had_pair_entry<DIM, 3>(accA, accB, kp, fmA, fmB, mA[g], mB[g]);
-          } else if (fmA != 0) {
-            had_pair_entry<DIM, 1>(accA, accB, kp, fmA, fmB, mA[g], mB[g]);
-          } else {
-            had_pair_entry<DIM, 2>(accA, accB, kp, fmA, fmB, mA[g], mB[g]);
-          }
-        }
-      };
-      double2 mA0[kPairG], mB0[kPairG], mA1[kPairG], mB1[kPairG];
-      int pk0[kPairG], pk1[kPairG];
-      load(mA0, mB0, pk0, 0);
-      for (int g0 = 0; g0 < n; g0 += 2 * kPairG) {
-        load(mA1, mB1, pk1, g0 + kPairG);
-        compute(mA0, mB0, pk0, g0);
-        load(mA0, mB0, pk0, g0 + 2 * kPairG);
-        compute(mA1, mB1, pk1, g0 + kPairG);
-      }
-      if (fok) {
-#pragma unroll
-        for (int ct = 0; ct < NC; ++ct) {
-          if ((tmA >> ct) & 1) a.Lhat[(static_cast<size_t>(slotA) * NC + ct) * F + f] = accA[ct];
-          if ((tmB >> ct) & 1) a.Lhat[(static_cast<size_t>(slotB) * NC + ct) * F + f] = accB[ct];
-        }
-      }
-    }
-  }
-}
-
-// Source-parent-blocked variant of the scalar Hadamard accumulation.
-//
-// The tiled kernel above needs one 16-byte operator value from shared memory per complex FMA,
-// which saturates the 128 B/clk shared-memory pipe at half the DFMA rate.  Here the inner loop
-// runs over whole *source parents* (the 3^dim - 1 neighbours of the target parent): the
-// 2^dim x 2^dim (source child e, target child i) pairs of one source parent only touch the
-// 3^dim offsets  o = 2 d + delta,  delta = e - i in {-1, 0, 1}^dim,  so each operator value is
-// loaded once and used for every present pair with that delta (up to 2^dim, 2.5 on average for
-// a full block).  Lanes are still the 32 frequencies of the tile; the 2^dim source spectra of
-// the block and the 2^dim target accumulators live in registers; all guards are warp-uniform.
-template <int DIM>
-struct HadDelta {
-  static constexpr int NC = 1 << DIM;
-  static constexpr int ND = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
-  // bit (e * NC + i) set <=> e - i == delta (component-wise); delta index di in base 3, axis 0 most significant
-  static constexpr unsigned long long mask(int di) {
-    int dl[3] = {0, 0, 0};
-    for (int a = DIM - 1; a >= 0; --a) {
-      dl[a] = di % 3 - 1;
-      di /= 3;
-    }
-    unsigned long long m = 0;
-    for (int e = 0; e < NC; ++e)
-      for (int i = 0; i < NC; ++i) {
-        bool ok = true;
-        for (int a = 0; a < DIM; ++a) ok = ok && (((e >> (DIM - 1 - a)) & 1) - ((i >> (DIM - 1 - a)) & 1) == dl[a]);
-        if (ok) m |= 1ull << (e * NC + i);
-      }
-    return m;
-  }
-  static constexpr int koff(int di) {  // sum_a delta_a 7^(DIM-1-a)
-    int dl[3] = {0, 0, 0};
-    for (int a = DIM - 1; a >= 0; --a) {
-      dl[a] = di % 3 - 1;
-      di /= 3;
-    }
-    int o = 0;
-    for (int a = 0; a < DIM; ++a) o = o * 7 + dl[a];
-    return o;
-  }
-};
-
-template <int DIM, int DI, int E, int I>
-__device__ __forceinline__ void had_pair(double2 (&acc)[1 << DIM], const double2 (&mh)[1 << DIM], const double2& k,
-                                         unsigned long long pm) {
-  constexpr int NC = 1 << DIM;
-  if constexpr ((HadDelta<DIM>::mask(DI) >> (E * NC + I)) & 1ull) {
-    if ((pm >> (E * NC + I)) & 1ull) cfma(acc[I], k, mh[E]);
-  }
-}
-
-template <int DIM, int DI, int E>
-__device__ __forceinline__ void had_pairs_e(double2 (&acc)[1 << DIM], const double2 (&mh)[1 << DIM], const double2& k,
-                                            unsigned long long pm) {
-  // for a given (delta, e) there is at most one target child i = e - delta
-  had_pair<DIM, DI, E, 0>(acc, mh, k, pm);
-  if constexpr (DIM >= 1) had_pair<DIM, DI, E, 1>(acc, mh, k, pm);
-  if constexpr (DIM >= 2) {
-    had_pair<DIM, DI, E, 2>(acc, mh, k, pm);
-    had_pair<DIM, DI, E, 3>(acc, mh, k, pm);
-  }
-  if constexpr (DIM >= 3) {
-    had_pair<DIM, DI, E, 4>(acc, mh, k, pm);
-    had_pair<DIM, DI, E, 5>(acc, mh, k, pm);
-    had_pair<DIM, DI, E, 6>(acc, mh, k, pm);
-    had_pair<DIM, DI, E, 7>(acc, mh, k, pm);
-  }
-}
-
-template <int DIM, int DI>
-__device__ __forceinline__ void had_delta(double2 (&acc)[1 << DIM], const double2 (&mh)[1 << DIM], const double2* kp,
-                                          unsigned long long pm) {
-  constexpr unsigned long long DM = HadDelta<DIM>::mask(DI);
-  if (pm & DM) {
-    const double2 k = kp[HadDelta<DIM>::koff(DI) * kHadTF];
-    had_pairs_e<DIM, DI, 0>(acc, mh, k, pm);
-    had_pairs_e<DIM, DI, 1>(acc, mh, k, pm);
-    if constexpr (DIM >= 2) {
-      had_pairs_e<DIM, DI, 2>(acc, mh, k, pm);
-      had_pairs_e<DIM, DI, 3>(acc, mh, k, pm);
-    }
-    if constexpr (DIM >= 3) {
-      had_pairs_e<DIM, DI, 4>(acc, mh, k, pm);
-      had_pairs_e<DIM, DI, 5>(acc, mh, k, pm);
-      had_pairs_e<DIM, DI, 6>(acc, mh, k, pm);
-      had_pairs_e<DIM, DI, 7>(acc, mh, k, pm);
-    }
-  }
-  if constexpr (DI + 1 < HadDelta<DIM>::ND) had_delta<DIM, DI + 1>(acc, mh, kp, pm);
-}
-
-template <int DIM, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_m2l_hadamard_blocked(M2LArgs a, int F, int n_ftiles) {
-  constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN, NOFF = M2LGeom<DIM>::NOFF;
-  constexpr int NE = NN * NC;              // entries of the source-id table
-  constexpr int NCH = (NE + 31) / 32;      // 32-entry chunks
-  constexpr int NEP = NCH * 32;            // padded
-  extern __shared__ double2 sm2[];
-  double2* Ks = sm2;                                                        // [NOFF][TF]
-  unsigned long long* s_pm = reinterpret_cast<unsigned long long*>(Ks + NOFF * kHadTF);  // [warps][32]
-  int* s_ids = reinterpret_cast<int*>(s_pm + WARPS * 32);                  // [warps][NEP]
-  int* s_kbase = s_ids + WARPS * NEP;                                       // [32] operator row of (nb, delta = 0)
-  unsigned char* s_far = reinterpret_cast<unsigned char*>(s_kbase + 32);    // [NEP] far mask over target children
-  unsigned char* s_bits = s_far + NEP;                                      // [warps][NEP]
-  unsigned char* s_list = s_bits + WARPS * NEP;                             // [warps][32]
-  const int ftile = blockIdx.x % n_ftiles, pslice = blockIdx.x / n_ftiles, n_pslices = gridDim.x / n_ftiles;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f = ftile * kHadTF + lane;
-  const bool fok = f < F;
-
-  for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
-    const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
-    Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
-  }
-  for (int code = threadIdx.x; code < NEP; code += blockDim.x) {
-    int mask = 0;
-    if (code < NE) {
-      const int nb = code / NC, cs = code % NC;
-      int e3[DIM], r = nb;
-#pragma unroll
-      for (int d = DIM - 1; d >= 0; --d) {
-        e3[d] = (r % 3) - 1;
-        r /= 3;
-      }
-      for (int ct = 0; ct < NC; ++ct) {
-        bool far = false;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          const int o = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) - ((ct >> (DIM - 1 - d)) & 1);
-          far = far || o > 1 || o < -1;
-        }
-        if (far) mask |= 1 << ct;
-      }
-      if (cs == 0) {
-        int base = 0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) base = base * 7 + (2 * e3[d] + 3);
-        s_kbase[nb] = base;
-      }
-    }
-    s_far[code] = static_cast<unsigned char>(mask);
-  }
-  __syncthreads();
-
-  int* ids = s_ids + warp * NEP;
-  unsigned char* bits = s_bits + warp * NEP;
-  unsigned long long* pms = s_pm + warp * 32;
-  unsigned char* list = s_list + warp * 32;
-  for (int slot = pslice + n_pslices * warp; slot < a.n_active; slot += n_pslices * WARPS) {
-    const int* tab = a.src_ids + static_cast<size_t>(slot) * NE;
-    const int tmask = a.trg_mask[slot];
-    __syncwarp();  // previous parent done with the per-warp tables
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int idx = c * 32 + lane;
-      const int sid = idx < NE ? tab[idx] : -1;
-      ids[idx] = sid;
-      bits[idx] = sid >= 0 ? static_cast<unsigned char>(s_far[idx] & tmask) : static_cast<unsigned char>(0);
-    }
-    __syncwarp();
-    // pair mask of source parent nb = lane: bit (e * NC + i) <=> source child e present, target child i present, far
-    unsigned long long pm = 0;
-    if (lane < NN) {
-#pragma unroll
-      for (int e = 0; e < NC; ++e) pm |= static_cast<unsigned long long>(bits[lane * NC + e]) << (e * NC);
-    }
-    pms[lane] = pm;
-    const unsigned bal = __ballot_sync(0xffffffffu, pm != 0ull);
-    if (pm != 0ull) list[__popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned char>(lane);
-    const int n = __popc(bal);
-    __syncwarp();
-
-    double2 acc[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
-
-    auto load = [&](double2 (&mh)[NC], int k) {
-      if (k < n) {
-        const int nb = list[k];
-        const unsigned long long q = pms[nb];
-#pragma unroll
-        for (int e = 0; e < NC; ++e) {
-          const bool on = ((q >> (e * NC)) & ((1ull << NC) - 1ull)) != 0ull;
-          mh[e] = (on && fok) ? a.Mhat[static_cast<size_t>(ids[nb * NC + e]) * F + f] : make_double2(0.0, 0.0);
-        }
-      }
-    };
-    auto compute = [&](const double2 (&mh)[NC], int k) {
-      if (k < n) {
-        const int nb = list[k];
-        had_delta<DIM, 0>(acc, mh, Ks + s_kbase[nb] * kHadTF + lane, pms[nb]);
-      }
-    };
-    double2 mhA[NC], mhB[NC];
-    load(mhA, 0);
-    for (int k = 0; k < n; k += 2) {
-      load(mhB, k + 1);
-      compute(mhA, k);
-      load(mhA, k + 2);
-      compute(mhB, k + 1);
-    }
-    if (fok) {
-#pragma unroll
-      for (int ct = 0; ct < NC; ++ct)
-        if ((tmask >> ct) & 1) a.Lhat[(static_cast<size_t>(slot) * NC + ct) * F + f] = acc[ct];
-    }
-  }
-}
-
 // Inverse DFT of the accumulated spectra, pruned to the order^dim nodes:  L[cell][b][:] = IDFT(Lhat)
 // One CTA per (slot, child, b).
 template <int DIM, int ORDER>
@@ -1854,21 +1480,6 @@ void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsign
 }
 
 namespace {
-// Parent slices per frequency tile: fill the 148 SMs with whole waves of one-CTA-per-SM.
-int hadamard_parent_slices(int n_ftiles, int n_batches) {
-  int best = 1;
-  double best_eff = 0.0;
-  for (int ps = 1; ps <= 16 && ps <= std::max(1, n_batches); ++ps) {
-    const int total = n_ftiles * ps;
-    const double eff = static_cast<double>(total) / (static_cast<double>(ceil_div(total, kNumSM)) * kNumSM);
-    if (eff > best_eff + 0.02) {
-      best_eff = eff;
-      best = ps;
-    }
-  }
-  return best;
-}
-
 template <int DIM>
 void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
   constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
@@ -1887,67 +1498,14 @@ void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounte
 }
 }  // namespace
 
-namespace {
-template <int DIM, int WARPS>
-void launch_hadamard_blocked(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
-  constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
-  constexpr int NEP = (NN * NC + 31) / 32 * 32;
-  const int n_ftiles = ceil_div(F, kHadTF);
-  const int ps = hadamard_parent_slices(n_ftiles, ceil_div(a.n_active, WARPS));
-  const size_t smem = sizeof(double2) * NOFF * kHadTF + static_cast<size_t>(WARPS) * (32 * 8 + NEP * 4 + NEP + 32) +
-                      32 * 4 + NEP;
-  smem_opt_in((const void*)k_m2l_hadamard_blocked<DIM, WARPS>, smem);
-  PLT_LAUNCH(c, (k_m2l_hadamard_blocked<DIM, WARPS>), n_ftiles * ps, WARPS * 32, smem, s, a, F, n_ftiles);
-}
-}  // namespace
-
-namespace {
-template <int DIM>
-void launch_hadamard_paired(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
-  constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
-  constexpr int NE = NN * NC;
-  const int n_ftiles = ceil_div(F, kHadTF);
-  const int n_pairs = (a.n_active + 1) / 2;
-  const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(n_pairs, kHadWarps);
-  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
-  const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * (NE + (NE & 1)) + sizeof(int4) * (NE - NC) * kHadWarps;
-  smem_opt_in((const void*)k_m2l_hadamard_paired<DIM>, smem);
-  PLT_LAUNCH(c, (k_m2l_hadamard_paired<DIM>), grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
-}
-}  // namespace
-
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   if (a.n_active == 0) return;
   const int F = freqs_per_cell(a.order, a.dim);
   static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
-  // PLT_HAD_VARIANT: 0 = frequency-tiled per-pair kernel, 8 / 12 / 16 = source-parent-blocked kernel with that many warps
-  static const int variant = getenv("PLT_HAD_VARIANT") ? atoi(getenv("PLT_HAD_VARIANT")) : 0;
-  if (!no_tiled && variant == 2 && a.kn * a.km == 1 && a.dim == 3) {
-    launch_hadamard_paired<3>(a, F, s, c);
-    return;
-  }
-  if (!no_tiled && (variant == 0 || variant == 2)) {
+  if (!no_tiled) {
     if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
     if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
     if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);
-    return;
-  }
-  if (a.kn == 1 && a.km == 1 && !no_tiled) {
-    if (variant == 0) {
-      if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
-      if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
-      if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);
-    } else if (a.dim == 1) {
-      launch_hadamard_blocked<1, 16>(a, F, s, c);
-    } else if (a.dim == 2) {
-      launch_hadamard_blocked<2, 16>(a, F, s, c);
-    } else if (variant == 8) {
-      launch_hadamard_blocked<3, 8>(a, F, s, c);
-    } else if (variant == 12) {
-      launch_hadamard_blocked<3, 12>(a, F, s, c);
-    } else {
-      launch_hadamard_blocked<3, 16>(a, F, s, c);
-    }
     return;
   }
   const int threads = F >= 256 ? 256 : ((F + 31) / 32 * 32);
