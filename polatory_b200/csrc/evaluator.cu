@@ -186,6 +186,8 @@ struct plt_eval {
   Plan plan;           // interaction plan of (src_tree, target_tree()); rebuilt with either tree
   Arena arena;         // temporaries of one evaluate()
   DevBuf<double> stage;  // host -> device staging of caller points
+  cudaStream_t copy_stream = nullptr;  // H2D of host targets, overlapped with the upward pass
+  cudaEvent_t copy_ready = nullptr, copy_done = nullptr;
   bool multipole_dirty = true;
   int up_order = 0, up_d = 0;  // configuration the cached multipoles were built with
   DevBuf<double> wt_sorted;    // [km][n_src] folded, sorted
@@ -199,6 +201,15 @@ struct plt_eval {
   plt_config config{0, 0, kClassic};
 
   int shard_rank = 0, shard_world = 1;
+
+  plt_eval() = default;
+  plt_eval(const plt_eval&) = delete;
+  plt_eval& operator=(const plt_eval&) = delete;
+  ~plt_eval() {
+    if (copy_ready) cudaEventDestroy(copy_ready);
+    if (copy_done) cudaEventDestroy(copy_done);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
 
   // -------------------------------------------------------------------------------
   const Tree& target_tree() const { return symmetric ? src_tree : trg_tree; }
@@ -313,8 +324,25 @@ struct plt_eval {
     const double* dev_pts = pts;
     if (n > 0 && !is_device_pointer(pts)) {
       stage.alloc(static_cast<size_t>(n) * dim, stream);
-      PLT_CUDA(cudaMemcpyAsync(stage.get(), pts, sizeof(double) * n * dim, cudaMemcpyHostToDevice, stream));
       dev_pts = stage.get();
+      if (!source && can_prefetch_upward()) {
+        // Host targets: their H2D copy (PCIe-bound, the longest single item of a host-buffer
+        // evaluation) runs on a copy stream while this stream does the source-side upward pass,
+        // which does not depend on the targets.
+        if (!copy_stream) {
+          PLT_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+          PLT_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
+          PLT_CUDA(cudaEventCreateWithFlags(&copy_done, cudaEventDisableTiming));
+        }
+        PLT_CUDA(cudaEventRecord(copy_ready, stream));  // staging buffer allocated, previous use finished
+        PLT_CUDA(cudaStreamWaitEvent(copy_stream, copy_ready, 0));
+        prefetch_upward(n);                             // asynchronous launches on `stream`
+        PLT_CUDA(cudaMemcpyAsync(stage.get(), pts, sizeof(double) * n * dim, cudaMemcpyHostToDevice, copy_stream));
+        PLT_CUDA(cudaEventRecord(copy_done, copy_stream));
+        PLT_CUDA(cudaStreamWaitEvent(stream, copy_done, 0));
+      } else {
+        PLT_CUDA(cudaMemcpyAsync(stage.get(), pts, sizeof(double) * n * dim, cudaMemcpyHostToDevice, stream));
+      }
     }
     DevBuf<double>& pos = source ? src_pos_c : trg_pos_c;
     pos.alloc(static_cast<size_t>(n) * dim, stream);
@@ -331,6 +359,33 @@ struct plt_eval {
     } else {
       n_trg = n;
       trg_tree.reset();      // fmm_evaluator.hpp:155-156
+    }
+  }
+
+  // The upward pass can be issued ahead of evaluate() when sources and weights are in place and
+  // the FMM branch will be taken for `n_targets` targets.
+  bool can_prefetch_upward() const {
+    return !direct_part && !symmetric && n_src > 0 && have_weights && !std::isfinite(rbf.support_radius);
+  }
+  void prefetch_upward(int64_t n_targets) {
+    if (n_src * n_targets < int64_t{1024} * 1024 && force_height == 0) return;  // brute-force branch
+    int height = fmm_tree_height(dim, std::max(n_src, n_targets));
+    if (force_height > 0) height = force_height;
+    if (height <= 2) return;
+    if (!src_tree.built() || src_tree.height() != height) {
+      src_tree.build(dim, height, box, src_pos_c.get(), n_src, stream, ctr);
+      wt_dirty = true;
+      multipole_dirty = true;
+      plan.reset();
+    }
+    ensure_sorted_weights();
+    const plt_config c = find_best_configuration(height);
+    if (multipole_dirty || up_order != c.order || up_d != c.d) {
+      Interpolator& ip = interpolator(height, c.order, c.d);
+      upward(src_tree, wt_sorted.get(), ip, M, Mhat, false);
+      multipole_dirty = false;
+      up_order = c.order;
+      up_d = c.d;
     }
   }
 
