@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(kBlock) k_l2p(TreeView tr, Box box, InterpDev 
 // per SM from order 10 on, so the CTA itself has to bring the warps.
 __host__ __device__ constexpr int leaf_threads(int order) { return order >= 10 ? 512 : (order >= 8 ? 256 : 128); }
 constexpr int kLeafMaxOrder = 12;
+constexpr int kLeafPosCap = 160;  // points of one parent staged in shared memory (else read from HBM)
 
 struct LeafTables {
   double child[2 * kLeafMaxOrder * kLeafMaxOrder];  // [2][p][p]
@@ -435,6 +436,10 @@ __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <
   double* lvl1 = DIM == 2 ? s_last : s_child + P;  // after axis 0 (DIM >= 2)
   __shared__ int s_first[NC];  // first point of the child, or -1
   __shared__ int s_count[NC];
+  // Positions of the parent's points (the children are consecutive leaves, so their points are one
+  // contiguous run of the sorted order): fetched once, coalesced, while the L2L stages run.
+  __shared__ double s_pos[DIM * kLeafPosCap];
+  __shared__ int s_run[2];     // first point and length of the run
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int leaf = tr.height - 1, pl = leaf - 1;
   const int pidx = par_lo + blockIdx.x;
@@ -442,15 +447,35 @@ __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <
   const bool has_parent = L != nullptr;  // parent level >= 2
   const int slot = leaf_slot ? leaf_slot[pidx] : -1;
 
-  if (tid < NC) {
-    const int cidx = tr.dense[tr.dense_off[leaf] + ((pkey << DIM) | tid)];
+  if (tid < 32) {
     int first = -1, cnt = 0;
-    if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
-      first = tr.leaf_start[cidx];
-      cnt = tr.leaf_start[cidx + 1] - first;
+    if (tid < NC) {
+      const int cidx = tr.dense[tr.dense_off[leaf] + ((pkey << DIM) | tid)];
+      if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
+        first = tr.leaf_start[cidx];
+        cnt = tr.leaf_start[cidx + 1] - first;
+      }
+      s_first[tid] = first;
+      s_count[tid] = cnt;
     }
-    s_first[tid] = first;
-    s_count[tid] = cnt;
+    int lo = first >= 0 ? first : 0x7fffffff, hi = first >= 0 ? first + cnt : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (tid == 0) {
+      s_run[0] = lo;
+      s_run[1] = hi > lo ? hi - lo : 0;
+    }
+  }
+  __syncthreads();
+  const int pos_base = s_run[0];
+  const bool pos_in_smem = s_run[1] <= kLeafPosCap;
+  if (pos_in_smem) {
+    for (int e = tid; e < DIM * s_run[1]; e += kLeafThreads) {
+      const int a = e / s_run[1], q = e - a * s_run[1];
+      s_pos[a * kLeafPosCap + q] = tr.pos[a * tr.n + pos_base + q];
+    }
   }
 
   for (int b = 0; b < kn; ++b) {
@@ -523,29 +548,52 @@ __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <
         const int j = (g - gbase) * PP + sub;
         const bool act = sub < PP && j < cnt;
         const int i = first + (act ? j : 0);
-        double bs[DIM][p];
+        // Barycentric basis in product form, shared by the p lanes of a point: lane i0 computes only
+        // its own un-normalised weights u_a = beta[i0] * prod_{m != i0} (t_a - x_m) on the three axes,
+        // the lanes exchange u_1, u_2 with shuffles, and the three normalisations 1 / sum_m u_a[m]
+        // are applied once to the point's total.
+        double u[DIM];
 #pragma unroll
-        for (int a = 0; a < DIM; ++a)
-          product_basis<p>(tb.beta, (tr.pos[a * tr.n + i] - c[a]) * inv_half, bs[a]);
-        double b0 = bs[0][0];  // register select instead of a dynamically indexed array
+        for (int a = 0; a < DIM; ++a) {
+          const double t = ((pos_in_smem ? s_pos[a * kLeafPosCap + (i - pos_base)] : tr.pos[a * tr.n + i]) - c[a]) * inv_half;
+          double prod = tb.beta[0];
 #pragma unroll
-        for (int m = 1; m < p; ++m)
-          if (i0 == m) b0 = bs[0][m];
+          for (int m = 1; m < p; ++m)
+            if (i0 == m) prod = tb.beta[m];
+#pragma unroll
+          for (int m = 0; m < p; ++m) {
+            const double dm = t - (-1.0 + 2.0 * m / (p - 1));
+            prod *= (i0 == m) ? 1.0 : dm;
+          }
+          u[a] = prod;
+        }
+        const int lane0 = sub * p;  // first lane of the point (lanes beyond PP * p idle along)
+        double u1[p], u2[p], s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < p; ++m) {
+          u1[m] = __shfl_sync(0xffffffffu, u[1], (lane0 + m) & 31);
+          u2[m] = __shfl_sync(0xffffffffu, u[2], (lane0 + m) & 31);
+          s1 += u1[m];
+          s2 += u2[m];
+        }
         const double* Ls = Lch + i0 * S;
         double ri = 0.0;
 #pragma unroll
         for (int i1 = 0; i1 < p; ++i1) {
           double r = 0.0;
 #pragma unroll
-          for (int k = 0; k < p; ++k) r = fma(bs[2][k], Ls[i1 * p + k], r);
-          ri = fma(bs[1][i1], r, ri);
+          for (int k = 0; k < p; ++k) r = fma(u2[k], Ls[i1 * p + k], r);
+          ri = fma(u1[i1], r, ri);
         }
-        const double v = b0 * ri;
-        // sum over the p lanes of the point; the group's first lane ends up with the total
-        double tot = v;
+        const double v = u[0] * ri;
+        // sums over the p lanes of the point; the point's first lane ends up with the totals
+        double tot = v, s0 = u[0];
 #pragma unroll
-        for (int m = 1; m < p; ++m) tot += __shfl_down_sync(0xffffffffu, v, m);
-        if (act && i0 == 0) vt[b * tr.n + i] = tot;
+        for (int m = 1; m < p; ++m) {
+          tot += __shfl_down_sync(0xffffffffu, v, m);
+          s0 += __shfl_down_sync(0xffffffffu, u[0], m);
+        }
+        if (act && i0 == 0) vt[b * tr.n + i] = tot / (s0 * s1 * s2);
       }
     } else {
       for (int ch = warp; ch < NC; ch += NW) {
