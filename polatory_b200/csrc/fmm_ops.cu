@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int idx = c * 32 + lane;
-        const int sid = idx < NE ? tab[idx] : -1;
+        const int sid = idx < NE ? __ldcs(tab + idx) : -1;
         int2 meta = make_int2(0, 0);
         if (idx < NE) meta = s_meta[idx];
         const int fm = meta.y & tmask;
@@ -948,7 +948,8 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
       if (fok) {
 #pragma unroll
         for (int ct = 0; ct < NC; ++ct)
-          if ((tmask >> ct) & 1) a.Lhat[((static_cast<size_t>(slot) * NC + ct) * kn + cb) * F + f] = acc[ct];
+          if ((tmask >> ct) & 1)  // written once, read once by the IDFT: evict-first keeps the Mhat rows in L2
+            __stcs(&a.Lhat[((static_cast<size_t>(slot) * NC + ct) * kn + cb) * F + f], acc[ct]);
       }
     }
     }
@@ -1059,7 +1060,7 @@ __global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
     if (!in) continue;
     double2 x[nf];
 #pragma unroll
-    for (int f = 0; f < nf; ++f) x[f] = in[f * (nf * p) + col];
+    for (int f = 0; f < nf; ++f) x[f] = __ldcs(in + f * (nf * p) + col);  // read once: streaming
 #pragma unroll
     for (int m = 0; m < p; ++m) {
       double re = 0.0, im = 0.0;
