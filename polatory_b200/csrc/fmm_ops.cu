@@ -956,214 +956,6 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
   }
 }
 
-// 3-D scalar variant with half of the operator reads served from Tensor Memory.
-//
-// The kernel above is bound by the 128 B/clk shared-memory pipe (one LDS.128 per complex FMA).
-// tcgen05.ld from TMEM is a separate path (measured 1.45 SM-cycles per 512-byte warp load, additive
-// to LDS: tools/ubench/kpath.cu), but a warp only reaches the 32 lanes of its own quarter, i.e.
-// 64 KiB = 128 operator values per lane.  The 5^3 "inner" offsets (|o| <= 2 on every axis; they
-// cover the most frequently used half of the far pairs) are therefore mirrored in all four
-// quarters of TMEM -- column 4 * idx5, lane = frequency -- and read with tcgen05.ld.32x32b.x4;
-// the outer shell of the 7^3 table stays in shared memory.  Every choice is warp-uniform.
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, double2& k) {
-  uint32_t r0, r1, r2, r3;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(taddr));
-  k.x = __hiloint2double(r1, r0);
-  k.y = __hiloint2double(r3, r2);
-}
-constexpr int kTmemG = 2;  // prefetch group (registers: 16 go to the TMEM staging)
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tmem(M2LArgs a, int F, int n_ftiles) {
-  constexpr int DIM = 3;
-  constexpr int NC = 8, NN = 27, NOFF = 343, NE = NN * NC, NCH = (NE + 31) / 32;
-  extern __shared__ double2 sm2[];
-  double2* Ks = sm2;                                           // [NOFF][TF]
-  int2* s_meta = reinterpret_cast<int2*>(Ks + NOFF * kHadTF);  // [NE]: x = base7 | base5 << 16, y = far | inner << 8
-  int2* s_list = s_meta + NE;                                  // [warps][NE]: (Mhat row, packed)
-  unsigned char* s_b5 = reinterpret_cast<unsigned char*>(s_list + kHadWarps * NE);  // [warps][NE]: TMEM slot base
-  __shared__ uint32_t s_tmem;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
-        static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  for (int code = threadIdx.x; code < NE; code += blockDim.x) {
-    const int nb = code / NC, cs = code % NC;
-    int e3[DIM], r = nb;
-#pragma unroll
-    for (int d = DIM - 1; d >= 0; --d) {
-      e3[d] = (r % 3) - 1;
-      r /= 3;
-    }
-    int base7 = 0, base5 = 0, far_mask = 0, inner_mask = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      const int u = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1);
-      base7 = base7 * 7 + (u + 3);
-      base5 = base5 * 5 + (u + 2);
-    }
-    for (int ct = 0; ct < NC; ++ct) {
-      bool far = false, inner = true;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        const int o = 2 * e3[d] + ((cs >> (DIM - 1 - d)) & 1) - ((ct >> (DIM - 1 - d)) & 1);
-        far = far || o > 1 || o < -1;
-        inner = inner && o >= -2 && o <= 2;
-      }
-      if (far) far_mask |= 1 << ct;
-      if (far && inner) inner_mask |= 1 << ct;
-    }
-    s_meta[code] = make_int2(base7 | (base5 << 16), far_mask | (inner_mask << 8));
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tbase = s_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-
-  const long long n_items = static_cast<long long>(n_ftiles) * a.n_active;
-  const long long q_lo = n_items * blockIdx.x / gridDim.x, q_hi = n_items * (blockIdx.x + 1) / gridDim.x;
-  int2* list = s_list + warp * NE;
-  unsigned char* list5 = s_b5 + warp * NE;
-  for (long long q0 = q_lo; q0 < q_hi;) {
-    const int ftile = static_cast<int>(q0 / a.n_active);
-    const int slot_lo = static_cast<int>(q0 - static_cast<long long>(ftile) * a.n_active);
-    const long long seg_end = min(q_hi, static_cast<long long>(ftile + 1) * a.n_active);
-    const int slot_hi = slot_lo + static_cast<int>(seg_end - q0);
-    q0 = seg_end;
-    const int f = ftile * kHadTF + lane;
-    const bool fok = f < F;
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();  // previous tile's operators (shared memory and TMEM) no longer in use
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
-      const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
-      Ks[e] = ff < F ? a.Khat[static_cast<size_t>(oi) * F + ff] : make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-    if (warp < 4) {  // one warp per TMEM quarter mirrors the inner 5^3 block
-      for (int i5 = 0; i5 < 125; ++i5) {
-        const int ox = i5 / 25 - 2, oy = (i5 / 5) % 5 - 2, oz = i5 % 5 - 2;
-        const int oi7 = ((ox + 3) * 7 + (oy + 3)) * 7 + (oz + 3);
-        const double2 v = Ks[oi7 * kHadTF + lane];
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbase + 4 * i5),
-                     "r"(__double2loint(v.x)), "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)),
-                     "r"(__double2hiint(v.y)));
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-
-    for (int slot = slot_lo + warp; slot < slot_hi; slot += kHadWarps) {
-      const int* tab = a.src_ids + static_cast<size_t>(slot) * NE;
-      const int tmask = a.trg_mask[slot];
-      int n = 0;
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int idx = c * 32 + lane;
-        const int sid = idx < NE ? __ldcs(tab + idx) : -1;
-        int2 meta = make_int2(0, 0);
-        if (idx < NE) meta = s_meta[idx];
-        const int fm = meta.y & tmask;                // far & present
-        const int im = (meta.y >> 8) & tmask;         // ... of which inner (TMEM)
-        const bool pres = sid >= 0 && fm != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, pres);
-        // packed: base7 (9 bits) | fm << 16 | im << 24 ; base5 (8 bits) in a byte list
-        if (pres) {
-          const int at = n + __popc(m & ((1u << lane) - 1u));
-          list[at] = make_int2(sid, (meta.x & 0x1ff) | (fm << 16) | (im << 24));
-          list5[at] = static_cast<unsigned char>(meta.x >> 16);
-        }
-        n += __popc(m);
-      }
-      __syncwarp();
-      double2 acc[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = make_double2(0.0, 0.0);
-
-      auto load = [&](double2 (&mh)[kTmemG], int (&pk)[kTmemG], int base) {
-#pragma unroll
-        for (int g = 0; g < kTmemG; ++g) {
-          const int e = base + g;
-          int2 le = make_int2(0, 0);
-          if (e < n) le = list[e];
-          pk[g] = le.y;
-          mh[g] = (e < n && fok) ? a.Mhat[static_cast<size_t>(le.x) * F + f] : make_double2(0.0, 0.0);
-        }
-      };
-      auto compute = [&](const double2 (&mh)[kTmemG], const int (&pk)[kTmemG], int base) {
-#pragma unroll
-        for (int g = 0; g < kTmemG; ++g) {
-          if (base + g >= n) break;  // warp-uniform
-          const int fm = (pk[g] >> 16) & 0xff, im = (pk[g] >> 24) & 0xff;
-          const double2* kp = Ks + (pk[g] & 0x1ff) * kHadTF + lane;
-          const uint32_t tp = tbase + 4u * static_cast<uint32_t>(list5[base + g]);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            double2 kt[4];
-            // the four TMEM reads of this half are issued back to back into distinct registers and
-            // retired by one wait; a child whose offset is not in TMEM reads slot 0 (ignored)
-            if ((im >> (half * 4)) & 0xf) {
-              constexpr int c5[8] = {0, 1, 5, 6, 25, 26, 30, 31};  // sum_d ct_d 5^(2-d)
-              uint32_t ta[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) ta[q] = ((im >> (half * 4 + q)) & 1) ? tp - 4u * c5[half * 4 + q] : tbase;
-              uint32_t r[16];
-              asm volatile(
-                  "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%16];\n\t"
-                  "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%17];\n\t"
-                  "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%18];\n\t"
-                  "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [%19];\n\t"
-                  "tcgen05.wait::ld.sync.aligned;"
-                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-                    "=r"(r[15])
-                  : "r"(ta[0]), "r"(ta[1]), "r"(ta[2]), "r"(ta[3])
-                  : "memory");
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                kt[q] = make_double2(__hiloint2double(r[4 * q + 1], r[4 * q]), __hiloint2double(r[4 * q + 3], r[4 * q + 2]));
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int ct = half * 4 + q;
-              constexpr int c7[8] = {0, 1, 7, 8, 49, 50, 56, 57};  // sum_d ct_d 7^(2-d)
-              if ((fm >> ct) & 1) {
-                const double2 k = ((im >> ct) & 1) ? kt[q] : kp[-c7[ct] * kHadTF];
-                cfma(acc[ct], k, mh[g]);
-              }
-            }
-          }
-        }
-      };
-      double2 mhA[kTmemG], mhB[kTmemG];
-      int pkA[kTmemG], pkB[kTmemG];
-      load(mhA, pkA, 0);
-      for (int g0 = 0; g0 < n; g0 += 2 * kTmemG) {
-        load(mhB, pkB, g0 + kTmemG);
-        compute(mhA, pkA, g0);
-        load(mhA, pkA, g0 + 2 * kTmemG);
-        compute(mhB, pkB, g0 + kTmemG);
-      }
-      if (fok) {
-#pragma unroll
-        for (int ct = 0; ct < NC; ++ct)
-          if ((tmask >> ct) & 1) __stcs(&a.Lhat[(static_cast<size_t>(slot) * NC + ct) * F + f], acc[ct]);
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_tmem));
-}
-
 // Inverse DFT of the accumulated spectra, pruned to the order^dim nodes:  L[cell][b][:] = IDFT(Lhat)
 // One CTA per (slot, child, b).
 template <int DIM, int ORDER>
@@ -1759,16 +1551,6 @@ void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   if (a.n_active == 0) return;
   const int F = freqs_per_cell(a.order, a.dim);
   static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
-  static const bool use_tmem = getenv("PLT_HAD_TMEM") != nullptr;  // experimental, see k_m2l_hadamard_tmem
-  if (!no_tiled && use_tmem && a.dim == 3 && a.kn * a.km == 1) {
-    const int n_ftiles = ceil_div(F, kHadTF);
-    const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(a.n_active, kHadWarps);
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
-    const size_t smem = sizeof(double2) * 343 * kHadTF + sizeof(int2) * 216 * (1 + kHadWarps) + 216 * kHadWarps;
-    smem_opt_in((const void*)k_m2l_hadamard_tmem, smem);
-    PLT_LAUNCH(c, k_m2l_hadamard_tmem, grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
-    return;
-  }
   if (!no_tiled) {
     if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
     if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
