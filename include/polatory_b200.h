@@ -137,6 +137,15 @@ int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size);
 int plt_eval_get_permutation(plt_eval* h, int32_t* perm, int64_t n);
 int plt_eval_get_target_shard_range(plt_eval* h, int64_t* begin, int64_t* end);
 
+/* Batched Gram matrices of the value kernel for the RAS preconditioner's local problems: replaces
+ * preconditioner::mat_a (include/polatory/preconditioner/mat_a.hpp:10-61, value block) for all domains
+ * of a level at once.  points: DEVICE [n_batch][m][dim] row-major, original coordinates (the handle's
+ * anisotropy is applied); counts: DEVICE int32 [n_batch], rows / columns >= counts[b] are filled with the
+ * identity; out: DEVICE [n_batch][m][m].  out[b][i][j] = phi(x_bi - x_bj) + nugget * (i == j).
+ * The handle must be a K-kind evaluator of the RBF (it carries the constants); n_batch <= 65535. */
+int plt_eval_gram_batched(plt_eval* h, const double* points, const int32_t* counts, int64_t n_batch, int64_t m,
+                          double nugget, double* out);
+
 /* Per-phase device time of the last evaluate() in milliseconds (CUDA events on the
  * handle's stream).  names/ms: arrays of capacity cap; returns the number of phases. */
 int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap);

@@ -85,7 +85,60 @@ __global__ void k_reduce_chunks(const double* __restrict__ partial, int n_chunks
   out[i] = s;
 }
 
+// Batched Gram matrices of the value kernel: the reference's preconditioner::mat_a
+// (include/polatory/preconditioner/mat_a.hpp:10-61, value block) for B point sets at once, i.e. the
+// local matrices of all RAS domains of a level in one launch.
+//   out[b][i][j] = phi(A (x_bi - x_bj)) + nugget * (i == j)      i, j < count[b]
+//   out[b][i][j] = (i == j)                                       otherwise (identity padding)
+struct Aniso3 {
+  double a[9];
+};
+template <int FAM, int DIM>
+__global__ void __launch_bounds__(256) k_gram_batched(RbfConst k, Aniso3 A, const double* __restrict__ pts,
+                                                      const int* __restrict__ counts, int m, double nugget,
+                                                      double* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int i = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i >= m || j >= m) return;
+  const int cnt = counts[b];
+  double v;
+  if (i < cnt && j < cnt) {
+    const double* pi = pts + (static_cast<size_t>(b) * m + i) * DIM;
+    const double* pj = pts + (static_cast<size_t>(b) * m + j) * DIM;
+    double diff[DIM], d[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) diff[c] = pi[c] - pj[c];
+    double r2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < DIM; ++r) {
+      d[r] = 0.0;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) d[r] = fma(A.a[r * DIM + c], diff[c], d[r]);
+      r2 = fma(d[r], d[r], r2);
+    }
+    double phi = 0.0, g = 0.0, gh = 0.0;
+    rbf_radial<FAM, NEED_PHI>(k, r2, phi, g, gh);
+    v = phi + (i == j ? nugget : 0.0);
+  } else {
+    v = i == j ? 1.0 : 0.0;
+  }
+  out[(static_cast<size_t>(b) * m + i) * m + j] = v;
+}
+
 }  // namespace
+
+void launch_gram_batched(int dim, const RbfConst& k, const double* aniso, const double* pts, const int* counts,
+                         int64_t n_batch, int m, double nugget, double* out, cudaStream_t stream, LaunchCounter& ctr) {
+  if (n_batch == 0 || m == 0) return;
+  Aniso3 A{};
+  for (int i = 0; i < dim * dim; ++i) A.a[i] = aniso[i];
+  PLT_REQUIRE(n_batch <= 65535, "gram_batched: at most 65535 point sets per call");
+  dim3 grid(ceil_div(m, 16), ceil_div(m, 16), static_cast<unsigned>(n_batch));
+  dispatch_fkd(k.family, KIND_K, dim, [&](auto fam, auto, auto dm) {
+    PLT_LAUNCH(ctr, (k_gram_batched<fam.value, dm.value>), grid, 256, 0, stream, k, A, pts, counts, m, nugget, out);
+  });
+}
 
 int direct_plan_chunks(int64_t ns, int64_t nt) {
   const int64_t t_blocks = (nt + kThreads * kTPT - 1) / (kThreads * kTPT);

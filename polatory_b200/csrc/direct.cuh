@@ -24,4 +24,9 @@ int direct_plan_chunks(int64_t ns, int64_t nt);
 
 void launch_direct(int kind, int dim, DirectArgs a, cudaStream_t stream, LaunchCounter& ctr);
 
+// Batched Gram matrices of the value kernel over B padded point sets (row-major [B][m][dim], original
+// coordinates; aniso row-major dim x dim): the RAS domain matrices (preconditioner/mat_a.hpp).
+void launch_gram_batched(int dim, const RbfConst& k, const double* aniso, const double* pts, const int* counts,
+                         int64_t n_batch, int m, double nugget, double* out, cudaStream_t stream, LaunchCounter& ctr);
+
 }  // namespace plt

@@ -1063,6 +1063,23 @@ int plt_eval_get_target_shard_range(plt_eval* h, int64_t* begin, int64_t* end) {
   });
 }
 
+int plt_eval_gram_batched(plt_eval* h, const double* points, const int32_t* counts, int64_t n_batch, int64_t m,
+                          double nugget, double* out) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(points && counts && out, "null argument");
+    PLT_REQUIRE(h->kind == KIND_K, "gram_batched needs a value-kernel (K) handle");
+    PLT_REQUIRE(h->rbf_part == 0 || !h->direct_part, "gram_batched: not available on a split handle");
+    PLT_REQUIRE(plt_eval::is_device_pointer(points) && plt_eval::is_device_pointer(counts) &&
+                    plt_eval::is_device_pointer(out),
+                "gram_batched works on device buffers");
+    double a[9];
+    for (int r = 0; r < h->dim; ++r)
+      for (int c = 0; c < h->dim; ++c) a[r * h->dim + c] = h->aniso[r * h->dim + c];
+    launch_gram_batched(h->dim, h->rbf.k, a, points, counts, n_batch, static_cast<int>(m), nugget, out, h->stream,
+                        h->ctr);
+  });
+}
+
 int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap) {
   if (!h) return 0;
   int n = 0;

@@ -140,6 +140,19 @@ class _EvaluatorBase:
         _lib.check(self._h, self._lib.plt_eval_get_target_shard_range(self._h, ctypes.byref(b), ctypes.byref(e)))
         return b.value, e.value
 
+    def gram_batched(self, points, counts, nugget, out):
+        """Batched Gram matrices (RAS local problems): CUDA tensors points (B, m, dim) float64,
+        counts (B,) int32, out (B, m, m) float64."""
+        b, m = int(points.shape[0]), int(points.shape[1])
+        assert points.is_cuda and counts.is_cuda and out.is_cuda and points.is_contiguous() and out.is_contiguous()
+        assert tuple(out.shape) == (b, m, m) and int(points.shape[2]) == self.dim and counts.numel() == b
+        for b0 in range(0, b, 65535):
+            b1 = min(b, b0 + 65535)
+            _lib.check(self._h, self._lib.plt_eval_gram_batched(
+                self._h, ctypes.c_void_p(points[b0:b1].data_ptr()), ctypes.c_void_p(counts[b0:b1].data_ptr()),
+                b1 - b0, m, float(nugget), ctypes.c_void_p(out[b0:b1].data_ptr())))
+        return out
+
     def phase_times(self):
         cap = 32
         names = (ctypes.c_char_p * cap)()

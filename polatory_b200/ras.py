@@ -1,0 +1,451 @@
+"""Restricted additive Schwarz preconditioner of the fit, on the device.
+
+Restates, for value data (sigma = 0: no gradient points in this round),
+  preconditioner::RasPreconditioner   include/polatory/preconditioner/ras_preconditioner.hpp:34-364
+  preconditioner::DomainDivider       include/polatory/preconditioner/domain_divider.hpp:17-321
+  preconditioner::Domain              include/polatory/preconditioner/domain.hpp:16-52
+  preconditioner::FineGrid            include/polatory/preconditioner/fine_grid.hpp:33-195
+  preconditioner::CoarseGrid          include/polatory/preconditioner/coarse_grid.hpp:20-159
+  preconditioner::mat_a               include/polatory/preconditioner/mat_a.hpp:10-61
+  polynomial::UnisolventPointSet      include/polatory/polynomial/unisolvent_point_set.hpp:16-74
+  polynomial::LagrangeBasis           include/polatory/polynomial/lagrange_basis.hpp:17-75
+
+What stays on the host (numpy, once per fit): the level structure, the choice of coarse points, the
+recursive bisection into overlapping domains -- index bookkeeping the reference also does serially.
+What runs on the device: the Gram matrices of all domains of a level (one batched kernel launch through
+the C ABI, `plt_eval_gram_batched`), their reduced factorisations Q^T A Q = L L^T (batched Cholesky:
+cuSOLVER through torch -- library code, used like cuBLAS), the local solves of one level as ONE
+batched product with the explicit inverses kept in HBM (the reference spills its factors to a temp
+file, preconditioner/binary_cache.hpp; 1M points need ~17 GB here), and the level transfers
+`update_residuals`, which are generic FMM evaluations (order 6, accuracy = infinity as the
+reference's `Evaluator` default) whose trees / plans / operators stay resident between applications.
+"""
+from __future__ import annotations
+
+import heapq
+import math
+
+import numpy as np
+
+from . import fmm
+from .operator import monomial_basis
+
+K_FINE_TO_COARSE_RATIO = 10.0   # ras_preconditioner.hpp:53
+K_N_COARSEST_POINTS = 2048      # ras_preconditioner.hpp:54
+K_OVERLAP_QUOTA = 0.5           # domain_divider.hpp:25
+K_MAX_LEAF_SIZE = 1024          # domain_divider.hpp:26
+
+
+# ---------------------------------------------------------------------------------------------
+# std::mt19937 (default seed) + libstdc++'s uniform_int_distribution (Lemire's method for 32-bit
+# engines, bits/uniform_int_dist.h), as used by UnisolventPointSet.
+# ---------------------------------------------------------------------------------------------
+class _StdMt19937:
+    def __init__(self, seed=5489):
+        self._rs = np.random.RandomState(seed)  # init_genrand(seed): the std::mt19937 stream
+
+    def __call__(self):
+        return int.from_bytes(self._rs.bytes(4), "little")
+
+    def uniform_index(self, n):
+        """uniform_int_distribution<Index>(0, n - 1)(gen) for n <= 2^32."""
+        product = self() * n
+        low = product & 0xFFFFFFFF
+        if low < n:
+            threshold = ((1 << 32) - n) % n
+            while low < threshold:
+                product = self() * n
+                low = product & 0xFFFFFFFF
+        return product >> 32
+
+
+def unisolvent_point_set(points, degree, dim):
+    """UnisolventPointSet: the best-conditioned of 100 random candidate sets (sorted indices).
+    Degree 0 is exact (every single point has rcond 1, the first trial wins); for higher degrees the
+    reference ranks by Eigen's FullPivLU::rcond(), restated here as 1 / cond_1."""
+    if degree < 0:
+        return []
+    n = len(points)
+    from math import comb
+    l = comb(dim + degree, degree)
+    gen = _StdMt19937()
+    best, best_rcond, found = None, 0.0, False
+    for _ in range(100):
+        s = set()
+        while len(s) < l:
+            s.add(gen.uniform_index(n))
+        idx = sorted(s)
+        p = monomial_basis(dim, degree, points[idx])
+        try:
+            rcond = 1.0 / np.linalg.cond(p, 1)
+        except np.linalg.LinAlgError:
+            continue
+        if not np.isfinite(rcond) or rcond < 1e-15:
+            continue
+        found = True
+        if best_rcond < rcond:
+            best_rcond, best = rcond, idx
+    if not found:
+        raise RuntimeError("could not find a unisolvent set of points")
+    return best
+
+
+def lagrange_basis_matrix(points, poly_idcs, degree, dim):
+    """LagrangeBasis(degree, points[poly_idcs]).evaluate(points): (mu x l)."""
+    coeffs = np.linalg.inv(monomial_basis(dim, degree, points[poly_idcs]))
+    return monomial_basis(dim, degree, points) @ coeffs
+
+
+def _round_half_to_even(d):
+    return math.ceil((d - 0.5) / 2.0) + math.floor((d + 0.5) / 2.0)  # domain_divider.hpp:308-310
+
+
+def _sort_by_axes(pts):
+    """Order of `pts` sorted lexicographically along the axes by decreasing bbox width
+    (domain_divider.hpp:188-203, 288-305)."""
+    width = pts.max(axis=0) - pts.min(axis=0)
+    axes = sorted(range(pts.shape[1]), key=lambda a: -width[a])  # stable, like std::sort on distinct widths
+    return np.lexsort(tuple(pts[:, a] for a in reversed(axes)))
+
+
+class Domain:
+    __slots__ = ("point_indices", "inner_point")
+
+    def __init__(self, point_indices, inner_point):
+        self.point_indices = point_indices
+        self.inner_point = inner_point
+
+
+def divide_domains(a_points, point_idcs, poly_idcs):
+    """DomainDivider::divide_domains + Domain::merge_poly_points for value points only."""
+    point_idcs = np.asarray(point_idcs, dtype=np.int64)
+    queue = [Domain(point_idcs, np.ones(len(point_idcs), dtype=bool))]
+    leaves = []
+    head = 0
+    while head < len(queue):
+        d = queue[head]
+        head += 1
+        n = len(d.point_indices)
+        if n <= K_MAX_LEAF_SIZE:
+            leaves.append(d)
+            continue
+        order = _sort_by_axes(a_points[d.point_indices])
+        idx, inner = d.point_indices[order], d.inner_point[order]
+        q = K_OVERLAP_QUOTA * K_MAX_LEAF_SIZE / n
+        n_sub = int(_round_half_to_even((1.0 + q) / 2.0 * n))
+        left_part, right_part = n - n_sub, n_sub
+        mid = int(_round_half_to_even((left_part + right_part) / 2.0))
+        pos = np.arange(n)
+        queue.append(Domain(idx[:right_part], inner[:right_part] & (pos[:right_part] < mid)))
+        queue.append(Domain(idx[left_part:], inner[left_part:] & (pos[left_part:] >= mid)))
+        queue[head - 1] = None
+    poly = np.asarray(poly_idcs, dtype=np.int64)
+    for d in leaves:  # merge_poly_points (domain.hpp:33-51)
+        order = np.argsort(d.point_indices, kind="stable")
+        idx, inner = d.point_indices[order], d.inner_point[order]
+        if len(poly):
+            pos = np.searchsorted(idx, poly)
+            present = (pos < len(idx)) & (idx[np.minimum(pos, len(idx) - 1)] == poly)
+            front_inner = np.zeros(len(poly), dtype=bool)
+            front_inner[present] = inner[pos[present]]
+            keep = np.ones(len(idx), dtype=bool)
+            keep[pos[present]] = False
+            idx = np.concatenate([poly, idx[keep]])
+            inner = np.concatenate([front_inner, inner[keep]])
+        d.point_indices, d.inner_point = idx, inner
+    return leaves
+
+
+def choose_coarse_points(a_points, point_idcs, poly_idcs, n_coarse_points):
+    """DomainDivider::choose_coarse_points (domain_divider.hpp:52-123): split the bounding-box
+    clusters breadth-first (largest box first within a level) until there are n_coarse_points of
+    them; the point nearest to each box centre is kept."""
+    poly_set = set(int(i) for i in poly_idcs)
+    root = np.array([i for i in point_idcs if int(i) not in poly_set], dtype=np.int64)
+
+    def init(idx):
+        pts = a_points[idx]
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        centre = 0.5 * (lo + hi)
+        c = int(idx[np.argmin(((pts - centre) ** 2).sum(axis=1))])  # first minimum, as std::min_element
+        return float(np.prod(hi - lo)), c, idx[_sort_by_axes(pts)]
+
+    counter = 0
+    vol, c, sorted_idx = init(root)
+    heap = [(0, -vol, counter, c, sorted_idx)]
+    while len(heap) < n_coarse_points:
+        level, _, _, _, idx = heapq.heappop(heap)
+        size = len(idx)
+        if size % 2 == 0:
+            mid = size // 2
+        else:  # tie between (size-1)/2 and (size+1)/2: the even index wins (domain_divider.hpp:83-88)
+            a = (size - 1) // 2
+            mid = a if a % 2 == 0 else a + 1
+            if size == 1:
+                mid = 0
+        for part in (idx[:mid], idx[mid:]):
+            if len(part):
+                counter += 1
+                vol, c, s = init(part)
+                heapq.heappush(heap, (level + 1, -vol, counter, c, s))
+        if size == 1 and len(heap) >= len(root):
+            break
+    centres = []
+    while heap:
+        centres.append(heapq.heappop(heap)[3])
+    return np.concatenate([np.asarray(poly_idcs, dtype=np.int64), np.asarray(centres, dtype=np.int64)])
+
+
+def level_structure(n_rows):
+    """Number of levels and the coarse point counts per level (ras_preconditioner.hpp:70-75,132-136)."""
+    n_levels = max(int(math.ceil(math.log(n_rows / K_N_COARSEST_POINTS) / math.log(K_FINE_TO_COARSE_RATIO))), 0) + 1
+    finest = math.log(n_rows) / math.log(K_FINE_TO_COARSE_RATIO)
+    coarsest = math.log(K_N_COARSEST_POINTS) / math.log(K_FINE_TO_COARSE_RATIO)
+    counts = {}
+    for level in range(n_levels - 1, 0, -1):
+        counts[level - 1] = int(K_FINE_TO_COARSE_RATIO ** (coarsest + (level - 1) * (finest - coarsest) / (n_levels - 1)))
+    return n_levels, counts
+
+
+# ---------------------------------------------------------------------------------------------
+# Device side
+# ---------------------------------------------------------------------------------------------
+class _FineLevel:
+    """All FineGrids of one level, batched: padded point lists, explicit inverses of Q^T A Q."""
+
+    def __init__(self, ras, domains):
+        torch = ras.torch
+        dev, l = ras.device, ras.l
+        self.n_dom = len(domains)
+        m_max = max(len(d.point_indices) for d in domains)
+        self.m = m_max
+        r = m_max - l
+        idx = np.zeros((self.n_dom, m_max), dtype=np.int64)
+        cnt = np.zeros(self.n_dom, dtype=np.int32)
+        inner_glob, inner_loc = [], []
+        for b, d in enumerate(domains):
+            k = len(d.point_indices)
+            idx[b, :k] = d.point_indices
+            cnt[b] = k
+            sel = np.nonzero(d.inner_point)[0]
+            inner_glob.append(d.point_indices[sel])
+            inner_loc.append(b * m_max + sel)
+        self.idx = torch.from_numpy(idx).to(dev)
+        self.cnt = torch.from_numpy(cnt).to(dev)
+        self.valid = (torch.arange(m_max, device=dev)[None, :] < self.cnt[:, None])
+        self.inner_glob = torch.from_numpy(np.concatenate(inner_glob)).to(dev)
+        self.inner_loc = torch.from_numpy(np.concatenate(inner_loc)).to(dev)
+        # Q = [q_top; I], q_top = -lagrange_p[rest]^T (fine_grid.hpp:71-73); padded rows are zero
+        if l > 0:
+            lag = ras.lagrange_p[self.idx]                      # (B, m, l)
+            lag = lag * self.valid[:, :, None]
+            self.q_top = -lag[:, l:, :].transpose(1, 2).contiguous()  # (B, l, r)
+        else:
+            self.q_top = None
+        self.inv = torch.empty((self.n_dom, r, r), dtype=torch.float64, device=dev)
+        chunk = max(1, min(self.n_dom, int(2 ** 31 // (8 * m_max * m_max))))
+        for b0 in range(0, self.n_dom, chunk):
+            b1 = min(self.n_dom, b0 + chunk)
+            a = ras.gram(ras.points_dev[self.idx[b0:b1]].contiguous(), self.cnt[b0:b1].contiguous())  # (b, m, m)
+            if l > 0:
+                q = self.q_top[b0:b1]
+                att, atr, art, arr = a[:, :l, :l], a[:, :l, l:], a[:, l:, :l], a[:, l:, l:]
+                red = arr + q.transpose(1, 2) @ (att @ q + atr) + art @ q
+            else:
+                red = a
+            chol = torch.linalg.cholesky(red)
+            self.inv[b0:b1] = torch.cholesky_inverse(chol)
+            del a, red, chol
+
+    def solve(self, ras, residuals, weights):
+        """FineGrid::solve + set_solution_to for every domain of the level (fine_grid.hpp:103-147)."""
+        l = ras.l
+        vals = residuals[self.idx] * self.valid                # (B, m)
+        if l > 0:
+            qtd = vals[:, l:] + (vals[:, None, :l] @ self.q_top).squeeze(1)
+            gamma = (self.inv @ qtd[:, :, None]).squeeze(2)
+            top = (self.q_top @ gamma[:, :, None]).squeeze(2)
+            lam = ras.torch.cat([top, gamma], dim=1)
+        else:
+            lam = (self.inv @ vals[:, :, None]).squeeze(2)
+        weights[self.inner_glob] = lam.reshape(-1)[self.inner_loc]
+
+
+class _CoarseGrid:
+    def __init__(self, ras, idcs):
+        torch = ras.torch
+        dev, l = ras.device, ras.l
+        self.idx = torch.from_numpy(np.asarray(idcs, dtype=np.int64)).to(dev)
+        m = len(idcs)
+        self.m = m
+        cnt = torch.tensor([m], dtype=torch.int32, device=dev)
+        a = ras.gram(ras.points_dev[self.idx][None].contiguous(), cnt)[0]
+        if l > 0:
+            lag = ras.lagrange_p[self.idx]
+            self.q_top = -lag[l:, :].T.contiguous()             # (l, m - l)
+            q = self.q_top
+            red = a[l:, l:] + q.T @ (a[:l, :l] @ q + a[:l, l:]) + a[l:, :l] @ q
+            self.a_top = a[:l, :].clone()
+            p_top = torch.from_numpy(monomial_basis(ras.dim, ras.model.poly_degree, ras.points[idcs[:l]])).to(dev)
+            self.p_top_inv = torch.linalg.inv(p_top)
+        else:
+            red = a
+        self.chol = torch.linalg.cholesky(red)
+
+    def solve(self, ras, residuals, weights):
+        """CoarseGrid::solve + set_solution_to (coarse_grid.hpp:84-128)."""
+        torch = ras.torch
+        l = ras.l
+        vals = residuals[self.idx]
+        if l > 0:
+            qtd = self.q_top.T @ vals[:l] + vals[l:]
+            gamma = torch.cholesky_solve(qtd[:, None], self.chol)[:, 0]
+            lam = torch.cat([self.q_top @ gamma, gamma])
+            weights[self.idx] = lam
+            weights[ras.mu:] = self.p_top_inv @ (vals[:l] - self.a_top @ lam)
+        else:
+            weights[self.idx] = torch.cholesky_solve(vals[:, None], self.chol)[:, 0]
+
+
+class RasPreconditioner:
+    """preconditioner::RasPreconditioner for value data; `apply(v, out)` on CUDA tensors."""
+
+    def __init__(self, model, points, device=None, verbose=False):
+        import torch
+        self.torch = torch
+        self.model = model
+        self.dim = model.dim
+        self.l = model.poly_basis_size()
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
+        self.mu = len(self.points)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        if len(model.rbfs) != 1:
+            raise NotImplementedError("RAS: one RBF per model in this round")
+        rbf = model.rbfs[0]
+        self.bbox = fmm.Bbox.from_points(self.points)
+        self._gram_ev = fmm.make_fmm_evaluator(rbf, self.bbox)   # carries the RBF constants for the Gram kernel
+        n_levels, counts = level_structure(self.mu)
+        self.n_levels = n_levels
+        mu, l = self.mu, self.l
+        self.points_dev = torch.from_numpy(self.points).to(self.device)
+
+        poly_idcs = unisolvent_point_set(self.points, model.poly_degree, self.dim) if l > 0 else []
+        self.poly_idcs = poly_idcs
+        if l > 0:
+            self.lagrange_p = torch.from_numpy(
+                lagrange_basis_matrix(self.points, poly_idcs, model.poly_degree, self.dim)).to(self.device)
+        point_idcs = [None] * n_levels
+        rest = np.ones(mu, dtype=bool)
+        rest[poly_idcs] = False
+        point_idcs[n_levels - 1] = np.concatenate([np.asarray(poly_idcs, dtype=np.int64), np.nonzero(rest)[0]])
+        aniso = np.asarray(rbf.anisotropy(), dtype=np.float64)
+        a_points = self.points @ aniso.T if not np.allclose(aniso, np.eye(self.dim)) else self.points
+        self.fine = [None] * n_levels
+        for level in range(n_levels - 1, 0, -1):
+            point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
+            domains = divide_domains(a_points, point_idcs[level], poly_idcs)
+            self.fine[level] = _FineLevel(self, domains)
+            if verbose:
+                print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points", flush=True)
+        self.point_idcs = point_idcs
+        self.idx_dev = [torch.from_numpy(np.asarray(p, dtype=np.int64)).to(self.device) for p in point_idcs]
+        self.coarse = _CoarseGrid(self, point_idcs[0])
+        if verbose:
+            print(f"level 0: 1 domain, {len(point_idcs[0])} points", flush=True)
+        self._evaluators = {}
+        self.p = self.ap = None
+        if n_levels > 1 and l > 0:
+            # orthonormalised monomials and A p (ras_preconditioner.hpp:165-180)
+            p = monomial_basis(self.dim, model.poly_degree, self.points)
+            for i in range(l):
+                p[:, i] /= np.linalg.norm(p[:, i])
+                for j in range(i + 1, l):
+                    p[:, j] -= (p[:, i] @ p[:, j]) * p[:, i]
+            self.p = torch.from_numpy(p).to(self.device)
+            ev = fmm.make_fmm_symmetric_evaluator(rbf, self.bbox)
+            ev.set_points(self.points_dev)
+            self.ap = torch.empty_like(self.p)
+            col = torch.empty(mu, dtype=torch.float64, device=self.device)
+            for i in range(l):
+                ev.set_weights(self.p[:, i].contiguous())
+                ev.evaluate(col)
+                self.ap[:, i] = col + model.nugget * self.p[:, i]
+            del ev
+        if l > 0:
+            self.p_mono = torch.from_numpy(monomial_basis(self.dim, model.poly_degree, self.points)).to(self.device)
+
+    # -- device helpers ------------------------------------------------------------------
+    def gram(self, pts, counts):
+        """mat_a for a batch of point sets: (B, m, dim) points, counts (B,) -> (B, m, m); rows/cols
+        beyond a set's count are identity."""
+        out = self.torch.empty((pts.shape[0], pts.shape[1], pts.shape[1]), dtype=self.torch.float64, device=self.device)
+        self._gram_ev.gram_batched(pts, counts, self.model.nugget, out)
+        return out
+
+    def _evaluator(self, src_level, trg_level):
+        key = (src_level, trg_level)
+        if key not in self._evaluators:
+            ev = fmm.make_fmm_evaluator(self.model.rbfs[0], self.bbox)
+            ev.set_source_points(self.points_dev[self.idx_dev[src_level]].contiguous())
+            ev.set_target_points(self.points_dev[self.idx_dev[trg_level]].contiguous())
+            out = self.torch.empty(len(self.point_idcs[trg_level]), dtype=self.torch.float64, device=self.device)
+            self._evaluators[key] = (ev, out)
+        return self._evaluators[key]
+
+    def _solve(self, level, residuals):
+        weights = self.torch.zeros(self.mu + self.l, dtype=self.torch.float64, device=self.device)
+        if level == 0:
+            self.coarse.solve(self, residuals, weights)
+        else:
+            self.fine[level].solve(self, residuals, weights)
+        return weights
+
+    def _update_residuals(self, src_level, trg_level, weights, residuals):
+        ev, fit = self._evaluator(src_level, trg_level)
+        ev.set_weights(weights[self.idx_dev[src_level]].contiguous())
+        ev.evaluate(fit)
+        trg = self.idx_dev[trg_level]
+        if self.l > 0:
+            fit = fit + self.p_mono[trg] @ weights[self.mu:]
+        residuals[trg] -= fit
+
+    def _orthogonalize(self, weights, residuals):
+        if self.l > 0:
+            dot = self.p.T @ weights[:self.mu]
+            weights[:self.mu] -= self.p @ dot
+            residuals += self.ap @ dot
+
+    # -- RasPreconditioner::operator() (ras_preconditioner.hpp:183-246) -----------------------
+    def apply(self, v, out):
+        n = self.n_levels
+        residuals = v[:self.mu].clone()
+        if n == 1:
+            out.copy_(self._solve(0, residuals))
+            return out
+        total = self.torch.zeros_like(v)
+        w = self._solve(0, residuals)
+        self._update_residuals(0, n - 1, w, residuals)
+        total += w
+        for level in range(1, n - 1):
+            w = self._solve(level, residuals)
+            self._update_residuals(level, n - 1, w, residuals)
+            total += w
+            self._orthogonalize(total, residuals)
+            w = self._solve(0, residuals)
+            self._update_residuals(0, n - 1, w, residuals)
+            total += w
+        for level in range(n - 1, 0, -1):
+            w = self._solve(level, residuals)
+            self._update_residuals(level, level - 1, w, residuals)
+            total += w
+            self._orthogonalize(total, residuals)
+            w = self._solve(0, residuals)
+            if level > 1:
+                self._update_residuals(0, level - 1, w, residuals)
+            total += w
+        out.copy_(total)
+        return out
+
+    def __call__(self, v):
+        out = self.torch.empty_like(v)
+        return self.apply(v, out)

@@ -1,0 +1,70 @@
+"""GPU tests of the RAS preconditioner (polatory_b200/ras.py) and of the preconditioned fit.
+
+Acceptance: the criterion of the reference's fit tests (test/interpolation/test_fitter.cpp:57-64,
+test_rbf_incremental_fitter.cpp): interpolation conditions met to the absolute tolerance; plus, against
+the exact dense system (oracle), the fitted weights and the Gram kernel."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def test_gram_batched_matches_oracle(torch):
+    import polatory_b200 as pb
+    from conftest import random_anisotropy
+    from oracle import direct as odir, rbf as orbf
+    rng = np.random.default_rng(0)
+    dev = torch.device("cuda")
+    for name, params, dim in (("bh3", [1.0, 0.0], 3), ("exp", [1.1, 0.7], 3), ("bh2", [1.0, 0.0], 2)):
+        aniso = random_anisotropy(dim, rng)
+        rbf = pb.make_rbf(name, params, dim, aniso)
+        ev = pb.make_fmm_evaluator(rbf, pb.Bbox(-np.ones(dim), np.ones(dim)))
+        b, m = 3, 50
+        pts = rng.uniform(-1, 1, (b, m, dim))
+        counts = np.array([50, 37, 1], dtype=np.int32)
+        out = torch.empty((b, m, m), dtype=torch.float64, device=dev)
+        ev.gram_batched(torch.from_numpy(pts).to(dev), torch.from_numpy(counts).to(dev), 0.25, out)
+        got = out.cpu().numpy()
+        o = orbf.make_rbf(name, params, dim, aniso)
+        for k in range(b):
+            c = counts[k]
+            ref = np.eye(m)
+            cols = np.stack([odir.full_direct(o, 0, pts[k, :c], pts[k, :c], np.eye(c)[:, j]) for j in range(c)], axis=1)
+            ref[:c, :c] = cols + 0.25 * np.eye(c)
+            assert np.max(np.abs(got[k] - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("n,degree", [(1500, 0), (6000, 0), (6000, 1)])
+def test_ras_fit_bh3(torch, n, degree):
+    """FGMRES + RAS on a bh3 cloud: 1 level (coarse grid only) and 2 levels (fine domains + coarse)."""
+    import polatory_b200 as pb
+    from polatory_b200.operator import Model, Operator, solve
+    from polatory_b200.ras import RasPreconditioner, level_structure
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-1, 1, (n, 3))
+    values = np.sin(np.pi * pts).sum(axis=1)
+    model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=degree, nugget=0.0)
+    op = Operator(model, pb.Bbox(-np.ones(3), np.ones(3)), accuracy=1e-8)
+    op.set_points(pts)
+    pc = RasPreconditioner(model, pts)
+    assert pc.n_levels == level_structure(n)[0] == (1 if n <= 2048 else 2)
+    tol = 1e-6
+    w, iters = solve(op, values, tol, 60, preconditioner=pc.apply)
+    assert iters <= (2 if pc.n_levels == 1 else 25), iters
+    # interpolation conditions against the EXACT operator (direct sums)
+    from oracle import direct as odir, rbf as orbf
+    from polatory_b200.operator import monomial_basis
+    o = orbf.make_rbf("bh3", [1.0, 0.0], 3, np.eye(3))
+    wv = w.cpu().numpy()
+    sub = rng.choice(n, 200, replace=False)
+    fit = odir.full_direct(o, 0, pts, pts[sub], wv[:n]) + monomial_basis(3, degree, pts[sub]) @ wv[n:]
+    assert np.max(np.abs(fit - values[sub])) <= 10 * tol
+    # orthogonality of the RBF weights to the polynomials (solver.hpp / ras orthogonalize)
+    assert np.max(np.abs(monomial_basis(3, degree, pts).T @ wv[:n])) <= 1e-6 * np.max(np.abs(wv[:n])) * n ** 0.5

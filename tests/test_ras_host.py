@@ -1,0 +1,74 @@
+"""CPU checks of the host-side logic of the RAS preconditioner (polatory_b200/ras.py): the level
+structure, the coarse-point choice and the domain decomposition restated from
+include/polatory/preconditioner/{ras_preconditioner,domain_divider,domain}.hpp."""
+import numpy as np
+
+from polatory_b200 import ras
+
+
+def test_std_mt19937_and_uniform_index():
+    g = ras._StdMt19937()
+    assert g() == 3499211612 and g() == 581869302  # std::mt19937 default seed, first two outputs
+    g = ras._StdMt19937()
+    # Lemire: (x * n) >> 32 when the low word is not below the threshold
+    assert g.uniform_index(1000) == (3499211612 * 1000) >> 32
+    assert all(0 <= ras._StdMt19937().uniform_index(n) < n for n in (1, 2, 7, 10 ** 6))
+
+
+def test_level_structure_matches_reference_formula():
+    # ras_preconditioner.hpp:70-75: 1M rows -> 4 levels; coarse sizes 10^(3.311 + k * 0.896)
+    n_levels, counts = ras.level_structure(1_000_000)
+    assert n_levels == 4
+    assert counts[0] == 2048 or counts[0] == 2047  # pow() truncation
+    assert 15_000 < counts[1] < 17_000 and 120_000 < counts[2] < 135_000
+    assert ras.level_structure(2048)[0] == 1 and ras.level_structure(2049)[0] == 2
+    assert ras.level_structure(30_000)[0] == 3
+
+
+def test_round_half_to_even():
+    assert [ras._round_half_to_even(x) for x in (0.5, 1.5, 2.5, 3.5, 2.4, 2.6)] == [0, 2, 2, 4, 2, 3]
+
+
+def test_divide_domains_invariants():
+    rng = np.random.default_rng(0)
+    n = 20_000
+    pts = rng.uniform(-1, 1, (n, 3))
+    poly = [17, 4242, 9001, 15000]
+    idcs = np.concatenate([poly, np.setdiff1d(np.arange(n), poly)])
+    doms = ras.divide_domains(pts, idcs, poly)
+    inner_count = np.zeros(n, dtype=int)
+    for d in doms:
+        assert len(d.point_indices) <= ras.K_MAX_LEAF_SIZE + len(poly)
+        assert list(d.point_indices[:len(poly)]) == poly                 # poly points first (domain.hpp:39-41)
+        rest = d.point_indices[len(poly):]
+        assert np.all(np.diff(rest) > 0)                                   # sorted, no duplicates
+        assert not set(rest) & set(poly)
+        assert len(np.unique(d.point_indices)) == len(d.point_indices)
+        inner_count[d.point_indices[d.inner_point]] += 1
+    assert np.all(inner_count == 1)                                        # every point is inner exactly once
+    # overlap: domains are larger than their inner sets
+    assert sum(len(d.point_indices) for d in doms) > 1.5 * n
+
+
+def test_choose_coarse_points():
+    rng = np.random.default_rng(1)
+    n = 5000
+    pts = rng.uniform(-1, 1, (n, 3))
+    poly = [3]
+    idcs = np.concatenate([poly, np.setdiff1d(np.arange(n), poly)])
+    c = ras.choose_coarse_points(pts, idcs, poly, 500)
+    assert c[0] == 3 and len(c) == 501 and len(np.unique(c)) == 501
+    # cluster centres spread over the cloud: every octant is represented
+    oct_ = ((pts[c[1:]] > 0) * [1, 2, 4]).sum(axis=1)
+    assert len(np.unique(oct_)) == 8
+
+
+def test_unisolvent_and_lagrange():
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-1, 1, (1000, 3))
+    assert ras.unisolvent_point_set(pts, 0, 3) == [(3499211612 * 1000) >> 32]  # degree 0: the first draw
+    idx = ras.unisolvent_point_set(pts, 1, 3)
+    assert len(idx) == 4 and idx == sorted(idx)
+    lag = ras.lagrange_basis_matrix(pts, idx, 1, 3)
+    np.testing.assert_allclose(lag[idx], np.eye(4), atol=1e-10)   # cardinal at the poly points
+    np.testing.assert_allclose(lag.sum(axis=1), 1.0, atol=1e-10)  # partition of unity (degree >= 0)
