@@ -201,6 +201,28 @@ int plt_fgmres_status(plt_fgmres* h, int* iteration_count, double* absolute_resi
 int64_t plt_fgmres_launch_count(plt_fgmres* h);
 const char* plt_fgmres_last_error(plt_fgmres* h);
 
+/* ---------------------------------------------------------------------------------------
+ * Host-side index bookkeeping of the RAS preconditioner (no device work, multi-threaded):
+ *   DomainDivider::choose_coarse_points   include/polatory/preconditioner/domain_divider.hpp:52-123
+ *   DomainDivider::divide_domains + Domain::merge_poly_points
+ *                                         include/polatory/preconditioner/domain_divider.hpp:171-286, domain.hpp:33-51
+ * for value points.  a_points: HOST row-major [*][dim] anisotropy-transformed coordinates, addressed by the
+ * global indices in idcs / poly.
+ * ------------------------------------------------------------------------------------- */
+/* out: n_poly + n_coarse global indices (the poly points first, then the cluster centres). */
+int plt_ras_choose_coarse_points(const double* a_points, int dim, const int64_t* idcs, int64_t n_idcs,
+                                 const int64_t* poly, int64_t n_poly, int64_t n_coarse, int64_t* out);
+typedef struct plt_ras_domains plt_ras_domains;
+/* Recursive bisection into overlapping domains of at most max_leaf points (+ the poly points, which are
+ * put first in every domain); reference constants: max_leaf 1024, overlap_quota 0.5. */
+int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs, int64_t n_idcs, const int64_t* poly,
+                           int64_t n_poly, int64_t max_leaf, double overlap_quota, plt_ras_domains** out);
+int64_t plt_ras_domains_count(plt_ras_domains* h);
+int64_t plt_ras_domains_total(plt_ras_domains* h);
+/* offsets: count + 1 entries; indices / inner: total entries (inner = 1 where the domain owns the point). */
+int plt_ras_domains_get(plt_ras_domains* h, int64_t* offsets, int64_t* indices, uint8_t* inner);
+void plt_ras_domains_destroy(plt_ras_domains* h);
+
 /* Library/ABI version and a device probe (returns PLT_ERR_CUDA without a usable GPU). */
 int plt_version(void);
 int plt_device_check(void);

@@ -60,6 +60,14 @@ SYMBOLS = [
     ("plt_fgmres_status", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), _c_double_p, _c_double_p]),
     ("plt_fgmres_launch_count", ctypes.c_int64, [_vp]),
     ("plt_fgmres_last_error", ctypes.c_char_p, [_vp]),
+    ("plt_ras_choose_coarse_points", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64, _vp, ctypes.c_int64,
+                                                    ctypes.c_int64, _vp]),
+    ("plt_ras_divide_domains", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64, _vp, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_double, ctypes.POINTER(_vp)]),
+    ("plt_ras_domains_count", ctypes.c_int64, [_vp]),
+    ("plt_ras_domains_total", ctypes.c_int64, [_vp]),
+    ("plt_ras_domains_get", ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    ("plt_ras_domains_destroy", None, [_vp]),
     ("plt_version", ctypes.c_int, []),
     ("plt_device_check", ctypes.c_int, []),
 ]

@@ -117,7 +117,32 @@ class Domain:
 
 
 def divide_domains(a_points, point_idcs, poly_idcs):
-    """DomainDivider::divide_domains + Domain::merge_poly_points for value points only."""
+    """DomainDivider::divide_domains + Domain::merge_poly_points for value points only: the native
+    multi-threaded implementation of the C ABI (csrc/ras_host.cu)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    a = np.ascontiguousarray(a_points, dtype=np.float64)
+    idcs = np.ascontiguousarray(point_idcs, dtype=np.int64)
+    poly = np.ascontiguousarray(poly_idcs, dtype=np.int64)
+    h = ctypes.c_void_p()
+    st = lib.plt_ras_divide_domains(a.ctypes.data, a.shape[1], idcs.ctypes.data, len(idcs), poly.ctypes.data, len(poly),
+                                    K_MAX_LEAF_SIZE, K_OVERLAP_QUOTA, ctypes.byref(h))
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_ras_divide_domains failed")
+    try:
+        n, total = lib.plt_ras_domains_count(h), lib.plt_ras_domains_total(h)
+        off = np.empty(n + 1, dtype=np.int64)
+        ind = np.empty(total, dtype=np.int64)
+        inner = np.empty(total, dtype=np.uint8)
+        lib.plt_ras_domains_get(h, off.ctypes.data, ind.ctypes.data, inner.ctypes.data)
+    finally:
+        lib.plt_ras_domains_destroy(h)
+    return [Domain(ind[off[i]:off[i + 1]], inner[off[i]:off[i + 1]].astype(bool)) for i in range(n)]
+
+
+def divide_domains_numpy(a_points, point_idcs, poly_idcs):
+    """numpy restatement of the same algorithm (cross-check of the native one in the CPU tests)."""
     point_idcs = np.asarray(point_idcs, dtype=np.int64)
     queue = [Domain(point_idcs, np.ones(len(point_idcs), dtype=bool))]
     leaves = []
@@ -159,7 +184,22 @@ def divide_domains(a_points, point_idcs, poly_idcs):
 def choose_coarse_points(a_points, point_idcs, poly_idcs, n_coarse_points):
     """DomainDivider::choose_coarse_points (domain_divider.hpp:52-123): split the bounding-box
     clusters breadth-first (largest box first within a level) until there are n_coarse_points of
-    them; the point nearest to each box centre is kept."""
+    them; the point nearest to each box centre is kept.  Native implementation (csrc/ras_host.cu)."""
+    from . import _lib
+    lib = _lib.load()
+    a = np.ascontiguousarray(a_points, dtype=np.float64)
+    idcs = np.ascontiguousarray(point_idcs, dtype=np.int64)
+    poly = np.ascontiguousarray(poly_idcs, dtype=np.int64)
+    out = np.empty(len(poly) + int(n_coarse_points), dtype=np.int64)
+    st = lib.plt_ras_choose_coarse_points(a.ctypes.data, a.shape[1], idcs.ctypes.data, len(idcs), poly.ctypes.data,
+                                          len(poly), int(n_coarse_points), out.ctypes.data)
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_ras_choose_coarse_points failed")
+    return out
+
+
+def choose_coarse_points_numpy(a_points, point_idcs, poly_idcs, n_coarse_points):
+    """numpy / heapq restatement of the reference's priority-queue walk (cross-check in the CPU tests)."""
     poly_set = set(int(i) for i in poly_idcs)
     root = np.array([i for i in point_idcs if int(i) not in poly_set], dtype=np.int64)
 
@@ -341,12 +381,23 @@ class RasPreconditioner:
         aniso = np.asarray(rbf.anisotropy(), dtype=np.float64)
         a_points = self.points @ aniso.T if not np.allclose(aniso, np.eye(self.dim)) else self.points
         self.fine = [None] * n_levels
+        import time
+        self.setup_seconds = {"coarse_points": 0.0, "divide_domains": 0.0, "factorize": 0.0}
         for level in range(n_levels - 1, 0, -1):
+            t0 = time.perf_counter()
             point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
+            t1 = time.perf_counter()
             domains = divide_domains(a_points, point_idcs[level], poly_idcs)
+            t2 = time.perf_counter()
             self.fine[level] = _FineLevel(self, domains)
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            self.setup_seconds["coarse_points"] += t1 - t0
+            self.setup_seconds["divide_domains"] += t2 - t1
+            self.setup_seconds["factorize"] += t3 - t2
             if verbose:
-                print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points", flush=True)
+                print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points "
+                      f"(coarse points {t1 - t0:.2f}s, domains {t2 - t1:.2f}s, factorisation {t3 - t2:.2f}s)", flush=True)
         self.point_idcs = point_idcs
         self.idx_dev = [torch.from_numpy(np.asarray(p, dtype=np.int64)).to(self.device) for p in point_idcs]
         self.coarse = _CoarseGrid(self, point_idcs[0])

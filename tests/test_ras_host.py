@@ -72,3 +72,24 @@ def test_unisolvent_and_lagrange():
     lag = ras.lagrange_basis_matrix(pts, idx, 1, 3)
     np.testing.assert_allclose(lag[idx], np.eye(4), atol=1e-10)   # cardinal at the poly points
     np.testing.assert_allclose(lag.sum(axis=1), 1.0, atol=1e-10)  # partition of unity (degree >= 0)
+
+
+def test_native_matches_numpy_restatement():
+    rng = np.random.default_rng(3)
+    n = 30_000
+    pts = rng.uniform(-1, 1, (n, 3)) * [3.0, 1.0, 0.5]
+    poly = [5, 777, 12345, 20000]
+    idcs = np.concatenate([poly, np.setdiff1d(np.arange(n), poly)])
+    a = ras.divide_domains(pts, idcs, poly)
+    b = ras.divide_domains_numpy(pts, idcs, poly)
+    key = lambda d: (tuple(d.point_indices[:8]), len(d.point_indices))
+    a, b = sorted(a, key=key), sorted(b, key=key)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x.point_indices, y.point_indices)
+        np.testing.assert_array_equal(x.inner_point, y.inner_point)
+    for target in (64, 1000, 3001):
+        ca = ras.choose_coarse_points(pts, idcs, poly, target)
+        cb = ras.choose_coarse_points_numpy(pts, idcs, poly, target)
+        assert list(ca[:4]) == poly and len(ca) == len(cb) == target + 4
+        assert set(ca.tolist()) == set(cb.tolist())
