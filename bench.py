@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
-    ap.add_argument("--no-fit", action="store_true", help="skip the auxiliary config #2 FGMRES-iteration timing")
+    ap.add_argument("--no-fit", action="store_true", help="skip the auxiliary config #2 fit (FGMRES + RAS) timing")
     ap.add_argument("--cpu-sample-layers", type=int, default=216,
                     help="x-layers of the target grid (central slab) the CPU arm evaluates per step "
                          "(default: all of them, ~10 s of CPU work on 16 cores)")
@@ -316,7 +316,7 @@ def main():
     }
 
     if world == 1 and not args.no_fit:
-        line["fit"] = fit_iteration_timing(src, dev)
+        line["fit"] = fit_timing(src, dev)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub, height, desc = cpu_sample(args, src, w, trg, lo, hi)
@@ -338,40 +338,53 @@ def main():
         dist.destroy_process_group()
 
 
-def fit_iteration_timing(points, dev, iters=12):
-    """Auxiliary figure for the second half of BASELINE.json's metric (the 1M-point fit): device time
-    of one FGMRES iteration (FMM matvec at accuracy 0 -> order 12 / d 8, Arnoldi, Givens) on the
-    config #2 centres.  The RAS preconditioner is not built, so this is a
-    per-iteration cost, not a fit wall-time."""
+def fit_timing(points, dev, tol=1e-4):
+    """Second half of BASELINE.json's metric: wall-time of the 1M-point fit (config #2: bh3 SDF centres,
+    degree 0, absolute tolerance 1e-4, evaluator accuracy tol / 100), end to end from host arrays:
+    operator set-up (tree, plan, accuracy search), RAS set-up (coarse points, domains, batched
+    factorisations), FGMRES iterations with the FMM matvec and the RAS preconditioner.  Convergence is
+    the max-norm of the true residual through the FMM operator; a sample is re-checked against exact
+    sums by tests/test_gpu_ras.py and tools/dev_fit.py."""
     import torch
     import polatory_b200 as pb
-    from polatory_b200.krylov import Fgmres
-    from polatory_b200.operator import Model, Operator
+    from polatory_b200.operator import Model, Operator, solve
+    from polatory_b200.ras import RasPreconditioner
     n = len(points)
-    model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.0)
-    op = Operator(model, pb.Bbox(points.min(axis=0), points.max(axis=0)), accuracy=0.0)
-    op.set_points(points)
-    rhs = torch.zeros(op.size(), dtype=torch.float64, device=dev)
     third = (n + 2) // 3
-    rhs[third:2 * third] = 1e-2   # SDF offsets (+d, -d) as the right-hand side
-    rhs[2 * third:n] = -1e-2
-    solver = Fgmres(op, rhs, iters + 3)
-    solver.setup()
-    for _ in range(3):
-        solver.iterate_process()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    values = np.concatenate([np.zeros(third), np.full(third, 1e-2), np.full(n - 2 * third, -1e-2)])
+    model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.0)
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(iters):
-        solver.iterate_process()
-    e1.record()
+    t0 = time.perf_counter()
+    op = Operator(model, pb.Bbox(points.min(axis=0), points.max(axis=0)), accuracy=tol / 100.0)
+    op.set_points(points)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    t1 = time.perf_counter()
+    pc = RasPreconditioner(model, points)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    w, iters = solve(op, values, tol, 100, preconditioner=pc.apply)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    # steady-state cost of the two operators of an iteration
+    x = torch.cat([torch.from_numpy(values).to(dev), torch.zeros(1, dtype=torch.float64, device=dev)])
+    y = torch.empty_like(x)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    op.apply(w, y)
+    pc.apply(x, y)
+    e[0].record()
+    op.apply(w, y)
+    e[1].record()
+    pc.apply(x, y)
+    e[2].record()
+    torch.cuda.synchronize()
     ph = op.a[0].phase_times()
-    return {"workload": f"config #2 matvec inside FGMRES: {n} bh3 centres, degree 0, accuracy 0",
-            "config": op.a[0].config(), "fgmres_ms_per_iteration": ms, "matvec_ms": float(sum(ph.values())),
-            "iterations_timed": iters, "krylov_dim_at_end": solver.iteration_count(),
-            "preconditioner": "none (RAS not built): per-iteration cost only",
+    return {"workload": f"config #2 fit: {n} bh3 centres (sphere surface + normal offsets, values 0 / +-1e-2), degree 0, "
+                        f"tolerance {tol} absolute, FGMRES + RAS",
+            "wall_s": t3 - t0, "operator_setup_s": t1 - t0, "ras_setup_s": t2 - t1, "solve_s": t3 - t2,
+            "ras_setup_breakdown_s": {k: round(v, 3) for k, v in pc.setup_seconds.items()},
+            "iterations": iters, "levels": pc.n_levels, "domains": [f.n_dom if f else 1 for f in pc.fine],
+            "matvec_config": op.a[0].config(), "matvec_ms": e[0].elapsed_time(e[1]),
+            "ras_apply_ms": e[1].elapsed_time(e[2]),
             "matvec_phases_ms": {k: round(v, 4) for k, v in ph.items()}}
 
 
