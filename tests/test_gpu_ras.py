@@ -68,3 +68,31 @@ def test_ras_fit_bh3(torch, n, degree):
     assert np.max(np.abs(fit - values[sub])) <= 10 * tol
     # orthogonality of the RBF weights to the polynomials (solver.hpp / ras orthogonalize)
     assert np.max(np.abs(monomial_basis(3, degree, pts).T @ wv[:n])) <= 1e-6 * np.max(np.abs(wv[:n])) * n ** 0.5
+
+
+@pytest.mark.parametrize("name,params,dim,degree", [("exp", [1.0, 0.3], 3, 0), ("th3", [1.0, 0.0], 3, 1),
+                                                     ("bh2", [1.0, 0.0], 2, 1)])
+def test_ras_fit_other_kernels(torch, name, params, dim, degree):
+    """Two-level RAS + FGMRES for a covariance kernel, a cpd-order-2 kernel with linear polynomial and the
+    2-D path; acceptance as above (interpolation conditions against exact sums)."""
+    import polatory_b200 as pb
+    from oracle import direct as odir, rbf as orbf
+    from polatory_b200.operator import Model, Operator, monomial_basis, solve
+    from polatory_b200.ras import RasPreconditioner
+    rng = np.random.default_rng(21)
+    n = 5000
+    pts = rng.uniform(-1, 1, (n, dim))
+    values = np.sin(np.pi * pts).sum(axis=1)
+    model = Model(pb.make_rbf(name, params, dim), poly_degree=degree, nugget=0.0)
+    op = Operator(model, pb.Bbox(-np.ones(dim), np.ones(dim)), accuracy=1e-9)
+    op.set_points(pts)
+    pc = RasPreconditioner(model, pts)
+    assert pc.n_levels == 2
+    tol = 1e-6
+    w, iters = solve(op, values, tol, 80, preconditioner=pc.apply)
+    assert iters <= 40, iters
+    o = orbf.make_rbf(name, params, dim, np.eye(dim))
+    wv = w.cpu().numpy()
+    sub = rng.choice(n, 200, replace=False)
+    fit = odir.full_direct(o, 0, pts, pts[sub], wv[:n]) + monomial_basis(dim, degree, pts[sub]) @ wv[n:]
+    assert np.max(np.abs(fit - values[sub])) <= 10 * tol
