@@ -22,7 +22,6 @@ reference's `Evaluator` default) whose trees / plans / operators stay resident b
 """
 from __future__ import annotations
 
-import heapq
 import math
 
 import numpy as np
@@ -141,46 +140,6 @@ def divide_domains(a_points, point_idcs, poly_idcs):
     return [Domain(ind[off[i]:off[i + 1]], inner[off[i]:off[i + 1]].astype(bool)) for i in range(n)]
 
 
-def divide_domains_numpy(a_points, point_idcs, poly_idcs):
-    """numpy restatement of the same algorithm (cross-check of the native one in the CPU tests)."""
-    point_idcs = np.asarray(point_idcs, dtype=np.int64)
-    queue = [Domain(point_idcs, np.ones(len(point_idcs), dtype=bool))]
-    leaves = []
-    head = 0
-    while head < len(queue):
-        d = queue[head]
-        head += 1
-        n = len(d.point_indices)
-        if n <= K_MAX_LEAF_SIZE:
-            leaves.append(d)
-            continue
-        order = _sort_by_axes(a_points[d.point_indices])
-        idx, inner = d.point_indices[order], d.inner_point[order]
-        q = K_OVERLAP_QUOTA * K_MAX_LEAF_SIZE / n
-        n_sub = int(_round_half_to_even((1.0 + q) / 2.0 * n))
-        left_part, right_part = n - n_sub, n_sub
-        mid = int(_round_half_to_even((left_part + right_part) / 2.0))
-        pos = np.arange(n)
-        queue.append(Domain(idx[:right_part], inner[:right_part] & (pos[:right_part] < mid)))
-        queue.append(Domain(idx[left_part:], inner[left_part:] & (pos[left_part:] >= mid)))
-        queue[head - 1] = None
-    poly = np.asarray(poly_idcs, dtype=np.int64)
-    for d in leaves:  # merge_poly_points (domain.hpp:33-51)
-        order = np.argsort(d.point_indices, kind="stable")
-        idx, inner = d.point_indices[order], d.inner_point[order]
-        if len(poly):
-            pos = np.searchsorted(idx, poly)
-            present = (pos < len(idx)) & (idx[np.minimum(pos, len(idx) - 1)] == poly)
-            front_inner = np.zeros(len(poly), dtype=bool)
-            front_inner[present] = inner[pos[present]]
-            keep = np.ones(len(idx), dtype=bool)
-            keep[pos[present]] = False
-            idx = np.concatenate([poly, idx[keep]])
-            inner = np.concatenate([front_inner, inner[keep]])
-        d.point_indices, d.inner_point = idx, inner
-    return leaves
-
-
 def choose_coarse_points(a_points, point_idcs, poly_idcs, n_coarse_points):
     """DomainDivider::choose_coarse_points (domain_divider.hpp:52-123): split the bounding-box
     clusters breadth-first (largest box first within a level) until there are n_coarse_points of
@@ -196,44 +155,6 @@ def choose_coarse_points(a_points, point_idcs, poly_idcs, n_coarse_points):
     if st != _lib.PLT_OK:
         raise RuntimeError("plt_ras_choose_coarse_points failed")
     return out
-
-
-def choose_coarse_points_numpy(a_points, point_idcs, poly_idcs, n_coarse_points):
-    """numpy / heapq restatement of the reference's priority-queue walk (cross-check in the CPU tests)."""
-    poly_set = set(int(i) for i in poly_idcs)
-    root = np.array([i for i in point_idcs if int(i) not in poly_set], dtype=np.int64)
-
-    def init(idx):
-        pts = a_points[idx]
-        lo, hi = pts.min(axis=0), pts.max(axis=0)
-        centre = 0.5 * (lo + hi)
-        c = int(idx[np.argmin(((pts - centre) ** 2).sum(axis=1))])  # first minimum, as std::min_element
-        return float(np.prod(hi - lo)), c, idx[_sort_by_axes(pts)]
-
-    counter = 0
-    vol, c, sorted_idx = init(root)
-    heap = [(0, -vol, counter, c, sorted_idx)]
-    while len(heap) < n_coarse_points:
-        level, _, _, _, idx = heapq.heappop(heap)
-        size = len(idx)
-        if size % 2 == 0:
-            mid = size // 2
-        else:  # tie between (size-1)/2 and (size+1)/2: the even index wins (domain_divider.hpp:83-88)
-            a = (size - 1) // 2
-            mid = a if a % 2 == 0 else a + 1
-            if size == 1:
-                mid = 0
-        for part in (idx[:mid], idx[mid:]):
-            if len(part):
-                counter += 1
-                vol, c, s = init(part)
-                heapq.heappush(heap, (level + 1, -vol, counter, c, s))
-        if size == 1 and len(heap) >= len(root):
-            break
-    centres = []
-    while heap:
-        centres.append(heapq.heappop(heap)[3])
-    return np.concatenate([np.asarray(poly_idcs, dtype=np.int64), np.asarray(centres, dtype=np.int64)])
 
 
 def level_structure(n_rows):
@@ -350,8 +271,12 @@ class _CoarseGrid:
 class RasPreconditioner:
     """preconditioner::RasPreconditioner for value data; `apply(v, out)` on CUDA tensors."""
 
-    def __init__(self, model, points, device=None, verbose=False):
+    def __init__(self, model, points, device=None, verbose=False, transfer_config=None):
+        """transfer_config: optional (order, d) forced on the level-transfer evaluators (default: the
+        reference's accuracy = infinity, i.e. order 6) -- used by the parity tests to separate the FMM
+        discretisation error of the transfers from everything else."""
         import torch
+        self.transfer_config = transfer_config
         self.torch = torch
         self.model = model
         self.dim = model.dim
@@ -414,6 +339,8 @@ class RasPreconditioner:
                     p[:, j] -= (p[:, i] @ p[:, j]) * p[:, i]
             self.p = torch.from_numpy(p).to(self.device)
             ev = fmm.make_fmm_symmetric_evaluator(rbf, self.bbox)
+            if transfer_config:
+                ev.force_config(*transfer_config)
             ev.set_points(self.points_dev)
             self.ap = torch.empty_like(self.p)
             col = torch.empty(mu, dtype=torch.float64, device=self.device)
@@ -437,6 +364,8 @@ class RasPreconditioner:
         key = (src_level, trg_level)
         if key not in self._evaluators:
             ev = fmm.make_fmm_evaluator(self.model.rbfs[0], self.bbox)
+            if self.transfer_config:
+                ev.force_config(*self.transfer_config)
             ev.set_source_points(self.points_dev[self.idx_dev[src_level]].contiguous())
             ev.set_target_points(self.points_dev[self.idx_dev[trg_level]].contiguous())
             out = self.torch.empty(len(self.point_idcs[trg_level]), dtype=self.torch.float64, device=self.device)

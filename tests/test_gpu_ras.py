@@ -96,3 +96,63 @@ def test_ras_fit_other_kernels(torch, name, params, dim, degree):
     sub = rng.choice(n, 200, replace=False)
     fit = odir.full_direct(o, 0, pts, pts[sub], wv[:n]) + monomial_basis(dim, degree, pts[sub]) @ wv[n:]
     assert np.max(np.abs(fit - values[sub])) <= 10 * tol
+
+
+@pytest.mark.parametrize("degree", [1])
+def test_ras_iteration_parity_with_oracle(torch, degree):
+    """The device RAS + FGMRES against the dense numpy restatement (oracle/ras.py + oracle/krylov.py) on the same
+    3-level problem: same level sizes, one application agrees to 1e-6 relative (FMM level transfers at order 6
+    vs exact sums), FGMRES iteration counts within +-1 (north_star's Krylov criterion)."""
+    import polatory_b200 as pb
+    from oracle import direct as odir, rbf as orbf
+    from oracle.krylov import Fgmres as OracleFgmres
+    from oracle.ras import RasOracle, monomials
+    from polatory_b200.operator import Model, Operator, solve
+    from polatory_b200.ras import RasPreconditioner
+    rng = np.random.default_rng(33)
+    n, dim = 20_600, 3
+    pts = rng.uniform(-1, 1, (n, dim))
+    values = np.sin(np.pi * pts).sum(axis=1)
+    model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=degree, nugget=0.0)
+    op = Operator(model, pb.Bbox(-np.ones(dim), np.ones(dim)), accuracy=1e-9)
+    op.set_points(pts)
+    pc = RasPreconditioner(model, pts)
+    assert pc.n_levels == 3
+
+    def kernel(x, y):  # bh3, s = 1, c = 0 (polyharmonic_odd.hpp:32-45), row-chunked exact differences
+        out = np.empty((len(x), len(y)))
+        for i0 in range(0, len(x), 512):
+            d = x[i0:i0 + 512, None, :] - y[None, :, :]
+            out[i0:i0 + 512] = -np.sqrt((d * d).sum(axis=2))
+        return out
+
+    a_dense = kernel(pts, pts)
+    o = RasOracle(a_dense, pts, dim, degree, 0.0, pc.poly_idcs)
+    assert [len(p) for p in o.point_idcs] == [len(p) for p in pc.point_idcs]
+    for lvl in range(pc.n_levels):
+        assert set(o.point_idcs[lvl].tolist()) == set(np.asarray(pc.point_idcs[lvl]).tolist())
+    l = pc.l
+    v = np.concatenate([values, np.zeros(l)])
+    ref = o(v)
+    got = pc(torch.from_numpy(v).cuda()).cpu().numpy()
+    # order-6 level transfers (the reference's default) carry the FMM discretisation error of that order ...
+    assert np.max(np.abs(got - ref)) <= 5e-3 * np.max(np.abs(ref))
+    # ... with order-12 transfers the device sweep reproduces the dense restatement
+    pc12 = RasPreconditioner(model, pts, transfer_config=(12, 8))
+    got12 = pc12(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert np.max(np.abs(got12 - ref)) <= 1e-6 * np.max(np.abs(ref))
+    del pc12
+    tol = 1e-6
+    w, iters = solve(op, values, tol, 60, preconditioner=pc.apply)
+    p = monomials(dim, degree, pts)
+    full = np.block([[a_dense, p], [p.T, np.zeros((l, l))]])
+    s = OracleFgmres(lambda x: full @ x, v, 60)
+    s.set_right_preconditioner(o)
+    s.setup()
+    while True:
+        x = s.solution_vector()
+        if s.absolute_residual() <= tol * np.sqrt(len(v)) and np.max(np.abs((full @ x)[:n] - values)) <= tol:
+            break
+        s.iterate_process()
+    assert abs(iters - s.iteration_count()) <= 1, (iters, s.iteration_count())
+    assert np.max(np.abs(w.cpu().numpy() - x)) <= 1e-3 * np.max(np.abs(x))

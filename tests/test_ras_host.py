@@ -74,14 +74,15 @@ def test_unisolvent_and_lagrange():
     np.testing.assert_allclose(lag.sum(axis=1), 1.0, atol=1e-10)  # partition of unity (degree >= 0)
 
 
-def test_native_matches_numpy_restatement():
+def test_native_matches_oracle_restatement():
     rng = np.random.default_rng(3)
     n = 30_000
     pts = rng.uniform(-1, 1, (n, 3)) * [3.0, 1.0, 0.5]
     poly = [5, 777, 12345, 20000]
     idcs = np.concatenate([poly, np.setdiff1d(np.arange(n), poly)])
+    from oracle import ras as oras
     a = ras.divide_domains(pts, idcs, poly)
-    b = ras.divide_domains_numpy(pts, idcs, poly)
+    b = oras.divide_domains(pts, idcs, poly)
     key = lambda d: (tuple(d.point_indices[:8]), len(d.point_indices))
     a, b = sorted(a, key=key), sorted(b, key=key)
     assert len(a) == len(b)
@@ -90,6 +91,33 @@ def test_native_matches_numpy_restatement():
         np.testing.assert_array_equal(x.inner_point, y.inner_point)
     for target in (64, 1000, 3001):
         ca = ras.choose_coarse_points(pts, idcs, poly, target)
-        cb = ras.choose_coarse_points_numpy(pts, idcs, poly, target)
+        cb = oras.choose_coarse_points(pts, idcs, poly, target)
         assert list(ca[:4]) == poly and len(ca) == len(cb) == target + 4
         assert set(ca.tolist()) == set(cb.tolist())
+
+
+def test_oracle_ras_preconditions_dense_system():
+    """oracle/ras.py + oracle/krylov.py on a 2-level bh3 problem with linear polynomial: right-preconditioned
+    FGMRES reaches 1e-8 in a handful of iterations and the weights are orthogonal to the polynomials."""
+    from oracle.krylov import Fgmres
+    from oracle.ras import RasOracle, monomials
+    rng = np.random.default_rng(1)
+    n = 3000
+    pts = rng.uniform(-1, 1, (n, 3))
+    a = -np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(axis=2))
+    o = RasOracle(a, pts, 3, 1, 0.0, [5, 100, 900, 2000])
+    assert o.n_levels == 2 and len(o.point_idcs[0]) in (2047 + 4, 2048 + 4)  # pow() truncation
+    p = monomials(3, 1, pts)
+    full = np.block([[a, p], [p.T, np.zeros((4, 4))]])
+    v = np.concatenate([np.sin(np.pi * pts).sum(axis=1), np.zeros(4)])
+    s = Fgmres(lambda x: full @ x, v, 30)
+    s.set_right_preconditioner(o)
+    s.setup()
+    for _ in range(8):
+        s.iterate_process()
+        if s.relative_residual() < 1e-8:
+            break
+    assert s.relative_residual() < 1e-8
+    x = s.solution_vector()
+    assert np.linalg.norm(full @ x - v) <= 1e-7 * np.linalg.norm(v)
+    assert np.max(np.abs(p.T @ x[:n])) <= 1e-8 * np.max(np.abs(x[:n])) * n
