@@ -115,6 +115,11 @@ int plt_eval_evaluate(plt_eval* h, double* out, int64_t len);
  * unless tree_height_override > 0. */
 int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_override);
 
+/* Always evaluate by exact direct summation (the brute-force branch of src/fmm/fmm_evaluator.hpp:226-234
+ * regardless of the problem size): what interpolation::DirectEvaluator does for the <= 1024 sampled targets
+ * of ResidualEvaluator (include/polatory/interpolation/residual_evaluator.hpp:55-88). */
+int plt_eval_force_direct(plt_eval* h, int on);
+
 /* The configuration used by the last evaluate() (tree_height 0 = brute force). */
 int plt_eval_get_config(plt_eval* h, plt_config* out);
 

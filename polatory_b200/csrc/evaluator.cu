@@ -169,6 +169,7 @@ struct plt_eval {
   Box box;
   double accuracy = std::numeric_limits<double>::infinity();
   int force_order = 0, force_d = kClassic, force_height = 0;
+  bool force_direct = false;  // always take the brute-force branch (exact sums: the fit's residual sample)
   cudaStream_t stream = nullptr;
   LaunchCounter ctr;
   std::string err;
@@ -774,7 +775,8 @@ struct plt_eval {
     const bool compact = std::isfinite(rbf.support_radius);
     const int64_t nt = targets();
     const bool small = symmetric ? n_src < 1024 : n_src * nt < int64_t{1024} * 1024;
-    return (small && !compact && force_height == 0) || (compact && compact_height() <= 2 && shard_world == 1);
+    return force_direct || (small && !compact && force_height == 0) ||
+           (compact && compact_height() <= 2 && shard_world == 1);
   }
 
   // Builds the source / target trees of the FMM (or compact) branch if they are not current.
@@ -864,7 +866,8 @@ struct plt_eval {
     const bool compact = std::isfinite(rbf.support_radius);
     // src/fmm/fmm_evaluator.hpp:226-234 / fmm_symmetric_evaluator.hpp:222-230
     const bool small = symmetric ? n_src < 1024 : n_src * nt < int64_t{1024} * 1024;
-    if ((small && !compact && force_height == 0) || (compact && compact_height() <= 2 && shard_world == 1)) {
+    if (force_direct || (small && !compact && force_height == 0) ||
+        (compact && compact_height() <= 2 && shard_world == 1)) {
       if (shard_world > 1) {
         // brute force is not sharded: rank 0 computes it, other ranks contribute zeros
         if (shard_rank != 0) {
@@ -1027,6 +1030,13 @@ int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_overrid
     if (h->direct_part) {
       apply(h->fast_part.get());
     }
+  });
+}
+
+int plt_eval_force_direct(plt_eval* h, int on) {
+  return guarded(h, [&] {
+    h->force_direct = on != 0;
+    if (h->direct_part) h->direct_part->force_direct = h->fast_part->force_direct = on != 0;
   });
 }
 

@@ -116,6 +116,10 @@ class _EvaluatorBase:
     def force_config(self, order, d=kClassic, tree_height=0):
         _lib.check(self._h, self._lib.plt_eval_force_config(self._h, int(order), int(d), int(tree_height)))
 
+    def force_direct(self, on=True):
+        """Exact direct summation whatever the size (the residual sample of the fit)."""
+        _lib.check(self._h, self._lib.plt_eval_force_direct(self._h, int(bool(on))))
+
     def config(self):
         c = _lib.PltConfig()
         _lib.check(self._h, self._lib.plt_eval_get_config(self._h, ctypes.byref(c)))

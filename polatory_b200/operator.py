@@ -261,12 +261,68 @@ class Operator:
         return y
 
 
+class ResidualEvaluator:
+    """interpolation::ResidualEvaluator for value data (include/polatory/interpolation/residual_evaluator.hpp:26-164):
+    the residual |fit - value| is first measured EXACTLY (direct sums on the device) on at most 1024 sampled points
+    with non-zero values, and only when that passes on all points through the fast operator.  The sample is a
+    deterministic shuffle followed by a stable partition on `value != 0`; the reference's std::shuffle sequence is
+    not reproduced (different, equally arbitrary 1024 points)."""
+
+    K_DIRECT_TARGETS = 1024
+
+    def __init__(self, op):
+        self.op = op
+        self._direct = []
+
+    def set_values(self, values):
+        import torch
+        op = self.op
+        self.values = values
+        host = values.detach().cpu().numpy()
+        perm = np.random.RandomState(5489).permutation(op.mu)
+        perm = np.concatenate([perm[host[perm] != 0.0], perm[host[perm] == 0.0]])
+        self.idx = np.sort(perm[:min(op.mu, self.K_DIRECT_TARGETS)])
+        self.idx_dev = torch.from_numpy(self.idx).to(op.device)
+        self.exact = len(self.idx) == op.mu
+        pts = op._points
+        self._direct = []
+        for rbf in op.model.rbfs:
+            ev = fmm.make_fmm_evaluator(rbf, fmm.Bbox.from_points(pts))
+            ev.force_direct(True)
+            ev.set_source_points(pts)
+            ev.set_target_points(np.ascontiguousarray(pts[self.idx]))
+            self._direct.append(ev)
+        self._fit = torch.empty(len(self.idx), dtype=torch.float64, device=op.device)
+        self._full = torch.empty(op.size(), dtype=torch.float64, device=op.device)
+
+    def converged(self, weights, tolerance):
+        """(converged, residual, exact) as residual_evaluator.hpp:55-108."""
+        op = self.op
+        mu = op.mu
+        fit = op.model.nugget * weights[self.idx_dev]
+        for ev in self._direct:
+            ev.set_weights(weights[:mu].contiguous())
+            ev.evaluate(self._fit)
+            fit = fit + self._fit
+        if op.l:
+            fit = fit + op.p[self.idx_dev] @ weights[mu:]
+        residual = float((fit - self.values[self.idx_dev]).abs().max())
+        if residual > tolerance:
+            return False, residual, self.exact
+        if self.exact:
+            return True, residual, True
+        op.apply(weights, self._full)
+        residual = float((self._full[:mu] - self.values).abs().max())
+        return residual <= tolerance, residual, True
+
+
 def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=None):
     """The loop of interpolation::Solver::solve (solver.hpp:99-139) on the device: FGMRES with an
     optional right preconditioner over `op`; `values` is this rank's shard of the right-hand side
-    (without the `l` zeros, which are appended here).  Convergence: max-norm of the true residual
-    <= tolerance, checked with one extra matvec once the solver's own 2-norm estimate allows it
-    (the reference's sampled ResidualEvaluator, SURVEY.md 8f-4, is not built).
+    (without the `l` zeros, which are appended here).  Convergence on one GPU with value data: the
+    reference's ResidualEvaluator (exact residual on <= 1024 sampled points, then on all points through
+    the fast operator); sharded or with gradient data: max-norm of the true residual through the
+    operator once the solver's own 2-norm estimate allows it.
     Returns (weights shard, iteration count)."""
     import torch
     from .krylov import Fgmres
@@ -283,6 +339,17 @@ def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=
     weights = solver.solution_vector()
     if solver.relative_residual() == 0.0:
         return weights, 0
+    if op.group is None and op.sigma == 0:
+        # the reference's convergence test: exact residual on a sample first, then everywhere (solver.hpp:112-135)
+        res_eval = ResidualEvaluator(op)
+        res_eval.set_values(values)
+        while True:
+            weights = solver.solution_vector()
+            if res_eval.converged(weights, tolerance)[0]:
+                return weights, solver.iteration_count()
+            if solver.iteration_count() == solver.max_iterations():
+                raise RuntimeError("reached the maximum number of iterations")  # solver.hpp:132-134
+            solver.iterate_process()
     n_glob = op.size()
     fit = torch.empty_like(rhs)
     while True:

@@ -130,7 +130,9 @@ def test_fit_small_bh3_matches_oracle_fgmres(torch):
     pts = rng.uniform(-1, 1, (mu, dim))
     values = np.sin(np.pi * pts).sum(axis=1)
     nugget = 0.05  # keeps the unpreconditioned system well enough conditioned for a short test
-    dense = _dense_operator(orbf, odir, "bh3", [1.0, 0.0], dim, np.eye(3), pts, np.zeros((0, 3)), 0, nugget)
+    # the saddle-point matrix in closed form (bh3: phi = -r, polyharmonic_odd.hpp:32-45; degree 0: one column of ones)
+    a = -np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(axis=2)) + nugget * np.eye(mu)
+    dense = np.block([[a, np.ones((mu, 1))], [np.ones((1, mu)), np.zeros((1, 1))]])
     model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=nugget)
     op = Operator(model, pb.Bbox(-np.ones(dim), np.ones(dim)), accuracy=0.0)  # order 12 / d 8
     op.set_points(pts)
@@ -169,8 +171,9 @@ pts = rng.uniform(-1, 1, (mu, dim))
 values = np.sin(np.pi * pts).sum(axis=1)
 model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.05)
 bbox = pb.Bbox(-np.ones(dim), np.ones(dim))
-single = Operator(model, bbox); single.set_points(pts)
-sharded = Operator(model, bbox, group=dist.group.WORLD); sharded.set_points(pts)
+# evaluator accuracy two orders below the fit tolerance, as the reference's fitter sets it
+single = Operator(model, bbox, accuracy=1e-7); single.set_points(pts)
+sharded = Operator(model, bbox, accuracy=1e-7, group=dist.group.WORLD); sharded.set_points(pts)
 assert sharded.a[0].config is not None
 w = rng.uniform(-1, 1, single.size())
 ref = single(w)
