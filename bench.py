@@ -174,6 +174,11 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core it can.
+    # The variable is read when libgomp initialises, i.e. before the oracle library is loaded.
+    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1") or "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity")
+                                            else (os.cpu_count() or 1))
     from oracle import fmm as ofmm
     src, w, trg, lo, hi = workload(args)
     order, d = (6, -1) if np.isinf(args.accuracy) else ((12, 8) if args.accuracy == 0 else (10, -1))
