@@ -151,6 +151,12 @@ int plt_eval_get_target_shard_range(plt_eval* h, int64_t* begin, int64_t* end);
 int plt_eval_gram_batched(plt_eval* h, const double* points, const int32_t* counts, int64_t n_batch, int64_t m,
                           double nugget, double* out);
 
+/* The same for Hermite data (the F / F^T / H blocks of mat_a): one row per value point and `dim` rows per
+ * gradient point.  types: DEVICE int8 [n_batch][m]: 0 = value row, 1 + c = gradient component c, negative =
+ * padding (identity); points: the coordinates of each ROW's point. */
+int plt_eval_gram_mixed(plt_eval* h, const double* points, const int8_t* types, int64_t n_batch, int64_t m,
+                        double nugget, double* out);
+
 /* Per-phase device time of the last evaluate() in milliseconds (CUDA events on the
  * handle's stream).  names/ms: arrays of capacity cap; returns the number of phases. */
 int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap);

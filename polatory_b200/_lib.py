@@ -43,6 +43,7 @@ SYMBOLS = [
     ("plt_eval_get_target_shard_range", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64),
                                                        ctypes.POINTER(ctypes.c_int64)]),
     ("plt_eval_gram_batched", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, _vp]),
+    ("plt_eval_gram_mixed", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, _vp]),
     ("plt_eval_phase_times", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), _c_double_p, ctypes.c_int]),
     ("plt_eval_work_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                            ctypes.POINTER(ctypes.c_int64)]),

@@ -126,7 +126,76 @@ __global__ void __launch_bounds__(256) k_gram_batched(RbfConst k, Aniso3 A, cons
   out[(static_cast<size_t>(b) * m + i) * m + j] = v;
 }
 
+// Mixed value / gradient rows (Hermite data): the full mat_a of preconditioner/mat_a.hpp:10-61.
+//   types[b][r] = 0: value row of point r; 1 + c: row of gradient component c; < 0: padding (identity).
+//   pts[b][r][:] = coordinates of the row's point (the `dim` rows of a gradient point repeat them).
+//   (value, value)      phi(x_r - x_c) + nugget (r == c)
+//   (value, grad c)     -d_c phi (x_r - g_c)           = [F_iso(d) A]_c,   d = A (x_r - g_c)
+//   (grad r, value)     the transpose                   = [F_iso(d) A]_r,   d = A (x_c - g_r)
+//   (grad r, grad c)    -d_r d_c phi (g_r - g_c)        = [A^T H_iso(d) A]_{rc}
+template <int FAM, int DIM>
+__global__ void __launch_bounds__(256) k_gram_mixed(RbfConst k, Aniso3 A, const double* __restrict__ pts,
+                                                    const signed char* __restrict__ types, int m, double nugget,
+                                                    double* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int c = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int r = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (r >= m || c >= m) return;
+  const int tr = types[static_cast<size_t>(b) * m + r], tc = types[static_cast<size_t>(b) * m + c];
+  double v;
+  if (tr < 0 || tc < 0) {
+    v = r == c ? 1.0 : 0.0;
+  } else {
+    const double* pr = pts + (static_cast<size_t>(b) * m + r) * DIM;
+    const double* pc = pts + (static_cast<size_t>(b) * m + c) * DIM;
+    // value rows look at gradient columns; for (grad, value) use the transposed pair
+    const bool swap = tr > 0 && tc == 0;
+    double diff[DIM], d[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) diff[a] = swap ? pc[a] - pr[a] : pr[a] - pc[a];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      d[i] = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) d[i] = fma(A.a[i * DIM + a], diff[a], d[i]);
+    }
+    if (tr == 0 && tc == 0) {
+      double blk[1];
+      kernel_block<FAM, KIND_K, DIM>(k, d, blk);
+      v = blk[0] + (r == c ? nugget : 0.0);
+    } else if (tr == 0 || tc == 0) {
+      const int comp = (tr == 0 ? tc : tr) - 1;
+      double blk[DIM];
+      kernel_block<FAM, KIND_F, DIM>(k, d, blk);
+      v = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) v = fma(blk[a], A.a[a * DIM + comp], v);
+    } else {
+      double blk[DIM * DIM];
+      kernel_block<FAM, KIND_H, DIM>(k, d, blk);
+      v = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) v += A.a[i * DIM + (tr - 1)] * blk[i * DIM + j] * A.a[j * DIM + (tc - 1)];
+    }
+  }
+  out[(static_cast<size_t>(b) * m + r) * m + c] = v;
+}
+
 }  // namespace
+
+void launch_gram_mixed(int dim, const RbfConst& k, const double* aniso, const double* pts, const signed char* types,
+                       int64_t n_batch, int m, double nugget, double* out, cudaStream_t stream, LaunchCounter& ctr) {
+  if (n_batch == 0 || m == 0) return;
+  Aniso3 A{};
+  for (int i = 0; i < dim * dim; ++i) A.a[i] = aniso[i];
+  PLT_REQUIRE(n_batch <= 65535, "gram_mixed: at most 65535 point sets per call");
+  dim3 grid(ceil_div(m, 16), ceil_div(m, 16), static_cast<unsigned>(n_batch));
+  dispatch_fkd(k.family, KIND_K, dim, [&](auto fam, auto, auto dm) {
+    PLT_LAUNCH(ctr, (k_gram_mixed<fam.value, dm.value>), grid, 256, 0, stream, k, A, pts, types, m, nugget, out);
+  });
+}
 
 void launch_gram_batched(int dim, const RbfConst& k, const double* aniso, const double* pts, const int* counts,
                          int64_t n_batch, int m, double nugget, double* out, cudaStream_t stream, LaunchCounter& ctr) {

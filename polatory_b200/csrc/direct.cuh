@@ -29,4 +29,8 @@ void launch_direct(int kind, int dim, DirectArgs a, cudaStream_t stream, LaunchC
 void launch_gram_batched(int dim, const RbfConst& k, const double* aniso, const double* pts, const int* counts,
                          int64_t n_batch, int m, double nugget, double* out, cudaStream_t stream, LaunchCounter& ctr);
 
+// The same with mixed value / gradient rows: types[b][r] = 0 value, 1 + c gradient component c, < 0 padding.
+void launch_gram_mixed(int dim, const RbfConst& k, const double* aniso, const double* pts, const signed char* types,
+                       int64_t n_batch, int m, double nugget, double* out, cudaStream_t stream, LaunchCounter& ctr);
+
 }  // namespace plt

@@ -1090,6 +1090,22 @@ int plt_eval_gram_batched(plt_eval* h, const double* points, const int32_t* coun
   });
 }
 
+int plt_eval_gram_mixed(plt_eval* h, const double* points, const int8_t* types, int64_t n_batch, int64_t m,
+                        double nugget, double* out) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(points && types && out, "null argument");
+    PLT_REQUIRE(plt_eval::is_device_pointer(points) && plt_eval::is_device_pointer(types) &&
+                    plt_eval::is_device_pointer(out),
+                "gram_mixed works on device buffers");
+    PLT_REQUIRE(!(h->rbf_id == PLT_RBF_SPH || h->rbf_id == PLT_RBF_CUB), "Hessian of cov_spherical / cov_cubic");
+    double a[9];
+    for (int r = 0; r < h->dim; ++r)
+      for (int c = 0; c < h->dim; ++c) a[r * h->dim + c] = h->aniso[r * h->dim + c];
+    launch_gram_mixed(h->dim, h->rbf.k, a, points, reinterpret_cast<const signed char*>(types), n_batch,
+                      static_cast<int>(m), nugget, out, h->stream, h->ctr);
+  });
+}
+
 int plt_eval_phase_times(plt_eval* h, const char** names, double* ms, int cap) {
   if (!h) return 0;
   int n = 0;

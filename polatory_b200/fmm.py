@@ -157,6 +157,19 @@ class _EvaluatorBase:
                 b1 - b0, m, float(nugget), ctypes.c_void_p(out[b0:b1].data_ptr())))
         return out
 
+    def gram_mixed(self, points, types, nugget, out):
+        """Batched mat_a with value and gradient rows: CUDA tensors points (B, m, dim) float64 (coordinates of each
+        row's point), types (B, m) int8 (0 value, 1 + c gradient component, < 0 padding), out (B, m, m)."""
+        b, m = int(points.shape[0]), int(points.shape[1])
+        assert points.is_cuda and types.is_cuda and out.is_cuda and points.is_contiguous() and out.is_contiguous()
+        assert types.is_contiguous() and tuple(types.shape) == (b, m) and tuple(out.shape) == (b, m, m)
+        for b0 in range(0, b, 65535):
+            b1 = min(b, b0 + 65535)
+            _lib.check(self._h, self._lib.plt_eval_gram_mixed(
+                self._h, ctypes.c_void_p(points[b0:b1].data_ptr()), ctypes.c_void_p(types[b0:b1].data_ptr()),
+                b1 - b0, m, float(nugget), ctypes.c_void_p(out[b0:b1].data_ptr())))
+        return out
+
     def phase_times(self):
         cap = 32
         names = (ctypes.c_char_p * cap)()

@@ -156,3 +156,32 @@ def test_ras_iteration_parity_with_oracle(torch, degree):
         s.iterate_process()
     assert abs(iters - s.iteration_count()) <= 1, (iters, s.iteration_count())
     assert np.max(np.abs(w.cpu().numpy() - x)) <= 1e-3 * np.max(np.abs(x))
+
+
+def test_gram_mixed_matches_oracle(torch):
+    """The Hermite mat_a (value + gradient rows, include/polatory/preconditioner/mat_a.hpp:10-61) against the
+    oracle's exact direct evaluator applied to unit vectors (the four kernel kinds with anisotropy)."""
+    import polatory_b200 as pb
+    from conftest import random_anisotropy
+    from oracle import direct as odir, rbf as orbf
+    rng = np.random.default_rng(4)
+    dev = torch.device("cuda")
+    for name, params, dim in (("th3", [1.0, 0.0], 3), ("gau", [1.1, 0.7], 3), ("th2", [1.0, 0.1], 2)):
+        aniso = random_anisotropy(dim, rng)
+        ev = pb.make_fmm_evaluator(pb.make_rbf(name, params, dim, aniso), pb.Bbox(-np.ones(dim), np.ones(dim)))
+        mu, sigma, pad = 14, 9, 5
+        p = rng.uniform(-1, 1, (mu, dim))
+        g = rng.uniform(-1, 1, (sigma, dim))
+        m = mu + dim * sigma
+        rows = np.concatenate([p, np.repeat(g, dim, axis=0), np.zeros((pad, dim))])
+        types = np.concatenate([np.zeros(mu), np.tile(1 + np.arange(dim), sigma), -np.ones(pad)]).astype(np.int8)
+        out = torch.empty((1, m + pad, m + pad), dtype=torch.float64, device=dev)
+        ev.gram_mixed(torch.from_numpy(rows[None]).to(dev), torch.from_numpy(types[None]).to(dev), 0.125, out)
+        got = out[0].cpu().numpy()
+        o = orbf.make_rbf(name, params, dim, aniso)
+        ref = np.eye(m + pad)
+        for c in range(m):
+            ref[:m, c] = odir.direct_evaluator(o, 0.0, p, g, np.eye(m)[:, c], p, g)
+        ref[:mu, :mu] += 0.125 * np.eye(mu)
+        assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref))), name
+        assert np.max(np.abs(got - got.T)) <= 1e-12 * max(1.0, np.max(np.abs(got)))
