@@ -22,6 +22,7 @@ reference's `Evaluator` default) whose trees / plans / operators stay resident b
 """
 from __future__ import annotations
 
+import heapq
 import math
 
 import numpy as np
@@ -169,27 +170,141 @@ def level_structure(n_rows):
 
 
 # ---------------------------------------------------------------------------------------------
+# Hermite data (gradient points, multiplicity `dim`): the same two algorithms with the reference's
+# multiplicity-weighted prefix sums (domain_divider.hpp:205-231, 66-90).  numpy / heapq on the host; the
+# native code of csrc/ras_host.cu covers value data only in this round.
+# ---------------------------------------------------------------------------------------------
+class MixedDomain:
+    __slots__ = ("point_indices", "inner_point", "grad_point_indices", "inner_grad_point")
+
+
+def _mixed_coords(a_points, a_grad_points, idx, is_grad):
+    out = np.empty((len(idx), a_points.shape[1]))
+    out[~is_grad] = a_points[idx[~is_grad]]
+    out[is_grad] = a_grad_points[idx[is_grad]]
+    return out
+
+
+def divide_domains_mixed(a_points, a_grad_points, point_idcs, grad_idcs, poly_idcs):
+    dim = a_points.shape[1]
+    idx0 = np.concatenate([np.asarray(point_idcs, dtype=np.int64), np.asarray(grad_idcs, dtype=np.int64)])
+    g0 = np.concatenate([np.zeros(len(point_idcs), dtype=bool), np.ones(len(grad_idcs), dtype=bool)])
+    queue = [(idx0, g0, np.ones(len(idx0), dtype=bool))]
+    leaves, head = [], 0
+    while head < len(queue):
+        idx, isg, inner = queue[head]
+        queue[head] = None
+        head += 1
+        mult = np.where(isg, dim, 1)
+        prefix = np.concatenate([[0], np.cumsum(mult)])
+        n_mult = int(prefix[-1])
+        if n_mult <= K_MAX_LEAF_SIZE:
+            leaves.append((idx, isg, inner))
+            continue
+        order = _sort_by_axes(_mixed_coords(a_points, a_grad_points, idx, isg))
+        idx, isg, inner = idx[order], isg[order], inner[order]
+        prefix = np.concatenate([[0], np.cumsum(np.where(isg, dim, 1))])
+        q = K_OVERLAP_QUOTA * K_MAX_LEAF_SIZE / n_mult
+        n_sub = int(_round_half_to_even((1.0 + q) / 2.0 * n_mult))
+        left_mult, right_mult = n_mult - n_sub, n_sub
+        mid_mult = int(_round_half_to_even((left_mult + right_mult) / 2.0))
+        ub = lambda x: int(np.searchsorted(prefix, x, side="right")) - 1  # upper_bound(...) - 1
+        left_part, right_part, mid = ub(left_mult), ub(right_mult), ub(mid_mult)
+        pos = np.arange(len(idx))
+        queue.append((idx[:right_part], isg[:right_part], inner[:right_part] & (pos[:right_part] < mid)))
+        queue.append((idx[left_part:], isg[left_part:], inner[left_part:] & (pos[left_part:] >= mid)))
+    poly = np.asarray(poly_idcs, dtype=np.int64)
+    out = []
+    for idx, isg, inner in leaves:
+        d = MixedDomain()
+        pi, pin = idx[~isg], inner[~isg]
+        order = np.argsort(pi, kind="stable")
+        pi, pin = pi[order], pin[order]
+        if len(poly):  # merge_poly_points (domain.hpp:33-51)
+            pos = np.searchsorted(pi, poly)
+            present = (pos < len(pi)) & (pi[np.minimum(pos, max(len(pi) - 1, 0))] == poly) if len(pi) else np.zeros(len(poly), bool)
+            front_inner = np.zeros(len(poly), dtype=bool)
+            front_inner[present] = pin[pos[present]]
+            keep = np.ones(len(pi), dtype=bool)
+            keep[pos[present]] = False
+            pi = np.concatenate([poly, pi[keep]])
+            pin = np.concatenate([front_inner, pin[keep]])
+        d.point_indices, d.inner_point = pi, pin
+        d.grad_point_indices, d.inner_grad_point = idx[isg], inner[isg]
+        out.append(d)
+    return out
+
+
+def choose_coarse_points_mixed(a_points, a_grad_points, point_idcs, grad_idcs, poly_idcs, n_coarse_rows):
+    """choose_coarse_points with gradient points (a gradient centre counts `dim` rows)."""
+    dim = a_points.shape[1]
+    poly_set = set(int(i) for i in poly_idcs)
+    pv = np.array([i for i in point_idcs if int(i) not in poly_set], dtype=np.int64)
+    idx0 = np.concatenate([pv, np.asarray(grad_idcs, dtype=np.int64)])
+    g0 = np.concatenate([np.zeros(len(pv), dtype=bool), np.ones(len(grad_idcs), dtype=bool)])
+
+    def init(idx, isg):
+        pts = _mixed_coords(a_points, a_grad_points, idx, isg)
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        k = int(np.argmin(((pts - 0.5 * (lo + hi)) ** 2).sum(axis=1)))
+        order = _sort_by_axes(pts)
+        return float(np.prod(hi - lo)), (int(idx[k]), bool(isg[k])), idx[order], isg[order]
+
+    counter = 0
+    vol, c, si, sg = init(idx0, g0)
+    heap = [(0, -vol, counter, c, si, sg)]
+    size = dim if c[1] else 1
+    while size < n_coarse_rows:
+        level, _, _, c, idx, isg = heapq.heappop(heap)
+        size -= dim if c[1] else 1
+        prefix = np.concatenate([[0], np.cumsum(np.where(isg, dim, 1))])
+        total = int(prefix[-1])
+        d = np.abs(2 * prefix[:len(idx)] - total)
+        best = int(d.min())
+        cand = np.nonzero(d == best)[0]
+        mid = int(cand[0])
+        for k in cand[1:]:      # min_element with "equal and even index wins" (domain_divider.hpp:83-88)
+            if k % 2 == 0:
+                mid = int(k)
+        for part_i, part_g in ((idx[:mid], isg[:mid]), (idx[mid:], isg[mid:])):
+            if len(part_i):
+                counter += 1
+                vol, c2, si, sg = init(part_i, part_g)
+                size += dim if c2[1] else 1
+                heapq.heappush(heap, (level + 1, -vol, counter, c2, si, sg))
+        if len(idx) == 1 and len(heap) >= len(idx0):
+            break
+    pts_out, grads_out = [int(i) for i in poly_idcs], []
+    while heap:
+        c = heapq.heappop(heap)[3]
+        (grads_out if c[1] else pts_out).append(c[0])
+    return np.asarray(pts_out, dtype=np.int64), np.asarray(grads_out, dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
 # Device side
 # ---------------------------------------------------------------------------------------------
 class _FineLevel:
-    """All FineGrids of one level, batched: padded point lists, explicit inverses of Q^T A Q."""
+    """All FineGrids of one level, batched.  A domain is a list of ROWS of the global system (value row i =
+    point i, rows mu + dim*j + c = component c of gradient point j), the l polynomial points first; padded to
+    the level's largest domain; explicit inverses of Q^T A Q."""
 
     def __init__(self, ras, domains):
         torch = ras.torch
         dev, l = ras.device, ras.l
         self.n_dom = len(domains)
-        m_max = max(len(d.point_indices) for d in domains)
+        m_max = max(len(rows) for rows, _ in domains)
         self.m = m_max
         r = m_max - l
         idx = np.zeros((self.n_dom, m_max), dtype=np.int64)
         cnt = np.zeros(self.n_dom, dtype=np.int32)
         inner_glob, inner_loc = [], []
-        for b, d in enumerate(domains):
-            k = len(d.point_indices)
-            idx[b, :k] = d.point_indices
+        for b, (rows, inner) in enumerate(domains):
+            k = len(rows)
+            idx[b, :k] = rows
             cnt[b] = k
-            sel = np.nonzero(d.inner_point)[0]
-            inner_glob.append(d.point_indices[sel])
+            sel = np.nonzero(inner)[0]
+            inner_glob.append(rows[sel])
             inner_loc.append(b * m_max + sel)
         self.idx = torch.from_numpy(idx).to(dev)
         self.cnt = torch.from_numpy(cnt).to(dev)
@@ -207,7 +322,7 @@ class _FineLevel:
         chunk = max(1, min(self.n_dom, int(2 ** 31 // (8 * m_max * m_max))))
         for b0 in range(0, self.n_dom, chunk):
             b1 = min(self.n_dom, b0 + chunk)
-            a = ras.gram(ras.points_dev[self.idx[b0:b1]].contiguous(), self.cnt[b0:b1].contiguous())  # (b, m, m)
+            a = ras.gram(self.idx[b0:b1], self.cnt[b0:b1])      # (b, m, m)
             if l > 0:
                 q = self.q_top[b0:b1]
                 att, atr, art, arr = a[:, :l, :l], a[:, :l, l:], a[:, l:, :l], a[:, l:, l:]
@@ -233,21 +348,21 @@ class _FineLevel:
 
 
 class _CoarseGrid:
-    def __init__(self, ras, idcs):
+    def __init__(self, ras, rows):
         torch = ras.torch
         dev, l = ras.device, ras.l
-        self.idx = torch.from_numpy(np.asarray(idcs, dtype=np.int64)).to(dev)
-        m = len(idcs)
+        self.idx = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(dev)
+        m = len(rows)
         self.m = m
         cnt = torch.tensor([m], dtype=torch.int32, device=dev)
-        a = ras.gram(ras.points_dev[self.idx][None].contiguous(), cnt)[0]
+        a = ras.gram(self.idx[None], cnt)[0]
         if l > 0:
             lag = ras.lagrange_p[self.idx]
             self.q_top = -lag[l:, :].T.contiguous()             # (l, m - l)
             q = self.q_top
             red = a[l:, l:] + q.T @ (a[:l, :l] @ q + a[:l, l:]) + a[l:, :l] @ q
             self.a_top = a[:l, :].clone()
-            p_top = torch.from_numpy(monomial_basis(ras.dim, ras.model.poly_degree, ras.points[idcs[:l]])).to(dev)
+            p_top = torch.from_numpy(monomial_basis(ras.dim, ras.model.poly_degree, ras.points[rows[:l]])).to(dev)
             self.p_top_inv = torch.linalg.inv(p_top)
         else:
             red = a
@@ -263,56 +378,82 @@ class _CoarseGrid:
             gamma = torch.cholesky_solve(qtd[:, None], self.chol)[:, 0]
             lam = torch.cat([self.q_top @ gamma, gamma])
             weights[self.idx] = lam
-            weights[ras.mu:] = self.p_top_inv @ (vals[:l] - self.a_top @ lam)
+            weights[ras.m_rows:] = self.p_top_inv @ (vals[:l] - self.a_top @ lam)
         else:
             weights[self.idx] = torch.cholesky_solve(vals[:, None], self.chol)[:, 0]
 
 
 class RasPreconditioner:
-    """preconditioner::RasPreconditioner for value data; `apply(v, out)` on CUDA tensors."""
+    """preconditioner::RasPreconditioner; `apply(v, out)` on CUDA tensors laid out as the operator's vectors
+    [mu values | dim * sigma gradient components | l polynomial coefficients]."""
 
-    def __init__(self, model, points, device=None, verbose=False, transfer_config=None):
+    def __init__(self, model, points, grad_points=None, device=None, verbose=False, transfer_config=None):
         """transfer_config: optional (order, d) forced on the level-transfer evaluators (default: the
         reference's accuracy = infinity, i.e. order 6) -- used by the parity tests to separate the FMM
         discretisation error of the transfers from everything else."""
+        import time
         import torch
         self.transfer_config = transfer_config
         self.torch = torch
         self.model = model
-        self.dim = model.dim
+        dim = self.dim = model.dim
         self.l = model.poly_basis_size()
-        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
-        self.mu = len(self.points)
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, dim)
+        self.grad_points = np.zeros((0, dim)) if grad_points is None else \
+            np.ascontiguousarray(grad_points, dtype=np.float64).reshape(-1, dim)
+        self.mu, self.sigma = len(self.points), len(self.grad_points)
+        mu, sigma, l = self.mu, self.sigma, self.l
+        self.m_rows = mu + dim * sigma
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         if len(model.rbfs) != 1:
             raise NotImplementedError("RAS: one RBF per model in this round")
+        if l > 0 and model.poly_degree == 1 and mu == 1 and sigma >= 1:
+            raise NotImplementedError("RAS: the single-value-point special case of the reference is not restated")
         rbf = model.rbfs[0]
-        self.bbox = fmm.Bbox.from_points(self.points)
-        self._gram_ev = fmm.make_fmm_evaluator(rbf, self.bbox)   # carries the RBF constants for the Gram kernel
-        n_levels, counts = level_structure(self.mu)
+        self.bbox = fmm.Bbox.from_points(np.concatenate([self.points, self.grad_points]))
+        self._gram_ev = fmm.make_fmm_evaluator(rbf, self.bbox)   # carries the RBF constants for the Gram kernels
+        n_levels, counts = level_structure(self.m_rows)
         self.n_levels = n_levels
-        mu, l = self.mu, self.l
         self.points_dev = torch.from_numpy(self.points).to(self.device)
+        self.grad_points_dev = torch.from_numpy(self.grad_points).to(self.device)
+        # per-ROW tables of the global system: coordinates of the row's point and the row type
+        self.row_coords = torch.cat([self.points_dev, self.grad_points_dev.repeat_interleave(dim, dim=0)])
+        self.row_types = torch.cat([torch.zeros(mu, dtype=torch.int8, device=self.device),
+                                    (1 + torch.arange(dim, dtype=torch.int8, device=self.device)).repeat(sigma)])
 
-        poly_idcs = unisolvent_point_set(self.points, model.poly_degree, self.dim) if l > 0 else []
+        poly_idcs = unisolvent_point_set(self.points, model.poly_degree, dim) if l > 0 else []
         self.poly_idcs = poly_idcs
         if l > 0:
+            coeffs = np.linalg.inv(monomial_basis(dim, model.poly_degree, self.points[poly_idcs]))
             self.lagrange_p = torch.from_numpy(
-                lagrange_basis_matrix(self.points, poly_idcs, model.poly_degree, self.dim)).to(self.device)
-        point_idcs = [None] * n_levels
+                monomial_basis(dim, model.poly_degree, self.points, self.grad_points) @ coeffs).to(self.device)
+        point_idcs, grad_idcs = [None] * n_levels, [None] * n_levels
         rest = np.ones(mu, dtype=bool)
         rest[poly_idcs] = False
         point_idcs[n_levels - 1] = np.concatenate([np.asarray(poly_idcs, dtype=np.int64), np.nonzero(rest)[0]])
+        grad_idcs[n_levels - 1] = np.arange(sigma, dtype=np.int64)
         aniso = np.asarray(rbf.anisotropy(), dtype=np.float64)
-        a_points = self.points @ aniso.T if not np.allclose(aniso, np.eye(self.dim)) else self.points
+        iso = np.allclose(aniso, np.eye(dim))
+        a_points = self.points if iso else self.points @ aniso.T
+        a_grad_points = self.grad_points if iso else self.grad_points @ aniso.T
         self.fine = [None] * n_levels
-        import time
         self.setup_seconds = {"coarse_points": 0.0, "divide_domains": 0.0, "factorize": 0.0}
         for level in range(n_levels - 1, 0, -1):
             t0 = time.perf_counter()
-            point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
+            if sigma == 0:
+                point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
+                grad_idcs[level - 1] = np.zeros(0, dtype=np.int64)
+            else:
+                point_idcs[level - 1], grad_idcs[level - 1] = choose_coarse_points_mixed(
+                    a_points, a_grad_points, point_idcs[level], grad_idcs[level], poly_idcs, counts[level - 1])
             t1 = time.perf_counter()
-            domains = divide_domains(a_points, point_idcs[level], poly_idcs)
+            if sigma == 0:
+                domains = [(d.point_indices, d.inner_point) for d in divide_domains(a_points, point_idcs[level], poly_idcs)]
+            else:
+                domains = [(self._rows(d.point_indices, d.grad_point_indices),
+                            np.concatenate([d.inner_point, np.repeat(d.inner_grad_point, dim)]))
+                           for d in divide_domains_mixed(a_points, a_grad_points, point_idcs[level], grad_idcs[level],
+                                                         poly_idcs)]
             t2 = time.perf_counter()
             self.fine[level] = _FineLevel(self, domains)
             torch.cuda.synchronize()
@@ -321,59 +462,96 @@ class RasPreconditioner:
             self.setup_seconds["divide_domains"] += t2 - t1
             self.setup_seconds["factorize"] += t3 - t2
             if verbose:
-                print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points "
-                      f"(coarse points {t1 - t0:.2f}s, domains {t2 - t1:.2f}s, factorisation {t3 - t2:.2f}s)", flush=True)
-        self.point_idcs = point_idcs
+                print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points, {len(grad_idcs[level])} "
+                      f"gradient points (coarse points {t1 - t0:.2f}s, domains {t2 - t1:.2f}s, factorisation {t3 - t2:.2f}s)",
+                      flush=True)
+        self.point_idcs, self.grad_idcs = point_idcs, grad_idcs
         self.idx_dev = [torch.from_numpy(np.asarray(p, dtype=np.int64)).to(self.device) for p in point_idcs]
-        self.coarse = _CoarseGrid(self, point_idcs[0])
+        self.gidx_dev = [torch.from_numpy(np.asarray(g, dtype=np.int64)).to(self.device) for g in grad_idcs]
+        # flat rows of the gradient components of a level's gradient points, point-major (mu + dim*j + c)
+        self.grows_dev = [(mu + dim * g[:, None] + torch.arange(dim, device=self.device)[None, :]).reshape(-1)
+                          for g in self.gidx_dev]
+        self.coarse = _CoarseGrid(self, self._rows(point_idcs[0], grad_idcs[0]))
         if verbose:
-            print(f"level 0: 1 domain, {len(point_idcs[0])} points", flush=True)
+            print(f"level 0: 1 domain, {len(point_idcs[0])} points, {len(grad_idcs[0])} gradient points", flush=True)
         self._evaluators = {}
         self.p = self.ap = None
+        if l > 0:
+            self.p_mono = torch.from_numpy(monomial_basis(dim, model.poly_degree, self.points, self.grad_points)).to(self.device)
         if n_levels > 1 and l > 0:
             # orthonormalised monomials and A p (ras_preconditioner.hpp:165-180)
-            p = monomial_basis(self.dim, model.poly_degree, self.points)
+            p = monomial_basis(dim, model.poly_degree, self.points, self.grad_points)
             for i in range(l):
                 p[:, i] /= np.linalg.norm(p[:, i])
                 for j in range(i + 1, l):
                     p[:, j] -= (p[:, i] @ p[:, j]) * p[:, i]
             self.p = torch.from_numpy(p).to(self.device)
-            ev = fmm.make_fmm_symmetric_evaluator(rbf, self.bbox)
+            from .operator import Model as _Model, Operator
+            fin = Operator(_Model(model.rbfs, poly_degree=-1, nugget=model.nugget), self.bbox, device=self.device)
             if transfer_config:
-                ev.force_config(*transfer_config)
-            ev.set_points(self.points_dev)
+                for ev in fin.a + fin.f + fin.ft + fin.h:
+                    ev.force_config(*transfer_config)
+            fin.set_points(self.points, self.grad_points if sigma else None)
             self.ap = torch.empty_like(self.p)
-            col = torch.empty(mu, dtype=torch.float64, device=self.device)
+            col = torch.empty(self.m_rows, dtype=torch.float64, device=self.device)
             for i in range(l):
-                ev.set_weights(self.p[:, i].contiguous())
-                ev.evaluate(col)
-                self.ap[:, i] = col + model.nugget * self.p[:, i]
-            del ev
-        if l > 0:
-            self.p_mono = torch.from_numpy(monomial_basis(self.dim, model.poly_degree, self.points)).to(self.device)
+                fin.apply(self.p[:, i].contiguous(), col)
+                self.ap[:, i] = col
+            del fin
 
-    # -- device helpers ------------------------------------------------------------------
-    def gram(self, pts, counts):
-        """mat_a for a batch of point sets: (B, m, dim) points, counts (B,) -> (B, m, m); rows/cols
-        beyond a set's count are identity."""
-        out = self.torch.empty((pts.shape[0], pts.shape[1], pts.shape[1]), dtype=self.torch.float64, device=self.device)
-        self._gram_ev.gram_batched(pts, counts, self.model.nugget, out)
+    # -- helpers ---------------------------------------------------------------------------
+    def _rows(self, point_indices, grad_point_indices):
+        """Flat rows of the global system for a set of value and gradient points (values first)."""
+        g = np.asarray(grad_point_indices, dtype=np.int64)
+        grows = (self.mu + self.dim * g[:, None] + np.arange(self.dim)[None, :]).reshape(-1)
+        return np.concatenate([np.asarray(point_indices, dtype=np.int64), grows])
+
+    def gram(self, rows, counts):
+        """mat_a for a batch of row sets: rows (B, m) flat row indices, counts (B,) valid rows -> (B, m, m);
+        rows / columns beyond a set's count are identity."""
+        torch = self.torch
+        b, m = rows.shape
+        out = torch.empty((b, m, m), dtype=torch.float64, device=self.device)
+        pts = self.row_coords[rows].contiguous()
+        if self.sigma == 0:
+            self._gram_ev.gram_batched(pts, counts.contiguous(), self.model.nugget, out)
+        else:
+            types = self.row_types[rows]
+            valid = torch.arange(m, device=self.device)[None, :] < counts[:, None]
+            types = torch.where(valid, types, torch.full_like(types, -1)).contiguous()
+            self._gram_ev.gram_mixed(pts, types, self.model.nugget, out)
         return out
 
     def _evaluator(self, src_level, trg_level):
+        """interpolation::Evaluator(model, source level points) with the target level's points set
+        (ras_preconditioner.hpp:251-265): the four kernel kinds, created for the non-empty blocks only."""
         key = (src_level, trg_level)
         if key not in self._evaluators:
-            ev = fmm.make_fmm_evaluator(self.model.rbfs[0], self.bbox)
-            if self.transfer_config:
-                ev.force_config(*self.transfer_config)
-            ev.set_source_points(self.points_dev[self.idx_dev[src_level]].contiguous())
-            ev.set_target_points(self.points_dev[self.idx_dev[trg_level]].contiguous())
-            out = self.torch.empty(len(self.point_idcs[trg_level]), dtype=self.torch.float64, device=self.device)
-            self._evaluators[key] = (ev, out)
+            torch = self.torch
+            rbf = self.model.rbfs[0]
+            sp = self.points_dev[self.idx_dev[src_level]].contiguous()
+            sg = self.grad_points_dev[self.gidx_dev[src_level]].contiguous()
+            tp = self.points_dev[self.idx_dev[trg_level]].contiguous()
+            tg = self.grad_points_dev[self.gidx_dev[trg_level]].contiguous()
+            evs = {}
+            for name, make, s_pts, t_pts in (("a", fmm.make_fmm_evaluator, sp, tp),
+                                             ("f", fmm.make_fmm_gradient_evaluator, sg, tp),
+                                             ("ft", fmm.make_fmm_gradient_transpose_evaluator, sp, tg),
+                                             ("h", fmm.make_fmm_hessian_evaluator, sg, tg)):
+                if len(s_pts) == 0 or len(t_pts) == 0:
+                    continue
+                ev = make(rbf, self.bbox)
+                if self.transfer_config:
+                    ev.force_config(*self.transfer_config)
+                ev.set_source_points(s_pts)
+                ev.set_target_points(t_pts)
+                kn = self.dim if name in ("ft", "h") else 1
+                evs[name] = (ev, torch.empty(kn * len(t_pts), dtype=torch.float64, device=self.device))
+            self._evaluators[key] = evs
         return self._evaluators[key]
 
     def _solve(self, level, residuals):
-        weights = self.torch.zeros(self.mu + self.l, dtype=self.torch.float64, device=self.device)
+        weights = self.torch.zeros(self.m_rows + self.l, dtype=self.torch.float64, device=self.device)
         if level == 0:
             self.coarse.solve(self, residuals, weights)
         else:
@@ -381,24 +559,33 @@ class RasPreconditioner:
         return weights
 
     def _update_residuals(self, src_level, trg_level, weights, residuals):
-        ev, fit = self._evaluator(src_level, trg_level)
-        ev.set_weights(weights[self.idx_dev[src_level]].contiguous())
-        ev.evaluate(fit)
-        trg = self.idx_dev[trg_level]
+        """ras_preconditioner.hpp:287-321."""
+        evs = self._evaluator(src_level, trg_level)
+        w_v = weights[self.idx_dev[src_level]].contiguous()
+        w_g = weights[self.grows_dev[src_level]].contiguous()
+        trg_v, trg_g = self.idx_dev[trg_level], self.grows_dev[trg_level]
+        for name, w, rows in (("a", w_v, trg_v), ("f", w_g, trg_v), ("ft", w_v, trg_g), ("h", w_g, trg_g)):
+            if name in evs:
+                ev, fit = evs[name]
+                ev.set_weights(w)
+                ev.evaluate(fit)
+                residuals[rows] -= fit
         if self.l > 0:
-            fit = fit + self.p_mono[trg] @ weights[self.mu:]
-        residuals[trg] -= fit
+            c = weights[self.m_rows:]
+            residuals[trg_v] -= self.p_mono[trg_v] @ c
+            if len(trg_g):
+                residuals[trg_g] -= self.p_mono[trg_g] @ c
 
     def _orthogonalize(self, weights, residuals):
         if self.l > 0:
-            dot = self.p.T @ weights[:self.mu]
-            weights[:self.mu] -= self.p @ dot
+            dot = self.p.T @ weights[:self.m_rows]
+            weights[:self.m_rows] -= self.p @ dot
             residuals += self.ap @ dot
 
     # -- RasPreconditioner::operator() (ras_preconditioner.hpp:183-246) -----------------------
     def apply(self, v, out):
         n = self.n_levels
-        residuals = v[:self.mu].clone()
+        residuals = v[:self.m_rows].clone()
         if n == 1:
             out.copy_(self._solve(0, residuals))
             return out

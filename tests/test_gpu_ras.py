@@ -185,3 +185,41 @@ def test_gram_mixed_matches_oracle(torch):
         ref[:mu, :mu] += 0.125 * np.eye(mu)
         assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref))), name
         assert np.max(np.abs(got - got.T)) <= 1e-12 * max(1.0, np.max(np.abs(got)))
+
+
+def test_ras_fit_hermite_th3_aniso(torch):
+    """Config C4 in small: th3, anisotropic, value + gradient data (Hermite-Birkhoff), linear polynomial; two-level
+    RAS with mixed domains.  Acceptance: values and gradients reproduced to the tolerance against exact sums."""
+    import polatory_b200 as pb
+    from conftest import random_anisotropy
+    from oracle import direct as odir, rbf as orbf
+    from polatory_b200.operator import Model, Operator, monomial_basis, solve
+    from polatory_b200.ras import RasPreconditioner
+    rng = np.random.default_rng(17)
+    dim, mu, sigma = 3, 3000, 1200
+    aniso = random_anisotropy(dim, rng)
+    pts = rng.uniform(-1, 1, (mu, dim))
+    gpts = rng.uniform(-1, 1, (sigma, dim))
+    f = lambda x: np.sin(np.pi * x).sum(axis=1)
+    values = np.concatenate([f(pts), (np.pi * np.cos(np.pi * gpts)).reshape(-1)])
+    model = Model(pb.make_rbf("th3", [1.0, 0.0], dim, aniso), poly_degree=1, nugget=0.0)
+    bbox = pb.Bbox(-np.ones(dim), np.ones(dim))
+    op = Operator(model, bbox, accuracy=1e-6, grad_accuracy=1e-6)  # two orders below the tolerance
+    op.set_points(pts, gpts)
+    pc = RasPreconditioner(model, pts, gpts)
+    assert pc.n_levels == 2 and pc.m_rows == mu + dim * sigma
+    # every row is owned (inner) by exactly one fine domain
+    owned = torch.zeros(pc.m_rows, device="cuda")
+    owned[pc.fine[1].inner_glob] += 1
+    assert bool((owned == 1).all())
+    tol = 1e-4
+    w, iters = solve(op, values, tol, 100, preconditioner=pc.apply)
+    assert iters <= 50, iters
+    wv = w.cpu().numpy()
+    o = orbf.make_rbf("th3", [1.0, 0.0], dim, aniso)
+    sp, sg = rng.choice(mu, 100, replace=False), rng.choice(sigma, 50, replace=False)
+    m = mu + dim * sigma
+    fit = odir.direct_evaluator(o, 0.0, pts, gpts, wv[:m], pts[sp], gpts[sg]) + \
+        monomial_basis(dim, 1, pts[sp], gpts[sg]) @ wv[m:]
+    ref = np.concatenate([values[sp], values[mu:].reshape(sigma, dim)[sg].reshape(-1)])
+    assert np.max(np.abs(fit - ref)) <= 10 * tol
