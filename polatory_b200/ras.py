@@ -319,6 +319,7 @@ class _FineLevel:
         else:
             self.q_top = None
         self.inv = torch.empty((self.n_dom, r, r), dtype=torch.float64, device=dev)
+        self.info = []
         chunk = max(1, min(self.n_dom, int(2 ** 31 // (8 * m_max * m_max))))
         for b0 in range(0, self.n_dom, chunk):
             b1 = min(self.n_dom, b0 + chunk)
@@ -329,7 +330,8 @@ class _FineLevel:
                 red = arr + q.transpose(1, 2) @ (att @ q + atr) + art @ q
             else:
                 red = a
-            chol = torch.linalg.cholesky(red)
+            chol, info = torch.linalg.cholesky_ex(red)   # no host synchronisation: the set-up stays asynchronous
+            self.info.append(info)
             self.inv[b0:b1] = torch.cholesky_inverse(chol)
             del a, red, chol
 
@@ -439,14 +441,9 @@ class RasPreconditioner:
         self.fine = [None] * n_levels
         self.setup_seconds = {"coarse_points": 0.0, "divide_domains": 0.0, "factorize": 0.0}
         for level in range(n_levels - 1, 0, -1):
+            # The domains of this level first: their factorisations are enqueued on the device and run while
+            # the host chooses the coarse points of the next level (independent of the domains).
             t0 = time.perf_counter()
-            if sigma == 0:
-                point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
-                grad_idcs[level - 1] = np.zeros(0, dtype=np.int64)
-            else:
-                point_idcs[level - 1], grad_idcs[level - 1] = choose_coarse_points_mixed(
-                    a_points, a_grad_points, point_idcs[level], grad_idcs[level], poly_idcs, counts[level - 1])
-            t1 = time.perf_counter()
             if sigma == 0:
                 domains = [(d.point_indices, d.inner_point) for d in divide_domains(a_points, point_idcs[level], poly_idcs)]
             else:
@@ -454,17 +451,23 @@ class RasPreconditioner:
                             np.concatenate([d.inner_point, np.repeat(d.inner_grad_point, dim)]))
                            for d in divide_domains_mixed(a_points, a_grad_points, point_idcs[level], grad_idcs[level],
                                                          poly_idcs)]
-            t2 = time.perf_counter()
+            t1 = time.perf_counter()
             self.fine[level] = _FineLevel(self, domains)
-            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            if sigma == 0:
+                point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
+                grad_idcs[level - 1] = np.zeros(0, dtype=np.int64)
+            else:
+                point_idcs[level - 1], grad_idcs[level - 1] = choose_coarse_points_mixed(
+                    a_points, a_grad_points, point_idcs[level], grad_idcs[level], poly_idcs, counts[level - 1])
             t3 = time.perf_counter()
-            self.setup_seconds["coarse_points"] += t1 - t0
-            self.setup_seconds["divide_domains"] += t2 - t1
-            self.setup_seconds["factorize"] += t3 - t2
+            self.setup_seconds["divide_domains"] += t1 - t0
+            self.setup_seconds["factorize"] += t2 - t1   # host time to enqueue; the device part overlaps what follows
+            self.setup_seconds["coarse_points"] += t3 - t2
             if verbose:
                 print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points, {len(grad_idcs[level])} "
-                      f"gradient points (coarse points {t1 - t0:.2f}s, domains {t2 - t1:.2f}s, factorisation {t3 - t2:.2f}s)",
-                      flush=True)
+                      f"gradient points (domains {t1 - t0:.2f}s, factorisation enqueue {t2 - t1:.2f}s, coarse points "
+                      f"{t3 - t2:.2f}s)", flush=True)
         self.point_idcs, self.grad_idcs = point_idcs, grad_idcs
         self.idx_dev = [torch.from_numpy(np.asarray(p, dtype=np.int64)).to(self.device) for p in point_idcs]
         self.gidx_dev = [torch.from_numpy(np.asarray(g, dtype=np.int64)).to(self.device) for g in grad_idcs]
@@ -474,6 +477,9 @@ class RasPreconditioner:
         self.coarse = _CoarseGrid(self, self._rows(point_idcs[0], grad_idcs[0]))
         if verbose:
             print(f"level 0: 1 domain, {len(point_idcs[0])} points, {len(grad_idcs[0])} gradient points", flush=True)
+        for f in self.fine:
+            if f is not None and any(int(i.max()) != 0 for i in f.info):
+                raise RuntimeError("RAS: a local problem is not positive definite (duplicate points?)")
         self._evaluators = {}
         self.p = self.ap = None
         if l > 0:
