@@ -332,8 +332,12 @@ class _FineLevel:
                 red = a
             chol, info = torch.linalg.cholesky_ex(red)   # no host synchronisation: the set-up stays asynchronous
             self.info.append(info)
-            self.inv[b0:b1] = torch.cholesky_inverse(chol)
-            del a, red, chol
+            # (L L^T)^-1 = L^-T L^-1 through a batched triangular solve + product (cholesky_inverse is 2.5x
+            # slower for this shape and synchronises the host)
+            eye = torch.eye(r, dtype=torch.float64, device=dev).expand(b1 - b0, r, r)
+            linv = torch.linalg.solve_triangular(chol, eye, upper=False)
+            torch.bmm(linv.transpose(1, 2), linv, out=self.inv[b0:b1])
+            del a, red, chol, linv
 
     def solve(self, ras, residuals, weights):
         """FineGrid::solve + set_solution_to for every domain of the level (fine_grid.hpp:103-147)."""
