@@ -320,6 +320,7 @@ def main():
         "fp64_peak_tflops_measured": fp64_peak,
     }
 
+    line["phase_rooflines"] = phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, ev)
     if world == 1 and not args.no_fit:
         line["fit"] = fit_timing(src, dev)
 
@@ -391,6 +392,34 @@ def fit_timing(points, dev, tol=1e-4):
             "matvec_config": op.a[0].config(), "matvec_ms": e[0].elapsed_time(e[1]),
             "ras_apply_ms": e[1].elapsed_time(e[2]),
             "matvec_phases_ms": {k: round(v, 4) for k, v in ph.items()}}
+
+
+def phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, ev):
+    """Roofline fractions of the secondary phases whose algorithmic work is known from the device counters
+    (DESIGN.md section 5): the pruned inverse DFT and the fused leaf pass against HBM, the near field against FP64
+    (SURVEY 8d counting rule: 12 flop per bh3 pair)."""
+    out = {}
+    try:
+        stats = ev.work_stats()
+        p = cfg.get("order") or 0
+        F, P = (2 * p - 1) ** 2 * p, p ** 3
+        if phases.get("m2l_idft") and stats.get("m2l_target_cells"):
+            gbs = (16.0 * F + 8.0 * P) * stats["m2l_target_cells"] / (phases["m2l_idft"] * 1e-3) / 1e9
+            out["m2l_idft"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}
+        if phases.get("l2l_l2p_leaf"):
+            # 8 P bytes of parent local per 2^dim leaves + compact leaf M2L result + 8 (D + 1) bytes per target
+            nb = 8.0 * P * stats.get("m2l_target_cells", 0) + 8.0 * (3 + 1) * n_trg
+            gbs = nb / (phases["l2l_l2p_leaf"] * 1e-3) / 1e9
+            out["l2l_l2p_leaf"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": gbs / hbm_peak, "note": "latency-bound (5 CTA barriers per parent), DESIGN.md"}
+        if phases.get("p2p") and stats.get("p2p_pairs"):
+            tf = 12.0 * stats["p2p_pairs"] / (phases["p2p"] * 1e-3) / 1e12
+            out["p2p"] = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": tf / fp64_peak if fp64_peak else None,
+                          "note": "12 flop per pair by the counting rule; 15 FP64-pipe instructions per pair in SASS"}
+    except Exception as e:  # diagnostics only
+        out["error"] = str(e)
+    return out
 
 
 def measured_traffic(kernel):
