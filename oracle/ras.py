@@ -1,5 +1,5 @@
 """ORACLE (test infrastructure, never imported by the product path): numpy restatement of the reference's
-RAS preconditioner for value data, dense and exact (every kernel sum is a direct sum).
+RAS preconditioner for value and Hermite data, dense and exact (every kernel sum is a direct sum).
 
   RasPreconditioner   include/polatory/preconditioner/ras_preconditioner.hpp:34-364
   DomainDivider       include/polatory/preconditioner/domain_divider.hpp:17-321
@@ -124,59 +124,193 @@ def choose_coarse_points(a_points, point_idcs, poly_idcs, n_coarse_points):
 
 
 
-def monomials(dim, degree, points):
-    """polynomial::MonomialBasis::evaluate for value points (monomial_basis.hpp): 1 | x y z | x^2 xy xz y^2 yz z^2."""
+def monomials(dim, degree, points, grad_points=None):
+    """polynomial::MonomialBasis::evaluate (monomial_basis.hpp): value rows 1 | x y z | x^2 xy xz y^2 yz z^2, then
+    `dim` derivative rows per gradient point (row mu + dim*j + k = d/dx_k at gradient point j)."""
     points = np.asarray(points, dtype=np.float64).reshape(-1, dim)
-    cols = []
+    exps = []
     if degree >= 0:
-        cols.append(np.ones(len(points)))
+        exps.append((0,) * dim)
     if degree >= 1:
-        cols += [points[:, a] for a in range(dim)]
+        exps += [tuple(1 if a == b else 0 for b in range(dim)) for a in range(dim)]
     if degree >= 2:
-        cols += [points[:, a] * points[:, b] for a in range(dim) for b in range(a, dim)]
-    return np.stack(cols, axis=1) if cols else np.zeros((len(points), 0))
+        for a in range(dim):
+            for b in range(a, dim):
+                e = [0] * dim
+                e[a] += 1
+                e[b] += 1
+                exps.append(tuple(e))
+    gp = np.zeros((0, dim)) if grad_points is None else np.asarray(grad_points, dtype=np.float64).reshape(-1, dim)
+    mu, sigma = len(points), len(gp)
+    out = np.zeros((mu + dim * sigma, len(exps)))
+    for c, e in enumerate(exps):
+        out[:mu, c] = np.prod(points ** np.asarray(e), axis=1)
+        for k in range(dim):
+            if e[k]:
+                ek = list(e)
+                ek[k] -= 1
+                out[mu + k:mu + dim * sigma:dim, c] = e[k] * np.prod(gp ** np.asarray(ek), axis=1)
+    return out
+
+
+# -- the same two algorithms with gradient points (multiplicity dim), domain_divider.hpp:205-231, 66-90 ----------
+def _mixed_coords(a_points, a_grad_points, idx, is_grad):
+    out = np.empty((len(idx), a_points.shape[1]))
+    out[~is_grad] = a_points[idx[~is_grad]]
+    out[is_grad] = a_grad_points[idx[is_grad]]
+    return out
+
+
+def divide_domains_mixed(a_points, a_grad_points, point_idcs, grad_idcs, poly_idcs):
+    """Returns a list of (point_indices, inner_point, grad_point_indices, inner_grad_point)."""
+    dim = a_points.shape[1]
+    idx0 = np.concatenate([np.asarray(point_idcs, dtype=np.int64), np.asarray(grad_idcs, dtype=np.int64)])
+    g0 = np.concatenate([np.zeros(len(point_idcs), dtype=bool), np.ones(len(grad_idcs), dtype=bool)])
+    queue, leaves, head = [(idx0, g0, np.ones(len(idx0), dtype=bool))], [], 0
+    while head < len(queue):
+        idx, isg, inner = queue[head]
+        head += 1
+        n_mult = int(np.where(isg, dim, 1).sum())
+        if n_mult <= K_MAX_LEAF_SIZE:
+            leaves.append((idx, isg, inner))
+            continue
+        order = _sort_by_axes(_mixed_coords(a_points, a_grad_points, idx, isg))
+        idx, isg, inner = idx[order], isg[order], inner[order]
+        prefix = np.concatenate([[0], np.cumsum(np.where(isg, dim, 1))])
+        q = K_OVERLAP_QUOTA * K_MAX_LEAF_SIZE / n_mult
+        n_sub = int(_round_half_to_even((1.0 + q) / 2.0 * n_mult))
+        left_mult, right_mult = n_mult - n_sub, n_sub
+        mid_mult = int(_round_half_to_even((left_mult + right_mult) / 2.0))
+        ub = lambda x: int(np.searchsorted(prefix, x, side="right")) - 1
+        left_part, right_part, mid = ub(left_mult), ub(right_mult), ub(mid_mult)
+        pos = np.arange(len(idx))
+        queue.append((idx[:right_part], isg[:right_part], inner[:right_part] & (pos[:right_part] < mid)))
+        queue.append((idx[left_part:], isg[left_part:], inner[left_part:] & (pos[left_part:] >= mid)))
+    out = []
+    for idx, isg, inner in leaves:
+        d = Domain(np.sort(idx[~isg]), None)
+        order = np.argsort(idx[~isg], kind="stable")
+        pi, pin = idx[~isg][order], inner[~isg][order]
+        front = []
+        for q_ in poly_idcs:  # merge_poly_points
+            hit = np.nonzero(pi == q_)[0]
+            front.append(bool(pin[hit[0]]) if len(hit) else False)
+        keep = ~np.isin(pi, np.asarray(poly_idcs, dtype=np.int64))
+        pi = np.concatenate([np.asarray(poly_idcs, dtype=np.int64), pi[keep]])
+        pin = np.concatenate([np.asarray(front, dtype=bool), pin[keep]])
+        out.append((pi, pin, idx[isg], inner[isg]))
+    return out
+
+
+def choose_coarse_points_mixed(a_points, a_grad_points, point_idcs, grad_idcs, poly_idcs, n_coarse_rows):
+    dim = a_points.shape[1]
+    poly_set = set(int(i) for i in poly_idcs)
+    pv = np.array([i for i in point_idcs if int(i) not in poly_set], dtype=np.int64)
+    idx0 = np.concatenate([pv, np.asarray(grad_idcs, dtype=np.int64)])
+    g0 = np.concatenate([np.zeros(len(pv), dtype=bool), np.ones(len(grad_idcs), dtype=bool)])
+
+    def init(idx, isg):
+        pts = _mixed_coords(a_points, a_grad_points, idx, isg)
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        k = int(np.argmin(((pts - 0.5 * (lo + hi)) ** 2).sum(axis=1)))
+        order = _sort_by_axes(pts)
+        return float(np.prod(hi - lo)), (int(idx[k]), bool(isg[k])), idx[order], isg[order]
+
+    counter = 0
+    vol, c, si, sg = init(idx0, g0)
+    heap = [(0, -vol, counter, c, si, sg)]
+    size = dim if c[1] else 1
+    while size < n_coarse_rows:
+        level, _, _, c, idx, isg = heapq.heappop(heap)
+        size -= dim if c[1] else 1
+        prefix = np.concatenate([[0], np.cumsum(np.where(isg, dim, 1))])
+        d = np.abs(2 * prefix[:len(idx)] - int(prefix[-1]))
+        cand = np.nonzero(d == d.min())[0]
+        mid = int(cand[0])
+        for k in cand[1:]:
+            if k % 2 == 0:
+                mid = int(k)
+        for pi_, pg_ in ((idx[:mid], isg[:mid]), (idx[mid:], isg[mid:])):
+            if len(pi_):
+                counter += 1
+                vol, c2, si, sg = init(pi_, pg_)
+                size += dim if c2[1] else 1
+                heapq.heappush(heap, (level + 1, -vol, counter, c2, si, sg))
+    pts_out, grads_out = [int(i) for i in poly_idcs], []
+    while heap:
+        c = heapq.heappop(heap)[3]
+        (grads_out if c[1] else pts_out).append(c[0])
+    return np.asarray(pts_out, dtype=np.int64), np.asarray(grads_out, dtype=np.int64)
 
 
 class RasOracle:
-    """Dense restatement of RasPreconditioner for one RBF and value data.  `a_dense[i, j]` = phi(x_i - x_j)
-    over ALL points (anisotropy included, no nugget); `poly_idcs` are the unisolvent points to use."""
+    """Dense restatement of RasPreconditioner for one RBF.  `a_dense` is the full matrix of the global system
+    WITHOUT nugget and polynomial (mat_a over all rows: value row i = point i, rows mu + dim*j + c = component c
+    of gradient point j; anisotropy included); `a_points` / `a_grad_points` are the coordinates the domain
+    decomposition works on (anisotropy-transformed for one anisotropic RBF, ras_preconditioner.hpp:107-117);
+    `poly_idcs` are the unisolvent points to use."""
 
-    def __init__(self, a_dense, points, dim, degree, nugget, poly_idcs):
-        self.a_dense, self.points, self.dim, self.degree = a_dense, np.asarray(points, dtype=np.float64), dim, degree
-        self.mu = len(self.points)
-        self.l = monomials(dim, degree, self.points[:1]).shape[1]
+    def __init__(self, a_dense, points, dim, degree, nugget, poly_idcs, grad_points=None, a_points=None,
+                 a_grad_points=None):
+        self.a_dense, self.dim, self.degree = a_dense, dim, degree
+        self.points = np.asarray(points, dtype=np.float64)
+        self.grad_points = np.zeros((0, dim)) if grad_points is None else np.asarray(grad_points, dtype=np.float64)
+        a_points = self.points if a_points is None else a_points
+        a_grad_points = self.grad_points if a_grad_points is None else a_grad_points
+        self.mu, self.sigma = len(self.points), len(self.grad_points)
+        mu, sigma = self.mu, self.sigma
+        self.m_rows = mu + dim * sigma
+        self.p_rows = monomials(dim, degree, self.points, self.grad_points)
+        self.l = self.p_rows.shape[1]
         self.nugget = nugget
-        mu, l = self.mu, self.l
-        n_levels = max(int(math.ceil(math.log(mu / K_N_COARSEST_POINTS) / math.log(K_FINE_TO_COARSE_RATIO))), 0) + 1
+        l = self.l
+        n_levels = max(int(math.ceil(math.log(self.m_rows / K_N_COARSEST_POINTS) / math.log(K_FINE_TO_COARSE_RATIO))), 0) + 1
         self.n_levels = n_levels
         poly_idcs = list(poly_idcs)
+        self.poly_idcs = poly_idcs
         if l:
-            self.lagrange_p = monomials(dim, degree, self.points) @ np.linalg.inv(monomials(dim, degree, self.points[poly_idcs]))
+            self.lagrange_p = self.p_rows @ np.linalg.inv(monomials(dim, degree, self.points[poly_idcs]))
         rest = np.ones(mu, dtype=bool)
         rest[poly_idcs] = False
-        self.point_idcs = [None] * n_levels
+        self.point_idcs, self.grad_idcs = [None] * n_levels, [None] * n_levels
         self.point_idcs[-1] = np.concatenate([np.asarray(poly_idcs, dtype=np.int64), np.nonzero(rest)[0]])
-        finest = math.log(mu) / math.log(K_FINE_TO_COARSE_RATIO)
+        self.grad_idcs[-1] = np.arange(sigma, dtype=np.int64)
+        finest = math.log(self.m_rows) / math.log(K_FINE_TO_COARSE_RATIO)
         coarsest = math.log(K_N_COARSEST_POINTS) / math.log(K_FINE_TO_COARSE_RATIO)
         self.fine = [None] * n_levels
         for level in range(n_levels - 1, 0, -1):
             n_coarse = int(K_FINE_TO_COARSE_RATIO ** (coarsest + (level - 1) * (finest - coarsest) / (n_levels - 1)))
-            self.point_idcs[level - 1] = choose_coarse_points(self.points, self.point_idcs[level], poly_idcs, n_coarse)
-            self.fine[level] = [self._grid(d.point_indices, d.inner_point)
-                                for d in divide_domains(self.points, self.point_idcs[level], poly_idcs)]
-        self.coarse = self._grid(self.point_idcs[0], None)
+            if sigma == 0:
+                self.point_idcs[level - 1] = choose_coarse_points(a_points, self.point_idcs[level], poly_idcs, n_coarse)
+                self.grad_idcs[level - 1] = np.zeros(0, dtype=np.int64)
+                doms = [(d.point_indices, d.inner_point, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=bool))
+                        for d in divide_domains(a_points, self.point_idcs[level], poly_idcs)]
+            else:
+                self.point_idcs[level - 1], self.grad_idcs[level - 1] = choose_coarse_points_mixed(
+                    a_points, a_grad_points, self.point_idcs[level], self.grad_idcs[level], poly_idcs, n_coarse)
+                doms = divide_domains_mixed(a_points, a_grad_points, self.point_idcs[level], self.grad_idcs[level], poly_idcs)
+            self.fine[level] = [self._grid(self._rows(pi, gi), np.concatenate([pin, np.repeat(gin, dim)]))
+                                for pi, pin, gi, gin in doms]
+        self.level_rows = [self._rows(self.point_idcs[k], self.grad_idcs[k]) for k in range(n_levels)]
+        self.coarse = self._grid(self.level_rows[0], None)
         if n_levels > 1 and l:
-            p = monomials(dim, degree, self.points)
+            p = self.p_rows.copy()
             for i in range(l):
                 p[:, i] /= np.linalg.norm(p[:, i])
                 for j in range(i + 1, l):
                     p[:, j] -= (p[:, i] @ p[:, j]) * p[:, i]
             self.p = p
-            self.ap = self.a_dense @ p + nugget * p
+            self.ap = self.a_dense @ p
+            self.ap[:mu] += nugget * p[:mu]
+
+    def _rows(self, point_indices, grad_indices):
+        g = np.asarray(grad_indices, dtype=np.int64)
+        grows = (self.mu + self.dim * g[:, None] + np.arange(self.dim)[None, :]).reshape(-1)
+        return np.concatenate([np.asarray(point_indices, dtype=np.int64), grows])
 
     def _grid(self, idx, inner):
         l = self.l
-        a = self.a_dense[np.ix_(idx, idx)] + self.nugget * np.eye(len(idx))  # mat_a
+        a = self.a_dense[np.ix_(idx, idx)] + self.nugget * np.diag((np.asarray(idx) < self.mu).astype(float))  # mat_a
         g = {"idx": np.asarray(idx), "inner": inner, "a_top": a[:l]}
         if l:
             q_top = -self.lagrange_p[idx][l:].T
@@ -201,7 +335,7 @@ class RasOracle:
         return chol_solve(d)
 
     def _solve(self, level, residuals):
-        w = np.zeros(self.mu + self.l)
+        w = np.zeros(self.m_rows + self.l)
         if level == 0:
             g = self.coarse
             lam = self._local(g, residuals)
@@ -209,7 +343,7 @@ class RasOracle:
             if self.l:
                 l = self.l
                 p_top = monomials(self.dim, self.degree, self.points[g["idx"][:l]])
-                w[self.mu:] = np.linalg.solve(p_top, residuals[g["idx"][:l]] - g["a_top"] @ lam)
+                w[self.m_rows:] = np.linalg.solve(p_top, residuals[g["idx"][:l]] - g["a_top"] @ lam)
         else:
             for g in self.fine[level]:
                 lam = self._local(g, residuals)
@@ -217,24 +351,24 @@ class RasOracle:
         return w
 
     def _update(self, src, trg, w, residuals):
-        si, ti = self.point_idcs[src], self.point_idcs[trg]
+        si, ti = self.level_rows[src], self.level_rows[trg]
         fit = self.a_dense[np.ix_(ti, si)] @ w[si]
         if self.l:
-            fit = fit + monomials(self.dim, self.degree, self.points[ti]) @ w[self.mu:]
+            fit = fit + self.p_rows[ti] @ w[self.m_rows:]
         residuals[ti] -= fit
 
     def _orthogonalize(self, w, residuals):
         if self.l:
-            dot = self.p.T @ w[:self.mu]
-            w[:self.mu] -= self.p @ dot
+            dot = self.p.T @ w[:self.m_rows]
+            w[:self.m_rows] -= self.p @ dot
             residuals += self.ap @ dot
 
     def __call__(self, v):
         n = self.n_levels
-        residuals = np.array(v[:self.mu], dtype=np.float64)
+        residuals = np.array(v[:self.m_rows], dtype=np.float64)
         if n == 1:
             return self._solve(0, residuals)
-        total = np.zeros(self.mu + self.l)
+        total = np.zeros(self.m_rows + self.l)
         w = self._solve(0, residuals)
         self._update(0, n - 1, w, residuals)
         total += w

@@ -223,3 +223,82 @@ def test_ras_fit_hermite_th3_aniso(torch):
         monomial_basis(dim, 1, pts[sp], gpts[sg]) @ wv[m:]
     ref = np.concatenate([values[sp], values[mu:].reshape(sigma, dim)[sg].reshape(-1)])
     assert np.max(np.abs(fit - ref)) <= 10 * tol
+
+
+def _dense_th3_hermite(pts, gpts, aniso):
+    """mat_a for th3 (phi = r^3, s = 1, c = 0; polyharmonic_odd.hpp:32-67) with anisotropy, rows [values | dim per
+    gradient point]: K = phi, F = -(grad phi) A, H = -A^T (Hess phi) A on the transformed differences."""
+    dim = pts.shape[1]
+    mu, sigma = len(pts), len(gpts)
+    tp, tg = pts @ aniso.T, gpts @ aniso.T
+    m = mu + dim * sigma
+    a = np.zeros((m, m))
+    d = tp[:, None, :] - tp[None, :, :]
+    a[:mu, :mu] = np.sqrt((d * d).sum(axis=2)) ** 3
+    d = tp[:, None, :] - tg[None, :, :]                      # value row i, gradient column j
+    r = np.sqrt((d * d).sum(axis=2))
+    f = -(3.0 * r[:, :, None] * d) @ aniso                   # -(grad_iso A)
+    a[:mu, mu:] = f.reshape(mu, dim * sigma)
+    a[mu:, :mu] = a[:mu, mu:].T
+    d = tg[:, None, :] - tg[None, :, :]
+    r = np.sqrt((d * d).sum(axis=2))
+    with np.errstate(all="ignore"):
+        hess = 3.0 * (r[:, :, None, None] * np.eye(dim) + np.where(r[:, :, None, None] > 0,
+                      d[:, :, :, None] * d[:, :, None, :] / r[:, :, None, None], 0.0))
+    h = -np.einsum("ai,pqab,bj->pqij", aniso, hess, aniso)
+    a[mu:, mu:] = h.transpose(0, 2, 1, 3).reshape(dim * sigma, dim * sigma)
+    return a
+
+
+def test_ras_hermite_parity_with_oracle(torch):
+    """Hermite data: the device RAS (mixed domains, Hermite Gram kernel, four-kind transfers) against the dense oracle
+    on the same 2-level th3 problem with anisotropy: same level sets, one sweep to 1e-6 (order-12 transfers), FGMRES
+    iteration counts within +-1."""
+    import polatory_b200 as pb
+    from conftest import random_anisotropy
+    from oracle import direct as odir, rbf as orbf
+    from oracle.krylov import Fgmres as OracleFgmres
+    from oracle.ras import RasOracle, monomials
+    from polatory_b200.operator import Model, Operator, solve
+    from polatory_b200.ras import RasPreconditioner
+    rng = np.random.default_rng(41)
+    dim, mu, sigma = 3, 2600, 900
+    aniso = random_anisotropy(dim, rng)
+    pts, gpts = rng.uniform(-1, 1, (mu, dim)), rng.uniform(-1, 1, (sigma, dim))
+    m = mu + dim * sigma
+    a_dense = _dense_th3_hermite(pts, gpts, aniso)
+    o_rbf = orbf.make_rbf("th3", [1.0, 0.0], dim, aniso)
+    for col in (3, mu + 7, m - 1):   # the closed-form builder against the oracle's direct evaluator
+        ref = odir.direct_evaluator(o_rbf, 0.0, pts, gpts, np.eye(m)[:, col], pts, gpts)
+        assert np.max(np.abs(a_dense[:, col] - ref)) <= 1e-11 * np.max(np.abs(ref))
+    values = np.concatenate([np.sin(np.pi * pts).sum(axis=1), (np.pi * np.cos(np.pi * gpts)).reshape(-1)])
+    model = Model(pb.make_rbf("th3", [1.0, 0.0], dim, aniso), poly_degree=1, nugget=0.0)
+    pc = RasPreconditioner(model, pts, gpts, transfer_config=(12, 8))
+    o = RasOracle(a_dense, pts, dim, 1, 0.0, pc.poly_idcs, grad_points=gpts, a_points=pts @ aniso.T,
+                  a_grad_points=gpts @ aniso.T)
+    assert pc.n_levels == o.n_levels == 2
+    for lvl in range(2):
+        assert set(o.point_idcs[lvl].tolist()) == set(np.asarray(pc.point_idcs[lvl]).tolist())
+        assert set(o.grad_idcs[lvl].tolist()) == set(np.asarray(pc.grad_idcs[lvl]).tolist())
+    l = pc.l
+    v = np.concatenate([values, np.zeros(l)])
+    ref = o(v)
+    got = pc(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-6 * np.max(np.abs(ref))
+    # FGMRES over the exact dense system with the oracle RAS vs the device solver with the device RAS
+    p = monomials(dim, 1, pts, gpts)
+    full = np.block([[a_dense, p], [p.T, np.zeros((l, l))]])
+    tol = 1e-5
+    s = OracleFgmres(lambda x: full @ x, v, 80)
+    s.set_right_preconditioner(o)
+    s.setup()
+    while True:
+        x = s.solution_vector()
+        if s.absolute_residual() <= tol * np.sqrt(len(v)) and np.max(np.abs((full @ x)[:m] - values)) <= tol:
+            break
+        s.iterate_process()
+    op = Operator(model, pb.Bbox(-np.ones(dim), np.ones(dim)), accuracy=0.0, grad_accuracy=0.0)  # order 12 / d 8
+    op.set_points(pts, gpts)
+    w, iters = solve(op, values, tol, 80, preconditioner=pc.apply)
+    assert abs(iters - s.iteration_count()) <= 1, (iters, s.iteration_count())
+    assert np.max(np.abs(w.cpu().numpy() - x)) <= 1e-3 * np.max(np.abs(x))
