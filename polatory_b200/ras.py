@@ -394,9 +394,9 @@ class RasPreconditioner:
     [mu values | dim * sigma gradient components | l polynomial coefficients]."""
 
     def __init__(self, model, points, grad_points=None, device=None, verbose=False, transfer_config=None):
-        """transfer_config: optional (order, d) forced on the level-transfer evaluators (default: the
-        reference's accuracy = infinity, i.e. order 6) -- used by the parity tests to separate the FMM
-        discretisation error of the transfers from everything else."""
+        """transfer_config: optional (order, d) forced on the level-transfer evaluators, or "direct" for exact
+        sums (default: the reference's accuracy = infinity, i.e. order 6) -- used by the parity tests to
+        separate the FMM discretisation error of the transfers from everything else."""
         import time
         import torch
         self.transfer_config = transfer_config
@@ -498,9 +498,8 @@ class RasPreconditioner:
             self.p = torch.from_numpy(p).to(self.device)
             from .operator import Model as _Model, Operator
             fin = Operator(_Model(model.rbfs, poly_degree=-1, nugget=model.nugget), self.bbox, device=self.device)
-            if transfer_config:
-                for ev in fin.a + fin.f + fin.ft + fin.h:
-                    ev.force_config(*transfer_config)
+            for ev in fin.a + fin.f + fin.ft + fin.h:
+                self._configure_transfer(ev)
             fin.set_points(self.points, self.grad_points if sigma else None)
             self.ap = torch.empty_like(self.p)
             col = torch.empty(self.m_rows, dtype=torch.float64, device=self.device)
@@ -510,6 +509,12 @@ class RasPreconditioner:
             del fin
 
     # -- helpers ---------------------------------------------------------------------------
+    def _configure_transfer(self, ev):
+        if self.transfer_config == "direct":
+            ev.force_direct(True)
+        elif self.transfer_config:
+            ev.force_config(*self.transfer_config)
+
     def _rows(self, point_indices, grad_point_indices):
         """Flat rows of the global system for a set of value and gradient points (values first)."""
         g = np.asarray(grad_point_indices, dtype=np.int64)
@@ -551,8 +556,7 @@ class RasPreconditioner:
                 if len(s_pts) == 0 or len(t_pts) == 0:
                     continue
                 ev = make(rbf, self.bbox)
-                if self.transfer_config:
-                    ev.force_config(*self.transfer_config)
+                self._configure_transfer(ev)
                 ev.set_source_points(s_pts)
                 ev.set_target_points(t_pts)
                 kn = self.dim if name in ("ft", "h") else 1
