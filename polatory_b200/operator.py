@@ -261,6 +261,23 @@ class Operator:
         return y
 
 
+class ShardedPreconditioner:
+    """Right preconditioner for sharded Krylov vectors out of a preconditioner that works on the full
+    (caller-order) vector and is replicated on every rank (e.g. ras.RasPreconditioner): assemble the shards
+    (one all_reduce), apply, keep this rank's shard.  The FMM matvec and the Krylov reductions scale with the
+    ranks; the preconditioner is computed redundantly (a domain-sharded RAS is the next step)."""
+
+    def __init__(self, op, preconditioner):
+        self.op, self.pc = op, preconditioner
+
+    def apply(self, x_local, y_local):
+        full = self.op.gather(x_local)
+        y_local.copy_(self.op.scatter(self.pc(full)))
+        return y_local
+
+    __call__ = apply
+
+
 class ResidualEvaluator:
     """interpolation::ResidualEvaluator for value data (include/polatory/interpolation/residual_evaluator.hpp:26-164):
     the residual |fit - value| is first measured EXACTLY (direct sums on the device) on at most 1024 sampled points

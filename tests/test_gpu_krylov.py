@@ -190,8 +190,20 @@ wl, it2 = solve(sharded, sharded.scatter(np.concatenate([values, [0.0]]))[:shard
 w2 = sharded.gather(wl)
 assert abs(it1 - it2) <= 1, (it1, it2)
 assert float((w1 - w2).abs().max() / w1.abs().max()) < 1e-6
+# preconditioned fit: replicated RAS behind the sharded matvec (operator.ShardedPreconditioner)
+from polatory_b200.operator import ShardedPreconditioner
+from polatory_b200.ras import RasPreconditioner
+model0 = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.0)
+s1 = Operator(model0, bbox, accuracy=1e-7); s1.set_points(pts)
+sN = Operator(model0, bbox, accuracy=1e-7, group=dist.group.WORLD); sN.set_points(pts)
+pc = RasPreconditioner(model0, pts)
+wa, ia = solve(s1, values, 1e-5, 60, preconditioner=pc.apply)
+wb, ib = solve(sN, sN.scatter(np.concatenate([values, [0.0]]))[:sN.hi - sN.lo], 1e-5, 60,
+               preconditioner=ShardedPreconditioner(sN, pc).apply)
+assert abs(ia - ib) <= 1 and ia <= 15, (ia, ib)
+assert float((wa - sN.gather(wb)).abs().max() / wa.abs().max()) < 1e-5
 if rank == 0:
-    print("sharded ok", err, it1, it2)
+    print("sharded ok", err, it1, it2, ia, ib)
 dist.destroy_process_group()
 """
 
