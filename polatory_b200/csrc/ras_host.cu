@@ -6,7 +6,7 @@
 //   preconditioner::Domain::merge_poly_points             include/polatory/preconditioner/domain.hpp:33-51
 // for value points.  The reference walks a priority queue / a list one cluster at a time; here the work
 // is level-synchronous (every cluster of a level is independent of its siblings) and spread over the
-// host threads, and a child keeps its parent's order when the sort axes did not change.
+// host threads, and the reference's sort-then-cut becomes a selection at the cut ranks (same sets, O(n)).
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -70,26 +70,48 @@ BoxInfo box_of(const PointsView& pv, const int64_t* idx, size_t n) {
   return b;
 }
 
-void sort_along(const PointsView& pv, const std::array<int, 3>& axes, int64_t* idx, size_t n) {
-  std::sort(idx, idx + n, [&](int64_t x, int64_t y) {
+// Lexicographic order along `axes`; identical coordinates fall back to the index (deterministic).
+struct AxisLess {
+  const PointsView& pv;
+  const std::array<int, 3>& axes;
+  bool operator()(int64_t x, int64_t y) const {
     const double *p = pv.row(x), *q = pv.row(y);
     for (int k = 0; k < pv.dim; ++k) {
       const int a = axes[k];
       if (p[a] != q[a]) return p[a] < q[a];
     }
-    return x < y;  // identical coordinates: deterministic
-  });
+    return x < y;
+  }
+};
+
+// The reference sorts a cluster / domain and then cuts it at fixed ranks; only WHICH points fall on which side
+// of a cut is ever used, so a selection (nth_element) at the cut ranks replaces the sort: O(n) instead of
+// O(n log n), same sets.
+void select_ranks(const PointsView& pv, const std::array<int, 3>& axes, int64_t* idx, size_t n,
+                  std::initializer_list<size_t> ranks) {
+  const AxisLess less{pv, axes};
+  size_t lo = 0;
+  for (size_t r : ranks) {  // ascending ranks: each selection works on the part right of the previous cut
+    if (r > lo && r < n) std::nth_element(idx + lo, idx + r, idx + n, less);
+    lo = std::max(lo, std::min(r, n));
+  }
+}
+
+size_t split_position(size_t size) {
+  if (size % 2 == 0) return size / 2;
+  const size_t a = (size - 1) / 2;  // |2 i - size| ties between a and a + 1: the even index wins
+  return a % 2 == 0 ? a : a + 1;
 }
 
 struct Cluster {
-  std::vector<int64_t> idx;  // sorted along `axes`
-  std::array<int, 3> axes;
+  std::vector<int64_t> idx;
+  std::array<int, 3> axes;  // by decreasing width of the cluster's box
   double volume;
   int64_t centre;
 };
 
-// bbox, centre (first point nearest to the box centre, in the incoming order) and sort.
-void init_cluster(const PointsView& pv, Cluster& c, const std::array<int, 3>* parent_axes) {
+// bbox, axes and centre (the point nearest to the box centre).
+void init_cluster(const PointsView& pv, Cluster& c) {
   const BoxInfo b = box_of(pv, c.idx.data(), c.idx.size());
   double best = std::numeric_limits<double>::infinity();
   c.centre = c.idx.empty() ? -1 : c.idx[0];
@@ -108,16 +130,16 @@ void init_cluster(const PointsView& pv, Cluster& c, const std::array<int, 3>* pa
     }
   }
   c.axes = b.axes;
-  bool same = parent_axes != nullptr;
-  if (same)
-    for (int k = 0; k < pv.dim; ++k) same = same && (*parent_axes)[k] == b.axes[k];
-  if (!same) sort_along(pv, c.axes, c.idx.data(), c.idx.size());
 }
 
-size_t split_position(size_t size) {
-  if (size % 2 == 0) return size / 2;
-  const size_t a = (size - 1) / 2;  // |2 i - size| ties between a and a + 1: the even index wins
-  return a % 2 == 0 ? a : a + 1;
+// Splits c at the reference's mid rank into (l, r).
+void split_cluster(const PointsView& pv, Cluster& c, Cluster& l, Cluster& r) {
+  const size_t mid = c.idx.size() > 1 ? split_position(c.idx.size()) : 0;
+  select_ranks(pv, c.axes, c.idx.data(), c.idx.size(), {mid});
+  l.idx.assign(c.idx.begin(), c.idx.begin() + mid);
+  r.idx.assign(c.idx.begin() + mid, c.idx.end());
+  if (!l.idx.empty()) init_cluster(pv, l);
+  if (!r.idx.empty()) init_cluster(pv, r);
 }
 
 double round_half_to_even(double d) { return std::ceil((d - 0.5) / 2.0) + std::floor((d + 0.5) / 2.0); }
@@ -147,7 +169,7 @@ int plt_ras_choose_coarse_points(const double* a_points, int dim, const int64_t*
     for (int64_t k = 0; k < n_idcs; ++k)
       if (!std::binary_search(poly_sorted.begin(), poly_sorted.end(), idcs[k])) root.idx.push_back(idcs[k]);
     if (static_cast<int64_t>(root.idx.size()) < n_coarse) return PLT_ERR_INVALID;
-    init_cluster(pv, root, nullptr);
+    init_cluster(pv, root);
     std::vector<Cluster> level;
     level.push_back(std::move(root));
     // Whole levels are split while the count stays below the target (the queue orders by level first).
@@ -156,15 +178,7 @@ int plt_ras_choose_coarse_points(const double* a_points, int dim, const int64_t*
       for (auto& c : level) splittable += c.idx.size() > 1 ? 1 : 0;
       if (level.size() + splittable > static_cast<size_t>(n_coarse) || splittable == 0) break;
       std::vector<Cluster> next(level.size() * 2);
-      parallel_for(level.size(), [&](size_t i) {
-        Cluster& c = level[i];
-        const size_t mid = c.idx.size() > 1 ? split_position(c.idx.size()) : 0;
-        Cluster &l = next[2 * i], &r = next[2 * i + 1];
-        l.idx.assign(c.idx.begin(), c.idx.begin() + mid);
-        r.idx.assign(c.idx.begin() + mid, c.idx.end());
-        if (!l.idx.empty()) init_cluster(pv, l, &c.axes);
-        if (!r.idx.empty()) init_cluster(pv, r, &c.axes);
-      });
+      parallel_for(level.size(), [&](size_t i) { split_cluster(pv, level[i], next[2 * i], next[2 * i + 1]); });
       level.clear();
       for (auto& c : next)
         if (!c.idx.empty()) level.push_back(std::move(c));
@@ -178,15 +192,8 @@ int plt_ras_choose_coarse_points(const double* a_points, int dim, const int64_t*
     for (size_t k = 0; k < order.size() && to_split.size() < need; ++k)
       if (level[order[k]].idx.size() > 1) to_split.push_back(order[k]);
     std::vector<Cluster> children(to_split.size() * 2);
-    parallel_for(to_split.size(), [&](size_t i) {
-      Cluster& c = level[to_split[i]];
-      const size_t mid = split_position(c.idx.size());
-      Cluster &l = children[2 * i], &r = children[2 * i + 1];
-      l.idx.assign(c.idx.begin(), c.idx.begin() + mid);
-      r.idx.assign(c.idx.begin() + mid, c.idx.end());
-      init_cluster(pv, l, &c.axes);
-      init_cluster(pv, r, &c.axes);
-    });
+    parallel_for(to_split.size(),
+                 [&](size_t i) { split_cluster(pv, level[to_split[i]], children[2 * i], children[2 * i + 1]); });
     std::vector<char> was_split(level.size(), 0);
     for (size_t i : to_split) was_split[i] = 1;
     int64_t w = 0;
@@ -213,7 +220,6 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
     struct Dom {
       std::vector<int64_t> idx;
       std::vector<uint8_t> inner;
-      std::array<int, 3> axes{{-1, -1, -1}};  // order the points are currently sorted along (none at the root)
     };
     std::vector<Dom> level(1), leaves;
     level[0].idx.assign(idcs, idcs + n_idcs);
@@ -229,19 +235,29 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
           return;
         }
         const BoxInfo b = box_of(pv, d.idx.data(), d.idx.size());
-        bool same = true;
-        for (int k = 0; k < dim; ++k) same = same && d.axes[k] == b.axes[k];
-        if (!same) {
+        // domain_divider.hpp:209-225 with unit multiplicities
+        const double q = overlap_quota * static_cast<double>(max_leaf) / static_cast<double>(n);
+        const int64_t n_sub = static_cast<int64_t>(round_half_to_even((1.0 + q) / 2.0 * static_cast<double>(n)));
+        const int64_t left_part = n - n_sub, right_part = n_sub;
+        const int64_t mid = static_cast<int64_t>(round_half_to_even(static_cast<double>(left_part + right_part) / 2.0));
+        {
+          // order (index, inner) pairs by rank classes [0, left_part) [left_part, mid) [mid, right_part) [right_part, n)
           std::vector<int64_t> perm(n);
           std::iota(perm.begin(), perm.end(), 0);
-          std::sort(perm.begin(), perm.end(), [&](int64_t x, int64_t y) {
+          const std::array<int, 3> axes = b.axes;
+          auto less = [&](int64_t x, int64_t y) {
             const double *p = pv.row(d.idx[x]), *q = pv.row(d.idx[y]);
             for (int k = 0; k < dim; ++k) {
-              const int a = b.axes[k];
+              const int a = axes[k];
               if (p[a] != q[a]) return p[a] < q[a];
             }
             return d.idx[x] < d.idx[y];
-          });
+          };
+          size_t lo = 0;
+          for (int64_t r : {left_part, mid, right_part}) {
+            if (static_cast<size_t>(r) > lo && r < n) std::nth_element(perm.begin() + lo, perm.begin() + r, perm.end(), less);
+            lo = std::max<size_t>(lo, static_cast<size_t>(std::min<int64_t>(r, n)));
+          }
           std::vector<int64_t> idx2(n);
           std::vector<uint8_t> in2(n);
           for (int64_t k = 0; k < n; ++k) {
@@ -251,11 +267,6 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
           d.idx.swap(idx2);
           d.inner.swap(in2);
         }
-        // domain_divider.hpp:209-225 with unit multiplicities
-        const double q = overlap_quota * static_cast<double>(max_leaf) / static_cast<double>(n);
-        const int64_t n_sub = static_cast<int64_t>(round_half_to_even((1.0 + q) / 2.0 * static_cast<double>(n)));
-        const int64_t left_part = n - n_sub, right_part = n_sub;
-        const int64_t mid = static_cast<int64_t>(round_half_to_even(static_cast<double>(left_part + right_part) / 2.0));
         Dom &l = next[2 * i], &r = next[2 * i + 1];
         l.idx.assign(d.idx.begin(), d.idx.begin() + right_part);
         l.inner.resize(right_part);
@@ -263,7 +274,6 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
         r.idx.assign(d.idx.begin() + left_part, d.idx.end());
         r.inner.resize(n - left_part);
         for (int64_t k = left_part; k < n; ++k) r.inner[k - left_part] = d.inner[k] && k >= mid;
-        l.axes = r.axes = b.axes;
       });
       std::vector<Dom> keep;
       for (size_t i = 0; i < level.size(); ++i) {

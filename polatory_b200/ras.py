@@ -116,9 +116,10 @@ class Domain:
         self.inner_point = inner_point
 
 
-def divide_domains(a_points, point_idcs, poly_idcs):
+def divide_domains(a_points, point_idcs, poly_idcs, flat=False):
     """DomainDivider::divide_domains + Domain::merge_poly_points for value points only: the native
-    multi-threaded implementation of the C ABI (csrc/ras_host.cu)."""
+    multi-threaded implementation of the C ABI (csrc/ras_host.cu).  flat=True returns (offsets, indices,
+    inner) instead of a list of Domain objects."""
     import ctypes
     from . import _lib
     lib = _lib.load()
@@ -138,6 +139,8 @@ def divide_domains(a_points, point_idcs, poly_idcs):
         lib.plt_ras_domains_get(h, off.ctypes.data, ind.ctypes.data, inner.ctypes.data)
     finally:
         lib.plt_ras_domains_destroy(h)
+    if flat:
+        return off, ind, inner.astype(bool)
     return [Domain(ind[off[i]:off[i + 1]], inner[off[i]:off[i + 1]].astype(bool)) for i in range(n)]
 
 
@@ -289,23 +292,22 @@ class _FineLevel:
     point i, rows mu + dim*j + c = component c of gradient point j), the l polynomial points first; padded to
     the level's largest domain; explicit inverses of Q^T A Q."""
 
-    def __init__(self, ras, domains):
+    def __init__(self, ras, offsets, rows, inner):
+        """offsets (n_dom + 1), rows (total) flat row indices domain after domain, inner (total) ownership flags."""
         torch = ras.torch
         dev, l = ras.device, ras.l
-        self.n_dom = len(domains)
-        m_max = max(len(rows) for rows, _ in domains)
+        self.n_dom = len(offsets) - 1
+        cnt = np.diff(offsets).astype(np.int32)
+        m_max = int(cnt.max())
         self.m = m_max
         r = m_max - l
+        dom_of = np.repeat(np.arange(self.n_dom), cnt)
+        col_of = np.arange(len(rows)) - np.repeat(offsets[:-1], cnt)
         idx = np.zeros((self.n_dom, m_max), dtype=np.int64)
-        cnt = np.zeros(self.n_dom, dtype=np.int32)
-        inner_glob, inner_loc = [], []
-        for b, (rows, inner) in enumerate(domains):
-            k = len(rows)
-            idx[b, :k] = rows
-            cnt[b] = k
-            sel = np.nonzero(inner)[0]
-            inner_glob.append(rows[sel])
-            inner_loc.append(b * m_max + sel)
+        idx[dom_of, col_of] = rows
+        inner = np.asarray(inner, dtype=bool)
+        inner_glob = [np.asarray(rows)[inner]]
+        inner_loc = [(dom_of * m_max + col_of)[inner]]
         self.idx = torch.from_numpy(idx).to(dev)
         self.cnt = torch.from_numpy(cnt).to(dev)
         self.valid = (torch.arange(m_max, device=dev)[None, :] < self.cnt[:, None])
@@ -449,14 +451,18 @@ class RasPreconditioner:
             # the host chooses the coarse points of the next level (independent of the domains).
             t0 = time.perf_counter()
             if sigma == 0:
-                domains = [(d.point_indices, d.inner_point) for d in divide_domains(a_points, point_idcs[level], poly_idcs)]
+                d_off, d_rows, d_inner = divide_domains(a_points, point_idcs[level], poly_idcs, flat=True)
             else:
-                domains = [(self._rows(d.point_indices, d.grad_point_indices),
-                            np.concatenate([d.inner_point, np.repeat(d.inner_grad_point, dim)]))
-                           for d in divide_domains_mixed(a_points, a_grad_points, point_idcs[level], grad_idcs[level],
-                                                         poly_idcs)]
+                doms = [(self._rows(d.point_indices, d.grad_point_indices),
+                         np.concatenate([d.inner_point, np.repeat(d.inner_grad_point, dim)]))
+                        for d in divide_domains_mixed(a_points, a_grad_points, point_idcs[level], grad_idcs[level],
+                                                      poly_idcs)]
+                d_off = np.concatenate([[0], np.cumsum([len(r_) for r_, _ in doms])]).astype(np.int64)
+                d_rows = np.concatenate([r_ for r_, _ in doms])
+                d_inner = np.concatenate([i_ for _, i_ in doms])
+            n_domains = len(d_off) - 1
             t1 = time.perf_counter()
-            self.fine[level] = _FineLevel(self, domains)
+            self.fine[level] = _FineLevel(self, d_off, d_rows, d_inner)
             t2 = time.perf_counter()
             if sigma == 0:
                 point_idcs[level - 1] = choose_coarse_points(a_points, point_idcs[level], poly_idcs, counts[level - 1])
@@ -469,7 +475,7 @@ class RasPreconditioner:
             self.setup_seconds["factorize"] += t2 - t1   # host time to enqueue; the device part overlaps what follows
             self.setup_seconds["coarse_points"] += t3 - t2
             if verbose:
-                print(f"level {level}: {len(domains)} domains, {len(point_idcs[level])} points, {len(grad_idcs[level])} "
+                print(f"level {level}: {n_domains} domains, {len(point_idcs[level])} points, {len(grad_idcs[level])} "
                       f"gradient points (domains {t1 - t0:.2f}s, factorisation enqueue {t2 - t1:.2f}s, coarse points "
                       f"{t3 - t2:.2f}s)", flush=True)
         self.point_idcs, self.grad_idcs = point_idcs, grad_idcs
