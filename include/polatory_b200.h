@@ -228,6 +228,19 @@ typedef struct plt_ras_domains plt_ras_domains;
  * put first in every domain); reference constants: max_leaf 1024, overlap_quota 0.5. */
 int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs, int64_t n_idcs, const int64_t* poly,
                            int64_t n_poly, int64_t max_leaf, double overlap_quota, plt_ras_domains** out);
+/* The same two for Hermite data: value points and gradient points (multiplicity dim) mixed, with the reference's
+ * multiplicity-weighted cut ranks (domain_divider.hpp:66-90, 205-231).  n_coarse_rows counts rows (a gradient
+ * centre counts dim).  out_points needs n_poly + n_coarse_rows entries, out_grads n_coarse_rows. */
+int plt_ras_choose_coarse_points_mixed(const double* a_points, const double* a_grad_points, int dim,
+                                       const int64_t* point_idcs, int64_t n_points, const int64_t* grad_idcs,
+                                       int64_t n_grads, const int64_t* poly, int64_t n_poly, int64_t n_coarse_rows,
+                                       int64_t* out_points, int64_t* n_out_points, int64_t* out_grads,
+                                       int64_t* n_out_grads);
+int plt_ras_divide_domains_mixed(const double* a_points, const double* a_grad_points, int dim, const int64_t* point_idcs,
+                                 int64_t n_points, const int64_t* grad_idcs, int64_t n_grads, const int64_t* poly,
+                                 int64_t n_poly, int64_t max_leaf, double overlap_quota, plt_ras_domains** out);
+int64_t plt_ras_domains_total_grads(plt_ras_domains* h);
+int plt_ras_domains_get_grads(plt_ras_domains* h, int64_t* offsets, int64_t* indices, uint8_t* inner);
 int64_t plt_ras_domains_count(plt_ras_domains* h);
 int64_t plt_ras_domains_total(plt_ras_domains* h);
 /* offsets: count + 1 entries; indices / inner: total entries (inner = 1 where the domain owns the point). */

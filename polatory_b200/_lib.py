@@ -66,6 +66,14 @@ SYMBOLS = [
                                                     ctypes.c_int64, _vp]),
     ("plt_ras_divide_domains", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64, _vp, ctypes.c_int64,
                                               ctypes.c_int64, ctypes.c_double, ctypes.POINTER(_vp)]),
+    ("plt_ras_choose_coarse_points_mixed", ctypes.c_int,
+     [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_int64,
+      _vp, ctypes.POINTER(ctypes.c_int64), _vp, ctypes.POINTER(ctypes.c_int64)]),
+    ("plt_ras_divide_domains_mixed", ctypes.c_int,
+     [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_int64,
+      ctypes.c_double, ctypes.POINTER(_vp)]),
+    ("plt_ras_domains_total_grads", ctypes.c_int64, [_vp]),
+    ("plt_ras_domains_get_grads", ctypes.c_int, [_vp, _vp, _vp, _vp]),
     ("plt_ras_domains_count", ctypes.c_int64, [_vp]),
     ("plt_ras_domains_total", ctypes.c_int64, [_vp]),
     ("plt_ras_domains_get", ctypes.c_int, [_vp, _vp, _vp, _vp]),

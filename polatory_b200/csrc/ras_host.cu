@@ -153,6 +153,10 @@ struct plt_ras_domains {
   std::vector<int64_t> offsets{0};
   std::vector<int64_t> indices;
   std::vector<uint8_t> inner;
+  // gradient points of the domains (Hermite data only)
+  std::vector<int64_t> offsets_g;
+  std::vector<int64_t> indices_g;
+  std::vector<uint8_t> inner_g;
 };
 
 extern "C" {
@@ -326,6 +330,289 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
   } catch (const std::exception&) {
     return PLT_ERR_INVALID;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hermite data: value points and gradient points (multiplicity dim) mixed.  A mixed point is coded as
+// idx (value point) or ~idx (gradient point).  The cut ranks are multiplicity-weighted
+// (domain_divider.hpp:205-231, 66-90), so clusters are sorted (not just selected) before cutting.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct MixedView {
+  const double* p;
+  const double* g;
+  int dim;
+  const double* row(int64_t code) const { return code >= 0 ? p + code * dim : g + (~code) * dim; }
+  int mult(int64_t code) const { return code >= 0 ? 1 : dim; }
+};
+
+struct MixedBox {
+  std::array<double, 3> lo, hi;
+  std::array<int, 3> axes;
+};
+
+MixedBox mixed_box(const MixedView& mv, const std::vector<int64_t>& codes) {
+  MixedBox b;
+  for (int a = 0; a < 3; ++a) {
+    b.lo[a] = std::numeric_limits<double>::infinity();
+    b.hi[a] = -std::numeric_limits<double>::infinity();
+  }
+  for (int64_t c : codes) {
+    const double* r = mv.row(c);
+    for (int a = 0; a < mv.dim; ++a) {
+      b.lo[a] = std::min(b.lo[a], r[a]);
+      b.hi[a] = std::max(b.hi[a], r[a]);
+    }
+  }
+  for (int a = 0; a < 3; ++a) b.axes[a] = a;
+  std::stable_sort(b.axes.begin(), b.axes.begin() + mv.dim,
+                   [&](int i, int j) { return b.hi[i] - b.lo[i] > b.hi[j] - b.lo[j]; });
+  return b;
+}
+
+// Sorts codes (and the parallel flags, if given) lexicographically along the axes of their box.
+void mixed_sort(const MixedView& mv, const std::array<int, 3>& axes, std::vector<int64_t>& codes,
+                std::vector<uint8_t>* flags) {
+  const size_t n = codes.size();
+  std::vector<size_t> perm(n);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::sort(perm.begin(), perm.end(), [&](size_t x, size_t y) {
+    const double *p = mv.row(codes[x]), *q = mv.row(codes[y]);
+    for (int k = 0; k < mv.dim; ++k) {
+      const int a = axes[k];
+      if (p[a] != q[a]) return p[a] < q[a];
+    }
+    return x < y;  // stable
+  });
+  std::vector<int64_t> c2(n);
+  for (size_t k = 0; k < n; ++k) c2[k] = codes[perm[k]];
+  codes.swap(c2);
+  if (flags) {
+    std::vector<uint8_t> f2(n);
+    for (size_t k = 0; k < n; ++k) f2[k] = (*flags)[perm[k]];
+    flags->swap(f2);
+  }
+}
+
+struct MixedCluster {
+  std::vector<int64_t> codes;  // sorted along the axes of the cluster's box
+  double volume = 0.0;
+  int64_t centre = 0;
+};
+
+void mixed_init_cluster(const MixedView& mv, MixedCluster& c) {
+  const MixedBox b = mixed_box(mv, c.codes);
+  c.volume = 1.0;
+  for (int a = 0; a < mv.dim; ++a) c.volume *= b.hi[a] - b.lo[a];
+  double best = std::numeric_limits<double>::infinity();
+  c.centre = c.codes[0];
+  for (int64_t code : c.codes) {  // first minimum in the incoming order, as std::min_element
+    const double* r = mv.row(code);
+    double d2 = 0.0;
+    for (int a = 0; a < mv.dim; ++a) {
+      const double d = r[a] - 0.5 * (b.lo[a] + b.hi[a]);
+      d2 += d * d;
+    }
+    if (d2 < best) {
+      best = d2;
+      c.centre = code;
+    }
+  }
+  mixed_sort(mv, b.axes, c.codes, nullptr);
+}
+
+void mixed_split_cluster(const MixedView& mv, const MixedCluster& c, MixedCluster& l, MixedCluster& r) {
+  const size_t n = c.codes.size();
+  std::vector<int64_t> prefix(n + 1, 0);
+  for (size_t k = 0; k < n; ++k) prefix[k + 1] = prefix[k] + mv.mult(c.codes[k]);
+  const int64_t total = prefix[n];
+  size_t mid = 0;
+  int64_t best = std::numeric_limits<int64_t>::max();
+  for (size_t i = 0; i < n; ++i) {  // min_element of |2 prefix[i] - total|, ties: the even index wins
+    const int64_t d = std::llabs(2 * prefix[i] - total);
+    if (d < best || (d == best && i % 2 == 0)) {
+      best = d;
+      mid = i;
+    }
+  }
+  l.codes.assign(c.codes.begin(), c.codes.begin() + mid);
+  r.codes.assign(c.codes.begin() + mid, c.codes.end());
+  if (!l.codes.empty()) mixed_init_cluster(mv, l);
+  if (!r.codes.empty()) mixed_init_cluster(mv, r);
+}
+}  // namespace
+
+int plt_ras_choose_coarse_points_mixed(const double* a_points, const double* a_grad_points, int dim,
+                                       const int64_t* point_idcs, int64_t n_points, const int64_t* grad_idcs,
+                                       int64_t n_grads, const int64_t* poly, int64_t n_poly, int64_t n_coarse_rows,
+                                       int64_t* out_points, int64_t* n_out_points, int64_t* out_grads,
+                                       int64_t* n_out_grads) {
+  if (!a_points || !out_points || !out_grads || !n_out_points || !n_out_grads || dim < 1 || dim > 3) return PLT_ERR_INVALID;
+  try {
+    const MixedView mv{a_points, a_grad_points, dim};
+    std::vector<int64_t> poly_sorted(poly, poly + n_poly);
+    std::sort(poly_sorted.begin(), poly_sorted.end());
+    MixedCluster root;
+    for (int64_t k = 0; k < n_points; ++k)
+      if (!std::binary_search(poly_sorted.begin(), poly_sorted.end(), point_idcs[k])) root.codes.push_back(point_idcs[k]);
+    for (int64_t k = 0; k < n_grads; ++k) root.codes.push_back(~grad_idcs[k]);
+    if (root.codes.empty()) return PLT_ERR_INVALID;
+    mixed_init_cluster(mv, root);
+    std::vector<MixedCluster> level;
+    level.push_back(std::move(root));
+    int64_t size = mv.mult(level[0].centre);
+    std::vector<int64_t> centres_done;  // centres of clusters that stay (pop order: level, then volume)
+    while (size < n_coarse_rows) {
+      // children of every cluster of the level, in parallel
+      std::vector<MixedCluster> next(level.size() * 2);
+      parallel_for(level.size(), [&](size_t i) { mixed_split_cluster(mv, level[i], next[2 * i], next[2 * i + 1]); });
+      // the queue pops the level's clusters largest box first and stops as soon as the target is reached
+      std::vector<size_t> order(level.size());
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return level[x].volume > level[y].volume; });
+      std::vector<MixedCluster> new_level;
+      std::vector<char> was_split(level.size(), 0);
+      bool progress = false;
+      for (size_t k : order) {
+        if (size >= n_coarse_rows) break;
+        was_split[k] = 1;
+        size -= mv.mult(level[k].centre);
+        for (MixedCluster* ch : {&next[2 * k], &next[2 * k + 1]})
+          if (!ch->codes.empty()) {
+            size += mv.mult(ch->centre);
+            new_level.push_back(std::move(*ch));
+          }
+        progress = progress || level[k].codes.size() > 1;
+      }
+      if (size >= n_coarse_rows) {
+        // final pop order: unsplit clusters of this level (by volume), then the children (by volume)
+        for (size_t k : order)
+          if (!was_split[k]) centres_done.push_back(level[k].centre);
+        std::stable_sort(new_level.begin(), new_level.end(),
+                         [](const MixedCluster& x, const MixedCluster& y) { return x.volume > y.volume; });
+        for (auto& c : new_level) centres_done.push_back(c.centre);
+        level.clear();
+        break;
+      }
+      if (!progress) break;  // only singletons left: cannot reach the target
+      level.swap(new_level);
+    }
+    for (auto& c : level) centres_done.push_back(c.centre);
+    int64_t np = 0, ng = 0;
+    for (int64_t k = 0; k < n_poly; ++k) out_points[np++] = poly[k];
+    for (int64_t code : centres_done) {
+      if (code >= 0) out_points[np++] = code;
+      else out_grads[ng++] = ~code;
+    }
+    *n_out_points = np;
+    *n_out_grads = ng;
+    return PLT_OK;
+  } catch (const std::exception&) {
+    return PLT_ERR_INVALID;
+  }
+}
+
+int plt_ras_divide_domains_mixed(const double* a_points, const double* a_grad_points, int dim, const int64_t* point_idcs,
+                                 int64_t n_points, const int64_t* grad_idcs, int64_t n_grads, const int64_t* poly,
+                                 int64_t n_poly, int64_t max_leaf, double overlap_quota, plt_ras_domains** out) {
+  if (!a_points || !out || dim < 1 || dim > 3 || max_leaf < 2) return PLT_ERR_INVALID;
+  try {
+    const MixedView mv{a_points, a_grad_points, dim};
+    struct Dom {
+      std::vector<int64_t> codes;
+      std::vector<uint8_t> inner;
+    };
+    std::vector<Dom> level(1), leaves;
+    for (int64_t k = 0; k < n_points; ++k) level[0].codes.push_back(point_idcs[k]);
+    for (int64_t k = 0; k < n_grads; ++k) level[0].codes.push_back(~grad_idcs[k]);
+    level[0].inner.assign(level[0].codes.size(), 1);
+    while (!level.empty()) {
+      std::vector<Dom> next(level.size() * 2);
+      std::vector<char> is_leaf(level.size(), 0);
+      parallel_for(level.size(), [&](size_t i) {
+        Dom& d = level[i];
+        const int64_t n = static_cast<int64_t>(d.codes.size());
+        int64_t n_mult = 0;
+        for (int64_t c : d.codes) n_mult += mv.mult(c);
+        if (n_mult <= max_leaf) {
+          is_leaf[i] = 1;
+          return;
+        }
+        const MixedBox b = mixed_box(mv, d.codes);
+        mixed_sort(mv, b.axes, d.codes, &d.inner);
+        std::vector<int64_t> prefix(n + 1, 0);
+        for (int64_t k = 0; k < n; ++k) prefix[k + 1] = prefix[k] + mv.mult(d.codes[k]);
+        const double q = overlap_quota * static_cast<double>(max_leaf) / static_cast<double>(n_mult);
+        const int64_t n_sub = static_cast<int64_t>(round_half_to_even((1.0 + q) / 2.0 * static_cast<double>(n_mult)));
+        const int64_t left_mult = n_mult - n_sub, right_mult = n_sub;
+        const int64_t mid_mult = static_cast<int64_t>(round_half_to_even(static_cast<double>(left_mult + right_mult) / 2.0));
+        auto ub = [&](int64_t x) {  // upper_bound(prefix, x) - 1
+          return static_cast<int64_t>(std::upper_bound(prefix.begin(), prefix.end(), x) - prefix.begin()) - 1;
+        };
+        const int64_t left_part = ub(left_mult), right_part = ub(right_mult), mid = ub(mid_mult);
+        Dom &l = next[2 * i], &r = next[2 * i + 1];
+        l.codes.assign(d.codes.begin(), d.codes.begin() + right_part);
+        l.inner.resize(right_part);
+        for (int64_t k = 0; k < right_part; ++k) l.inner[k] = d.inner[k] && k < mid;
+        r.codes.assign(d.codes.begin() + left_part, d.codes.end());
+        r.inner.resize(n - left_part);
+        for (int64_t k = left_part; k < n; ++k) r.inner[k - left_part] = d.inner[k] && k >= mid;
+      });
+      std::vector<Dom> keep;
+      for (size_t i = 0; i < level.size(); ++i) {
+        if (is_leaf[i]) {
+          leaves.push_back(std::move(level[i]));
+        } else {
+          keep.push_back(std::move(next[2 * i]));
+          keep.push_back(std::move(next[2 * i + 1]));
+        }
+      }
+      level.swap(keep);
+    }
+    std::vector<int64_t> poly_v(poly, poly + n_poly);
+    auto res = std::make_unique<plt_ras_domains>();
+    res->offsets_g.push_back(0);
+    for (auto& d : leaves) {
+      // value points sorted by index with the poly points first (merge_poly_points); gradient points in domain order
+      std::vector<std::pair<int64_t, uint8_t>> pv;
+      std::vector<uint8_t> front(n_poly, 0);
+      for (size_t k = 0; k < d.codes.size(); ++k) {
+        if (d.codes[k] < 0) {
+          res->indices_g.push_back(~d.codes[k]);
+          res->inner_g.push_back(d.inner[k]);
+          continue;
+        }
+        const auto it = std::find(poly_v.begin(), poly_v.end(), d.codes[k]);
+        if (it != poly_v.end()) front[it - poly_v.begin()] = d.inner[k];
+        else pv.emplace_back(d.codes[k], d.inner[k]);
+      }
+      std::sort(pv.begin(), pv.end());
+      for (int64_t k = 0; k < n_poly; ++k) {
+        res->indices.push_back(poly_v[k]);
+        res->inner.push_back(front[k]);
+      }
+      for (auto& e : pv) {
+        res->indices.push_back(e.first);
+        res->inner.push_back(e.second);
+      }
+      res->offsets.push_back(static_cast<int64_t>(res->indices.size()));
+      res->offsets_g.push_back(static_cast<int64_t>(res->indices_g.size()));
+    }
+    *out = res.release();
+    return PLT_OK;
+  } catch (const std::exception&) {
+    return PLT_ERR_INVALID;
+  }
+}
+
+int64_t plt_ras_domains_total_grads(plt_ras_domains* h) { return h ? static_cast<int64_t>(h->indices_g.size()) : 0; }
+
+int plt_ras_domains_get_grads(plt_ras_domains* h, int64_t* offsets, int64_t* indices, uint8_t* inner) {
+  if (!h || !offsets || !indices || !inner || h->offsets_g.empty()) return PLT_ERR_INVALID;
+  std::memcpy(offsets, h->offsets_g.data(), sizeof(int64_t) * h->offsets_g.size());
+  std::memcpy(indices, h->indices_g.data(), sizeof(int64_t) * h->indices_g.size());
+  std::memcpy(inner, h->inner_g.data(), h->inner_g.size());
+  return PLT_OK;
 }
 
 int64_t plt_ras_domains_count(plt_ras_domains* h) { return h ? static_cast<int64_t>(h->offsets.size()) - 1 : 0; }

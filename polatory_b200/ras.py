@@ -22,7 +22,6 @@ reference's `Evaluator` default) whose trees / plans / operators stay resident b
 """
 from __future__ import annotations
 
-import heapq
 import math
 
 import numpy as np
@@ -174,114 +173,63 @@ def level_structure(n_rows):
 
 # ---------------------------------------------------------------------------------------------
 # Hermite data (gradient points, multiplicity `dim`): the same two algorithms with the reference's
-# multiplicity-weighted prefix sums (domain_divider.hpp:205-231, 66-90).  numpy / heapq on the host; the
-# native code of csrc/ras_host.cu covers value data only in this round.
+# multiplicity-weighted cut ranks (domain_divider.hpp:205-231, 66-90), native as well (csrc/ras_host.cu).
 # ---------------------------------------------------------------------------------------------
 class MixedDomain:
     __slots__ = ("point_indices", "inner_point", "grad_point_indices", "inner_grad_point")
 
 
-def _mixed_coords(a_points, a_grad_points, idx, is_grad):
-    out = np.empty((len(idx), a_points.shape[1]))
-    out[~is_grad] = a_points[idx[~is_grad]]
-    out[is_grad] = a_grad_points[idx[is_grad]]
-    return out
-
-
 def divide_domains_mixed(a_points, a_grad_points, point_idcs, grad_idcs, poly_idcs):
-    dim = a_points.shape[1]
-    idx0 = np.concatenate([np.asarray(point_idcs, dtype=np.int64), np.asarray(grad_idcs, dtype=np.int64)])
-    g0 = np.concatenate([np.zeros(len(point_idcs), dtype=bool), np.ones(len(grad_idcs), dtype=bool)])
-    queue = [(idx0, g0, np.ones(len(idx0), dtype=bool))]
-    leaves, head = [], 0
-    while head < len(queue):
-        idx, isg, inner = queue[head]
-        queue[head] = None
-        head += 1
-        mult = np.where(isg, dim, 1)
-        prefix = np.concatenate([[0], np.cumsum(mult)])
-        n_mult = int(prefix[-1])
-        if n_mult <= K_MAX_LEAF_SIZE:
-            leaves.append((idx, isg, inner))
-            continue
-        order = _sort_by_axes(_mixed_coords(a_points, a_grad_points, idx, isg))
-        idx, isg, inner = idx[order], isg[order], inner[order]
-        prefix = np.concatenate([[0], np.cumsum(np.where(isg, dim, 1))])
-        q = K_OVERLAP_QUOTA * K_MAX_LEAF_SIZE / n_mult
-        n_sub = int(_round_half_to_even((1.0 + q) / 2.0 * n_mult))
-        left_mult, right_mult = n_mult - n_sub, n_sub
-        mid_mult = int(_round_half_to_even((left_mult + right_mult) / 2.0))
-        ub = lambda x: int(np.searchsorted(prefix, x, side="right")) - 1  # upper_bound(...) - 1
-        left_part, right_part, mid = ub(left_mult), ub(right_mult), ub(mid_mult)
-        pos = np.arange(len(idx))
-        queue.append((idx[:right_part], isg[:right_part], inner[:right_part] & (pos[:right_part] < mid)))
-        queue.append((idx[left_part:], isg[left_part:], inner[left_part:] & (pos[left_part:] >= mid)))
-    poly = np.asarray(poly_idcs, dtype=np.int64)
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    a = np.ascontiguousarray(a_points, dtype=np.float64)
+    g = np.ascontiguousarray(a_grad_points, dtype=np.float64)
+    pi = np.ascontiguousarray(point_idcs, dtype=np.int64)
+    gi = np.ascontiguousarray(grad_idcs, dtype=np.int64)
+    poly = np.ascontiguousarray(poly_idcs, dtype=np.int64)
+    h = ctypes.c_void_p()
+    st = lib.plt_ras_divide_domains_mixed(a.ctypes.data, g.ctypes.data, a.shape[1], pi.ctypes.data, len(pi),
+                                          gi.ctypes.data, len(gi), poly.ctypes.data, len(poly), K_MAX_LEAF_SIZE,
+                                          K_OVERLAP_QUOTA, ctypes.byref(h))
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_ras_divide_domains_mixed failed")
+    try:
+        n, total, total_g = lib.plt_ras_domains_count(h), lib.plt_ras_domains_total(h), lib.plt_ras_domains_total_grads(h)
+        off, ind, inner = np.empty(n + 1, dtype=np.int64), np.empty(total, dtype=np.int64), np.empty(total, dtype=np.uint8)
+        offg, indg, innerg = np.empty(n + 1, dtype=np.int64), np.empty(total_g, dtype=np.int64), np.empty(total_g, dtype=np.uint8)
+        lib.plt_ras_domains_get(h, off.ctypes.data, ind.ctypes.data, inner.ctypes.data)
+        lib.plt_ras_domains_get_grads(h, offg.ctypes.data, indg.ctypes.data, innerg.ctypes.data)
+    finally:
+        lib.plt_ras_domains_destroy(h)
     out = []
-    for idx, isg, inner in leaves:
+    for i in range(n):
         d = MixedDomain()
-        pi, pin = idx[~isg], inner[~isg]
-        order = np.argsort(pi, kind="stable")
-        pi, pin = pi[order], pin[order]
-        if len(poly):  # merge_poly_points (domain.hpp:33-51)
-            pos = np.searchsorted(pi, poly)
-            present = (pos < len(pi)) & (pi[np.minimum(pos, max(len(pi) - 1, 0))] == poly) if len(pi) else np.zeros(len(poly), bool)
-            front_inner = np.zeros(len(poly), dtype=bool)
-            front_inner[present] = pin[pos[present]]
-            keep = np.ones(len(pi), dtype=bool)
-            keep[pos[present]] = False
-            pi = np.concatenate([poly, pi[keep]])
-            pin = np.concatenate([front_inner, pin[keep]])
-        d.point_indices, d.inner_point = pi, pin
-        d.grad_point_indices, d.inner_grad_point = idx[isg], inner[isg]
+        d.point_indices, d.inner_point = ind[off[i]:off[i + 1]], inner[off[i]:off[i + 1]].astype(bool)
+        d.grad_point_indices, d.inner_grad_point = indg[offg[i]:offg[i + 1]], innerg[offg[i]:offg[i + 1]].astype(bool)
         out.append(d)
     return out
 
 
 def choose_coarse_points_mixed(a_points, a_grad_points, point_idcs, grad_idcs, poly_idcs, n_coarse_rows):
     """choose_coarse_points with gradient points (a gradient centre counts `dim` rows)."""
-    dim = a_points.shape[1]
-    poly_set = set(int(i) for i in poly_idcs)
-    pv = np.array([i for i in point_idcs if int(i) not in poly_set], dtype=np.int64)
-    idx0 = np.concatenate([pv, np.asarray(grad_idcs, dtype=np.int64)])
-    g0 = np.concatenate([np.zeros(len(pv), dtype=bool), np.ones(len(grad_idcs), dtype=bool)])
-
-    def init(idx, isg):
-        pts = _mixed_coords(a_points, a_grad_points, idx, isg)
-        lo, hi = pts.min(axis=0), pts.max(axis=0)
-        k = int(np.argmin(((pts - 0.5 * (lo + hi)) ** 2).sum(axis=1)))
-        order = _sort_by_axes(pts)
-        return float(np.prod(hi - lo)), (int(idx[k]), bool(isg[k])), idx[order], isg[order]
-
-    counter = 0
-    vol, c, si, sg = init(idx0, g0)
-    heap = [(0, -vol, counter, c, si, sg)]
-    size = dim if c[1] else 1
-    while size < n_coarse_rows:
-        level, _, _, c, idx, isg = heapq.heappop(heap)
-        size -= dim if c[1] else 1
-        prefix = np.concatenate([[0], np.cumsum(np.where(isg, dim, 1))])
-        total = int(prefix[-1])
-        d = np.abs(2 * prefix[:len(idx)] - total)
-        best = int(d.min())
-        cand = np.nonzero(d == best)[0]
-        mid = int(cand[0])
-        for k in cand[1:]:      # min_element with "equal and even index wins" (domain_divider.hpp:83-88)
-            if k % 2 == 0:
-                mid = int(k)
-        for part_i, part_g in ((idx[:mid], isg[:mid]), (idx[mid:], isg[mid:])):
-            if len(part_i):
-                counter += 1
-                vol, c2, si, sg = init(part_i, part_g)
-                size += dim if c2[1] else 1
-                heapq.heappush(heap, (level + 1, -vol, counter, c2, si, sg))
-        if len(idx) == 1 and len(heap) >= len(idx0):
-            break
-    pts_out, grads_out = [int(i) for i in poly_idcs], []
-    while heap:
-        c = heapq.heappop(heap)[3]
-        (grads_out if c[1] else pts_out).append(c[0])
-    return np.asarray(pts_out, dtype=np.int64), np.asarray(grads_out, dtype=np.int64)
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    a = np.ascontiguousarray(a_points, dtype=np.float64)
+    g = np.ascontiguousarray(a_grad_points, dtype=np.float64)
+    pi = np.ascontiguousarray(point_idcs, dtype=np.int64)
+    gi = np.ascontiguousarray(grad_idcs, dtype=np.int64)
+    poly = np.ascontiguousarray(poly_idcs, dtype=np.int64)
+    outp = np.empty(len(poly) + int(n_coarse_rows) + 8, dtype=np.int64)
+    outg = np.empty(int(n_coarse_rows) + 8, dtype=np.int64)
+    np_, ng_ = ctypes.c_int64(), ctypes.c_int64()
+    st = lib.plt_ras_choose_coarse_points_mixed(a.ctypes.data, g.ctypes.data, a.shape[1], pi.ctypes.data, len(pi),
+                                                gi.ctypes.data, len(gi), poly.ctypes.data, len(poly), int(n_coarse_rows),
+                                                outp.ctypes.data, ctypes.byref(np_), outg.ctypes.data, ctypes.byref(ng_))
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_ras_choose_coarse_points_mixed failed")
+    return outp[:np_.value].copy(), outg[:ng_.value].copy()
 
 
 # ---------------------------------------------------------------------------------------------

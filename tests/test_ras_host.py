@@ -121,3 +121,34 @@ def test_oracle_ras_preconditions_dense_system():
     x = s.solution_vector()
     assert np.linalg.norm(full @ x - v) <= 1e-7 * np.linalg.norm(v)
     assert np.max(np.abs(p.T @ x[:n])) <= 1e-8 * np.max(np.abs(x[:n])) * n
+
+
+def test_native_mixed_matches_oracle_restatement():
+    """Hermite bookkeeping (value + gradient points, multiplicity-weighted cuts): native C++ vs the oracle's numpy."""
+    from oracle import ras as oras
+    rng = np.random.default_rng(8)
+    mu, sg = 9000, 4000
+    p = rng.uniform(-1, 1, (mu, 3)) * [1.0, 2.0, 0.6]
+    g = rng.uniform(-1, 1, (sg, 3)) * [1.0, 2.0, 0.6]
+    poly = [11, 500, 4242, 8000]
+    pid = np.concatenate([poly, np.setdiff1d(np.arange(mu), poly)])
+    gid = np.arange(sg)
+    a = ras.divide_domains_mixed(p, g, pid, gid, poly)
+    b = oras.divide_domains_mixed(p, g, pid, gid, poly)
+    assert len(a) == len(b)
+    key_a = sorted((tuple(d.point_indices.tolist()), tuple(d.inner_point.tolist()),
+                    tuple(sorted(zip(d.grad_point_indices.tolist(), d.inner_grad_point.tolist())))) for d in a)
+    key_b = sorted((tuple(pi.tolist()), tuple(pin.tolist()), tuple(sorted(zip(gi.tolist(), gin.tolist()))))
+                   for pi, pin, gi, gin in b)
+    assert key_a == key_b
+    own_p, own_g = np.zeros(mu, int), np.zeros(sg, int)
+    for d in a:
+        assert len(d.point_indices) + 3 * len(d.grad_point_indices) <= ras.K_MAX_LEAF_SIZE + len(poly)
+        own_p[d.point_indices[d.inner_point]] += 1
+        own_g[d.grad_point_indices[d.inner_grad_point]] += 1
+    assert np.all(own_p == 1) and np.all(own_g == 1)
+    for target in (300, 2000, 5001):
+        pa, ga = ras.choose_coarse_points_mixed(p, g, pid, gid, poly, target)
+        pb_, gb = oras.choose_coarse_points_mixed(p, g, pid, gid, poly, target)
+        assert list(pa[:4]) == poly and set(pa.tolist()) == set(pb_.tolist()) and set(ga.tolist()) == set(gb.tolist())
+        assert target <= (len(pa) - 4) + 3 * len(ga) < target + 3
