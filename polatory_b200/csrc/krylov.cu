@@ -88,9 +88,7 @@ __global__ void __launch_bounds__(kRedBlock) k_gs_update(const double* __restric
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-// y = alpha * x + beta * y, with alpha = a_num / sqrt-or-not of a device scalar:
-//   mode 0: y = x / sqrt(*s)        (normalise)
-//   mode 1: y = y - x               (residual: rhs - A x0, y preloaded with rhs)
+// u /= sqrt(*norm2): normalisation by a device-resident squared norm (no host round trip)
 __global__ void k_scale_by_norm(double* __restrict__ u, int64_t n, const double* __restrict__ norm2) {
   const double inv = 1.0 / sqrt(*norm2);
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
@@ -98,6 +96,7 @@ __global__ void k_scale_by_norm(double* __restrict__ u, int64_t n, const double*
     u[k] *= inv;
 }
 
+// y -= x  (the initial residual rhs - A x0)
 __global__ void k_sub(double* __restrict__ y, const double* __restrict__ x, int64_t n) {
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -147,6 +146,9 @@ struct plt_fgmres {
   }
 
   double& R(int i, int j) { return r[static_cast<size_t>(j) * (max_iter + 1) + i]; }
+  // Dynamic shared memory of the kernels that stage m coefficients: the compiler reads them with 16-byte loads,
+  // so the buffer is padded to a whole number of double pairs (compute-sanitizer flagged the 8-byte overrun).
+  static size_t coeff_smem(int m) { return sizeof(double) * (static_cast<size_t>(std::max(m, 1) + 3) / 2 * 2); }
   double* v(int i) { return V.get() + stride * i; }
   double* z(int i) { return pc ? Z.get() + stride * i : v(i); }
 
@@ -248,8 +250,8 @@ struct plt_fgmres {
     if (allreduce && allreduce(ar_ctx, small.get(), m) != 0)
       throw Error(PLT_ERR_INVALID, "fgmres: allreduce callback failed");
     // v_{j+1} -= sum_i r(i, j) v_i ; r(j+1, j) = ||v_{j+1}|| ; v_{j+1} /= r(j+1, j)
-    PLT_LAUNCH(ctr, k_gs_update, kRedGrid, kRedBlock, sizeof(double) * m, stream, V.get(), stride, m, small.get(), u,
-               n, partial.get());
+    PLT_LAUNCH(ctr, k_gs_update, kRedGrid, kRedBlock, coeff_smem(m), stream, V.get(), stride, m, small.get(), u, n,
+               partial.get());
     PLT_LAUNCH(ctr, k_reduce_partials, 1, 32, 0, stream, partial.get(), kRedGrid, 1, small.get() + m);
     if (allreduce && allreduce(ar_ctx, small.get() + m, 1) != 0)
       throw Error(PLT_ERR_INVALID, "fgmres: allreduce callback failed");
@@ -296,8 +298,8 @@ struct plt_fgmres {
       dst = tmp.get();
     }
     if (iter > 0) PLT_CUDA(cudaMemcpyAsync(small.get(), y.data(), sizeof(double) * iter, cudaMemcpyHostToDevice, stream));
-    PLT_LAUNCH(ctr, k_combine, kRedGrid, kRedBlock, sizeof(double) * std::max(iter, 1), stream, pc ? Z.get() : V.get(),
-               stride, iter, small.get(), x0.get(), dst, n);
+    PLT_LAUNCH(ctr, k_combine, kRedGrid, kRedBlock, coeff_smem(iter), stream, pc ? Z.get() : V.get(), stride, iter,
+               small.get(), x0.get(), dst, n);
     if (!dev_out) {
       if (n) PLT_CUDA(cudaMemcpyAsync(x_out, dst, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
     }
