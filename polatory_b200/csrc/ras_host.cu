@@ -138,6 +138,12 @@ void split_cluster(const PointsView& pv, Cluster& c, Cluster& l, Cluster& r) {
   select_ranks(pv, c.axes, c.idx.data(), c.idx.size(), {mid});
   l.idx.assign(c.idx.begin(), c.idx.begin() + mid);
   r.idx.assign(c.idx.begin() + mid, c.idx.end());
+  // The centre is the FIRST point nearest to the box centre in the reference's order (the parent's sorted order);
+  // exact distance ties are the rule for two-point clusters (both are equidistant from their midpoint), so small
+  // children are put in that order before their centre is chosen.
+  const AxisLess less{pv, c.axes};
+  if (l.idx.size() <= 8) std::sort(l.idx.begin(), l.idx.end(), less);
+  if (r.idx.size() <= 8) std::sort(r.idx.begin(), r.idx.end(), less);
   if (!l.idx.empty()) init_cluster(pv, l);
   if (!r.idx.empty()) init_cluster(pv, r);
 }
