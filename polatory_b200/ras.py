@@ -95,18 +95,6 @@ def lagrange_basis_matrix(points, poly_idcs, degree, dim):
     return monomial_basis(dim, degree, points) @ coeffs
 
 
-def _round_half_to_even(d):
-    return math.ceil((d - 0.5) / 2.0) + math.floor((d + 0.5) / 2.0)  # domain_divider.hpp:308-310
-
-
-def _sort_by_axes(pts):
-    """Order of `pts` sorted lexicographically along the axes by decreasing bbox width
-    (domain_divider.hpp:188-203, 288-305)."""
-    width = pts.max(axis=0) - pts.min(axis=0)
-    axes = sorted(range(pts.shape[1]), key=lambda a: -width[a])  # stable, like std::sort on distinct widths
-    return np.lexsort(tuple(pts[:, a] for a in reversed(axes)))
-
-
 class Domain:
     __slots__ = ("point_indices", "inner_point")
 
