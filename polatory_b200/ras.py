@@ -1,6 +1,6 @@
 """Restricted additive Schwarz preconditioner of the fit, on the device.
 
-Restates, for value data (sigma = 0: no gradient points in this round),
+Restates, for value data and Hermite data (gradient points) and one RBF per model,
   preconditioner::RasPreconditioner   include/polatory/preconditioner/ras_preconditioner.hpp:34-364
   preconditioner::DomainDivider       include/polatory/preconditioner/domain_divider.hpp:17-321
   preconditioner::Domain              include/polatory/preconditioner/domain.hpp:16-52
@@ -10,15 +10,16 @@ Restates, for value data (sigma = 0: no gradient points in this round),
   polynomial::UnisolventPointSet      include/polatory/polynomial/unisolvent_point_set.hpp:16-74
   polynomial::LagrangeBasis           include/polatory/polynomial/lagrange_basis.hpp:17-75
 
-What stays on the host (numpy, once per fit): the level structure, the choice of coarse points, the
-recursive bisection into overlapping domains -- index bookkeeping the reference also does serially.
-What runs on the device: the Gram matrices of all domains of a level (one batched kernel launch through
-the C ABI, `plt_eval_gram_batched`), their reduced factorisations Q^T A Q = L L^T (batched Cholesky:
-cuSOLVER through torch -- library code, used like cuBLAS), the local solves of one level as ONE
-batched product with the explicit inverses kept in HBM (the reference spills its factors to a temp
-file, preconditioner/binary_cache.hpp; 1M points need ~17 GB here), and the level transfers
-`update_residuals`, which are generic FMM evaluations (order 6, accuracy = infinity as the
-reference's `Evaluator` default) whose trees / plans / operators stay resident between applications.
+Host, once per fit: the level structure and the unisolvent points here (numpy); the choice of the coarse points
+and the recursive bisection into overlapping domains in native multi-threaded code behind the C ABI
+(csrc/ras_host.cu: `plt_ras_choose_coarse_points[_mixed]`, `plt_ras_divide_domains[_mixed]`).
+Device: the Gram matrices of all domains of a level (batched kernels `plt_eval_gram_batched` /
+`plt_eval_gram_mixed`), their reduced factorisations Q^T A Q = L L^T (batched Cholesky and triangular
+solves: cuSOLVER / cuBLAS through torch -- library code), the local solves of one level as ONE batched
+product with the explicit inverses kept in HBM (the reference spills its factors to a temp file,
+preconditioner/binary_cache.hpp; 1M points need ~19 GB here), and the level transfers
+`update_residuals`, which are generic FMM evaluations (order 6, accuracy = infinity as the reference's
+`Evaluator` default) whose trees / plans / operators stay resident between applications.
 """
 from __future__ import annotations
 
