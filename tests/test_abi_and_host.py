@@ -234,3 +234,35 @@ def test_cpp_shim_compiles_and_links(tmp_path):
     subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
                            "-o", str(exe), "-L", libdir, "-lpolatory_b200", f"-Wl,-rpath,{libdir}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_host_side_abi_error_paths():
+    """Status codes instead of exceptions across the C ABI, on the entry points that need no device."""
+    import torch
+    from polatory_b200 import _lib
+    lib = _lib.load()
+    pts = np.random.default_rng(0).uniform(-1, 1, (50, 3))
+    idcs = np.arange(50, dtype=np.int64)
+    out = np.empty(60, dtype=np.int64)
+    empty = np.empty(0, dtype=np.int64)
+    # more coarse points than points, bad dimension, null pointers
+    assert lib.plt_ras_choose_coarse_points(pts.ctypes.data, 3, idcs.ctypes.data, 50, empty.ctypes.data, 0, 60,
+                                            out.ctypes.data) == _lib.PLT_ERR_INVALID
+    assert lib.plt_ras_choose_coarse_points(pts.ctypes.data, 4, idcs.ctypes.data, 50, empty.ctypes.data, 0, 10,
+                                            out.ctypes.data) == _lib.PLT_ERR_INVALID
+    assert lib.plt_ras_choose_coarse_points(None, 3, idcs.ctypes.data, 50, empty.ctypes.data, 0, 10,
+                                            out.ctypes.data) == _lib.PLT_ERR_INVALID
+    h = ctypes.c_void_p()
+    assert lib.plt_ras_divide_domains(pts.ctypes.data, 3, idcs.ctypes.data, 50, empty.ctypes.data, 0, 1, 0.5,
+                                      ctypes.byref(h)) == _lib.PLT_ERR_INVALID   # max_leaf < 2
+    assert lib.plt_ras_divide_domains(pts.ctypes.data, 3, idcs.ctypes.data, 50, empty.ctypes.data, 0, 16, 0.5,
+                                      ctypes.byref(h)) == _lib.PLT_OK
+    n = lib.plt_ras_domains_count(h)
+    assert n >= 4 and lib.plt_ras_domains_total(h) >= 50 and lib.plt_ras_domains_total_grads(h) == 0
+    lib.plt_ras_domains_destroy(h)
+    assert lib.plt_ras_domains_count(None) == 0
+    if not torch.cuda.is_available():
+        s = ctypes.c_void_p()
+        assert lib.plt_fgmres_create(100, 10, ctypes.byref(s)) == _lib.PLT_ERR_CUDA   # no CPU fallback
+        assert b"CUDA" in lib.plt_fgmres_last_error(None)
+    assert lib.plt_fgmres_iterate(None) == _lib.PLT_ERR_INVALID
