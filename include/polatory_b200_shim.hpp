@@ -2,9 +2,9 @@
 //
 // Two layers over the C ABI of polatory_b200.h:
 //
-//  1. plt::Evaluator -- a dependency-free RAII wrapper (std::vector in / out, status codes turned
-//     back into the exceptions the reference throws).  Always available; this is what the tests
-//     compile.
+//  1. plt::Evaluator, plt::Fgmres -- dependency-free RAII wrappers (std::vector in / out, status codes
+//     turned back into the exceptions the reference throws).  Always available; this is what the
+//     tests compile.
 //
 //  2. With -DPOLATORY_B200_WITH_POLATORY (i.e. inside a Polatory build, Eigen and the Polatory
 //     headers on the include path): polatory::fmm::B200Evaluator<Dim> /
@@ -97,6 +97,62 @@ class Evaluator {
   int dim_, km_, kn_;
   bool symmetric_;
   int64_t n_src_ = 0, n_trg_ = 0;
+};
+
+// Device-resident flexible GMRES with the method names of krylov::Fgmres / GmresBase
+// (include/polatory/krylov/gmres_base.hpp:11-91, fgmres.hpp:11-26).  The operator and the right preconditioner
+// are callables  int(const double* x_dev, double* y_dev)  on DEVICE pointers (return 0 on success); rhs / x0 /
+// solutions may be host or device pointers.
+class Fgmres {
+ public:
+  using LinOp = int (*)(void* ctx, const double* x_dev, double* y_dev);
+
+  Fgmres(LinOp op, void* op_ctx, const double* rhs, int64_t n, int max_iter) : rhs_(rhs), n_(n), max_iter_(max_iter) {
+    int st = plt_fgmres_create(n, max_iter, &h_);
+    if (st != PLT_OK) throw_status(st, plt_fgmres_last_error(nullptr));
+    check(plt_fgmres_set_operator(h_, op, op_ctx));
+  }
+  ~Fgmres() { plt_fgmres_destroy(h_); }
+  Fgmres(const Fgmres&) = delete;
+  Fgmres& operator=(const Fgmres&) = delete;
+
+  void set_initial_solution(const double* x0) { x0_ = x0; }
+  void set_right_preconditioner(LinOp pc, void* ctx) { check(plt_fgmres_set_right_preconditioner(h_, pc, ctx)); }
+  [[noreturn]] void set_left_preconditioner(LinOp, void*) {
+    throw std::runtime_error("set_left_preconditioner is not supported");  // fgmres.hpp:15-17
+  }
+  void set_allreduce(plt_allreduce_fn fn, void* ctx) { check(plt_fgmres_set_allreduce(h_, fn, ctx)); }
+  void setup() { check(plt_fgmres_setup(h_, rhs_, x0_)); }
+  void iterate_process() { check(plt_fgmres_iterate(h_)); }
+  void solution_vector(double* x) { check(plt_fgmres_solution(h_, x)); }
+  std::vector<double> solution_vector() {
+    std::vector<double> x(static_cast<size_t>(n_));
+    solution_vector(x.data());
+    return x;
+  }
+  int iteration_count() const { return status().iter; }
+  int max_iterations() const { return max_iter_; }
+  double absolute_residual() const { return status().abs; }
+  double relative_residual() const { return status().rel; }
+
+ private:
+  struct Status {
+    int iter;
+    double abs, rel;
+  };
+  Status status() const {
+    Status s{};
+    check(plt_fgmres_status(h_, &s.iter, &s.abs, &s.rel));
+    return s;
+  }
+  void check(int st) const {
+    if (st != PLT_OK) throw_status(st, plt_fgmres_last_error(h_));
+  }
+  plt_fgmres* h_ = nullptr;
+  const double* rhs_;
+  const double* x0_ = nullptr;
+  int64_t n_;
+  int max_iter_;
 };
 
 }  // namespace plt

@@ -225,7 +225,9 @@ def test_cpp_shim_compiles_and_links(tmp_path):
         "    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};\n"
         "    plt::Evaluator ev(PLT_KIND_K, false, 3, PLT_RBF_BH3, {1.0, 0.0}, {}, lo, hi);\n"
         "    ev.set_source_points(lo, 1); ev.set_target_points(hi, 1); ev.set_weights(lo, 1); ev.set_accuracy(0.0);\n"
-        "    return static_cast<int>(ev.evaluate().size());\n"
+        "    plt::Fgmres solver([](void*, const double*, double*) { return 0; }, nullptr, lo, 3, 5);\n"
+        "    solver.set_initial_solution(hi); solver.setup(); solver.iterate_process();\n"
+        "    return static_cast<int>(ev.evaluate().size()) + solver.iteration_count() + static_cast<int>(solver.solution_vector().size());\n"
         "  }\n"
         "  return plt_version() == 100 ? 0 : 3;\n"
         "}\n")
