@@ -1060,7 +1060,12 @@ __global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
     if (!in) continue;
     double2 x[nf];
 #pragma unroll
-    for (int f = 0; f < nf; ++f) x[f] = __ldcs(in + f * (nf * p) + col);  // read once: streaming
+    for (int f = 0; f < nf; ++f) {
+      // read once.  The streaming hint pays from order 8 on (order 12: 2.40 -> 1.67 ms); at order 6 the tail of the
+      // spectra the Hadamard kernel has just written is still in L2 and a plain load is faster (1.59 vs 1.70 ms).
+      const double2* q = in + f * (nf * p) + col;
+      x[f] = ORDER >= 8 ? __ldcs(q) : *q;
+    }
 #pragma unroll
     for (int m = 0; m < p; ++m) {
       double re = 0.0, im = 0.0;
