@@ -576,7 +576,7 @@ struct plt_eval {
       if (timed) timer.begin(fused ? "l2l_l2p_leaf" : "l2p", stream);
       bool done = false;
       if (fused)
-        done = launch_l2l_l2p_leaf(dim, kn, tv, box, ip.dev, leaf > 2 ? L : nullptr, Lc, pv.leaf_slot, vt, leaf_lo,
+        done = launch_l2l_l2p_leaf(dim, kn, tv, box, ip.dev, leaf > 2 ? L : nullptr, Lc, pv.leaf_meta, vt, leaf_lo,
                                    leaf_hi, lo[leaf - 1], hi[leaf - 1], stream, ctr);
       if (!done) {
         PLT_REQUIRE(!fused, "fused leaf pass rejected an order it was planned for");

@@ -416,7 +416,7 @@ template <int DIM, int ORDER>
 __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <= 8 ? 2 : 1)) k_l2l_l2p_leaf(TreeView tr, Box box, LeafTables tb, int kn,
                                                                const double* __restrict__ L,
                                                                const double* __restrict__ Lc,
-                                                               const int* __restrict__ leaf_slot,
+                                                               const int* __restrict__ leaf_meta,
                                                                double* __restrict__ vt, int par_lo, int leaf_lo,
                                                                int leaf_hi) {
   extern __shared__ double sm[];
@@ -443,17 +443,19 @@ __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int leaf = tr.height - 1, pl = leaf - 1;
   const int pidx = par_lo + blockIdx.x;
-  const uint32_t pkey = tr.keys[tr.cell_off[pl] + pidx];
+  // one coalesced read of the parent's metadata (plan.cuh: leaf_meta) replaces key -> dense map -> leaf_start
+  const int* meta = leaf_meta + static_cast<size_t>(pidx) * (2 + 3 * NC);
+  const uint32_t pkey = static_cast<uint32_t>(meta[0]);
   const bool has_parent = L != nullptr;  // parent level >= 2
-  const int slot = leaf_slot ? leaf_slot[pidx] : -1;
+  const int slot = meta[1];
 
   if (tid < 32) {
     int first = -1, cnt = 0;
     if (tid < NC) {
-      const int cidx = tr.dense[tr.dense_off[leaf] + ((pkey << DIM) | tid)];
+      const int cidx = meta[2 + 3 * tid];
       if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
-        first = tr.leaf_start[cidx];
-        cnt = tr.leaf_start[cidx + 1] - first;
+        first = meta[3 + 3 * tid];
+        cnt = meta[4 + 3 * tid];
       }
       s_first[tid] = first;
       s_count[tid] = cnt;
@@ -1419,7 +1421,7 @@ void dispatch_leaf(int dim, int order, F&& f) {
 }  // namespace
 
 bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
-                         const double* Lc, const int* leaf_slot, double* vt, int64_t leaf_lo, int64_t leaf_hi,
+                         const double* Lc, const int* leaf_meta, double* vt, int64_t leaf_lo, int64_t leaf_hi,
                          int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c) {
   const int n = par_hi - par_lo;
   if (n <= 0) return true;
@@ -1432,7 +1434,7 @@ bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, co
   const int lo = static_cast<int>(leaf_lo), hi = static_cast<int>(leaf_hi);
   dispatch_leaf(dim, it.order, [&](auto dm, auto od) {
     smem_opt_in((const void*)k_l2l_l2p_leaf<dm.value, od.value>, smem);
-    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, leaf_threads(od.value), smem, s, tr, box, tb, kn, L, Lc, leaf_slot, vt,
+    PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, leaf_threads(od.value), smem, s, tr, box, tb, kn, L, Lc, leaf_meta, vt,
                par_lo, lo, hi);
   });
   return true;

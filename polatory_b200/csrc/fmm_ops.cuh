@@ -90,11 +90,11 @@ void launch_l2l(int dim, int kn, const TreeView& tr, int child_level, const Inte
 void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
                 double* vt, int64_t lo, int64_t hi, cudaStream_t s, LaunchCounter& c);
 // Fused last level of the downward pass: for every parent of level leaf-1, L2L to its children
-// in shared memory (+ the children's own M2L result Lc, slot given by leaf_slot), then L2P.  The
+// in shared memory (+ the children's own M2L result Lc, slot given by the plan's leaf_meta), then L2P.  The
 // leaf-level local expansions never touch HBM.  Returns false when the order is too large for
 // the shared-memory staging (caller falls back to launch_l2l + launch_l2p).
 bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
-                         const double* Lc, const int* leaf_slot, double* vt, int64_t leaf_lo, int64_t leaf_hi,
+                         const double* Lc, const int* leaf_meta, double* vt, int64_t leaf_lo, int64_t leaf_hi,
                          int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c);
 size_t leaf_fused_smem_bytes(int dim, int order);
 bool leaf_fused_supported(int dim, int order);

@@ -140,6 +140,31 @@ __global__ void k_plan_fill(TreeView src, TreeView trg, const int* __restrict__ 
   }
 }
 
+// leaf_meta (plan.cuh): one thread per (parent of the leaf level, child).
+template <int DIM>
+__global__ void k_plan_leaf_meta(TreeView trg, const int* __restrict__ leaf_slot, int* __restrict__ meta) {
+  constexpr int NC = Stencil<DIM>::NC, W = 2 + 3 * NC;
+  const int leaf = trg.height - 1, pl = leaf - 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pidx = t / NC, ch = t % NC;
+  if (pidx >= trg.n_cells[pl]) return;
+  const uint32_t pkey = trg.keys[trg.cell_off[pl] + pidx];
+  int* m = meta + static_cast<size_t>(pidx) * W;
+  if (ch == 0) {
+    m[0] = static_cast<int>(pkey);
+    m[1] = leaf_slot[pidx];
+  }
+  const int cidx = trg.dense[trg.dense_off[leaf] + ((pkey << DIM) | ch)];
+  int first = 0, cnt = 0;
+  if (cidx >= 0) {
+    first = trg.leaf_start[cidx];
+    cnt = trg.leaf_start[cidx + 1] - first;
+  }
+  m[2 + 3 * ch] = cidx;
+  m[3 + 3 * ch] = first;
+  m[4 + 3 * ch] = cnt;
+}
+
 }  // namespace
 
 void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCounter& ctr) {
@@ -212,6 +237,15 @@ void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCo
     view_.src_ids = src_ids_.get();
     view_.trg_mask = trg_mask_.get();
     view_.leaf_slot = leaf_slot_.get();
+    const int n_lp = tv.n_cells[leaf - 1];
+    leaf_meta_.alloc(static_cast<size_t>(std::max(n_lp, 1)) * (2 + 3 * nc), stream);
+    if (n_lp > 0) {
+      const int threads = n_lp * nc;
+      if (dim == 1) PLT_LAUNCH(ctr, k_plan_leaf_meta<1>, ceil_div(threads, 256), 256, 0, stream, tv, leaf_slot_.get(), leaf_meta_.get());
+      if (dim == 2) PLT_LAUNCH(ctr, k_plan_leaf_meta<2>, ceil_div(threads, 256), 256, 0, stream, tv, leaf_slot_.get(), leaf_meta_.get());
+      if (dim == 3) PLT_LAUNCH(ctr, k_plan_leaf_meta<3>, ceil_div(threads, 256), 256, 0, stream, tv, leaf_slot_.get(), leaf_meta_.get());
+    }
+    view_.leaf_meta = leaf_meta_.get();
   }
   built_ = true;
 }

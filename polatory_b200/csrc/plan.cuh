@@ -23,6 +23,10 @@ struct PlanView {
   const int* src_ids;            // [n_active][3^dim * 2^dim] Mhat cell index (global id - cell_off[2]) or -1
   const unsigned char* trg_mask; // [n_active] bit ct set <=> target child ct exists
   const int* leaf_slot;          // [n_cells(leaf - 1)] slot - level_begin[leaf] of that parent, or -1
+  // Per parent of the leaf level, everything the fused leaf pass needs in ONE coalesced read instead of a chain of
+  // dependent lookups (key -> dense map -> leaf_start): [n_cells(leaf - 1)][2 + 3 * 2^dim] ints =
+  //   { Morton key, leaf slot, then per child { compact leaf id or -1, first point, point count } }
+  const int* leaf_meta;
   int level_begin[25];
   int n_active;
   // P2P: target leaves with at least one non-empty adjacent source leaf (ascending).
@@ -42,7 +46,7 @@ class Plan {
  private:
   bool built_ = false;
   PlanView view_{};
-  DevBuf<int> flags_, active_, src_ids_, leaf_slot_, p2p_flags_, p2p_leaves_, counts_;
+  DevBuf<int> flags_, active_, src_ids_, leaf_slot_, leaf_meta_, p2p_flags_, p2p_leaves_, counts_;
   DevBuf<unsigned char> trg_mask_, tmp_;
 };
 
