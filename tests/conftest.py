@@ -34,3 +34,28 @@ def default_params(name):
 @pytest.fixture
 def rng():
     return np.random.default_rng(12345)
+
+
+def dense_th3_hermite(pts, gpts, aniso):
+    """mat_a for th3 (phi = r^3, s = 1, c = 0; polyharmonic_odd.hpp:32-67) with anisotropy, rows [values | dim per
+    gradient point]: K = phi, F = -(grad phi) A, H = -A^T (Hess phi) A on the transformed differences."""
+    dim = pts.shape[1]
+    mu, sigma = len(pts), len(gpts)
+    tp, tg = pts @ aniso.T, gpts @ aniso.T
+    m = mu + dim * sigma
+    a = np.zeros((m, m))
+    d = tp[:, None, :] - tp[None, :, :]
+    a[:mu, :mu] = np.sqrt((d * d).sum(axis=2)) ** 3
+    d = tp[:, None, :] - tg[None, :, :]                      # value row i, gradient column j
+    r = np.sqrt((d * d).sum(axis=2))
+    f = -(3.0 * r[:, :, None] * d) @ aniso                   # -(grad_iso A)
+    a[:mu, mu:] = f.reshape(mu, dim * sigma)
+    a[mu:, :mu] = a[:mu, mu:].T
+    d = tg[:, None, :] - tg[None, :, :]
+    r = np.sqrt((d * d).sum(axis=2))
+    with np.errstate(all="ignore"):
+        hess = 3.0 * (r[:, :, None, None] * np.eye(dim) + np.where(r[:, :, None, None] > 0,
+                      d[:, :, :, None] * d[:, :, None, :] / r[:, :, None, None], 0.0))
+    h = -np.einsum("ai,pqab,bj->pqij", aniso, hess, aniso)
+    a[mu:, mu:] = h.transpose(0, 2, 1, 3).reshape(dim * sigma, dim * sigma)
+    return a

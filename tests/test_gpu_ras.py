@@ -225,31 +225,6 @@ def test_ras_fit_hermite_th3_aniso(torch):
     assert np.max(np.abs(fit - ref)) <= 10 * tol
 
 
-def _dense_th3_hermite(pts, gpts, aniso):
-    """mat_a for th3 (phi = r^3, s = 1, c = 0; polyharmonic_odd.hpp:32-67) with anisotropy, rows [values | dim per
-    gradient point]: K = phi, F = -(grad phi) A, H = -A^T (Hess phi) A on the transformed differences."""
-    dim = pts.shape[1]
-    mu, sigma = len(pts), len(gpts)
-    tp, tg = pts @ aniso.T, gpts @ aniso.T
-    m = mu + dim * sigma
-    a = np.zeros((m, m))
-    d = tp[:, None, :] - tp[None, :, :]
-    a[:mu, :mu] = np.sqrt((d * d).sum(axis=2)) ** 3
-    d = tp[:, None, :] - tg[None, :, :]                      # value row i, gradient column j
-    r = np.sqrt((d * d).sum(axis=2))
-    f = -(3.0 * r[:, :, None] * d) @ aniso                   # -(grad_iso A)
-    a[:mu, mu:] = f.reshape(mu, dim * sigma)
-    a[mu:, :mu] = a[:mu, mu:].T
-    d = tg[:, None, :] - tg[None, :, :]
-    r = np.sqrt((d * d).sum(axis=2))
-    with np.errstate(all="ignore"):
-        hess = 3.0 * (r[:, :, None, None] * np.eye(dim) + np.where(r[:, :, None, None] > 0,
-                      d[:, :, :, None] * d[:, :, None, :] / r[:, :, None, None], 0.0))
-    h = -np.einsum("ai,pqab,bj->pqij", aniso, hess, aniso)
-    a[mu:, mu:] = h.transpose(0, 2, 1, 3).reshape(dim * sigma, dim * sigma)
-    return a
-
-
 def test_ras_hermite_parity_with_oracle(torch):
     """Hermite data: the device RAS (mixed domains, Hermite Gram kernel, four-kind transfers) against the dense oracle
     on the same 2-level th3 problem with anisotropy: same level sets, one sweep to 1e-8 with exact level transfers (1e-4 at order 12), FGMRES
@@ -266,7 +241,8 @@ def test_ras_hermite_parity_with_oracle(torch):
     aniso = random_anisotropy(dim, rng)
     pts, gpts = rng.uniform(-1, 1, (mu, dim)), rng.uniform(-1, 1, (sigma, dim))
     m = mu + dim * sigma
-    a_dense = _dense_th3_hermite(pts, gpts, aniso)
+    from conftest import dense_th3_hermite
+    a_dense = dense_th3_hermite(pts, gpts, aniso)
     o_rbf = orbf.make_rbf("th3", [1.0, 0.0], dim, aniso)
     for col in (3, mu + 7, m - 1):   # the closed-form builder against the oracle's direct evaluator
         ref = odir.direct_evaluator(o_rbf, 0.0, pts, gpts, np.eye(m)[:, col], pts, gpts)

@@ -153,3 +153,45 @@ def test_native_mixed_matches_oracle_restatement():
         pb_, gb = oras.choose_coarse_points_mixed(p, g, pid, gid, poly, target)
         assert list(pa[:4]) == poly and set(pa.tolist()) == set(pb_.tolist()) and set(ga.tolist()) == set(gb.tolist())
         assert target <= (len(pa) - 4) + 3 * len(ga) < target + 3
+
+
+def test_oracle_ras_hermite_preconditions_dense_system():
+    """oracle/ras.py on Hermite data (values + gradients, anisotropic th3, linear polynomial, 2 levels): the
+    right-preconditioned FGMRES of oracle/krylov.py reaches 1e-10 in a handful of iterations on the exact dense
+    saddle-point system, and the interpolation conditions hold for values and gradients."""
+    from oracle import direct as odir, rbf as orbf
+    from oracle.krylov import Fgmres
+    from oracle.ras import RasOracle, monomials
+    rng = np.random.default_rng(41)
+    dim, mu, sigma = 3, 1500, 300
+    aniso = np.diag([1.5, 1.0, 0.7])
+    pts, gpts = rng.uniform(-1, 1, (mu, dim)), rng.uniform(-1, 1, (sigma, dim))
+    m = mu + dim * sigma
+    o_rbf = orbf.make_rbf("th3", [1.0, 0.0], dim, aniso)
+    from conftest import dense_th3_hermite
+    a = dense_th3_hermite(pts, gpts, aniso)     # closed-form mat_a, spot-checked against the exact direct evaluator
+    for col in (5, mu + 4, m - 1):
+        ref = odir.direct_evaluator(o_rbf, 0.0, pts, gpts, np.eye(m)[:, col], pts, gpts)
+        assert np.max(np.abs(a[:, col] - ref)) <= 1e-11 * np.max(np.abs(ref))
+    assert np.max(np.abs(a - a.T)) <= 1e-12 * np.max(np.abs(a))
+    o = RasOracle(a, pts, dim, 1, 0.0, [3, 400, 900, 1400], grad_points=gpts, a_points=pts @ aniso.T,
+                  a_grad_points=gpts @ aniso.T)
+    assert o.n_levels == 2
+    own = np.zeros(m, dtype=int)
+    for g in o.fine[1]:
+        own[g["idx"][g["inner"]]] += 1
+    assert np.all(own == 1)   # every row (value or gradient component) is owned by exactly one fine domain
+    p = monomials(dim, 1, pts, gpts)
+    full = np.block([[a, p], [p.T, np.zeros((4, 4))]])
+    values = np.concatenate([np.sin(np.pi * pts).sum(axis=1), (np.pi * np.cos(np.pi * gpts)).reshape(-1)])
+    v = np.concatenate([values, np.zeros(4)])
+    s = Fgmres(lambda x: full @ x, v, 30)
+    s.set_right_preconditioner(o)
+    s.setup()
+    for _ in range(12):
+        s.iterate_process()
+        if s.relative_residual() < 1e-10:
+            break
+    assert s.relative_residual() < 1e-10 and s.iteration_count() <= 12
+    x = s.solution_vector()
+    assert np.max(np.abs((full @ x)[:m] - values)) <= 1e-7
