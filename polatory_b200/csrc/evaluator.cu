@@ -236,8 +236,9 @@ struct plt_eval {
     } catch (const std::invalid_argument& e) {
       throw Error(PLT_ERR_INVALID, e.what());
     }
-    if (kind == KIND_H && !rbf.has_hessian)
-      throw Error(PLT_ERR_UNSUPPORTED, "evaluate_hessian_isotropic is not implemented for this RBF");
+    // cov_spherical / cov_cubic have no Hessian: the reference still instantiates their Hessian
+    // evaluators (src/fmm/make_fmm_evaluator.cpp CASE(CovCubic) / CASE(CovSpherical)) and only throws
+    // from evaluate_hessian_isotropic (cov_spherical.hpp:53-55), i.e. when a pair is evaluated.
     params.assign(params_, params_ + n_params);
     for (int i = 0; i < dim * dim; ++i) aniso[i] = aniso_ ? aniso_[i] : (i / dim == i % dim ? 1.0 : 0.0);
     // rbf_base.hpp:73-75
@@ -862,6 +863,8 @@ struct plt_eval {
       config = {0, 0, kClassic};
       return;
     }
+    if (kind == KIND_H && !rbf.has_hessian)
+      throw Error(PLT_ERR_UNSUPPORTED, "evaluate_hessian_isotropic is not implemented for this RBF");
 
     const bool compact = std::isfinite(rbf.support_radius);
     // src/fmm/fmm_evaluator.hpp:226-234 / fmm_symmetric_evaluator.hpp:222-230

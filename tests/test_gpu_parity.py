@@ -107,6 +107,38 @@ def test_fmm_matches_cpu_restatement(pb, dim, n, name, params, kind, rng):
             assert e_gpu < 1.5 * e_orc + 1e-12, (e_gpu, e_orc)
 
 
+@pytest.mark.parametrize("dim", [3, 2])
+@pytest.mark.parametrize("name,params", [("th2", [1.0, 0.02]), ("gau", [1.1, 0.6]), ("gc3", [0.9, 0.7]),
+                                         ("gc7", [1.2, 0.9]), ("gc9", [1.0, 1.1]), ("sp5", [1.0, 0.6]),
+                                         ("sp7", [1.3, 0.8])])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_fmm_branch_of_remaining_rbfs(pb, dim, name, params, kind, rng):
+    """FMM branch (not only the brute-force golden cases) for the RBFs the first test does not cover.
+    Spheroidals: compact direct part (exact) + FMM fast part, src/fmm/spheroidal_evaluator.hpp:24-29."""
+    odir, ofmm, _ = _oracle()
+    n = 9000
+    a = random_anisotropy(dim, rng)
+    src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (n // 2, dim))
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    lo, hi = -np.ones(dim), np.ones(dim)
+    ev = pb.FmmGenericEvaluator(kind, pb.make_rbf(name, params, dim, a), pb.Bbox(lo, hi))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    for order, d in ((6, -1), (10, -1)):
+        ev.force_config(order, d)
+        got = ev.evaluate()
+        cfg = ev.config()
+        assert cfg["order"] == order and cfg["tree_height"] == ofmm.tree_height(dim, n)
+        if name.startswith("sp"):
+            ref = ofmm.direct(name, params, dim, kind, src, trg, w, a, part=1) + \
+                ofmm.fmm(name, params, dim, kind, lo, hi, src, trg, w, order, d, 0, a, part=2)
+        else:
+            ref = ofmm.fmm(name, params, dim, kind, lo, hi, src, trg, w, order, d, 0, a)
+        assert _relerr(got, ref) < 1e-10, (order, _relerr(got, ref))
+
+
 # ---------------------------------------------------------------------------------------
 # 3. the reference's own test shapes
 # ---------------------------------------------------------------------------------------
@@ -223,11 +255,81 @@ def test_compact_support_evaluators(pb, name, params, kind, rng):
     assert _relerr(got, ref) < 1e-12
 
 
-def test_compact_hessian_is_unsupported(pb):
+@pytest.mark.parametrize("name,params", [("sph", [1.1, 0.3]), ("cub", [0.9, 0.25]), ("sp3", [1.0, 0.9])])
+def test_compact_support_symmetric_evaluator(pb, name, params, rng):
+    """src/fmm/direct_symmetric_evaluator.hpp:35-67: the symmetric compact-support evaluator (kd-tree radius
+    search over the points themselves, self term phi(0) w_i) -> device cell list; exact.  sp3: the direct part
+    of the symmetric spheroidal split (spheroidal_symmetric_evaluator.hpp) plus its FMM fast part."""
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 15000
+    a = random_anisotropy(dim, rng)
+    pts = rng.uniform(-1, 1, (n, dim))
+    w = rng.uniform(-1, 1, n)
+    ev = pb.make_fmm_symmetric_evaluator(pb.make_rbf(name, params, dim, a), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_points(pts)
+    ev.set_weights(w)
+    if name == "sp3":
+        ev.force_config(10, -1)
+        got = ev.evaluate()
+        ref = ofmm.direct(name, params, dim, 0, pts, None, w, a, part=1, symmetric=True) + \
+            ofmm.fmm(name, params, dim, 0, -np.ones(dim), np.ones(dim), pts, None, w, 10, -1, 0, a, part=2,
+                     symmetric=True)
+        assert _relerr(got, ref) < 1e-10
+        return
+    got = ev.evaluate()
+    assert ev.config()["tree_height"] > 2 and ev.config()["order"] == 0  # P2P on the cell list only
+    ref = ofmm.direct(name, params, dim, 0, pts, None, w, a, symmetric=True)
+    assert _relerr(got, ref) < 1e-12
+    # the Hessian-symmetric spheroidal direct part (H kind of a compact kernel that has a Hessian)
+    if name == "sph":
+        evh = pb.make_fmm_hessian_symmetric_evaluator(pb.make_rbf("sp5", [1.0, 0.8], dim, a),
+                                                      pb.Bbox(-np.ones(dim), np.ones(dim)))
+        gp = pts[:6000]
+        wg = rng.uniform(-1, 1, 3 * len(gp))
+        evh.set_points(gp)
+        evh.set_weights(wg)
+        evh.force_config(10, -1)
+        got = evh.evaluate()
+        ref = ofmm.direct("sp5", [1.0, 0.8], dim, 3, gp, None, wg, a, part=1, symmetric=True) + \
+            ofmm.fmm("sp5", [1.0, 0.8], dim, 3, -np.ones(dim), np.ones(dim), gp, None, wg, 10, -1, 0, a, part=2,
+                     symmetric=True)
+        assert _relerr(got, ref) < 1e-10
+
+
+def test_compact_hessian_is_unsupported(pb, rng):
+    """cov_spherical.hpp:53-55: the Hessian throws when a pair is evaluated, not when the evaluator is made
+    (make_fmm_evaluator.cpp instantiates the Hessian evaluators of sph / cub; interpolation::Operator creates
+    all four kinds for every RBF, operator.hpp:44-49, and value-only models never feed the H evaluator a point)."""
     from polatory_b200 import _lib
-    with pytest.raises(_lib.PolatoryB200Error) as e:
-        pb.make_fmm_hessian_evaluator(pb.make_rbf("sph", [1.0, 1.0]), pb.Bbox(-np.ones(3), np.ones(3)))
-    assert e.value.status == _lib.PLT_ERR_UNSUPPORTED
+    bbox = pb.Bbox(-np.ones(3), np.ones(3))
+    for make in (pb.make_fmm_hessian_evaluator, pb.make_fmm_hessian_symmetric_evaluator):
+        ev = make(pb.make_rbf("sph", [1.0, 1.0]), bbox)
+        pts = rng.uniform(-1, 1, (5, 3))
+        if make is pb.make_fmm_hessian_evaluator:
+            ev.set_source_points(np.zeros((0, 3)))
+            ev.set_target_points(pts)
+            ev.set_weights(np.zeros(0))
+            assert np.array_equal(ev.evaluate(), np.zeros(15))   # sigma = 0: no pair, no error
+            ev.set_source_points(pts)
+            ev.set_target_points(np.zeros((0, 3)))
+            ev.set_weights(np.zeros(15))
+            assert ev.evaluate().shape == (0,)
+            ev.set_target_points(pts)
+        else:
+            ev.set_points(np.zeros((0, 3)))
+            ev.set_weights(np.zeros(0))
+            assert ev.evaluate().shape == (0,)
+            ev.set_points(pts)
+            ev.set_weights(np.zeros(15))
+        with pytest.raises(_lib.PolatoryB200Error) as e:
+            ev.evaluate()
+        assert e.value.status == _lib.PLT_ERR_UNSUPPORTED
+    # the four-evaluator pattern of interpolation::Operator works for a value-only cov_spherical model
+    from polatory_b200.operator import Model, Operator
+    op = Operator(Model(pb.make_rbf("cub", [1.0, 0.5]), poly_degree=0), bbox)
+    op.set_points(rng.uniform(-1, 1, (300, 3)))
+    y = op(np.ones(op.size()))
+    assert np.isfinite(y.cpu().numpy()).all()
 
 
 @pytest.mark.parametrize("name", ["sp3", "sp9"])
