@@ -365,31 +365,41 @@ def main():
 
 def fit_timing(points, dev, tol=1e-4):
     """Second half of BASELINE.json's metric: wall-time of the 1M-point fit (config #2: bh3 SDF centres,
-    degree 0, absolute tolerance 1e-4, evaluator accuracy tol / 100), end to end from host arrays:
-    operator set-up (tree, plan, accuracy search), RAS set-up (coarse points, domains, batched
-    factorisations), FGMRES iterations with the FMM matvec and the RAS preconditioner.  Convergence is
-    the max-norm of the true residual through the FMM operator; a sample is re-checked against exact
-    sums by tests/test_gpu_ras.py and tools/dev_fit.py."""
+    degree 0, absolute tolerance 1e-4, evaluator accuracy tol / 100), end to end from host arrays, in the
+    reference's configuration (include/polatory/interpolation/solver.hpp:40-41,60): the matvec operator at
+    accuracy 0 (-> order 12, d 8), a separate residual evaluator at the user's accuracy (its accuracy search
+    included), RAS set-up (coarse points, domains, batched factorisations), FGMRES iterations with the FMM
+    matvec and the RAS preconditioner, convergence by the reference's ResidualEvaluator (exact sums on <= 1024
+    sampled data points, then every point through the fast evaluator).  The final residual on the exact sample
+    is asserted here."""
     import torch
     import polatory_b200 as pb
-    from polatory_b200.operator import Model, Operator, solve
+    from polatory_b200.operator import Model, Operator, ResidualEvaluator, solve
     from polatory_b200.ras import RasPreconditioner
     n = len(points)
     third = (n + 2) // 3
     values = np.concatenate([np.zeros(third), np.full(third, 1e-2), np.full(n - 2 * third, -1e-2)])
     model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.0)
+    bbox = pb.Bbox(points.min(axis=0), points.max(axis=0))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    op = Operator(model, pb.Bbox(points.min(axis=0), points.max(axis=0)), accuracy=tol / 100.0)
+    op = Operator(model, bbox, 0.0, 0.0)                      # solver.hpp:40
+    res_op = Operator(model, bbox, tol / 100.0, tol / 100.0)  # solver.hpp:41
     op.set_points(points)
+    res_op.set_points(points)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     pc = RasPreconditioner(model, points)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    w, iters = solve(op, values, tol, 100, preconditioner=pc.apply)
+    w, iters = solve(op, values, tol, 100, preconditioner=pc.apply, residual_op=res_op)
     torch.cuda.synchronize()
     t3 = time.perf_counter()
+    # acceptance (test/interpolation/test_fitter.cpp:57-64): the exact residual on the reference's sample
+    chk = ResidualEvaluator(res_op)
+    chk.set_values(torch.from_numpy(values).to(dev))
+    ok, res, _, _ = chk.converged(w, tol)
+    assert ok and res <= tol, f"fit did not meet the tolerance: residual {res}"
     # steady-state cost of the two operators of an iteration
     x = torch.cat([torch.from_numpy(values).to(dev), torch.zeros(1, dtype=torch.float64, device=dev)])
     y = torch.empty_like(x)
@@ -404,11 +414,13 @@ def fit_timing(points, dev, tol=1e-4):
     torch.cuda.synchronize()
     ph = op.a[0].phase_times()
     return {"workload": f"config #2 fit: {n} bh3 centres (sphere surface + normal offsets, values 0 / +-1e-2), degree 0, "
-                        f"tolerance {tol} absolute, FGMRES + RAS",
+                        f"tolerance {tol} absolute, accuracy tol/100, FGMRES + RAS, reference configuration "
+                        f"(matvec at accuracy 0, separate residual evaluator)",
             "wall_s": t3 - t0, "operator_setup_s": t1 - t0, "ras_setup_s": t2 - t1, "solve_s": t3 - t2,
             "ras_setup_breakdown_s": {k: round(v, 3) for k, v in pc.setup_seconds.items()},
             "iterations": iters, "levels": pc.n_levels, "domains": [f.n_dom if f else 1 for f in pc.fine],
-            "matvec_config": op.a[0].config(), "matvec_ms": e[0].elapsed_time(e[1]),
+            "residual_max_abs": res, "matvec_config": op.a[0].config(),
+            "residual_evaluator_config": res_op.a[0].config(), "matvec_ms": e[0].elapsed_time(e[1]),
             "ras_apply_ms": e[1].elapsed_time(e[2]),
             "matvec_phases_ms": {k: round(v, 4) for k, v in ph.items()}}
 

@@ -247,6 +247,12 @@ int64_t plt_ras_domains_total(plt_ras_domains* h);
 int plt_ras_domains_get(plt_ras_domains* h, int64_t* offsets, int64_t* indices, uint8_t* inner);
 void plt_ras_domains_destroy(plt_ras_domains* h);
 
+/* The data points on which interpolation::ResidualEvaluator measures the residual exactly
+ * (include/polatory/interpolation/residual_evaluator.hpp:123-136): out[0..n) = iota shuffled by a default-seeded
+ * std::mt19937 (std::shuffle), then std::partition'ed so that points whose `block` values are not all zero come
+ * first.  Host pointers. */
+int plt_residual_sample_indices(const double* values, int64_t n, int block, int64_t* out);
+
 /* Library/ABI version and a device probe (returns PLT_ERR_CUDA without a usable GPU). */
 int plt_version(void);
 int plt_device_check(void);

@@ -300,8 +300,8 @@ class RasOracle:
                 for j in range(i + 1, l):
                     p[:, j] -= (p[:, i] @ p[:, j]) * p[:, i]
             self.p = p
+            # ap_ comes from SymmetricEvaluator, which applies no nugget (ras_preconditioner.hpp:165-180)
             self.ap = self.a_dense @ p
-            self.ap[:mu] += nugget * p[:mu]
 
     def _rows(self, point_indices, grad_indices):
         g = np.asarray(grad_indices, dtype=np.int64)

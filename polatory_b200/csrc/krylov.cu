@@ -212,10 +212,13 @@ struct plt_fgmres {
     x0_zero = true;
     if (x0_in) {
       if (n) PLT_CUDA(cudaMemcpyAsync(x0.get(), x0_in, sizeof(double) * n, cudaMemcpyDefault, stream));
-      x0_zero = norm2_of(x0.get()) == 0.0;  // x0_.isZero(), gmres_base.cpp:46
     } else {
       x0.zero(stream);
     }
+    // x0_.isZero(), gmres_base.cpp:46.  With sharded vectors the decision must be the same on every rank
+    // and every rank must take part in the reduction, whether or not it was given an x0 (a rank with an
+    // empty shard passes none): a missing x0 counts as zeros.
+    if (x0_in || allreduce) x0_zero = norm2_of(x0.get()) == 0.0;
     // r0 = rhs - A x0
     double* v0 = v(0);
     if (n) PLT_CUDA(cudaMemcpyAsync(v0, rhs.get(), sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));

@@ -15,6 +15,7 @@
 #include <memory>
 #include <numeric>
 #include <thread>
+#include <random>
 #include <vector>
 
 #include "common.cuh"
@@ -633,5 +634,28 @@ int plt_ras_domains_get(plt_ras_domains* h, int64_t* offsets, int64_t* indices, 
 }
 
 void plt_ras_domains_destroy(plt_ras_domains* h) { delete h; }
+
+// interpolation::ResidualEvaluator::set_values (include/polatory/interpolation/residual_evaluator.hpp:123-136): the
+// sample of data points whose residual is measured exactly.  iota -> std::shuffle with a default-seeded
+// std::mt19937 -> std::partition("value != 0" first); the caller keeps the first min(n, 1024) entries.  `block`
+// doubles per point (1 for values, dim for gradient vectors, "not all zero").  Native so that the sequence is
+// the standard library's own, as in the reference.
+int plt_residual_sample_indices(const double* values, int64_t n, int block, int64_t* out) {
+  if (n < 0 || block < 1 || (n > 0 && (!values || !out))) return PLT_ERR_INVALID;
+  try {
+    std::vector<int64_t> idx(static_cast<size_t>(n));
+    std::iota(idx.begin(), idx.end(), int64_t{0});
+    std::shuffle(idx.begin(), idx.end(), std::mt19937{});
+    std::partition(idx.begin(), idx.end(), [&](int64_t i) {
+      for (int c = 0; c < block; ++c)
+        if (values[i * block + c] != 0.0) return true;
+      return false;
+    });
+    std::copy(idx.begin(), idx.end(), out);
+  } catch (const std::exception&) {
+    return PLT_ERR_INVALID;
+  }
+  return PLT_OK;
+}
 
 }  // extern "C"

@@ -17,7 +17,7 @@ namespace {
 
 template <int DIM>
 __global__ void k_point_keys(const double* __restrict__ pos, int64_t n, Box box, int level,
-                             uint32_t* __restrict__ keys, int* __restrict__ idx) {
+                             uint32_t* __restrict__ keys, int* __restrict__ idx, int* __restrict__ outside) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int nside = 1 << level;
@@ -26,7 +26,12 @@ __global__ void k_point_keys(const double* __restrict__ pos, int64_t n, Box box,
 #pragma unroll
   for (int a = 0; a < DIM; ++a) {
     double corner = box.center[a] - 0.5 * box.width;
-    int ci = static_cast<int>(floor((pos[a * n + i] - corner) * inv_w));
+    const double x = (pos[a * n + i] - corner) * inv_w;
+    // The root box is 1.01 x the bbox the evaluator was made with (src/fmm/utility.hpp:18-33), so points of
+    // that bbox are strictly inside.  A point outside it (NaN included) would be clamped into a boundary
+    // cell whose expansion does not cover it -- silent, unbounded error; reported instead.
+    if (!(x >= 0.0 && x <= static_cast<double>(nside))) *outside = 1;
+    int ci = static_cast<int>(floor(x));
     c[a] = min(max(ci, 0), nside - 1);
   }
   keys[i] = morton_encode<DIM>(c);
@@ -101,9 +106,16 @@ void Tree::build(int dim, int height, const Box& box, const double* pos_caller, 
   idx_tmp_.alloc(n, stream);
   pkey_.alloc(n, stream);
   perm_.alloc(n, stream);
-  if (dim == 1) PLT_LAUNCH(ctr, k_point_keys<1>, blocks, threads, 0, stream, pos_caller, n, box, leaf, key_tmp_.get(), idx_tmp_.get());
-  if (dim == 2) PLT_LAUNCH(ctr, k_point_keys<2>, blocks, threads, 0, stream, pos_caller, n, box, leaf, key_tmp_.get(), idx_tmp_.get());
-  if (dim == 3) PLT_LAUNCH(ctr, k_point_keys<3>, blocks, threads, 0, stream, pos_caller, n, box, leaf, key_tmp_.get(), idx_tmp_.get());
+  // scan_[total] (one past the exclusive scan) carries the "point outside the root box" flag.
+  dense_off_.assign(height + 1, 0);
+  for (int l = 0; l < height; ++l) dense_off_[l + 1] = dense_off_[l] + (int64_t{1} << (dim * l));
+  const int64_t total = dense_off_[height];
+  scan_.alloc(total + 1, stream);
+  int* outside = scan_.get() + total;
+  PLT_CUDA(cudaMemsetAsync(outside, 0, sizeof(int), stream));
+  if (dim == 1) PLT_LAUNCH(ctr, k_point_keys<1>, blocks, threads, 0, stream, pos_caller, n, box, leaf, key_tmp_.get(), idx_tmp_.get(), outside);
+  if (dim == 2) PLT_LAUNCH(ctr, k_point_keys<2>, blocks, threads, 0, stream, pos_caller, n, box, leaf, key_tmp_.get(), idx_tmp_.get(), outside);
+  if (dim == 3) PLT_LAUNCH(ctr, k_point_keys<3>, blocks, threads, 0, stream, pos_caller, n, box, leaf, key_tmp_.get(), idx_tmp_.get(), outside);
   size_t tmp_bytes = 0;
   const int end_bit = std::max(1, dim * leaf);
   PLT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_tmp_.get(), pkey_.get(), idx_tmp_.get(),
@@ -118,16 +130,12 @@ void Tree::build(int dim, int height, const Box& box, const double* pos_caller, 
   PLT_LAUNCH(ctr, k_gather_pos, blocks, threads, 0, stream, pos_caller, perm_.get(), n, dim, pos_.get());
 
   // 3. occupancy of every level, one scan over the concatenation.
-  dense_off_.assign(height + 1, 0);
-  for (int l = 0; l < height; ++l) dense_off_[l + 1] = dense_off_[l] + (int64_t{1} << (dim * l));
-  const int64_t total = dense_off_[height];
   DevBuf<int64_t>& d_off = d_off_;
   d_off.alloc(height + 1, stream);
   PLT_CUDA(cudaMemcpyAsync(d_off.get(), dense_off_.data(), (height + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
   DevBuf<int>& occ = occ_;
   DevBuf<int>& scan = scan_;
   occ.alloc(total, stream);
-  scan.alloc(total + 1, stream);
   occ.zero(stream);
   PLT_LAUNCH(ctr, k_mark_cells, blocks, threads, 0, stream, pkey_.get(), n, dim, height, d_off.get(), occ.get());
   size_t scan_bytes = 0;
@@ -140,10 +148,15 @@ void Tree::build(int dim, int height, const Box& box, const double* pos_caller, 
   std::vector<int> base(height + 1, 0);
   for (int l = 0; l < height; ++l)
     PLT_CUDA(cudaMemcpyAsync(&base[l], scan.get() + dense_off_[l], sizeof(int), cudaMemcpyDeviceToHost, stream));
-  int last_scan = 0, last_occ = 0;
+  int last_scan = 0, last_occ = 0, any_outside = 0;
   PLT_CUDA(cudaMemcpyAsync(&last_scan, scan.get() + total - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PLT_CUDA(cudaMemcpyAsync(&last_occ, occ.get() + total - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PLT_CUDA(cudaMemcpyAsync(&any_outside, outside, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PLT_CUDA(cudaStreamSynchronize(stream));
+  if (any_outside) {
+    height_ = 0;
+    throw Error(PLT_ERR_INVALID, "a point lies outside the bounding box the evaluator was created with");
+  }
   base[height] = last_scan + last_occ;
   total_cells_ = base[height];
   cell_off_.assign(height + 1, 0);

@@ -131,6 +131,7 @@ class Operator:
         else:
             self.perm = np.arange(self.mu)
         self._points = points
+        self._grad_points = gp
         for i in range(n_rbf):
             self.a[i].set_points(points)
             self.a[i].set_accuracy(acc)
@@ -153,6 +154,12 @@ class Operator:
         if self.l > 0:
             p = monomial_basis(dim, self.model.poly_degree, points, gp)
             self.p = torch.from_numpy(p).to(self.device)
+            q = p.copy()  # common::orthonormalize_cols (modified Gram-Schmidt), solver.hpp:62-66
+            for i in range(self.l):
+                q[:, i] /= np.linalg.norm(q[:, i])
+                for j in range(i + 1, self.l):
+                    q[:, j] -= (q[:, i] @ q[:, j]) * q[:, i]
+            self.p_orth = torch.from_numpy(q).to(self.device)
         m = self.mu + dim * self.sigma
         self._full = torch.zeros(m + self.l, dtype=torch.float64, device=self.device)
         self._tmp_mu = torch.empty(self.mu, dtype=torch.float64, device=self.device)
@@ -253,6 +260,23 @@ class Operator:
                 y[nloc:] = self.p.T @ full[:m]
         return y
 
+    def orthogonalize_against_polynomials(self, x):
+        """solver.hpp:88-96: the RBF part of an initial solution is made orthogonal to the polynomial space,
+        weights.head(m) -= P (P^T weights.head(m)) (the RAS preconditioner relies on v.tail(l) ~ 0,
+        ras_preconditioner.hpp:186-187).  `x` is this rank's shard; modified in place and returned."""
+        if self.l == 0:
+            return x
+        m = self.mu + self.dim * self.sigma
+        if self.world == 1:
+            x[:m] -= self.p_orth @ (self.p_orth.T @ x[:m])
+            return x
+        nloc = self.hi - self.lo
+        p_loc = self.p_orth[self.lo:self.hi]
+        dot = p_loc.T @ x[:nloc]
+        self._dist.all_reduce(dot, op=self._dist.ReduceOp.SUM, group=self.group)
+        x[:nloc] -= p_loc @ dot
+        return x
+
     def __call__(self, weights):
         torch = self._torch
         x = torch.as_tensor(weights, dtype=torch.float64).to(self.device)
@@ -279,66 +303,115 @@ class ShardedPreconditioner:
 
 
 class ResidualEvaluator:
-    """interpolation::ResidualEvaluator for value data (include/polatory/interpolation/residual_evaluator.hpp:26-164):
-    the residual |fit - value| is first measured EXACTLY (direct sums on the device) on at most 1024 sampled points
-    with non-zero values, and only when that passes on all points through the fast operator.  The sample is a
-    deterministic shuffle followed by a stable partition on `value != 0`; the reference's std::shuffle sequence is
-    not reproduced (different, equally arbitrary 1024 points)."""
+    """interpolation::ResidualEvaluator (include/polatory/interpolation/residual_evaluator.hpp:26-164), value and
+    Hermite data: the residual |fit - value| is first measured EXACTLY (direct sums on the device, the reference's
+    DirectEvaluator) on at most 1024 sampled value points and 1024 sampled gradient points with non-zero data, and
+    only when that passes on ALL points through the fast evaluator at the user's accuracy (`fast_op`, the
+    reference's separate SymmetricEvaluator of solver.hpp:41; its rows [0, m) are SymmetricEvaluator::evaluate() +
+    nugget * w).  The sample is the reference's own: std::shuffle with a default-seeded std::mt19937 followed by
+    std::partition, run natively (`plt_residual_sample_indices`)."""
 
-    K_DIRECT_TARGETS = 1024
+    K_DIRECT_TARGETS = 1024  # kDirectEvaluatorTargetSize
 
-    def __init__(self, op):
-        self.op = op
+    def __init__(self, fast_op):
+        self.op = fast_op
         self._direct = []
+
+    @staticmethod
+    def _sample(values_host, n, block):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        out = np.empty(n, dtype=np.int64)
+        v = np.ascontiguousarray(values_host, dtype=np.float64)
+        if n:
+            st = lib.plt_residual_sample_indices(v.ctypes.data, n, block, out.ctypes.data)
+            if st != _lib.PLT_OK:
+                raise RuntimeError("plt_residual_sample_indices failed")
+        return out
 
     def set_values(self, values):
+        """values: CUDA tensor (mu + dim * sigma), the right-hand side without the l zeros."""
         import torch
         op = self.op
+        mu, sigma, dim = op.mu, op.sigma, op.dim
         self.values = values
         host = values.detach().cpu().numpy()
-        perm = np.random.RandomState(5489).permutation(op.mu)
-        perm = np.concatenate([perm[host[perm] != 0.0], perm[host[perm] == 0.0]])
-        self.idx = np.sort(perm[:min(op.mu, self.K_DIRECT_TARGETS)])
-        self.idx_dev = torch.from_numpy(self.idx).to(op.device)
-        self.exact = len(self.idx) == op.mu
-        pts = op._points
+        self.direct_mu = min(mu, self.K_DIRECT_TARGETS)
+        self.direct_sigma = min(sigma, self.K_DIRECT_TARGETS)
+        self.idx = self._sample(host[:mu], mu, 1)[:self.direct_mu]
+        self.gidx = self._sample(host[mu:], sigma, dim)[:self.direct_sigma]
+        dev = op.device
+        self.idx_dev = torch.from_numpy(self.idx).to(dev)
+        self.gidx_dev = torch.from_numpy(self.gidx).to(dev)
+        self.grows_dev = (mu + dim * self.gidx_dev[:, None] + torch.arange(dim, device=dev)[None, :]).reshape(-1)
+        self.exact = self.direct_mu == mu and self.direct_sigma == sigma
+        pts, gp = op._points, op._grad_points
+        tp = np.ascontiguousarray(pts[self.idx])
+        tg = np.ascontiguousarray(gp[self.gidx])
+        bbox = fmm.Bbox.from_points(np.concatenate([pts, gp]))
+        # DirectEvaluator (interpolation/direct_evaluator.hpp:38-88): exact sums, the four blocks that exist
         self._direct = []
         for rbf in op.model.rbfs:
-            ev = fmm.make_fmm_evaluator(rbf, fmm.Bbox.from_points(pts))
-            ev.force_direct(True)
-            ev.set_source_points(pts)
-            ev.set_target_points(np.ascontiguousarray(pts[self.idx]))
-            self._direct.append(ev)
-        self._fit = torch.empty(len(self.idx), dtype=torch.float64, device=op.device)
-        self._full = torch.empty(op.size(), dtype=torch.float64, device=op.device)
+            evs = {}
+            for name, make, s_pts, t_pts in (("a", fmm.make_fmm_evaluator, pts, tp),
+                                             ("f", fmm.make_fmm_gradient_evaluator, gp, tp),
+                                             ("ft", fmm.make_fmm_gradient_transpose_evaluator, pts, tg),
+                                             ("h", fmm.make_fmm_hessian_evaluator, gp, tg)):
+                if len(s_pts) == 0 or len(t_pts) == 0:
+                    continue
+                ev = make(rbf, bbox)
+                ev.force_direct(True)
+                ev.set_source_points(s_pts)
+                ev.set_target_points(t_pts)
+                evs[name] = ev
+            self._direct.append(evs)
+        self._buf_v = torch.empty(self.direct_mu, dtype=torch.float64, device=dev)
+        self._buf_g = torch.empty(dim * self.direct_sigma, dtype=torch.float64, device=dev)
+        self._full = torch.empty(op.size(), dtype=torch.float64, device=dev)
 
-    def converged(self, weights, tolerance):
-        """(converged, residual, exact) as residual_evaluator.hpp:55-108."""
+    def converged(self, weights, tolerance, grad_tolerance=None):
+        """(converged, residual, grad_residual, exact) as residual_evaluator.hpp:55-108."""
+        import torch
         op = self.op
-        mu = op.mu
-        fit = op.model.nugget * weights[self.idx_dev]
-        for ev in self._direct:
-            ev.set_weights(weights[:mu].contiguous())
-            ev.evaluate(self._fit)
-            fit = fit + self._fit
+        grad_tolerance = tolerance if grad_tolerance is None else grad_tolerance
+        mu, m = op.mu, op.mu + op.dim * op.sigma
+        w_mu, w_sg = weights[:mu].contiguous(), weights[mu:m].contiguous()
+        fit_v = op.model.nugget * weights[self.idx_dev]
+        fit_g = torch.zeros(op.dim * self.direct_sigma, dtype=torch.float64, device=op.device)
+        for evs in self._direct:
+            for name, w, buf in (("a", w_mu, self._buf_v), ("f", w_sg, self._buf_v),
+                                 ("ft", w_mu, self._buf_g), ("h", w_sg, self._buf_g)):
+                if name in evs:
+                    evs[name].set_weights(w)
+                    evs[name].evaluate(buf)
+                    if buf is self._buf_v:
+                        fit_v = fit_v + buf
+                    else:
+                        fit_g = fit_g + buf
         if op.l:
-            fit = fit + op.p[self.idx_dev] @ weights[mu:]
-        residual = float((fit - self.values[self.idx_dev]).abs().max())
-        if residual > tolerance:
-            return False, residual, self.exact
+            fit_v = fit_v + op.p[self.idx_dev] @ weights[m:]
+            if self.direct_sigma:
+                fit_g = fit_g + op.p[self.grows_dev] @ weights[m:]
+        res = float((fit_v - self.values[self.idx_dev]).abs().max()) if self.direct_mu else 0.0
+        gres = float((fit_g - self.values[self.grows_dev]).abs().max()) if self.direct_sigma else 0.0
+        if res > tolerance or gres > grad_tolerance:
+            return False, res, gres, self.exact
         if self.exact:
-            return True, residual, True
+            return True, res, gres, True
         op.apply(weights, self._full)
-        residual = float((self._full[:mu] - self.values).abs().max())
-        return residual <= tolerance, residual, True
+        res = float((self._full[:mu] - self.values[:mu]).abs().max()) if mu else 0.0
+        gres = float((self._full[mu:m] - self.values[mu:m]).abs().max()) if op.sigma else 0.0
+        return (res <= tolerance and gres <= grad_tolerance), res, gres, True
 
 
-def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=None):
-    """The loop of interpolation::Solver::solve (solver.hpp:99-139) on the device: FGMRES with an
-    optional right preconditioner over `op`; `values` is this rank's shard of the right-hand side
-    (without the `l` zeros, which are appended here).  Convergence on one GPU with value data: the
-    reference's ResidualEvaluator (exact residual on <= 1024 sampled points, then on all points through
-    the fast operator); sharded or with gradient data: max-norm of the true residual through the
+def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=None, residual_op=None,
+          grad_tolerance=None, verbose=False):
+    """The loop of interpolation::Solver::solve (solver.hpp:75-142) on the device: FGMRES with an optional right
+    preconditioner over `op` (the matvec operator -- the reference builds it at accuracy 0, solver.hpp:40);
+    `values` is this rank's shard of the right-hand side (without the `l` zeros, which are appended here).
+    Convergence on one GPU: the reference's ResidualEvaluator over `residual_op`, a second Operator at the user's
+    accuracy (solver.hpp:41; default: `op` itself).  Sharded vectors: max-norm of the true residual through the
     operator once the solver's own 2-norm estimate allows it.
     Returns (weights shard, iteration count)."""
     import torch
@@ -349,20 +422,24 @@ def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=
     rhs = torch.cat([values, torch.zeros(n_tail, dtype=torch.float64, device=dev)])
     solver = Fgmres(op, rhs, max_iter, group=op.group)
     if initial_weights is not None:
-        solver.set_initial_solution(initial_weights)
+        solver.set_initial_solution(op.orthogonalize_against_polynomials(
+            torch.as_tensor(initial_weights, dtype=torch.float64).to(dev).clone()))
     if preconditioner is not None:
         solver.set_right_preconditioner(preconditioner)
     solver.setup()
     weights = solver.solution_vector()
     if solver.relative_residual() == 0.0:
         return weights, 0
-    if op.group is None and op.sigma == 0:
+    if op.group is None:
         # the reference's convergence test: exact residual on a sample first, then everywhere (solver.hpp:112-135)
-        res_eval = ResidualEvaluator(op)
+        res_eval = ResidualEvaluator(op if residual_op is None else residual_op)
         res_eval.set_values(values)
         while True:
             weights = solver.solution_vector()
-            if res_eval.converged(weights, tolerance)[0]:
+            ok, res, gres, exact = res_eval.converged(weights, tolerance, grad_tolerance)
+            if verbose:
+                print(f"{solver.iteration_count():8d} {'' if exact else '~'}{res:12.4e} {gres:12.4e}", flush=True)
+            if ok:
                 return weights, solver.iteration_count()
             if solver.iteration_count() == solver.max_iterations():
                 raise RuntimeError("reached the maximum number of iterations")  # solver.hpp:132-134
@@ -382,3 +459,45 @@ def solve(op, values, tolerance, max_iter, preconditioner=None, initial_weights=
         if solver.iteration_count() == solver.max_iterations():
             raise RuntimeError("reached the maximum number of iterations")  # solver.hpp:132-134
         solver.iterate_process()
+
+
+class Solver:
+    """interpolation::Solver (include/polatory/interpolation/solver.hpp:22-154): the matvec operator at accuracy 0
+    (-> order 12, d 8: `op_(model, points, grad_points, 0.0, 0.0)`, :40), a separate residual evaluator at the
+    user's accuracy (:41) and the RAS preconditioner (:60)."""
+
+    def __init__(self, model, points, grad_points=None, accuracy=float("inf"), grad_accuracy=float("inf"),
+                 device=None, ras_kwargs=None):
+        from .ras import RasPreconditioner
+        dim = model.dim
+        points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, dim)
+        gp = np.zeros((0, dim)) if grad_points is None else \
+            np.ascontiguousarray(grad_points, dtype=np.float64).reshape(-1, dim)
+        bbox = fmm.Bbox.from_points(np.concatenate([points, gp]))
+        self.model = model
+        self.op = Operator(model, bbox, 0.0, 0.0, device=device)
+        self.res_op = Operator(model, bbox, accuracy, grad_accuracy, device=device)
+        self.op.set_points(points, gp if len(gp) else None)
+        self.res_op.set_points(points, gp if len(gp) else None)
+        self.pc = RasPreconditioner(model, points, gp if len(gp) else None, device=device, **(ras_kwargs or {}))
+        self.iterations = None
+
+    def solve(self, values, tolerance, grad_tolerance=None, max_iter=100, initial_weights=None, verbose=False):
+        w, it = solve(self.op, values, tolerance, max_iter, preconditioner=self.pc.apply,
+                      initial_weights=initial_weights, residual_op=self.res_op, grad_tolerance=grad_tolerance,
+                      verbose=verbose)
+        self.iterations = it
+        return w
+
+
+class Fitter:
+    """interpolation::Fitter (include/polatory/interpolation/fitter.hpp:12-36)."""
+
+    def __init__(self, model, points, grad_points=None):
+        self.model, self.points, self.grad_points = model, points, grad_points
+        self.solver = None
+
+    def fit(self, values, tolerance, grad_tolerance=None, max_iter=100, accuracy=float("inf"),
+            grad_accuracy=float("inf"), initial_weights=None, verbose=False):
+        self.solver = Solver(self.model, self.points, self.grad_points, accuracy, grad_accuracy)
+        return self.solver.solve(values, tolerance, grad_tolerance, max_iter, initial_weights, verbose)

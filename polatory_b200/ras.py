@@ -1,6 +1,6 @@
 """Restricted additive Schwarz preconditioner of the fit, on the device.
 
-Restates, for value data and Hermite data (gradient points) and one RBF per model,
+Restates, for value data and Hermite data (gradient points), one or several RBFs per model,
   preconditioner::RasPreconditioner   include/polatory/preconditioner/ras_preconditioner.hpp:34-364
   preconditioner::DomainDivider       include/polatory/preconditioner/domain_divider.hpp:17-321
   preconditioner::Domain              include/polatory/preconditioner/domain.hpp:16-52
@@ -307,7 +307,13 @@ class _CoarseGrid:
             q = self.q_top
             red = a[l:, l:] + q.T @ (a[:l, :l] @ q + a[:l, l:]) + a[l:, :l] @ q
             self.a_top = a[:l, :].clone()
-            p_top = torch.from_numpy(monomial_basis(ras.dim, ras.model.poly_degree, ras.points[rows[:l]])).to(dev)
+            if ras.special_case:   # coarse_grid.hpp:75-77: the value point and the coarse grid's FIRST gradient point
+                first_grad = (int(rows[1]) - ras.mu) // ras.dim
+                p_top = monomial_basis(ras.dim, ras.model.poly_degree, ras.points[rows[:1]],
+                                       ras.grad_points[first_grad:first_grad + 1])
+            else:
+                p_top = monomial_basis(ras.dim, ras.model.poly_degree, ras.points[rows[:l]])
+            p_top = torch.from_numpy(p_top).to(dev)
             self.p_top_inv = torch.linalg.inv(p_top)
         else:
             red = a
@@ -350,13 +356,14 @@ class RasPreconditioner:
         mu, sigma, l = self.mu, self.sigma, self.l
         self.m_rows = mu + dim * sigma
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        if len(model.rbfs) != 1:
-            raise NotImplementedError("RAS: one RBF per model in this round")
-        if l > 0 and model.poly_degree == 1 and mu == 1 and sigma >= 1:
-            raise NotImplementedError("RAS: the single-value-point special case of the reference is not restated")
+        # "The special case" of ras_preconditioner.hpp:81-86 / coarse_grid.hpp:75-77: a linear polynomial pinned by
+        # ONE value point and the first gradient point (test/interpolation/test_fitter.cpp:73).
+        self.special_case = l > 0 and model.poly_degree == 1 and mu == 1 and sigma >= 1
         rbf = model.rbfs[0]
         self.bbox = fmm.Bbox.from_points(np.concatenate([self.points, self.grad_points]))
-        self._gram_ev = fmm.make_fmm_evaluator(rbf, self.bbox)   # carries the RBF constants for the Gram kernels
+        # one handle per RBF: they carry the RBF constants for the Gram kernels (mat_a sums over the RBFs,
+        # mat_a.hpp:23-55)
+        self._gram_evs = [fmm.make_fmm_evaluator(r, self.bbox) for r in model.rbfs]
         n_levels, counts = level_structure(self.m_rows)
         self.n_levels = n_levels
         self.points_dev = torch.from_numpy(self.points).to(self.device)
@@ -366,10 +373,15 @@ class RasPreconditioner:
         self.row_types = torch.cat([torch.zeros(mu, dtype=torch.int8, device=self.device),
                                     (1 + torch.arange(dim, dtype=torch.int8, device=self.device)).repeat(sigma)])
 
-        poly_idcs = unisolvent_point_set(self.points, model.poly_degree, dim) if l > 0 else []
+        if self.special_case:
+            poly_idcs = [0]
+            coeffs = np.linalg.inv(monomial_basis(dim, model.poly_degree, self.points, self.grad_points[:1]))
+        else:
+            poly_idcs = unisolvent_point_set(self.points, model.poly_degree, dim) if l > 0 else []
+            if l > 0:
+                coeffs = np.linalg.inv(monomial_basis(dim, model.poly_degree, self.points[poly_idcs]))
         self.poly_idcs = poly_idcs
         if l > 0:
-            coeffs = np.linalg.inv(monomial_basis(dim, model.poly_degree, self.points[poly_idcs]))
             self.lagrange_p = torch.from_numpy(
                 monomial_basis(dim, model.poly_degree, self.points, self.grad_points) @ coeffs).to(self.device)
         point_idcs, grad_idcs = [None] * n_levels, [None] * n_levels
@@ -378,7 +390,8 @@ class RasPreconditioner:
         point_idcs[n_levels - 1] = np.concatenate([np.asarray(poly_idcs, dtype=np.int64), np.nonzero(rest)[0]])
         grad_idcs[n_levels - 1] = np.arange(sigma, dtype=np.int64)
         aniso = np.asarray(rbf.anisotropy(), dtype=np.float64)
-        iso = np.allclose(aniso, np.eye(dim))
+        # ras_preconditioner.hpp:111-120: the divider works on transformed points only for a single anisotropic RBF
+        iso = len(model.rbfs) != 1 or np.array_equal(aniso, np.eye(dim))
         a_points = self.points if iso else self.points @ aniso.T
         a_grad_points = self.grad_points if iso else self.grad_points @ aniso.T
         self.fine = [None] * n_levels
@@ -440,7 +453,8 @@ class RasPreconditioner:
                     p[:, j] -= (p[:, i] @ p[:, j]) * p[:, i]
             self.p = torch.from_numpy(p).to(self.device)
             from .operator import Model as _Model, Operator
-            fin = Operator(_Model(model.rbfs, poly_degree=-1, nugget=model.nugget), self.bbox, device=self.device)
+            # SymmetricEvaluator applies no nugget (ras_preconditioner.hpp:165-180): A p, not (A + nugget I) p
+            fin = Operator(_Model(model.rbfs, poly_degree=-1, nugget=0.0), self.bbox, device=self.device)
             for ev in fin.a + fin.f + fin.ft + fin.h:
                 self._configure_transfer(ev)
             fin.set_points(self.points, self.grad_points if sigma else None)
@@ -471,13 +485,25 @@ class RasPreconditioner:
         b, m = rows.shape
         out = torch.empty((b, m, m), dtype=torch.float64, device=self.device)
         pts = self.row_coords[rows].contiguous()
-        if self.sigma == 0:
-            self._gram_ev.gram_batched(pts, counts.contiguous(), self.model.nugget, out)
-        else:
+        if self.sigma > 0:
             types = self.row_types[rows]
             valid = torch.arange(m, device=self.device)[None, :] < counts[:, None]
             types = torch.where(valid, types, torch.full_like(types, -1)).contiguous()
-            self._gram_ev.gram_mixed(pts, types, self.model.nugget, out)
+        tmp = None
+        for i, ev in enumerate(self._gram_evs):
+            dst = out
+            if i > 0:
+                tmp = torch.empty_like(out) if tmp is None else tmp
+                dst = tmp
+            if self.sigma == 0:
+                ev.gram_batched(pts, counts.contiguous(), self.model.nugget if i == 0 else 0.0, dst)
+            else:
+                ev.gram_mixed(pts, types, self.model.nugget if i == 0 else 0.0, dst)
+            if i > 0:
+                # rows / columns beyond a set's count are identity in every term: keep ONE identity
+                pad = (torch.arange(m, device=self.device)[None, :] >= counts[:, None])
+                tmp.diagonal(dim1=1, dim2=2)[pad] = 0.0
+                out += tmp
         return out
 
     def _evaluator(self, src_level, trg_level):
@@ -486,24 +512,24 @@ class RasPreconditioner:
         key = (src_level, trg_level)
         if key not in self._evaluators:
             torch = self.torch
-            rbf = self.model.rbfs[0]
             sp = self.points_dev[self.idx_dev[src_level]].contiguous()
             sg = self.grad_points_dev[self.gidx_dev[src_level]].contiguous()
             tp = self.points_dev[self.idx_dev[trg_level]].contiguous()
             tg = self.grad_points_dev[self.gidx_dev[trg_level]].contiguous()
-            evs = {}
-            for name, make, s_pts, t_pts in (("a", fmm.make_fmm_evaluator, sp, tp),
-                                             ("f", fmm.make_fmm_gradient_evaluator, sg, tp),
-                                             ("ft", fmm.make_fmm_gradient_transpose_evaluator, sp, tg),
-                                             ("h", fmm.make_fmm_hessian_evaluator, sg, tg)):
-                if len(s_pts) == 0 or len(t_pts) == 0:
-                    continue
-                ev = make(rbf, self.bbox)
-                self._configure_transfer(ev)
-                ev.set_source_points(s_pts)
-                ev.set_target_points(t_pts)
-                kn = self.dim if name in ("ft", "h") else 1
-                evs[name] = (ev, torch.empty(kn * len(t_pts), dtype=torch.float64, device=self.device))
+            evs = []
+            for rbf in self.model.rbfs:       # evaluator.hpp:53-58: four kinds per RBF
+                for name, make, s_pts, t_pts in (("a", fmm.make_fmm_evaluator, sp, tp),
+                                                 ("f", fmm.make_fmm_gradient_evaluator, sg, tp),
+                                                 ("ft", fmm.make_fmm_gradient_transpose_evaluator, sp, tg),
+                                                 ("h", fmm.make_fmm_hessian_evaluator, sg, tg)):
+                    if len(s_pts) == 0 or len(t_pts) == 0:
+                        continue
+                    ev = make(rbf, self.bbox)
+                    self._configure_transfer(ev)
+                    ev.set_source_points(s_pts)
+                    ev.set_target_points(t_pts)
+                    kn = self.dim if name in ("ft", "h") else 1
+                    evs.append((name, ev, torch.empty(kn * len(t_pts), dtype=torch.float64, device=self.device)))
             self._evaluators[key] = evs
         return self._evaluators[key]
 
@@ -521,12 +547,12 @@ class RasPreconditioner:
         w_v = weights[self.idx_dev[src_level]].contiguous()
         w_g = weights[self.grows_dev[src_level]].contiguous()
         trg_v, trg_g = self.idx_dev[trg_level], self.grows_dev[trg_level]
-        for name, w, rows in (("a", w_v, trg_v), ("f", w_g, trg_v), ("ft", w_v, trg_g), ("h", w_g, trg_g)):
-            if name in evs:
-                ev, fit = evs[name]
-                ev.set_weights(w)
-                ev.evaluate(fit)
-                residuals[rows] -= fit
+        src_w = {"a": w_v, "f": w_g, "ft": w_v, "h": w_g}
+        trg_rows = {"a": trg_v, "f": trg_v, "ft": trg_g, "h": trg_g}
+        for name, ev, fit in evs:
+            ev.set_weights(src_w[name])
+            ev.evaluate(fit)
+            residuals[trg_rows[name]] -= fit
         if self.l > 0:
             c = weights[self.m_rows:]
             residuals[trg_v] -= self.p_mono[trg_v] @ c

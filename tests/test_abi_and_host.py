@@ -268,3 +268,20 @@ def test_host_side_abi_error_paths():
         assert lib.plt_fgmres_create(100, 10, ctypes.byref(s)) == _lib.PLT_ERR_CUDA   # no CPU fallback
         assert b"CUDA" in lib.plt_fgmres_last_error(None)
     assert lib.plt_fgmres_iterate(None) == _lib.PLT_ERR_INVALID
+
+
+def test_residual_sample_is_the_standard_librarys():
+    """plt_residual_sample_indices = iota + std::shuffle(std::mt19937{}) + std::partition(value != 0)
+    (residual_evaluator.hpp:123-136): a permutation, non-zero values first, deterministic."""
+    from polatory_b200.operator import ResidualEvaluator
+    v = np.zeros(5000)
+    v[::3] = 1.0
+    a = ResidualEvaluator._sample(v, len(v), 1)
+    b = ResidualEvaluator._sample(v, len(v), 1)
+    assert np.array_equal(a, b) and np.array_equal(np.sort(a), np.arange(len(v)))
+    nz = int((v != 0).sum())
+    assert (v[a[:nz]] != 0).all() and (v[a[nz:]] == 0).all()
+    g = np.zeros((100, 3))
+    g[10:20, 1] = 2.0
+    c = ResidualEvaluator._sample(g.reshape(-1), 100, 3)
+    assert set(c[:10]) == set(range(10, 20))

@@ -283,3 +283,52 @@ def test_ras_hermite_parity_with_oracle(torch):
     w, iters = solve(op, values, tol, 80, preconditioner=pc.apply)
     assert abs(iters - s.iteration_count()) <= 1, (iters, s.iteration_count())
     assert np.max(np.abs(w.cpu().numpy() - x)) <= 1e-3 * np.max(np.abs(x))
+
+
+def test_ras_nugget_parity_with_oracle(torch):
+    """nugget != 0: mat_a carries the nugget on the value rows (mat_a.hpp:27-29) while `ap_` comes from
+    SymmetricEvaluator and the level transfers from Evaluator, neither of which applies it
+    (ras_preconditioner.hpp:165-180,287-321).  One sweep of the device RAS against the dense restatement."""
+    import polatory_b200 as pb
+    from oracle.ras import RasOracle
+    from polatory_b200.operator import Model
+    from polatory_b200.ras import RasPreconditioner
+    rng = np.random.default_rng(5)
+    n, dim, degree, nugget = 6000, 3, 1, 0.05
+    pts = rng.uniform(-1, 1, (n, dim))
+    values = np.sin(np.pi * pts).sum(axis=1)
+    model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=degree, nugget=nugget)
+    pc = RasPreconditioner(model, pts, transfer_config=(12, 8))
+    assert pc.n_levels == 2
+    d = pts[:, None, :] - pts[None, :, :]
+    a_dense = -np.sqrt((d * d).sum(axis=2))
+    o = RasOracle(a_dense, pts, dim, degree, nugget, pc.poly_idcs)
+    v = np.concatenate([values, np.zeros(pc.l)])
+    ref = o(v)
+    got = pc(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-6 * np.max(np.abs(ref))
+
+
+def test_fit_two_rbfs(torch):
+    """Several RBFs per model (operator.hpp:63-73 loops over them; mat_a sums them, mat_a.hpp:23-55): a nested
+    covariance model exp + gau with different anisotropies, two-level RAS, acceptance against exact sums."""
+    import polatory_b200 as pb
+    from conftest import random_anisotropy
+    from oracle import direct as odir, rbf as orbf
+    from polatory_b200.operator import Fitter, Model
+    rng = np.random.default_rng(9)
+    n, dim = 5000, 3
+    a1, a2 = random_anisotropy(dim, rng), random_anisotropy(dim, rng)
+    pts = rng.uniform(-1, 1, (n, dim))
+    values = np.sin(np.pi * pts).sum(axis=1)
+    model = Model([pb.make_rbf("exp", [0.7, 0.4], dim, a1), pb.make_rbf("gau", [0.3, 0.25], dim, a2)],
+                  poly_degree=0, nugget=0.01)
+    tol = 1e-5
+    fitter = Fitter(model, pts)
+    w = fitter.fit(values, tol, max_iter=80, accuracy=tol / 100).cpu().numpy()
+    assert fitter.solver.pc.n_levels == 2
+    sub = rng.choice(n, 200, replace=False)
+    fit = odir.full_direct(orbf.make_rbf("exp", [0.7, 0.4], dim, a1), 0, pts, pts[sub], w[:n]) + \
+        odir.full_direct(orbf.make_rbf("gau", [0.3, 0.25], dim, a2), 0, pts, pts[sub], w[:n]) + \
+        0.01 * w[sub] + w[n]
+    assert np.max(np.abs(fit - values[sub])) <= 2 * tol
