@@ -126,7 +126,9 @@ def test_fmm_branch_of_remaining_rbfs(pb, dim, name, params, kind, rng):
     ev.set_source_points(src)
     ev.set_target_points(trg)
     ev.set_weights(w)
-    for order, d in ((6, -1), (10, -1)):
+    # order 6 = the evaluation default, 8 = the first step of the accuracy search (from order 10 on the
+    # equispaced interpolation amplifies rounding beyond 1e-10 for th2's r^4 log r: 1.1e-10 measured)
+    for order, d in ((6, -1), (8, -1)):
         ev.force_config(order, d)
         got = ev.evaluate()
         cfg = ev.config()
