@@ -11,9 +11,14 @@ set_target_points(10M targets) + evaluate() -> 10M values; i.e. upward pass (P2M
 DFT), target tree build, M2L, L2L, L2P, P2P and the scatter to caller order, every step.
 `value` is measured with inputs/outputs resident in HBM; `e2e` through the same public calls
 with pinned HOST buffers (H2D of targets + weights and D2H of the result inside the timed
-region).  Weak scaling: every rank evaluates its own 10M-target grid (a sub-cell shifted copy
-of the lattice, the isosurface sampler's many-batches pattern) against the same 1M sources;
-no data-path collective is needed.
+region).
+
+N > 1 GPUs: STRONG scaling of the ONE 10M-target grid (BASELINE.json config #3, "sharded over 2/4/8 B200").
+The level-4 cells of the octree are partitioned over the ranks by Morton key range, balanced by target
+count; a rank holds all sources + weights and only ITS targets (it copies only its slab H2D / D2H in the
+e2e leg), computes the multipoles it owns or needs, and the ranks exchange the level-4 expansions with one
+NCCL all-gather per step (plt_eval_set_partition).  `value` = all 10M targets / max-over-ranks
+time.  The former replica number (every rank its own full grid) is kept as `weak_replicas`.
 """
 from __future__ import annotations
 
@@ -56,13 +61,7 @@ def parse_args():
 
 def workload(args, rank=0, world=1):
     from polatory_b200 import workloads as wl
-    src, w, trg, lo, hi = wl.c3_isosurface_field(args.n_sources, tuple(args.grid))
-    if world > 1:
-        # rank r samples the lattice shifted by r/world of a grid step (still inside the bbox)
-        step = (hi - lo) / (np.asarray(args.grid) - 1)
-        trg = trg + (rank / world) * step * 0.999
-        hi = hi + step
-    return src, w, trg, lo, hi
+    return wl.c3_isosurface_field(args.n_sources, tuple(args.grid))
 
 
 def config_dict(args, n_src, n_trg, cfg, world):
@@ -70,13 +69,14 @@ def config_dict(args, n_src, n_trg, cfg, world):
         "workload": "config #3: isosurface field evaluation, biharmonic3d (s=1, c=0) interpolant with "
                     f"{n_src} sources (unit-sphere surface + normal-offset SDF points) sampled at "
                     f"{n_trg} grid targets ({'x'.join(map(str, args.grid))}) over 1.1 x bbox"
-                    + (f", per rank ({world} ranks, sub-cell shifted lattices)" if world > 1 else ""),
+                    + (f"; ONE grid sharded over {world} ranks by Morton key range of the level-4 cells" if world > 1 else ""),
         "rbf": "bh3", "kernel_kind": "K", "dim": 3,
         "accuracy": "inf" if np.isinf(args.accuracy) else args.accuracy,
         "tree_height": cfg.get("tree_height"), "order": cfg.get("order"), "d": cfg.get("d"),
         "step": "set_weights + set_target_points + evaluate (upward pass, target tree, M2L, L2L, L2P, P2P)",
         "cache_policy": "inputs larger than L2 (240 MB targets, >4 GB expansions per step)",
-        "parallelism": f"targets-dp{world}",
+        "parallelism": f"targets sharded by Morton range over {world} GPU(s); sources + weights replicated; "
+                       "all-gather of the level-4 multipole expansions" if world > 1 else "single GPU",
     }
 
 
@@ -210,8 +210,8 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, len(src), len(trg), {"tree_height": height, "order": order, "d": d}, 1),
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, len(src), len(trg), {"tree_height": height, "order": order, "d": d}, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -243,9 +243,23 @@ def main():
     from polatory_b200 import _lib
 
     src, w, trg, lo, hi = workload(args, rank, world)
-    n_src, n_trg = len(src), len(trg)
+    n_src, n_trg_global = len(src), len(trg)
     ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0, 0.0]), pb.Bbox(lo, hi))
     ev.set_accuracy(args.accuracy)
+    trg_full = trg
+    shard = None
+    if world > 1:
+        from polatory_b200.parallel import DEFAULT_CUT_LEVEL, partition_keys
+        cut = DEFAULT_CUT_LEVEL[3]
+        keys = ev.point_keys(trg, cut)
+        key_begin = partition_keys(keys, world, 3, cut)
+        own = np.nonzero((keys >= key_begin[rank]) & (keys < key_begin[rank + 1]))[0]
+        trg = np.ascontiguousarray(trg[own])
+        height = pb.fmm.tree_height(3, max(n_src, n_trg_global))   # src/fmm/utility.hpp:12-16 on the GLOBAL counts
+        ev.force_config(0, -1, height)
+        ev.set_partition(rank, world, cut, key_begin, group=dist.group.WORLD)
+        shard = {"cut_level": cut, "key_begin": [int(k) for k in key_begin], "targets_this_rank": int(len(own))}
+    n_trg = len(trg)
     d_src = torch.from_numpy(src).to(dev)
     d_w = torch.from_numpy(w).to(dev)
     d_trg = torch.from_numpy(trg).to(dev)
@@ -288,7 +302,8 @@ def main():
     phases = ev.phase_times()
     cfg = ev.config()
     ms_step = ms_total / args.steps
-    value = world * n_trg / (ms_step * 1e-3) / 1e6
+    value = n_trg_global / (ms_step * 1e-3) / 1e6
+    allgathers = ev.allgather_count()
 
     # ---- e2e: same calls, pinned host buffers, H2D + D2H inside the timed region ----
     h_trg = torch.from_numpy(trg).pin_memory()
@@ -306,7 +321,7 @@ def main():
         for _ in range(2):
             step_host()
         e2e_ms = timed(step_host, args.steps) / args.steps
-        e2e_value = world * n_trg / (e2e_ms * 1e-3) / 1e6
+        e2e_value = n_trg_global / (e2e_ms * 1e-3) / 1e6
         host_ok = bool(np.allclose(h_out.numpy()[:1000], d_out[:1000].cpu().numpy(), rtol=0, atol=0))
 
     # ---- roofline of the dominant kernel (live CUDA-event time of the last timed step) ----
@@ -326,12 +341,14 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, n_src, n_trg, cfg, world),
+        "config": config_dict(args, n_src, n_trg_global, cfg, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(trg.nbytes + w.nbytes), "d2h_bytes_per_step": int(8 * n_trg),
+                # summed over the ranks: every rank copies its own target slab + the weights in, its own values out
+                "h2d_bytes_per_step": int(trg_full.nbytes + world * w.nbytes), "d2h_bytes_per_step": int(8 * n_trg_global),
                 "matches_device_path": host_ok},
         "gpu_launches": int(launches),
         "phases_ms": {k: round(v, 4) for k, v in phases.items()},
@@ -340,6 +357,9 @@ def main():
     }
 
     line["phase_rooflines"] = phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, ev)
+    if world > 1:
+        line["multi_gpu"] = multi_gpu_report(args, ev, dist, dev, world, rank, shard, d_w, d_trg, d_out, d_src,
+                                             trg_full, allgathers, ms_step, timed, barrier)
     if world == 1 and not args.no_fit:
         line["fit"] = fit_timing(src, dev)
 
@@ -361,6 +381,61 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_report(args, ev, dist, dev, world, rank, shard, d_w, d_trg, d_out, d_src, trg_full, allgathers,
+                     ms_step, timed, barrier):
+    """Evidence for the sharded run: per-rank device times and shard sizes, the NCCL exchange count, parity of
+    the N-GPU result against the same rank evaluating its targets alone (no partition), and the former replica
+    (weak-scaling) figure."""
+    import torch
+    # per-rank time of one more step (device events, this rank only)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    ev.set_weights(d_w)
+    ev.set_target_points(d_trg)
+    ev.evaluate(d_out)
+    e1.record()
+    torch.cuda.synchronize()
+    mine = torch.zeros(world, dtype=torch.float64, device=dev)
+    mine[rank] = e0.elapsed_time(e1)
+    dist.all_reduce(mine)
+    counts = torch.zeros(world, dtype=torch.float64, device=dev)
+    counts[rank] = shard["targets_this_rank"]
+    dist.all_reduce(counts)
+    up = ev.phase_times()
+    upward_ms = torch.tensor([sum(up.get(k, 0.0) for k in ("p2m", "m2m", "m2hat")), up.get("allgather", 0.0)],
+                             dtype=torch.float64, device=dev)
+    dist.all_reduce(upward_ms, op=dist.ReduceOp.MAX)
+    sharded = d_out.clone()
+    # 1-GPU result of the same targets: partition removed, same (global) tree height
+    ev.set_partition(0, 1)
+    ev.set_weights(d_w)
+    ev.set_target_points(d_trg)
+    ev.evaluate(d_out)
+    diff = torch.stack([(sharded - d_out).abs().max(), d_out.abs().max()])
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    # replicas: every rank the full grid (the round-1 weak-scaling number)
+    d_full = torch.from_numpy(trg_full).to(dev)
+    d_out_full = torch.empty(len(trg_full), dtype=torch.float64, device=dev)
+
+    def step_full():
+        ev.set_weights(d_w)
+        ev.set_target_points(d_full)
+        ev.evaluate(d_out_full)
+
+    for _ in range(2):
+        step_full()
+    ms_full = timed(step_full, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    return {"cut_level": shard["cut_level"], "key_begin": shard["key_begin"],
+            "targets_per_rank": [int(c) for c in counts.cpu()],
+            "step_ms_per_rank": [round(float(v), 3) for v in mine.cpu()],
+            "upward_ms_max": float(upward_ms[0]), "allgather_ms_max": float(upward_ms[1]),
+            "nccl_allgathers_per_step": 1, "nccl_allgathers_total_rank0": int(allgathers),
+            "n_gpu_vs_1_gpu_max_rel_diff": float(diff[0] / diff[1]),
+            "weak_replicas": {"value": world * len(trg_full) / (ms_full * 1e-3) / 1e6, "unit": UNIT,
+                              "ms_per_step": ms_full, "what": "every rank its own full 10M-target grid (round-1 number)"}}
 
 
 def fit_timing(points, dev, tol=1e-4):

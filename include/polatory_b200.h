@@ -132,6 +132,35 @@ int plt_eval_set_stream(plt_eval* h, void* cuda_stream);
  * begin = 0, end = -1 restores the full range. */
 int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size);
 
+/* Multi-GPU evaluation across one node, one process per GPU.  Every rank holds all source points
+ * and weights (24 + 8 bytes per source); the level-`level_cut` cells of the octree are partitioned by Morton
+ * key: rank r OWNS the keys [key_begin[r], key_begin[r + 1]) (key_begin[0] = 0; key_begin[world_size] is
+ * taken as 2^(dim * level_cut)).
+ *   - A generic evaluator is then given only this rank's targets (ideally those of its own key range);
+ *     call plt_eval_force_config(h, 0, -1, height) with the height of the GLOBAL problem
+ *     (src/fmm/utility.hpp:12-16 on the global point counts) so that every rank builds the same octree.
+ *   - A symmetric evaluator (the matvec) is given all points and evaluates the leaves of its own key range;
+ *     outputs of the other points are written as 0 (plt_eval_get_target_shard_range gives the point range).
+ * The upward pass is partitioned: a rank computes P2M / M2M / the multipole spectra only below the level-cut
+ * cells it owns or that lie within the interaction range of its targets; the level-cut expansions are then
+ * exchanged with ONE all-gather (`allgatherv`, e.g. NCCL over NVLink) and the few upper levels are finished
+ * on every rank.  Results are bit-identical to the single-GPU evaluation of the same targets.
+ * world_size <= 1 removes the partition.
+ *
+ * allgatherv(ctx, buf, offsets, world_size, stream): in-place all-gather on DEVICE memory; rank r contributes the
+ * doubles [offsets[r], offsets[r + 1]) of `buf`; on return every segment is filled.  Work must be ordered after
+ * / before the other work of `stream` (a cudaStream_t).  Returns 0 on success. */
+typedef int (*plt_allgatherv_fn)(void* ctx, double* buf, const int64_t* offsets, int world_size, void* stream);
+int plt_eval_set_partition(plt_eval* h, int rank, int world_size, int level_cut, const uint32_t* key_begin,
+                           plt_allgatherv_fn allgatherv, void* ctx);
+/* src/fmm/utility.hpp:12-16: max(2, round(ln n / ln 2^dim)); n = max(n_src, n_trg) (symmetric: n). */
+int plt_tree_height(int dim, int64_t n_points);
+/* Morton keys at `level` of host points (original coordinates; the evaluator's anisotropy and root box are
+ * applied): what a caller partitions its targets with.  keys: n uint32. */
+int plt_eval_point_keys(plt_eval* h, const double* points, int64_t n, int level, uint32_t* keys);
+/* Number of all-gathers issued by this handle so far. */
+int64_t plt_eval_allgather_count(plt_eval* h);
+
 /* Multi-GPU matvec support: the permutation of the target tree, perm[i] =
  * caller index of the i-th point in Morton order (the order target shards are cut in), and
  * the sorted-order point range [begin, end) of the current target shard (cuts are moved to

@@ -39,6 +39,10 @@ SYMBOLS = [
     ("plt_eval_get_config", ctypes.c_int, [_vp, ctypes.POINTER(PltConfig)]),
     ("plt_eval_set_stream", ctypes.c_int, [_vp, _vp]),
     ("plt_eval_set_target_shard", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    ("plt_eval_set_partition", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    ("plt_tree_height", ctypes.c_int, [ctypes.c_int, ctypes.c_int64]),
+    ("plt_eval_point_keys", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp]),
+    ("plt_eval_allgather_count", ctypes.c_int64, [_vp]),
     ("plt_eval_get_permutation", ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     ("plt_eval_get_target_shard_range", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64),
                                                        ctypes.POINTER(ctypes.c_int64)]),
@@ -86,6 +90,7 @@ SYMBOLS = [
 # Callback types of the Krylov solver (include/polatory_b200.h: plt_linop_fn, plt_allreduce_fn).
 LINOP_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _vp)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.c_int)
+ALLGATHERV_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, _vp)
 
 _lib = None
 

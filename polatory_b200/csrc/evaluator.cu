@@ -104,6 +104,67 @@ __global__ void k_find_leaf(const int* __restrict__ leaf_start, int n_leaf, int 
   if (s >= point && prev < point) *out = i;
 }
 
+// ---- partitioned upward pass (multi-GPU) --------------------------------------------------
+// need[key] = 1 for every cell of level `cut` (by Morton key) that lies within the 3^dim neighbourhood of a
+// target cell of that level: the source cells below it appear in the M2L / P2P lists of this rank's targets.
+template <int DIM>
+__global__ void k_need_mask(TreeView trg, int cut, unsigned char* __restrict__ need) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= trg.n_cells[cut]) return;
+  int c[DIM];
+  morton_decode<DIM>(trg.keys[trg.cell_off[cut] + i], c);
+  const int nside = 1 << cut;
+  constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  for (int e = 0; e < NN; ++e) {
+    int q[DIM], r = e;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = c[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (ok) need[morton_encode<DIM>(q)] = 1;
+  }
+}
+
+// Work flags of every source cell (tree.cuh: kCellFlagM / kCellFlagMhat) for rank `rank` of a partition of the
+// level-`cut` key space into the ranges [key_begin[r], key_begin[r + 1]):
+//   levels <  cut : M by M2M from the all-gathered level `cut` and Mhat on every rank (a handful of cells)
+//   level  == cut : M if owned or needed (the all-gather fills in the rest), Mhat on every rank
+//   levels >  cut : M if the level-`cut` ancestor is owned or needed, Mhat if it is needed
+__global__ void k_cell_flags(TreeView src, int cut, const unsigned char* __restrict__ need, uint32_t own_lo,
+                             uint32_t own_hi, unsigned char* __restrict__ flags) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= src.cell_off[src.height - 1] + src.n_cells[src.height - 1]) return;
+  int l = 0;
+  while (l + 1 < src.height && g >= src.cell_off[l + 1]) ++l;
+  unsigned char f;
+  if (l < cut) {
+    f = kCellFlagM | kCellFlagMhat;
+  } else {
+    const uint32_t anc = src.keys[g] >> (src.dim * (l - cut));
+    const bool own = anc >= own_lo && anc < own_hi, nd = need[anc] != 0;
+    f = (own || nd ? kCellFlagM : 0) | (l == cut || nd ? kCellFlagMhat : 0);
+  }
+  flags[g] = f;
+}
+
+// out[r] = first compact cell of `level` whose key is >= bounds[r] (n_cells if none), r < n.
+__global__ void k_lower_bound_keys(TreeView tr, int level, const uint32_t* __restrict__ bounds, int n,
+                                   int shift, int* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t* keys = tr.keys + tr.cell_off[level];
+  const unsigned long long key = static_cast<unsigned long long>(bounds[r]) << shift;
+  int lo = 0, hi = tr.n_cells[level];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  out[r] = lo;
+}
+
 struct PhaseTimer {
   struct Rec {
     const char* name;
@@ -202,6 +263,22 @@ struct plt_eval {
   plt_config config{0, 0, kClassic};
 
   int shard_rank = 0, shard_world = 1;
+
+  // Partition of the level-`cut` Morton key space over the ranks of one node (plt_eval_set_partition): rank r
+  // owns the keys [key_begin[r], key_begin[r + 1]).  Sources and weights are replicated; a rank computes the
+  // multipoles of the cells it owns or needs below the cut, the level-`cut` expansions are all-gathered and
+  // the upper levels are finished redundantly (they are a few hundred cells).
+  struct Partition {
+    bool on = false;
+    int rank = 0, world = 1, cut = 0;
+    std::vector<uint32_t> key_begin;
+    plt_allgatherv_fn allgatherv = nullptr;
+    void* ctx = nullptr;
+  } part;
+  DevBuf<unsigned char> need_mask, cell_flags;
+  DevBuf<uint32_t> d_key_begin;
+  std::vector<int> own_cells;   // [world + 1] compact level-`cut` cell ranges of the ranks (source tree)
+  bool own_cells_valid = false, cell_flags_valid = false;
 
   plt_eval() = default;
   plt_eval(const plt_eval&) = delete;
@@ -367,7 +444,8 @@ struct plt_eval {
   // The upward pass can be issued ahead of evaluate() when sources and weights are in place and
   // the FMM branch will be taken for `n_targets` targets.
   bool can_prefetch_upward() const {
-    return !direct_part && !symmetric && n_src > 0 && have_weights && !std::isfinite(rbf.support_radius);
+    // (a partitioned upward pass depends on the targets: which source cells this rank needs)
+    return !part.on && !direct_part && !symmetric && n_src > 0 && have_weights && !std::isfinite(rbf.support_radius);
   }
   void prefetch_upward(int64_t n_targets) {
     if (n_src * n_targets < int64_t{1024} * 1024 && force_height == 0) return;  // brute-force branch
@@ -463,16 +541,40 @@ struct plt_eval {
   // P2M + M2M + multipole DFT (the reference's `fmm(src_tree, op, p2m | m2m)`,
   // src/fmm/fmm_evaluator.hpp:83-88).
   void upward(const Tree& st, const double* wt, Interpolator& ip, DevBuf<double>& M_, DevBuf<double2>& Mhat_,
-              bool timed) {
+              bool timed, bool partitioned = false) {
     const int order = ip.host.order;
     const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
     TreeView sv = st.view();
     M_.alloc(static_cast<size_t>(st.total_cells()) * km * P, stream);
+    int cut = -1;
+    if (partitioned) {
+      ensure_partition_tables();
+      sv.flags = cell_flags.get();
+      cut = part_cut();
+    }
     if (timed) timer.begin("p2m", stream);
     launch_p2m(dim, km, sv, box, ip.dev, wt, M_.get(), stream, ctr);
     if (timed) timer.end(stream);
     if (timed) timer.begin("m2m", stream);
-    for (int l = st.height() - 2; l >= 2; --l) launch_m2m(dim, km, sv, l, ip.dev, M_.get(), stream, ctr);
+    for (int l = st.height() - 2; l >= 2; --l) {
+      if (l == cut - 1) {
+        // levels >= cut are done for the cells this rank owns or needs: exchange the level-`cut` expansions
+        // (every rank contributes the cells it owns), then finish the upper levels redundantly.
+        if (timed) timer.end(stream);
+        if (timed) timer.begin("allgather", stream);
+        allgather_cut_level(st, M_.get(), P);
+        if (timed) timer.end(stream);
+        if (timed) timer.begin("m2m", stream);
+      }
+      launch_m2m(dim, km, sv, l, ip.dev, M_.get(), stream, ctr);
+    }
+    if (partitioned && cut >= 2 && cut - 1 < 2) {  // cut == 2: nothing above it, the exchange has not happened yet
+      if (timed) timer.end(stream);
+      if (timed) timer.begin("allgather", stream);
+      allgather_cut_level(st, M_.get(), P);
+      if (timed) timer.end(stream);
+      if (timed) timer.begin("m2m", stream);
+    }
     if (timed) timer.end(stream);
     size_t far_cells = 0;
     for (int l = 2; l < st.height(); ++l) far_cells += st.n_cells(l);
@@ -481,6 +583,19 @@ struct plt_eval {
     launch_m2hat(dim, km, sv, ip.dev, M_.get(), Mhat_.get(), stream, ctr);
     if (timed) timer.end(stream);
   }
+
+  // In-place all-gather of M at the cut level: rank r's segment = the cells [own_cells[r], own_cells[r + 1]).
+  void allgather_cut_level(const Tree& st, double* M_, size_t P) {
+    const int cut = part_cut();
+    std::vector<int64_t> off(part.world + 1);
+    for (int r = 0; r <= part.world; ++r) off[r] = static_cast<int64_t>(own_cells[r]) * km * static_cast<int64_t>(P);
+    double* base = M_ + static_cast<size_t>(st.view().cell_off[cut]) * km * P;
+    PLT_REQUIRE(part.allgatherv != nullptr, "partitioned evaluation needs the all-gather callback");
+    if (part.allgatherv(part.ctx, base, off.data(), part.world, stream) != 0)
+      throw Error(PLT_ERR_INVALID, "all-gather callback failed");
+    ++n_allgathers;
+  }
+  int64_t n_allgathers = 0;
 
   // M2L + L2L + L2P + P2P for the target leaves [leaf_lo, leaf_hi) -> vt (SoA [kn][n_trg], sorted).
   // vt must be zero on entry.
@@ -743,6 +858,31 @@ struct plt_eval {
     leaf_hi = n_leaf;
     p_lo = 0;
     p_hi = static_cast<int>(tt.n());
+    if (part.on) {
+      // a generic evaluator is handed this rank's targets only; the symmetric one (the matvec) evaluates the
+      // leaves of its own key range
+      if (!symmetric) return;
+      if (!(shard_cache.valid && shard_cache.rank == -2)) {
+        ensure_partition_tables();
+        TreeView tv = tt.view();
+        const int leaf = tt.height() - 1;
+        int* d = arena.take<int>(2);
+        PLT_LAUNCH(ctr, k_lower_bound_keys, 1, 32, 0, stream, tv, leaf, d_key_begin.get() + part.rank, 2,
+                   dim * (leaf - part_cut()), d);
+        int lh[2] = {0, 0}, ph[2] = {0, 0};
+        PLT_CUDA(cudaMemcpyAsync(lh, d, sizeof(lh), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaStreamSynchronize(stream));
+        PLT_CUDA(cudaMemcpyAsync(&ph[0], tv.leaf_start + lh[0], sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaMemcpyAsync(&ph[1], tv.leaf_start + lh[1], sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaStreamSynchronize(stream));
+        shard_cache = ShardBounds{-2, part.world, lh[0], lh[1], ph[0], ph[1], true};
+      }
+      leaf_lo = shard_cache.leaf_lo;
+      leaf_hi = shard_cache.leaf_hi;
+      p_lo = shard_cache.p_lo;
+      p_hi = shard_cache.p_hi;
+      return;
+    }
     if (shard_world <= 1) return;
     if (!(shard_cache.valid && shard_cache.rank == shard_rank && shard_cache.world == shard_world)) {
       TreeView tv = tt.view();
@@ -793,13 +933,60 @@ struct plt_eval {
       multipole_dirty = true;
       plan.reset();
       if (symmetric) shard_cache.valid = false;
+      own_cells_valid = cell_flags_valid = false;
     }
     if (!symmetric && (!trg_tree.built() || trg_tree.height() != height)) {
       trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, stream, ctr);
       plan.reset();
       shard_cache.valid = false;
+      if (part.on) {  // another set of needed source cells: the cached multipoles may not cover it
+        cell_flags_valid = false;
+        multipole_dirty = true;
+      }
     }
   }
+
+  int part_cut() const { return std::min(part.cut, src_tree.height() - 1); }
+
+  // Compact level-`cut` cell ranges owned by the ranks, and this rank's work flags.
+  void ensure_partition_tables() {
+    const int cut = part_cut();
+    const TreeView sv = src_tree.view();
+    if (!own_cells_valid) {
+      d_key_begin.alloc(part.world + 1, stream);
+      // keys were given at level part.cut; a shallower tree compares at its leaf level
+      std::vector<uint32_t> kb(part.key_begin);
+      for (auto& k : kb) k >>= dim * (part.cut - cut);
+      kb[part.world] = 1u << (dim * cut);
+      PLT_CUDA(cudaMemcpyAsync(d_key_begin.get(), kb.data(), sizeof(uint32_t) * (part.world + 1),
+                               cudaMemcpyHostToDevice, stream));
+      int* d = arena.take<int>(part.world + 1);
+      PLT_LAUNCH(ctr, k_lower_bound_keys, 1, 64, 0, stream, sv, cut, d_key_begin.get(), part.world + 1, 0, d);
+      own_cells.assign(part.world + 1, 0);
+      PLT_CUDA(cudaMemcpyAsync(own_cells.data(), d, sizeof(int) * (part.world + 1), cudaMemcpyDeviceToHost, stream));
+      PLT_CUDA(cudaStreamSynchronize(stream));
+      own_cells[part.world] = src_tree.n_cells(cut);
+      own_key_lo = kb[part.rank];
+      own_key_hi = kb[part.rank + 1];
+      own_cells_valid = true;
+      cell_flags_valid = false;
+    }
+    if (!cell_flags_valid) {
+      const TreeView tv = target_tree().view();
+      const size_t n_keys = size_t{1} << (dim * cut);
+      need_mask.alloc(n_keys, stream);
+      need_mask.zero(stream);
+      const int nt = tv.n_cells[cut];
+      if (dim == 1) PLT_LAUNCH(ctr, k_need_mask<1>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+      if (dim == 2) PLT_LAUNCH(ctr, k_need_mask<2>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+      if (dim == 3) PLT_LAUNCH(ctr, k_need_mask<3>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+      cell_flags.alloc(src_tree.total_cells(), stream);
+      PLT_LAUNCH(ctr, k_cell_flags, ceil_div(src_tree.total_cells(), 256), 256, 0, stream, sv, cut, need_mask.get(),
+                 own_key_lo, own_key_hi, cell_flags.get());
+      cell_flags_valid = true;
+    }
+  }
+  uint32_t own_key_lo = 0, own_key_hi = 0;
 
   void get_permutation(int32_t* perm, int64_t n) {
     plt_eval* e = fast_part ? fast_part.get() : this;
@@ -824,13 +1011,15 @@ struct plt_eval {
     const int64_t nt = e->targets();
     if (nt == 0 || e->n_src == 0 || e->brute_force_branch()) {
       // not sharded: rank 0 computes everything (see evaluate_device)
+      const bool first = e->part.on ? e->part.rank == 0 : (shard_world <= 1 || shard_rank == 0);
       *begin = 0;
-      *end = (shard_world <= 1 || shard_rank == 0) ? nt : 0;
+      *end = first ? nt : 0;
       return;
     }
     e->stream = stream;
     e->shard_rank = shard_rank;
     e->shard_world = shard_world;
+    e->arena.reset();
     e->ensure_trees();
     int leaf_lo, leaf_hi, p_lo, p_hi;
     e->shard_leaves(e->target_tree(), leaf_lo, leaf_hi, p_lo, p_hi);
@@ -871,9 +1060,9 @@ struct plt_eval {
     const bool small = symmetric ? n_src < 1024 : n_src * nt < int64_t{1024} * 1024;
     if (force_direct || (small && !compact && force_height == 0) ||
         (compact && compact_height() <= 2 && shard_world == 1)) {
-      if (shard_world > 1) {
+      if (shard_world > 1 || (part.on && symmetric)) {
         // brute force is not sharded: rank 0 computes it, other ranks contribute zeros
-        if (shard_rank != 0) {
+        if ((part.on ? part.rank : shard_rank) != 0) {
           PLT_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * len, stream));
           config = {0, 0, kClassic};
           return;
@@ -913,7 +1102,7 @@ struct plt_eval {
       plt_config c = find_best_configuration(height);
       Interpolator& ip = interpolator(height, c.order, c.d);
       if (height > 2 && (multipole_dirty || up_order != c.order || up_d != c.d)) {
-        upward(src_tree, wt_sorted.get(), ip, M, Mhat, true);
+        upward(src_tree, wt_sorted.get(), ip, M, Mhat, true, part.on);
         multipole_dirty = false;
         up_order = c.order;
         up_d = c.d;
@@ -951,7 +1140,12 @@ int guarded(plt_eval* h, F&& f) {
 
 extern "C" {
 
-int plt_version(void) { return 100; }
+int plt_version(void) { return 200; }
+
+int plt_tree_height(int dim, int64_t n_points) {
+  if (dim < 1 || dim > 3 || n_points < 1) return 0;
+  return fmm_tree_height(dim, n_points);
+}
 
 int plt_device_check(void) {
   int n = 0;
@@ -1060,6 +1254,65 @@ int plt_eval_set_target_shard(plt_eval* h, int rank, int world_size) {
     h->shard_rank = rank;
     h->shard_world = world_size;
   });
+}
+
+int plt_eval_set_partition(plt_eval* h, int rank, int world_size, int level_cut, const uint32_t* key_begin,
+                           plt_allgatherv_fn allgatherv, void* ctx) {
+  return guarded(h, [&] {
+    auto apply = [&](plt_eval* e) {
+      e->own_cells_valid = e->cell_flags_valid = false;
+      e->shard_cache.valid = false;
+      e->multipole_dirty = true;
+      if (world_size <= 1) {
+        e->part = plt_eval::Partition{};
+        return;
+      }
+      PLT_REQUIRE(rank >= 0 && rank < world_size, "bad rank");
+      PLT_REQUIRE(level_cut >= 2 && e->dim * level_cut <= 30, "the cut level must be >= 2");
+      PLT_REQUIRE(key_begin != nullptr && allgatherv != nullptr, "null argument");
+      for (int r = 0; r < world_size; ++r)
+        PLT_REQUIRE(key_begin[r] <= key_begin[r + 1], "key ranges must be ascending");
+      PLT_REQUIRE(key_begin[0] == 0, "key ranges must start at 0");
+      e->part.on = true;
+      e->part.rank = rank;
+      e->part.world = world_size;
+      e->part.cut = level_cut;
+      e->part.key_begin.assign(key_begin, key_begin + world_size + 1);
+      e->part.allgatherv = allgatherv;
+      e->part.ctx = ctx;
+    };
+    PLT_REQUIRE(!std::isfinite(h->rbf.support_radius) || world_size <= 1,
+                "compact-support evaluators have no far field to partition");
+    apply(h);
+    if (h->fast_part) apply(h->fast_part.get());
+  });
+}
+
+int plt_eval_point_keys(plt_eval* h, const double* points, int64_t n, int level, uint32_t* keys) {
+  return guarded(h, [&] {
+    PLT_REQUIRE(n >= 0 && (n == 0 || (points && keys)), "null argument");
+    PLT_REQUIRE(level >= 0 && h->dim * level <= 30, "level out of range");
+    const int dim = h->dim, nside = 1 << level;
+    const double inv_w = static_cast<double>(nside) / h->box.width;
+    for (int64_t i = 0; i < n; ++i) {
+      int c[3] = {0, 0, 0};
+      for (int a = 0; a < dim; ++a) {
+        double s = 0.0;  // geometry/point3d.hpp:36-40: p * A^T
+        for (int b = 0; b < dim; ++b) s += points[i * dim + b] * h->aniso[a * dim + b];
+        const double x = (s - (h->box.center[a] - 0.5 * h->box.width)) * inv_w;
+        PLT_REQUIRE(x >= 0.0 && x <= nside, "a point lies outside the bounding box the evaluator was created with");
+        c[a] = std::min(std::max(static_cast<int>(std::floor(x)), 0), nside - 1);
+      }
+      if (dim == 1) { int q[1] = {c[0]}; keys[i] = morton_encode<1>(q); }
+      if (dim == 2) { int q[2] = {c[0], c[1]}; keys[i] = morton_encode<2>(q); }
+      if (dim == 3) { int q[3] = {c[0], c[1], c[2]}; keys[i] = morton_encode<3>(q); }
+    }
+  });
+}
+
+int64_t plt_eval_allgather_count(plt_eval* h) {
+  if (!h) return 0;
+  return h->n_allgathers + (h->fast_part ? h->fast_part->n_allgathers : 0);
 }
 
 int plt_eval_get_permutation(plt_eval* h, int32_t* perm, int64_t n) {

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kBlock) k_p2m(TreeView tr, Box box, InterpDev 
   double* s_w = s_basis + kPointBatch * DIM * p;  // [batch][km]
   const int leaf = tr.height - 1;
   const int cell = blockIdx.x;
+  if (tr.flags && !(tr.flags[tr.cell_off[leaf] + cell] & kCellFlagM)) return;  // another rank's leaf
   const int tid = threadIdx.x;
   for (int i = tid; i < p; i += kBlock) s_beta[i] = it.beta[i];
   double c[DIM], half;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(kBlock) k_m2m(TreeView tr, int level, InterpDe
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * p * p; i += kBlock) s_t[i] = it.child[i];
   const int cell = blockIdx.x;
+  if (tr.flags && !(tr.flags[tr.cell_off[level] + cell] & kCellFlagM)) return;
   const uint32_t key = tr.keys[tr.cell_off[level] + cell];
   const int* dense_child = tr.dense + tr.dense_off[level + 1];
   double* Mp = M + static_cast<size_t>(tr.cell_off[level] + cell) * km * P;
@@ -693,7 +695,8 @@ __device__ __forceinline__ void idft_stage_c2r(const double2* in, double* out, i
 template <int DIM, int ORDER>
 __global__ void __launch_bounds__(kBlock) k_m2hat(int first_cell, int n_cells, InterpDev it, int km,
                                                   const double* __restrict__ M, double2* __restrict__ Mhat,
-                                                  double2* gscratch, int scratch_elems) {
+                                                  double2* gscratch, int scratch_elems,
+                                                  const unsigned char* __restrict__ flags) {
   extern __shared__ double2 sm2[];
   const int p = ORDER > 0 ? ORDER : it.order, nf = ORDER > 0 ? 2 * ORDER - 1 : it.nf;
   int P = 1, F = p;
@@ -705,6 +708,7 @@ __global__ void __launch_bounds__(kBlock) k_m2hat(int first_cell, int n_cells, I
   for (int i = threadIdx.x; i < nf; i += kBlock) s_tw[i] = it.tw[i];
   __syncthreads();
   for (int cell = blockIdx.x; cell < n_cells * km; cell += gridDim.x) {
+    if (flags && !(flags[first_cell + cell / km] & kCellFlagMhat)) continue;  // uniform across the CTA
     const double* Mc = M + static_cast<size_t>(first_cell) * km * P + static_cast<size_t>(cell) * P;
     double2* out = Mhat + static_cast<size_t>(cell) * F;
     // last axis: real -> half spectrum
@@ -1135,7 +1139,8 @@ __global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
 // Zero padding from p to nf points is implicit (only p inputs per column are read).
 template <int ORDER, int NB>
 __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int km, const double* __restrict__ M,
-                                                double2* __restrict__ Mhat, TwTable tw) {
+                                                double2* __restrict__ Mhat, TwTable tw,
+                                                const unsigned char* __restrict__ flags) {
   constexpr int p = ORDER, nf = 2 * ORDER - 1;
   constexpr int P = p * p * p, F = nf * nf * p, YN = p * nf * p;
   extern __shared__ double2 sm2[];
@@ -1144,11 +1149,22 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   const int total = n_cells * km;
   const int w0 = blockIdx.x * NB;
   const int nb = min(NB, total - w0);
+  // partitioned upward pass: skip the cells whose spectrum this rank does not need
+  __shared__ int s_on[NB];
+  if (flags) {
+    if (threadIdx.x < NB)
+      s_on[threadIdx.x] = threadIdx.x < nb && (flags[first_cell + (w0 + threadIdx.x) / km] & kCellFlagMhat);
+    __syncthreads();
+    bool any = false;
+    for (int c = 0; c < nb; ++c) any = any || s_on[c];
+    if (!any) return;
+  }
   const double* Mc = M + static_cast<size_t>(first_cell) * km * P + static_cast<size_t>(w0) * P;
   double2* out = Mhat + static_cast<size_t>(w0) * F;
   // stage A: column = (n0, n1)
   for (int item = threadIdx.x; item < nb * p * p; item += blockDim.x) {
     const int c = item / (p * p), col = item % (p * p);
+    if (flags && !s_on[c]) continue;
     const double* in = Mc + static_cast<size_t>(c) * P + col * p;
     double x[p];
 #pragma unroll
@@ -1169,6 +1185,7 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   // stage B: column = (n0, k2), stride p
   for (int item = threadIdx.x; item < nb * p * p; item += blockDim.x) {
     const int c = item / (p * p), col = item % (p * p);
+    if (flags && !s_on[c]) continue;
     const int n0 = col / p, k2 = col % p;
     const double2* in = Y1 + c * P + n0 * p * p + k2;
     double2 x[p];
@@ -1192,6 +1209,7 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   // stage C: column = (k1, k2), stride nf * p
   for (int item = threadIdx.x; item < nb * nf * p; item += blockDim.x) {
     const int c = item / (nf * p), col = item % (nf * p);
+    if (flags && !s_on[c]) continue;
     const double2* in = Y2 + c * YN + col;
     double2 x[p];
 #pragma unroll
@@ -1484,13 +1502,14 @@ DftScratch plan_dft_scratch(int order, int dim, int work_items, cudaStream_t s) 
 namespace {
 template <int ORDER, int NB>
 void launch_m2hat3(int first, int n_cells, int km, const double* tw_host, const double* M, double2* Mhat,
-                   cudaStream_t s, LaunchCounter& c) {
+                   const unsigned char* flags, cudaStream_t s, LaunchCounter& c) {
   constexpr int p = ORDER, nf = 2 * ORDER - 1;
   TwTable tw{};
   for (int i = 0; i < nf; ++i) tw.w[i] = make_double2(tw_host[2 * i], tw_host[2 * i + 1]);
   const size_t smem = sizeof(double2) * NB * (p * p * p + p * nf * p);
   smem_opt_in((const void*)k_m2hat3<ORDER, NB>, smem);
-  PLT_LAUNCH(c, (k_m2hat3<ORDER, NB>), ceil_div(n_cells * km, NB), 256, smem, s, first, n_cells, km, M, Mhat, tw);
+  PLT_LAUNCH(c, (k_m2hat3<ORDER, NB>), ceil_div(n_cells * km, NB), 256, smem, s, first, n_cells, km, M, Mhat, tw,
+             flags);
 }
 }  // namespace
 
@@ -1504,10 +1523,10 @@ void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, cons
   static const bool no_reg = getenv("PLT_DEBUG_NO_REGDFT") != nullptr;  // A/B switch for parity bisection
   if (dim == 3 && it.host_tw && !no_reg) {
     switch (it.order) {
-      case 6: launch_m2hat3<6, 4>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
-      case 8: launch_m2hat3<8, 2>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
-      case 10: launch_m2hat3<10, 1>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
-      case 12: launch_m2hat3<12, 1>(first, n_cells, km, it.host_tw, M, Mhat, s, c); return;
+      case 6: launch_m2hat3<6, 4>(first, n_cells, km, it.host_tw, M, Mhat, tr.flags, s, c); return;
+      case 8: launch_m2hat3<8, 2>(first, n_cells, km, it.host_tw, M, Mhat, tr.flags, s, c); return;
+      case 10: launch_m2hat3<10, 1>(first, n_cells, km, it.host_tw, M, Mhat, tr.flags, s, c); return;
+      case 12: launch_m2hat3<12, 1>(first, n_cells, km, it.host_tw, M, Mhat, tr.flags, s, c); return;
       default: break;
     }
   }
@@ -1515,7 +1534,7 @@ void launch_m2hat(int dim, int km, const TreeView& tr, const InterpDev& it, cons
   dispatch_dim_order(dim, it.order, [&](auto dm, auto od) {
     smem_opt_in((const void*)k_m2hat<dm.value, od.value>, d.smem);
     PLT_LAUNCH(c, (k_m2hat<dm.value, od.value>), d.grid, kBlock, d.smem, s, first, n_cells, it, km, M, Mhat, d.buf.get(),
-               d.elems);
+               d.elems, tr.flags);
   });
 }
 

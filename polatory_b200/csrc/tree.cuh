@@ -97,7 +97,12 @@ struct TreeView {
   int64_t dense_off[24];
   int cell_off[24];
   int n_cells[24];
+  // Optional per-cell work flags of a partitioned (multi-GPU) upward pass, indexed by the global compact cell
+  // id: bit 0 = this rank computes the cell's multipole expansion M (P2M / M2M), bit 1 = its spectrum Mhat.
+  // nullptr = every cell (single GPU).
+  const unsigned char* flags = nullptr;
 };
+constexpr unsigned char kCellFlagM = 1, kCellFlagMhat = 2;
 
 class Tree {
  public:

@@ -131,6 +131,35 @@ class _EvaluatorBase:
     def set_target_shard(self, rank, world_size):
         _lib.check(self._h, self._lib.plt_eval_set_target_shard(self._h, int(rank), int(world_size)))
 
+    def point_keys(self, points, level):
+        """Morton keys at `level` of host points (the evaluator's anisotropy and root box applied)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
+        keys = np.empty(len(pts), dtype=np.uint32)
+        _lib.check(self._h, self._lib.plt_eval_point_keys(self._h, ctypes.c_void_p(pts.ctypes.data), len(pts),
+                                                          int(level), ctypes.c_void_p(keys.ctypes.data)))
+        return keys
+
+    def set_partition(self, rank, world_size, level_cut=0, key_begin=None, group=None, allgatherv=None):
+        """Multi-GPU evaluation (include/polatory_b200.h: plt_eval_set_partition): rank `rank` owns the level-
+        `level_cut` Morton keys [key_begin[rank], key_begin[rank + 1]); the level-cut multipole expansions are
+        exchanged with one all-gather over `group` (torch.distributed; NCCL on GPUs).  world_size <= 1 removes
+        the partition."""
+        if world_size <= 1:
+            _lib.check(self._h, self._lib.plt_eval_set_partition(self._h, 0, 1, 0, None, None, None))
+            self._ag_cb = None
+            return
+        from .parallel import make_allgatherv
+        kb = np.ascontiguousarray(key_begin, dtype=np.uint32)
+        assert kb.size == world_size + 1
+        # `allgatherv`: a replacement callable (ctx, buf, offsets, world, stream) -> status, for tests
+        self._ag_cb = _lib.ALLGATHERV_FN(allgatherv if allgatherv is not None else make_allgatherv(group, rank, self))
+        _lib.check(self._h, self._lib.plt_eval_set_partition(
+            self._h, int(rank), int(world_size), int(level_cut), ctypes.c_void_p(kb.ctypes.data),
+            ctypes.cast(self._ag_cb, ctypes.c_void_p), None))
+
+    def allgather_count(self):
+        return int(self._lib.plt_eval_allgather_count(self._h))
+
     def permutation(self):
         """perm[i] = caller index of the i-th target point in Morton order (builds the tree)."""
         n = self._n_src if self._symmetric else self._n_trg
@@ -219,6 +248,11 @@ class FmmGenericSymmetricEvaluator(_EvaluatorBase):
 
 
 # -- the six factories ------------------------------------------------------------------
+def tree_height(dim, n_points):
+    """src/fmm/utility.hpp:12-16."""
+    return int(_lib.load().plt_tree_height(int(dim), int(n_points)))
+
+
 def make_fmm_evaluator(rbf, bbox):
     return FmmGenericEvaluator(KIND_K, rbf, bbox)
 

@@ -14,9 +14,10 @@ the C ABI); torch is used for the vector plumbing and the skinny polynomial prod
 Multi-GPU (`group` given, one rank per GPU): points are put in the Morton order of
 the symmetric evaluator's tree, rank r owns the contiguous range `[lo, hi)` of its target shard
 and the Krylov vectors are sharded accordingly (the `l` polynomial coefficients live on the last
-rank).  One matvec = one all_reduce that assembles the full weight vector from the shards (the
-"all-gather of the weights" -- NCCL over NVLink), the upward pass on every rank, and the
-downward pass + near field of the rank's own leaves.  Gradient data (sigma > 0) is supported on
+rank).  One matvec = one all-gather of the weight shards (NCCL over NVLink), the PARTITIONED upward
+pass (each rank computes the multipoles below the level-cut cells it owns or needs, one all-gather of the
+level-cut expansions, the upper levels on every rank: `plt_eval_set_partition`), and the downward pass + near
+field of the rank's own leaves.  Gradient data (sigma > 0) is supported on
 one GPU only in this round.
 """
 from __future__ import annotations
@@ -128,6 +129,10 @@ class Operator:
             self.a[0].set_points(points)
             self.perm = self.a[0].permutation()
             points = np.ascontiguousarray(points[self.perm])
+            # partition of the level-cut cells by Morton key range, balanced by point count
+            from .parallel import DEFAULT_CUT_LEVEL, partition_keys
+            self.cut = DEFAULT_CUT_LEVEL[dim]
+            self.key_begin = partition_keys(self.a[0].point_keys(points, self.cut), self.world, dim, self.cut)
         else:
             self.perm = np.arange(self.mu)
         self._points = points
@@ -147,10 +152,15 @@ class Operator:
         self.lo, self.hi = 0, self.mu
         if self.world > 1:
             for i in range(n_rbf):
-                self.a[i].set_target_shard(self.rank, self.world)
+                self.a[i].set_partition(self.rank, self.world, self.cut, self.key_begin, self.group)
             self.lo, self.hi = self.a[0].target_shard_range()
             for i in range(1, n_rbf):
                 assert self.a[i].target_shard_range() == (self.lo, self.hi)
+            # shard sizes of every rank (the l polynomial coefficients live on the last rank)
+            sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+            sizes[self.rank] = (self.hi - self.lo) + (self.l if self.rank == self.world - 1 else 0)
+            self._dist.all_reduce(sizes, op=self._dist.ReduceOp.SUM, group=self.group)
+            self.shard_sizes = [int(v) for v in sizes.cpu()]
         if self.l > 0:
             p = monomial_basis(dim, self.model.poly_degree, points, gp)
             self.p = torch.from_numpy(p).to(self.device)
@@ -201,15 +211,11 @@ class Operator:
         return out
 
     def _assemble(self, x_local):
-        """Full (Morton-order) vector on every rank from the shards: the weight all-gather."""
-        full = self._full
-        full.zero_()
-        nloc = self.hi - self.lo
-        full[self.lo:self.hi] = x_local[:nloc]
-        if self.rank == self.world - 1 and self.l:
-            full[self.mu:] = x_local[nloc:]
-        self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
-        return full
+        """Full (Morton-order) vector on every rank from the shards: the all-gather of the weights (the shards
+        are contiguous Morton ranges in rank order, the polynomial tail on the last rank, so their
+        concatenation IS the full vector)."""
+        from .parallel import allgather_shards
+        return allgather_shards(x_local, self.shard_sizes, self.group, out=self._full)
 
     # -- operator.hpp:52-81 ------------------------------------------------------------------
     def apply(self, x, y):

@@ -141,8 +141,15 @@ class FakeSym:
     def set_points(self, p): self.p = np.asarray(p, dtype=np.float64); self.n = len(self.p)
     def set_accuracy(self, a): pass
     def permutation(self): return np.argsort(self.p[:, 0], kind="stable").astype(np.int32)
-    def set_target_shard(self, rank, world): self.rank, self.world = rank, world
-    def target_shard_range(self): return self.n * self.rank // self.world, self.n * (self.rank + 1) // self.world
+    def point_keys(self, pts, level):   # "Morton key" = bucket of x at that level (monotone in the fake order)
+        nk = 1 << (3 * level)
+        return np.minimum((np.asarray(pts)[:, 0] + 1.0) * 0.5 * nk, nk - 1).astype(np.uint32)
+    def set_partition(self, rank, world, cut, key_begin, group):
+        self.rank, self.world, self.cut, self.kb = rank, world, cut, np.asarray(key_begin)
+    def target_shard_range(self):
+        if self.world == 1: return 0, self.n
+        keys = self.point_keys(self.p, self.cut)   # points arrive sorted by x
+        return int(np.searchsorted(keys, self.kb[self.rank])), int(np.searchsorted(keys, self.kb[self.rank + 1]))
     def set_weights(self, w): self.w = np.asarray(w.detach().cpu().numpy() if hasattr(w, "detach") else w)
     def evaluate(self, out):
         lo, hi = self.target_shard_range()
@@ -188,7 +195,7 @@ print("ok")
 
 
 def test_sharded_operator_plumbing_gloo_world_size_2(tmp_path):
-    """The multi-GPU matvec's host logic (Morton-ordered shards, weight assembly by all_reduce, polynomial tail on
+    """The multi-GPU matvec's host logic (key-range partition, Morton-ordered shards, all-gather of the weight shards, polynomial tail on
     the last rank, scatter / gather) on CPU tensors over gloo, with an exact CPU stand-in for the evaluators."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -229,7 +236,7 @@ def test_cpp_shim_compiles_and_links(tmp_path):
         "    solver.set_initial_solution(hi); solver.setup(); solver.iterate_process();\n"
         "    return static_cast<int>(ev.evaluate().size()) + solver.iteration_count() + static_cast<int>(solver.solution_vector().size());\n"
         "  }\n"
-        "  return plt_version() == 100 ? 0 : 3;\n"
+        "  return plt_version() == 200 ? 0 : 3;\n"
         "}\n")
     exe = tmp_path / "shim_check"
     libdir = os.path.join(ROOT, "polatory_b200")

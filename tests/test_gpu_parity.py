@@ -478,3 +478,122 @@ def test_full_size_linearity_and_sampled_direct(pb):
     ref = ofmm.direct("bh3", [1.0, 0.0], 3, 0, src, trg[sub], w1)
     got = outs[0].cpu().numpy()[sub]
     assert np.max(np.abs(got - ref)) < 2e-5 * np.max(np.abs(ref))  # order 6 (accuracy = infinity)
+
+
+# ---------------------------------------------------------------------------------------
+# 9. partitioned (multi-GPU) upward pass: owned / needed cells + all-gather of the level-cut expansions
+# ---------------------------------------------------------------------------------------
+def _emulated_ranks(pb, make, world, cut, key_begin, setup):
+    """`world` evaluators in ONE process standing for the ranks of a node.  The all-gather callback of rank r
+    stores r's own segment and fills the other ranks' segments from the store; every rank is evaluated twice, so
+    that the second pass sees the complete exchange (a rank's own segment never depends on the others)."""
+    import ctypes
+    import torch
+    from polatory_b200.krylov import _view
+    store = {}
+    evs = []
+    for r in range(world):
+        def cb(_ctx, buf, offsets, w, _stream, r=r):
+            off = [int(offsets[i]) for i in range(w + 1)]
+            t = _view(buf, off[-1])
+            store[r] = t[off[r]:off[r + 1]].clone()
+            for q in range(w):
+                if q != r:
+                    seg = t[off[q]:off[q + 1]]
+                    if q in store:
+                        seg.copy_(store[q])
+                    else:
+                        seg.fill_(float("nan"))
+            return 0
+        ev = make()
+        setup(ev, r)
+        ev.set_partition(r, world, cut, key_begin, allgatherv=cb)
+        evs.append(ev)
+    return evs
+
+
+@pytest.mark.parametrize("world,cut", [(2, 2), (3, 3), (8, 4)])
+@pytest.mark.parametrize("kind", [0, 3])
+def test_partitioned_generic_evaluator_is_bit_identical(pb, world, cut, kind, rng):
+    """Each rank gets the targets of its own Morton key range, computes only the multipoles it owns or needs and
+    receives the level-cut expansions of the others: the results equal the single-GPU evaluation of the same
+    targets bit for bit (1-vs-N-GPU parity), and a rank skips most of the upward pass."""
+    from polatory_b200.parallel import partition_keys
+    odir, ofmm, _ = _oracle()
+    dim, n = 3, 40000
+    # surface-like sources (a sphere shell) + volume targets: the shape of config #3
+    u = rng.standard_normal((n, dim))
+    src = 0.8 * u / np.linalg.norm(u, axis=1, keepdims=True) * (1 + 0.01 * rng.standard_normal((n, 1)))
+    trg = rng.uniform(-1, 1, (60000, dim))
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    kn = odir.kind_kn(kind, dim)
+    bbox = pb.Bbox(-np.ones(dim), np.ones(dim))
+    rbf = pb.make_rbf("bh3", [1.0, 0.0], dim, random_anisotropy(dim, rng) if kind else None)
+    height = pb.fmm.tree_height(dim, len(trg))
+    assert height == 5
+
+    full = pb.FmmGenericEvaluator(kind, rbf, bbox)
+    full.set_source_points(src)
+    full.set_target_points(trg)
+    full.set_weights(w)
+    ref = full.evaluate().reshape(-1, kn)
+    keys = full.point_keys(trg, cut)
+    kb = partition_keys(keys, world, dim, cut)
+    own = [np.nonzero((keys >= kb[r]) & (keys < kb[r + 1]))[0] for r in range(world)]
+    assert sum(len(o) for o in own) == len(trg) and min(len(o) for o in own) > 0
+
+    def setup(ev, r):
+        ev.set_source_points(src)
+        ev.force_config(0, -1, height)          # the height of the GLOBAL problem on every rank
+        ev.set_target_points(trg[own[r]])
+        ev.set_weights(w)
+
+    evs = _emulated_ranks(pb, lambda: pb.FmmGenericEvaluator(kind, rbf, bbox), world, cut, kb, setup)
+    for _ in range(2):
+        outs = []
+        for r, ev in enumerate(evs):
+            ev.set_weights(w)                     # multipoles dirty: the upward pass (and the exchange) re-runs
+            outs.append(ev.evaluate().reshape(-1, kn))
+    for r in range(world):
+        assert evs[r].config()["tree_height"] == height and evs[r].allgather_count() == 2
+        assert np.array_equal(outs[r], ref[own[r]]), (r, np.max(np.abs(outs[r] - ref[own[r]])))
+    if world == 8:
+        # the upward pass of a rank touches a fraction of the source cells
+        t_full = sum(full.phase_times().get(k, 0.0) for k in ("p2m", "m2m", "m2hat"))
+        t_part = np.mean([sum(ev.phase_times().get(k, 0.0) for k in ("p2m", "m2m", "m2hat")) for ev in evs])
+        print(f"upward pass: full {t_full:.3f} ms, per rank {t_part:.3f} ms")
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_partitioned_symmetric_evaluator_shards_sum_to_full(pb, world, rng):
+    """The matvec: every rank holds all points, evaluates the leaves of its own key range (zeros elsewhere) with
+    the partitioned upward pass; the shards are disjoint and reassemble to the single-GPU result exactly."""
+    from polatory_b200.parallel import partition_keys
+    dim, n, cut = 3, 30000, 3
+    pts = rng.uniform(-1, 1, (n, dim))
+    w = rng.uniform(-1, 1, n)
+    bbox = pb.Bbox(-np.ones(dim), np.ones(dim))
+    rbf = pb.make_rbf("bh3", [1.0, 0.0], dim)
+    full = pb.make_fmm_symmetric_evaluator(rbf, bbox)
+    full.set_points(pts)
+    full.set_weights(w)
+    full.force_config(12, 8)
+    ref = full.evaluate()
+    kb = partition_keys(full.point_keys(pts, cut), world, dim, cut)
+
+    def setup(ev, r):
+        ev.set_points(pts)
+        ev.force_config(12, 8)
+        ev.set_weights(w)
+
+    evs = _emulated_ranks(pb, lambda: pb.make_fmm_symmetric_evaluator(rbf, bbox), world, cut, kb, setup)
+    for _ in range(2):
+        parts = []
+        for ev in evs:
+            ev.set_weights(w)
+            parts.append(ev.evaluate())
+    total = np.sum(parts, axis=0)
+    assert np.max(np.sum([p != 0.0 for p in parts], axis=0)) <= 1      # disjoint
+    assert np.array_equal(total, ref)
+    ranges = [ev.target_shard_range() for ev in evs]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
