@@ -71,3 +71,39 @@ def test_reference_fitter_shapes(n_points, n_grad_points, rng):
     want = np.concatenate([vals[sub], gvals[gsub].reshape(-1)])
     assert np.max(np.abs(exact - want)) < 1.5 * tol
     print(f"fit {n_points}+{n_grad_points}: {solver.iterations} iterations, levels {solver.pc.n_levels}")
+
+
+def test_config_c4_at_size():
+    """BASELINE.json config #4 at full size: th3 (Triharmonic3D) with gradient constraints (Hermite-Birkhoff),
+    500 000 value points + 500 000 gradient points in [-1, 1]^3 (2 000 000 rows), anisotropic model (10^(+-0.25)
+    stretch x rotation), linear polynomial, in the reference's fit configuration and with the parameters of the
+    reference's own th3 fit test (test/interpolation/test_fitter.cpp:27-45: nugget 0.01, tolerance 1e-3 for values
+    and gradients, accuracy tolerance / 100).  4-level RAS, FGMRES; acceptance: the reference's ResidualEvaluator
+    converged (exact sample + every row through the fast evaluator) and exact sums on sampled rows."""
+    import polatory_b200 as pb
+    from polatory_b200.operator import Model, Solver, monomial_basis
+    from oracle import direct as odir
+    from oracle import rbf as orbf
+    n, dim, tol, nugget = 500_000, 3, 1e-3, 0.01
+    pts = np.random.default_rng(0).uniform(-1, 1, (n, dim))
+    gpts = np.random.default_rng(1).uniform(-1, 1, (n, dim))
+    q, _ = np.linalg.qr(np.random.default_rng(2).standard_normal((dim, dim)))
+    aniso = np.diag(10.0 ** np.array([0.25, 0.0, -0.25])) @ q
+    values = np.concatenate([np.sin(np.pi * (pts @ aniso.T)).sum(axis=1),
+                             ((np.pi * np.cos(np.pi * (gpts @ aniso.T))) @ aniso).reshape(-1)])
+    model = Model(pb.make_rbf("th3", [1.0, 0.0], dim, aniso), poly_degree=1, nugget=nugget)
+    solver = Solver(model, pts, gpts, tol / 100, tol / 100)
+    assert solver.pc.n_levels == 4
+    w = solver.solve(values, tol, tol, max_iter=130).cpu().numpy()
+    assert solver.op.a[0].config() == {"tree_height": 6, "order": 12, "d": 8}
+    m = n + dim * n
+    rng = np.random.default_rng(9)
+    sp, sg = rng.choice(n, 48, replace=False), rng.choice(n, 24, replace=False)
+    o = orbf.make_rbf("th3", [1.0, 0.0], dim, aniso)
+    fit = odir.direct_evaluator(o, 0.0, pts, gpts, w[:m], pts[sp], gpts[sg]) + \
+        monomial_basis(dim, 1, pts[sp], gpts[sg]) @ w[m:]
+    fit[:len(sp)] += nugget * w[sp]
+    ref = np.concatenate([values[sp], values[n:].reshape(n, dim)[sg].reshape(-1)])
+    assert np.max(np.abs(fit[:len(sp)] - ref[:len(sp)])) < tol
+    assert np.max(np.abs(fit[len(sp):] - ref[len(sp):])) < tol
+    print(f"C4 at size: {solver.iterations} FGMRES iterations")
