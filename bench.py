@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--no-fit", action="store_true", help="skip the auxiliary config #2 fit (FGMRES + RAS) timing")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the per-layer isosurface sampler timing")
     ap.add_argument("--cpu-sample-layers", type=int, default=216,
                     help="x-layers of the target grid (central slab) the CPU arm evaluates per step "
                          "(default: all of them, ~10 s of CPU work on 16 cores)")
@@ -362,6 +363,8 @@ def main():
                                              trg_full, allgathers, ms_step, timed, barrier)
     if world == 1 and not args.no_fit:
         line["fit"] = fit_timing(src, dev)
+    if world == 1 and not args.no_sampler:
+        line["isosurface_sampler"] = sampler_timing(args, src, w, d_trg, lo, hi, d_out)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub, height, desc = cpu_sample(args, src, w, trg, lo, hi)
@@ -381,6 +384,38 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sampler_timing(args, src, w, d_trg, lo, hi, d_ref):
+    """Config #3 the way the isosurface generator drives it (include/polatory/isosurface/rmt/lattice.hpp:421-445):
+    the same 10M lattice nodes in per-layer batches against fixed centres + weights.  The source tree and the
+    multipole spectra stay resident (the reference rebuilds them per batch, src/fmm/fmm_evaluator.hpp:107-109), so a
+    batch is target-side work only.  Tree height per batch = max(n_src, n_batch) rule -> 7 (the one-shot grid: 8)."""
+    import torch
+    import polatory_b200 as pb
+    from polatory_b200.evaluator import RbfFieldFunction
+    from polatory_b200.operator import Model
+    g = args.grid
+    per_layer = g[1] * g[2]
+    field = RbfFieldFunction(Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=-1), src, w)
+    field.set_evaluation_bbox(pb.Bbox(lo, hi))
+    out = {}
+    for layers in (1, 8):
+        n_b = (g[0] + layers - 1) // layers
+        res = None
+        for rep in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for b in range(n_b):
+                res = field(d_trg[b * layers * per_layer:(b + 1) * layers * per_layer])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        out[f"{layers}_layer_batches"] = {"batches": n_b, "targets_per_batch": layers * per_layer, "total_ms": ms,
+                                          "Mtargets_per_s": g[0] * per_layer / (ms * 1e-3) / 1e6,
+                                          "config": field.evaluator.a[0].config()}
+    return out
 
 
 def multi_gpu_report(args, ev, dist, dev, world, rank, shard, d_w, d_trg, d_out, d_src, trg_full, allgathers,
