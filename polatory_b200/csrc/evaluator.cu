@@ -516,6 +516,7 @@ struct plt_eval {
       PLT_CUDA(cudaStreamSynchronize(stream));  // host tables are about to go out of scope of the copy
       ip->dev = InterpDev{order, h.nf, ip->beta.get(), ip->child.get(), ip->tw.get(),
                           h.tw.data(), h.child.data(), h.beta.data()};
+      ip->dev.polynomial = d < 0 || d >= order - 1;  // FH of degree order - 1 is the polynomial interpolant too
       const size_t F = freqs_per_cell(order, dim);
       ip->khat_level_stride = static_cast<size_t>(ipow(7, dim)) * kn * km * F;
       const int n_levels = std::max(0, height - 2);

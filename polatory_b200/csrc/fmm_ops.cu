@@ -634,6 +634,246 @@ __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <
 }
 
 // ------------------------------------------------------------------------------------
+// Leaf pass for the POLYNOMIAL interpolant (d = kClassic: orders 6, 8, 10), 3-D, without the last L2L.
+//
+// The parent's local expansion is the tensor polynomial F(x) = sum_m L_parent[m] S_m^parent(x) of degree
+// order - 1 per axis.  L2L samples it at the child's nodes and L2P interpolates those samples with the child's
+// basis -- again a polynomial of degree order - 1 through `order` samples per axis of a polynomial of that same
+// degree, i.e. F itself.  So
+//     v(x) = sum_m S_m^parent(x) L_parent[m]  +  sum_n S_n^child(x) Lc_child[n]
+// (Lc = the child's own M2L result) is the same function as L2P(L2L(L_parent) + Lc), evaluated without forming the
+// 2^dim child expansions: two tensor contractions per point and no CTA-wide barriers between dependent stages
+// (the fused kernel above: 3 contraction stages + 5 barriers per parent, 7 100 warp instructions per parent at
+// order 6, latency bound at 0.06 of HBM; this one: ~2 000).  Differences to the staged form are rounding only.
+//
+// One CTA per parent cell of level leaf-1:
+//   * warp 0 issues one TMA bulk copy (cp.async.bulk -> mbarrier) per i0-slab of the parent expansion and of the
+//     present children's Lc into a padded shared layout (slab stride p^2 + 2 doubles: the p lanes of a point read
+//     p different slabs, which must fall into different banks);
+//   * meanwhile all threads evaluate the normalised 1-D barycentric bases of the parent's points, one
+//     (point, axis) task per thread, in the child frame t and in the parent frame (t +- 1) / 2, product form
+//     (no special case at a node), into shared memory;
+//   * after the mbarrier flips: p lanes per point (lane <-> slab i0), 32 / p points per warp pass; each lane
+//     contracts its slab of both expansions with the point's bases, the p partial sums are added by shuffles.
+// ------------------------------------------------------------------------------------
+constexpr int kLeafDirectThreads = 128;
+constexpr int kLeafDirectCap = 64;  // points whose bases are staged at a time
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (16-byte aligned, size % 16 == 0).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Normalised barycentric basis S_m(t), m < p, product form (no division by t - x_m).
+template <int p>
+__device__ __forceinline__ void product_basis_store(const double* __restrict__ beta, double t, double* out) {
+  double d[p], pre[p], s[p];
+#pragma unroll
+  for (int m = 0; m < p; ++m) d[m] = t - (-1.0 + 2.0 * m / (p - 1));
+  pre[0] = 1.0;
+#pragma unroll
+  for (int m = 1; m < p; ++m) pre[m] = pre[m - 1] * d[m - 1];
+  double suf = 1.0, sum = 0.0;
+#pragma unroll
+  for (int m = p - 1; m >= 0; --m) {
+    s[m] = beta[m] * (pre[m] * suf);
+    sum += s[m];
+    suf *= d[m];
+  }
+  const double inv = 1.0 / sum;
+#pragma unroll
+  for (int m = 0; m < p; ++m) out[m] = s[m] * inv;
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(kLeafDirectThreads) k_leaf_direct3(TreeView tr, Box box, LeafTables tb, int kn,
+                                                                     const double* __restrict__ L,
+                                                                     const double* __restrict__ Lc,
+                                                                     const int* __restrict__ leaf_meta,
+                                                                     double* __restrict__ vt, int par_lo, int leaf_lo,
+                                                                     int leaf_hi) {
+  constexpr int DIM = 3, NC = 8, p = ORDER, P = p * p * p;
+  constexpr int S = p * p + 2;   // slab stride (doubles): 16-byte aligned, p slabs in p different banks
+  constexpr int ES = p * S;      // expansion stride
+  constexpr int PP = 32 / p;     // points per warp pass
+  constexpr int NW = kLeafDirectThreads / 32;
+  constexpr int BS = 2 * DIM * p;  // basis doubles per point: [frame: child, parent][axis][p]
+  extern __shared__ __align__(16) double sm[];
+  double* sL = sm;               // parent expansion [p][S]
+  double* sC = sL + ES;          // children's own M2L results [NC][p][S]
+  double* sB = sC + NC * ES;     // bases [kLeafDirectCap][BS]
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_first[NC], s_count[NC], s_run[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int leaf = tr.height - 1, pl = leaf - 1;
+  const int pidx = par_lo + blockIdx.x;
+  const int* meta = leaf_meta + static_cast<size_t>(pidx) * (2 + 3 * NC);
+  const uint32_t pkey = static_cast<uint32_t>(meta[0]);
+  const int slot = meta[1];
+  const bool has_parent = L != nullptr, has_own = slot >= 0;
+
+  if (tid < 32) {
+    int first = -1, cnt = 0;
+    if (tid < NC) {
+      const int cidx = meta[2 + 3 * tid];
+      if (cidx >= leaf_lo && cidx < leaf_hi) {  // also rejects -1
+        first = meta[3 + 3 * tid];
+        cnt = meta[4 + 3 * tid];
+      }
+      s_first[tid] = first;
+      s_count[tid] = cnt;
+    }
+    int lo = first >= 0 ? first : 0x7fffffff, hi = first >= 0 ? first + cnt : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (tid == 0) {
+      s_run[0] = lo;
+      s_run[1] = hi > lo ? hi - lo : 0;
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  const int run0 = s_run[0], n_run = s_run[1];
+  if (n_run == 0) return;  // no target of this shard below the parent (uniform)
+  // the children are consecutive leaves: a point's child = the range of the sorted order it falls into
+  int cfirst[NC], ccnt[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    cfirst[c] = s_first[c];
+    ccnt[c] = s_count[c];
+  }
+  double pc[DIM], phalf;
+  cell_center<DIM>(box, pl, pkey, pc, phalf);
+  const double inv_half = 2.0 / phalf;  // 1 / (half width of a child)
+
+  for (int b = 0; b < kn; ++b) {
+    // ---- stage the expansions of component b (asynchronous; overlapped with the basis evaluation) ----
+    uint32_t bytes = 0;
+    if (has_parent) bytes += P * 8;
+    if (has_own) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (cfirst[c] >= 0) bytes += P * 8;
+    }
+    if (b > 0) __syncthreads();  // the previous component's expansions are no longer read
+    if (warp == 0 && bytes > 0) {
+      if (lane == 0) mbar_expect_tx(&s_bar, bytes);
+      __syncwarp();
+      if (has_parent) {
+        const double* src = L + (static_cast<size_t>(tr.cell_off[pl] + pidx) * kn + b) * P;
+        if (lane < p) bulk_g2s(sL + lane * S, src + lane * p * p, p * p * 8, &s_bar);
+      }
+      if (has_own) {
+        for (int e = lane; e < NC * p; e += 32) {
+          const int c = e / p, i0 = e - c * p;
+          if (s_first[c] < 0) continue;
+          const double* src = Lc + ((static_cast<size_t>(slot) * NC + c) * kn + b) * P;
+          bulk_g2s(sC + c * ES + i0 * S, src + i0 * p * p, p * p * 8, &s_bar);
+        }
+      }
+    }
+
+    for (int q0 = 0; q0 < n_run; q0 += kLeafDirectCap) {
+      const int nq = min(kLeafDirectCap, n_run - q0);
+      // ---- bases: one (point, axis) task per thread, both frames ----
+      if (b == 0 || n_run > kLeafDirectCap) {
+        if (q0 > 0 || b > 0) __syncthreads();  // previous chunk's bases no longer read
+        for (int task = tid; task < nq * DIM; task += kLeafDirectThreads) {
+          const int q = task / DIM, a = task - q * DIM;
+          const int i = run0 + q0 + q;
+          int ch = 0;
+#pragma unroll
+          for (int c = 1; c < NC; ++c)
+            if (cfirst[c] >= 0 && i >= cfirst[c]) ch = c;  // children ascend with the sorted order
+          const int side = (ch >> (DIM - 1 - a)) & 1;
+          const double x = tr.pos[a * tr.n + i];
+          // child frame: centre of the child = parent centre -+ half of the child's width
+          const double cc = pc[a] + (side ? 0.5 : -0.5) * phalf;
+          const double t = (x - cc) * inv_half;
+          const double tp = (x - pc[a]) * (0.5 * inv_half);
+          double* dst = sB + q * BS + a * p;
+          product_basis_store<p>(tb.beta, t, dst);
+          product_basis_store<p>(tb.beta, tp, dst + DIM * p);
+        }
+        __syncthreads();
+      }
+      if (q0 == 0 && bytes > 0) mbar_wait(&s_bar, b & 1);
+
+      // ---- contraction: p lanes per point, PP points per warp pass ----
+      const int sub = lane / p, i0 = lane - sub * p;
+      for (int g = warp * PP; g < nq; g += NW * PP) {
+        const int q = g + sub;
+        const bool act = sub < PP && q < nq;
+        const int qq = act ? q : g;
+        const int i = run0 + q0 + qq;
+        int ch = 0;
+#pragma unroll
+        for (int c = 1; c < NC; ++c)
+          if (cfirst[c] >= 0 && i >= cfirst[c]) ch = c;
+        const double* bs = sB + qq * BS;
+        double val = 0.0;
+#pragma unroll
+        for (int fr = 0; fr < 2; ++fr) {
+          if (fr == 0 ? !has_own : !has_parent) continue;  // uniform
+          const double* E = (fr == 0 ? sC + ch * ES : sL) + i0 * S;
+          const double* u = bs + fr * DIM * p;
+          double u1[p], u2[p];
+#pragma unroll
+          for (int m = 0; m < p; m += 2) {
+            const double2 a1 = *reinterpret_cast<const double2*>(u + p + m);
+            const double2 a2 = *reinterpret_cast<const double2*>(u + 2 * p + m);
+            u1[m] = a1.x; u1[m + 1] = a1.y;
+            u2[m] = a2.x; u2[m + 1] = a2.y;
+          }
+          double acc = 0.0;
+#pragma unroll
+          for (int i1 = 0; i1 < p; ++i1) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < p; k += 2) {
+              const double2 e2 = *reinterpret_cast<const double2*>(E + i1 * p + k);
+              r = fma(u2[k], e2.x, r);
+              r = fma(u2[k + 1], e2.y, r);
+            }
+            acc = fma(u1[i1], r, acc);
+          }
+          val = fma(u[i0], acc, val);
+        }
+        // sum over the p lanes of the point; its first lane ends up with the total
+        double tot = val;
+#pragma unroll
+        for (int m = 1; m < p; ++m) tot += __shfl_down_sync(0xffffffffu, val, m);
+        if (act && i0 == 0) vt[b * tr.n + i] = tot;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Small dense DFT stages (generic pointers: shared or global).
 //   out[o][k][i] = sum_n in[o][n][i] * W^(k n),   W = e^{-2 pi i / nf} (or its conjugate)
 // ------------------------------------------------------------------------------------
@@ -1450,6 +1690,20 @@ bool launch_l2l_l2p_leaf(int dim, int kn, const TreeView& tr, const Box& box, co
   for (int i = 0; i < 2 * p * p; ++i) tb.child[i] = it.host_child[i];
   for (int i = 0; i < p; ++i) tb.beta[i] = it.host_beta[i];
   const int lo = static_cast<int>(leaf_lo), hi = static_cast<int>(leaf_hi);
+  static const bool no_direct = getenv("PLT_DEBUG_NO_LEAF_DIRECT") != nullptr;  // A/B switch
+  if (dim == 3 && it.polynomial && !no_direct && (p == 6 || p == 8 || p == 10)) {
+    auto run = [&](auto od) {
+      constexpr int P_ = od.value;
+      const size_t bytes = sizeof(double) * (9 * P_ * (P_ * P_ + 2) + kLeafDirectCap * 2 * 3 * P_);
+      smem_opt_in((const void*)k_leaf_direct3<P_>, bytes);
+      PLT_LAUNCH(c, (k_leaf_direct3<P_>), n, kLeafDirectThreads, bytes, s, tr, box, tb, kn, L, Lc, leaf_meta, vt,
+                 par_lo, lo, hi);
+    };
+    if (p == 6) run(std::integral_constant<int, 6>{});
+    if (p == 8) run(std::integral_constant<int, 8>{});
+    if (p == 10) run(std::integral_constant<int, 10>{});
+    return true;
+  }
   dispatch_leaf(dim, it.order, [&](auto dm, auto od) {
     smem_opt_in((const void*)k_l2l_l2p_leaf<dm.value, od.value>, smem);
     PLT_LAUNCH(c, (k_l2l_l2p_leaf<dm.value, od.value>), n, leaf_threads(od.value), smem, s, tr, box, tb, kn, L, Lc, leaf_meta, vt,

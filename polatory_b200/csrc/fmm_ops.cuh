@@ -26,6 +26,7 @@ struct InterpDev {
   const double* host_tw = nullptr;
   const double* host_child = nullptr;
   const double* host_beta = nullptr;
+  bool polynomial = false;  // d == kClassic: the interpolant is the polynomial one (not Floater-Hormann)
 };
 
 inline int ipow(int b, int e) {
