@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolatory_b200.so")
+# PLT_B200_LIB: an alternative build of the same library (A/B runs of kernel variants on the GPU box)
+LIB_PATH = os.environ.get("PLT_B200_LIB") or os.path.join(_HERE, "libpolatory_b200.so")
 
 PLT_OK, PLT_ERR_INVALID, PLT_ERR_CUDA, PLT_ERR_ACCURACY, PLT_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 

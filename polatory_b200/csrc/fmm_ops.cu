@@ -15,6 +15,12 @@ namespace plt {
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef PLT_HAD_WARPS3
+#define PLT_HAD_WARPS3 24
+#endif
+#ifndef PLT_HAD_G3
+#define PLT_HAD_G3 2
+#endif
 
 struct Mat3 {
   double a[9];
@@ -1066,18 +1072,24 @@ __global__ void __launch_bounds__(256) k_m2l_hadamard(M2LArgs a, int F) {
 // row, coalesced) before the arithmetic to keep several loads in flight per warp.  No CTA-wide
 // barrier inside the main loop.
 constexpr int kHadTF = 32;
-constexpr int kHadWarps = 16;
-constexpr int kHadG = 4;
+// Warps per CTA (one persistent CTA per SM) and Mhat rows in flight per warp and pipeline stage.  3-D: the 171.5 KiB
+// operator slice leaves room for one CTA per SM, so the CTA brings all the warps.  Measured on config #3
+// (profiles/r02_d_hadamard_variants.md): 16 warps x 4-row groups (120 registers) 12.46 ms; 20 x 3: 11.49;
+// 24 x 2 (80 registers): 11.43; 28 x 2: 11.45; 32 x 2 (64 registers, spills): 13.3.
+template <int DIM> struct HadCfg { static constexpr int kWarps = 16, kG = 4; };
+template <> struct HadCfg<3> { static constexpr int kWarps = PLT_HAD_WARPS3, kG = PLT_HAD_G3; };
 
 template <int DIM, bool VEC>
-__global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArgs a, int F, int n_ftiles) {
+__global__ void __launch_bounds__(HadCfg<DIM>::kWarps * 32, 1) k_m2l_hadamard_tiled(M2LArgs a, int F, int n_ftiles) {
   constexpr int NC = M2LGeom<DIM>::NC, NN = M2LGeom<DIM>::NN, NOFF = M2LGeom<DIM>::NOFF;
+  constexpr int kHadWarps = HadCfg<DIM>::kWarps, kHadG = HadCfg<DIM>::kG;
   constexpr int NE = NN * NC;              // entries of the source-id table
+  constexpr int NL = NE - NC;              // list capacity: the centre block has no far pair
   constexpr int NCH = (NE + 31) / 32;      // 32-entry chunks
   extern __shared__ double2 sm2[];
   double2* Ks = sm2;                                      // [NOFF][TF]
   int2* s_meta = reinterpret_cast<int2*>(Ks + NOFF * kHadTF);  // [NE]: x = offset index base, y = far mask
-  int2* s_list = s_meta + NE;                                   // [warps][NE]: (Mhat row, base | far mask << 16)
+  int2* s_list = s_meta + NE;                                   // [warps][NL]: (Mhat row, base | far mask << 16)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (int code = threadIdx.x; code < NE; code += blockDim.x) {
@@ -1108,7 +1120,7 @@ __global__ void __launch_bounds__(kHadWarps * 32, 1) k_m2l_hadamard_tiled(M2LArg
   // re-stages the operator slice when it crosses a tile boundary.
   const long long n_items = static_cast<long long>(n_ftiles) * a.n_active;
   const long long q_lo = n_items * blockIdx.x / gridDim.x, q_hi = n_items * (blockIdx.x + 1) / gridDim.x;
-  int2* list = s_list + warp * NE;
+  int2* list = s_list + warp * NL;
   for (long long q0 = q_lo; q0 < q_hi;) {
     const int ftile = static_cast<int>(q0 / a.n_active);
     const int slot_lo = static_cast<int>(q0 - static_cast<long long>(ftile) * a.n_active);
@@ -1812,11 +1824,12 @@ namespace {
 template <int DIM>
 void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c) {
   constexpr int NN = M2LGeom<DIM>::NN, NC = M2LGeom<DIM>::NC, NOFF = M2LGeom<DIM>::NOFF;
+  constexpr int kHadWarps = HadCfg<DIM>::kWarps;
   const int n_ftiles = ceil_div(F, kHadTF);
   // one persistent CTA per SM; fewer when there is not a warp-round of parents per CTA
   const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(a.n_active, kHadWarps);
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
-  const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * NN * NC * (1 + kHadWarps);
+  const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * (NN * NC + (NN * NC - NC) * kHadWarps);
   if (a.kn * a.km == 1) {
     smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM, false>, smem);
     PLT_LAUNCH(c, (k_m2l_hadamard_tiled<DIM, false>), grid, kHadWarps * 32, smem, s, a, F, n_ftiles);
