@@ -23,9 +23,53 @@ namespace {
 // ------------------------------------------------------------------------------------
 constexpr int kP2PWarps = 4;
 constexpr int kTG = 8;
+#ifndef PLT_P2P_MINB_K
+#define PLT_P2P_MINB_K 4
+#endif
+constexpr int kSrcCap = 384;  // sources staged per warp and chunk
+
+// Value kernels whose pair loop is written out by hand (below): the slope and the smoothing constant are folded
+// out of the loop (w' = -+s w per source; r^2 accumulated onto c^2 by the three FMAs), and the kTG / 2 independent
+// pair evaluations of a half group are interleaved stage by stage.  The generic loop compiles to ONE dependent chain
+// per pair at a time (19 instructions, 15 of them on the FP64 pipe, no ILP: profiles/r02_e_p2p.md), which left the
+// FP64 pipe at 52 % with 21 resident warps.
+template <int FAM, int KIND>
+struct FoldedPair { static constexpr bool value = KIND == KIND_K && (FAM == FAM_BH3 || FAM == FAM_TH3); };
+
+template <int FAM, int DIM, int N>
+__device__ __forceinline__ void folded_pairs(double c1e, const double (&sp)[DIM], double w0,
+                                             const double (*tp)[DIM], double (*v)[1]) {
+  double r2[N], y[N], xy[N], e[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    double acc = c1e;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+      const double d = tp[u][a] - sp[a];
+      acc = fma(d, d, acc);
+    }
+    r2[u] = acc;
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) y[u] = rsqrt_seed(r2[u]);
+#pragma unroll
+  for (int u = 0; u < N; ++u) xy[u] = r2[u] * y[u];
+#pragma unroll
+  for (int u = 0; u < N; ++u) e[u] = fma(-xy[u], y[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const double q = fma(0.375, e[u], 0.5);
+    const double rho = fma(xy[u] * e[u], q, xy[u]);  // sqrt(r^2 + c^2), as sqrt_fast
+    if constexpr (FAM == FAM_BH3) {
+      v[u][0] = fma(rho, w0, v[u][0]);               // phi = -s rho
+    } else {
+      v[u][0] = fma(r2[u] * rho, w0, v[u][0]);       // phi = +s rho^3
+    }
+  }
+}
 
 template <int FAM, int KIND, int DIM>
-__global__ void __launch_bounds__(kP2PWarps * 32, KIND == KIND_K ? 6 : 4)
+__global__ void __launch_bounds__(kP2PWarps * 32, KIND == KIND_K ? PLT_P2P_MINB_K : 4)
 k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, double* __restrict__ vt,
       const int* __restrict__ leaves, int n_leaves, int leaf_lo, int leaf_hi, int* __restrict__ queue,
       int n_split) {
@@ -34,6 +78,7 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
   constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
   __shared__ int s_start[kP2PWarps][32];   // first source point of neighbour nb
   __shared__ int s_prefix[kP2PWarps][32];  // exclusive prefix of the neighbour sizes; [NN] = total
+  extern __shared__ double s_dat[];        // [warps][DIM + KM][kSrcCap] staged sources
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // Persistent warps pull target leaves from a global queue: leaf populations of surface clouds
   // vary by an order of magnitude, and a static leaf -> warp map left a third of the resident
@@ -90,35 +135,58 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
   const int* pre = s_prefix[warp];
   const int* st = s_start[warp];
 
-  for (int tb = t0 + split * kTG; tb < t1; tb += n_split * kTG) {
-    double tp[kTG][DIM];
-    double v[kTG][KN];
+  // The concatenated source list is staged in shared memory once per (leaf, chunk of kSrcCap sources): SoA rows of
+  // DIM coordinates + KM weights, lane-contiguous (conflict-free LDS.64).  Every target group of the leaf then
+  // streams it from there: no prefix search and no global load inside the pair loop.
+  double* dat = s_dat + static_cast<size_t>(warp) * (DIM + KM) * kSrcCap;
+  for (int c0 = 0; c0 < total; c0 += kSrcCap) {
+    const int nc = min(kSrcCap, total - c0);
+    __syncwarp();  // previous chunk no longer read
+    for (int q = lane; q < nc; q += 32) {
+      const int jj = c0 + q;
+      // neighbour holding concatenated index jj: last nb with prefix[nb] <= jj
+      int lo = 0, hi = NN - 1;
 #pragma unroll
-    for (int u = 0; u < kTG; ++u) {
-      const int t = min(tb + u, t1 - 1);
+      for (int it = 0; it < 5; ++it) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (pre[mid] <= jj) lo = mid; else hi = mid - 1;
+      }
+      const int j = st[lo] + (jj - pre[lo]);
 #pragma unroll
-      for (int a = 0; a < DIM; ++a) tp[u][a] = trg.pos[a * trg.n + t];
+      for (int a = 0; a < DIM; ++a) dat[a * kSrcCap + q] = src.pos[a * src.n + j];
 #pragma unroll
-      for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
+      for (int m = 0; m < KM; ++m) {
+        double wv = swt[m * src.n + j];
+        if constexpr (FoldedPair<FAM, KIND>::value) wv *= (FAM == FAM_BH3 ? -k.c[0] : k.c[0]);  // slope folded in
+        dat[(DIM + m) * kSrcCap + q] = wv;
+      }
     }
-    const int nt = min(kTG, t1 - tb);
-    for (int jb = 0; jb < total; jb += 32) {
-      const int jj = jb + lane;
-      if (jj < total) {
-        // neighbour holding concatenated index jj: last nb with prefix[nb] <= jj
-        int lo = 0, hi = NN - 1;
+    __syncwarp();
+
+    for (int tb = t0 + split * kTG; tb < t1; tb += n_split * kTG) {
+      double tp[kTG][DIM];
+      double v[kTG][KN];
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (pre[mid] <= jj) lo = mid; else hi = mid - 1;
-        }
-        const int j = st[lo] + (jj - pre[lo]);
+      for (int u = 0; u < kTG; ++u) {
+        const int t = min(tb + u, t1 - 1);
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) tp[u][a] = trg.pos[a * trg.n + t];
+#pragma unroll
+        for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
+      }
+      const int nt = min(kTG, t1 - tb);
+      for (int q = lane; q < nc; q += 32) {
         double sp[DIM], w[KM];
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
+        for (int a = 0; a < DIM; ++a) sp[a] = dat[a * kSrcCap + q];
 #pragma unroll
-        for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j];
-        if (nt == kTG) {
+        for (int m = 0; m < KM; ++m) w[m] = dat[(DIM + m) * kSrcCap + q];
+        if constexpr (FoldedPair<FAM, KIND>::value) {
+          // all kTG slots are evaluated (slots beyond nt repeat the last target and are not stored)
+          const double c1e = k.c[1] + 1e-300;  // c^2 (+ the guard that keeps the seed finite at r = 0)
+          folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
+          folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
+        } else if (nt == kTG) {
           // full group: branch-free, the kTG independent pair evaluations interleave
 #pragma unroll
           for (int u = 0; u < kTG; ++u) {
@@ -139,14 +207,14 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
           }
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < kTG; ++u) {
+      for (int u = 0; u < kTG; ++u) {
 #pragma unroll
-      for (int b = 0; b < KN; ++b) {
-        double x = v[u][b];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && u < nt) vt[b * trg.n + tb + u] += x;
+        for (int b = 0; b < KN; ++b) {
+          double x = v[u][b];
+          for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+          if (lane == 0 && u < nt) vt[b * trg.n + tb + u] += x;
+        }
       }
     }
   }
@@ -278,7 +346,12 @@ void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div(static_cast<int64_t>(n_leaves) * n_split, kP2PWarps),
                                                       kNumSM * 8));
   dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
-    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), grid, kP2PWarps * 32, 0, s, k, src, swt, trg, vt, leaves,
+    constexpr int km = KindTraits<knd.value, dm.value>::km;
+    const size_t smem = sizeof(double) * kP2PWarps * (dm.value + km) * kSrcCap;
+    if (smem > 40 * 1024)  // static shared memory counts towards the 48 KiB default limit
+      PLT_CUDA(cudaFuncSetAttribute((const void*)k_p2p<fam.value, knd.value, dm.value>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    PLT_LAUNCH(c, (k_p2p<fam.value, knd.value, dm.value>), grid, kP2PWarps * 32, smem, s, k, src, swt, trg, vt, leaves,
                n_leaves, static_cast<int>(leaf_lo), static_cast<int>(leaf_hi), queue.get(), n_split);
   });
 }
