@@ -276,6 +276,19 @@ int64_t plt_ras_domains_total(plt_ras_domains* h);
 int plt_ras_domains_get(plt_ras_domains* h, int64_t* offsets, int64_t* indices, uint8_t* inner);
 void plt_ras_domains_destroy(plt_ras_domains* h);
 
+/* Dense local problems of the RAS preconditioner (preconditioner/fine_grid.hpp:59-142, coarse_grid.hpp:40-131),
+ * batched over the domains of a level, DEVICE pointers, row-major, hand-written kernels (no cuSOLVER / cuBLAS).
+ *   plt_ras_reduce_q:        red[b] = Q^T A Q = A_rr + Q_top^T (A_tt Q_top + A_tr) + A_rt Q_top; a: [B][m][m] (the l
+ *                            polynomial rows first), q_top: [B][l][m - l], red: [B][m - l][m - l]; l = 0: not needed.
+ *   plt_chol_batched:        in-place Cholesky L L^T of [B][n][n] (lower triangle overwritten by L); info[b] = 0 or
+ *                            1 + the first non-positive pivot (info may be NULL).
+ *   plt_chol_solve_batched:  per domain qtd = vals[l:] + Q_top^T vals[:l]; L L^T gamma = qtd;
+ *                            lam = [Q_top gamma; gamma]  (fine_grid.hpp:112-133); vals, lam: [B][l + n]. */
+int plt_ras_reduce_q(const double* a, const double* q_top, int64_t n_batch, int m, int l, double* red, void* stream);
+int plt_chol_batched(double* a, int64_t n_batch, int n, int* info, void* stream);
+int plt_chol_solve_batched(const double* factor, int64_t n_batch, int n, const double* q_top, int l, const double* vals,
+                           double* lam, void* stream);
+
 /* The data points on which interpolation::ResidualEvaluator measures the residual exactly
  * (include/polatory/interpolation/residual_evaluator.hpp:123-136): out[0..n) = iota shuffled by a default-seeded
  * std::mt19937 (std::shuffle), then std::partition'ed so that points whose `block` values are not all zero come

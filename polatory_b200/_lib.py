@@ -83,6 +83,9 @@ SYMBOLS = [
     ("plt_ras_domains_total", ctypes.c_int64, [_vp]),
     ("plt_ras_domains_get", ctypes.c_int, [_vp, _vp, _vp, _vp]),
     ("plt_ras_domains_destroy", None, [_vp]),
+    ("plt_ras_reduce_q", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    ("plt_chol_batched", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
+    ("plt_chol_solve_batched", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp]),
     ("plt_residual_sample_indices", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp]),
     ("plt_version", ctypes.c_int, []),
     ("plt_device_check", ctypes.c_int, []),

@@ -14,10 +14,11 @@ Host, once per fit: the level structure and the unisolvent points here (numpy); 
 and the recursive bisection into overlapping domains in native multi-threaded code behind the C ABI
 (csrc/ras_host.cu: `plt_ras_choose_coarse_points[_mixed]`, `plt_ras_divide_domains[_mixed]`).
 Device: the Gram matrices of all domains of a level (batched kernels `plt_eval_gram_batched` /
-`plt_eval_gram_mixed`), their reduced factorisations Q^T A Q = L L^T (batched Cholesky and triangular
-solves: cuSOLVER / cuBLAS through torch -- library code), the local solves of one level as ONE batched
-product with the explicit inverses kept in HBM (the reference spills its factors to a temp file,
-preconditioner/binary_cache.hpp; 1M points need ~19 GB here), and the level transfers
+`plt_eval_gram_mixed`), the reduction Q^T A Q, its batched Cholesky factorisation and the local solves of one
+level as ONE launch of two triangular solves per domain -- hand-written kernels behind the C ABI
+(csrc/ras_dense.cu: `plt_ras_reduce_q`, `plt_chol_batched`, `plt_chol_solve_batched`; no cuSOLVER / cuBLAS), with
+the factors kept in HBM (the reference spills them to a temp file, preconditioner/binary_cache.hpp; 1M points
+need ~19 GB here), and the level transfers
 `update_residuals`, which are generic FMM evaluations (order 6, accuracy = infinity as the reference's
 `Evaluator` default) whose trees / plans / operators stay resident between applications.
 """
@@ -29,6 +30,52 @@ import numpy as np
 
 from . import fmm
 from .operator import monomial_basis
+
+def _dense_lib():
+    from . import _lib
+    return _lib, _lib.load()
+
+
+def reduce_q(a, q_top, out):
+    """out[b] = Q^T A Q (fine_grid.hpp:71-81) on the device: a (B, m, m), q_top (B, l, m - l), out (B, m - l, m - l)."""
+    import ctypes
+    _lib, lib = _dense_lib()
+    b, m = int(a.shape[0]), int(a.shape[1])
+    l = int(q_top.shape[1])
+    assert a.is_contiguous() and q_top.is_contiguous() and out.is_contiguous() and tuple(out.shape) == (b, m - l, m - l)
+    st = lib.plt_ras_reduce_q(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(q_top.data_ptr()), b, m, l,
+                              ctypes.c_void_p(out.data_ptr()), None)
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_ras_reduce_q failed")
+    return out
+
+
+def chol_batched(a, info):
+    """In-place batched Cholesky (lower) of a (B, n, n); info (B,) int32: 0 or 1 + the first bad pivot."""
+    import ctypes
+    _lib, lib = _dense_lib()
+    assert a.is_contiguous() and info.is_contiguous() and info.numel() == a.shape[0]
+    st = lib.plt_chol_batched(ctypes.c_void_p(a.data_ptr()), int(a.shape[0]), int(a.shape[1]),
+                              ctypes.c_void_p(info.data_ptr()), None)
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_chol_batched failed")
+
+
+def chol_solve_batched(factor, q_top, vals, lam):
+    """lam[b] = [Q_top gamma; gamma] with L L^T gamma = vals[b, l:] + Q_top^T vals[b, :l] (fine_grid.hpp:112-133)."""
+    import ctypes
+    _lib, lib = _dense_lib()
+    b, n = int(factor.shape[0]), int(factor.shape[1])
+    l = 0 if q_top is None else int(q_top.shape[1])
+    assert factor.is_contiguous() and vals.is_contiguous() and lam.is_contiguous()
+    assert tuple(vals.shape) == (b, l + n) and tuple(lam.shape) == (b, l + n)
+    st = lib.plt_chol_solve_batched(ctypes.c_void_p(factor.data_ptr()), b, n,
+                                    ctypes.c_void_p(q_top.data_ptr()) if l else None, l,
+                                    ctypes.c_void_p(vals.data_ptr()), ctypes.c_void_p(lam.data_ptr()), None)
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_chol_solve_batched failed")
+    return lam
+
 
 K_FINE_TO_COARSE_RATIO = 10.0   # ras_preconditioner.hpp:53
 K_N_COARSEST_POINTS = 2048      # ras_preconditioner.hpp:54
@@ -257,38 +304,26 @@ class _FineLevel:
             self.q_top = -lag[:, l:, :].transpose(1, 2).contiguous()  # (B, l, r)
         else:
             self.q_top = None
-        self.inv = torch.empty((self.n_dom, r, r), dtype=torch.float64, device=dev)
-        self.info = []
+        # Cholesky factors of Q^T A Q of every domain, kept in HBM (the reference spills its LDLT factors to a temp
+        # file, binary_cache.hpp); hand-written batched kernels (csrc/ras_dense.cu), no host synchronisation
+        self.fac = torch.empty((self.n_dom, r, r), dtype=torch.float64, device=dev)
+        self.info = torch.zeros(self.n_dom, dtype=torch.int32, device=dev)
         chunk = max(1, min(self.n_dom, int(2 ** 31 // (8 * m_max * m_max))))
         for b0 in range(0, self.n_dom, chunk):
             b1 = min(self.n_dom, b0 + chunk)
             a = ras.gram(self.idx[b0:b1], self.cnt[b0:b1])      # (b, m, m)
             if l > 0:
-                q = self.q_top[b0:b1]
-                att, atr, art, arr = a[:, :l, :l], a[:, :l, l:], a[:, l:, :l], a[:, l:, l:]
-                red = arr + q.transpose(1, 2) @ (att @ q + atr) + art @ q
+                reduce_q(a, self.q_top[b0:b1], self.fac[b0:b1])
             else:
-                red = a
-            chol, info = torch.linalg.cholesky_ex(red)   # no host synchronisation: the set-up stays asynchronous
-            self.info.append(info)
-            # (L L^T)^-1 = L^-T L^-1 through a batched triangular solve + product (cholesky_inverse is 2.5x
-            # slower for this shape and synchronises the host)
-            eye = torch.eye(r, dtype=torch.float64, device=dev).expand(b1 - b0, r, r)
-            linv = torch.linalg.solve_triangular(chol, eye, upper=False)
-            torch.bmm(linv.transpose(1, 2), linv, out=self.inv[b0:b1])
-            del a, red, chol, linv
+                self.fac[b0:b1].copy_(a)
+            chol_batched(self.fac[b0:b1], self.info[b0:b1])
+            del a
 
     def solve(self, ras, residuals, weights):
         """FineGrid::solve + set_solution_to for every domain of the level (fine_grid.hpp:103-147)."""
-        l = ras.l
-        vals = residuals[self.idx] * self.valid                # (B, m)
-        if l > 0:
-            qtd = vals[:, l:] + (vals[:, None, :l] @ self.q_top).squeeze(1)
-            gamma = (self.inv @ qtd[:, :, None]).squeeze(2)
-            top = (self.q_top @ gamma[:, :, None]).squeeze(2)
-            lam = ras.torch.cat([top, gamma], dim=1)
-        else:
-            lam = (self.inv @ vals[:, :, None]).squeeze(2)
+        vals = (residuals[self.idx] * self.valid).contiguous()   # (B, m), the l polynomial rows first
+        lam = ras.torch.empty_like(vals)
+        chol_solve_batched(self.fac, self.q_top, vals, lam)
         weights[self.inner_glob] = lam.reshape(-1)[self.inner_loc]
 
 
@@ -300,38 +335,39 @@ class _CoarseGrid:
         m = len(rows)
         self.m = m
         cnt = torch.tensor([m], dtype=torch.int32, device=dev)
-        a = ras.gram(self.idx[None], cnt)[0]
+        a = ras.gram(self.idx[None], cnt)                          # (1, m, m)
+        self.fac = torch.empty((1, m - l, m - l), dtype=torch.float64, device=dev)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         if l > 0:
             lag = ras.lagrange_p[self.idx]
-            self.q_top = -lag[l:, :].T.contiguous()             # (l, m - l)
-            q = self.q_top
-            red = a[l:, l:] + q.T @ (a[:l, :l] @ q + a[:l, l:]) + a[l:, :l] @ q
-            self.a_top = a[:l, :].clone()
+            self.q_top = (-lag[l:, :].T).contiguous()[None]        # (1, l, m - l)
+            reduce_q(a, self.q_top, self.fac)
+            self.a_top = a[0, :l, :].clone()
             if ras.special_case:   # coarse_grid.hpp:75-77: the value point and the coarse grid's FIRST gradient point
                 first_grad = (int(rows[1]) - ras.mu) // ras.dim
                 p_top = monomial_basis(ras.dim, ras.model.poly_degree, ras.points[rows[:1]],
                                        ras.grad_points[first_grad:first_grad + 1])
             else:
                 p_top = monomial_basis(ras.dim, ras.model.poly_degree, ras.points[rows[:l]])
-            p_top = torch.from_numpy(p_top).to(dev)
-            self.p_top_inv = torch.linalg.inv(p_top)
+            self.p_top_inv = torch.from_numpy(np.linalg.inv(p_top)).to(dev)   # l x l, host
         else:
-            red = a
-        self.chol = torch.linalg.cholesky(red)
+            self.q_top = None
+            self.fac.copy_(a)
+        chol_batched(self.fac, self.info)
 
     def solve(self, ras, residuals, weights):
         """CoarseGrid::solve + set_solution_to (coarse_grid.hpp:84-128)."""
         torch = ras.torch
         l = ras.l
-        vals = residuals[self.idx]
+        vals = residuals[self.idx].contiguous()[None]              # (1, m)
+        lam = torch.empty_like(vals)
+        chol_solve_batched(self.fac, self.q_top, vals, lam)
+        lam = lam[0]
+        weights[self.idx] = lam
         if l > 0:
-            qtd = self.q_top.T @ vals[:l] + vals[l:]
-            gamma = torch.cholesky_solve(qtd[:, None], self.chol)[:, 0]
-            lam = torch.cat([self.q_top @ gamma, gamma])
-            weights[self.idx] = lam
-            weights[ras.m_rows:] = self.p_top_inv @ (vals[:l] - self.a_top @ lam)
-        else:
-            weights[self.idx] = torch.cholesky_solve(vals[:, None], self.chol)[:, 0]
+            # solve P c = d - A lambda at the polynomial points (l x l, l <= 10: element-wise products + sums)
+            rhs = vals[0, :l] - (self.a_top * lam[None, :]).sum(dim=1)
+            weights[ras.m_rows:] = (self.p_top_inv * rhs[None, :]).sum(dim=1)
 
 
 class RasPreconditioner:
@@ -437,8 +473,8 @@ class RasPreconditioner:
         self.coarse = _CoarseGrid(self, self._rows(point_idcs[0], grad_idcs[0]))
         if verbose:
             print(f"level 0: 1 domain, {len(point_idcs[0])} points, {len(grad_idcs[0])} gradient points", flush=True)
-        for f in self.fine:
-            if f is not None and any(int(i.max()) != 0 for i in f.info):
+        for f in self.fine + [self.coarse]:
+            if f is not None and int(f.info.max()) != 0:
                 raise RuntimeError("RAS: a local problem is not positive definite (duplicate points?)")
         self._evaluators = {}
         self.p = self.ap = None

@@ -332,3 +332,42 @@ def test_fit_two_rbfs(torch):
         odir.full_direct(orbf.make_rbf("gau", [0.3, 0.25], dim, a2), 0, pts, pts[sub], w[:n]) + \
         0.01 * w[sub] + w[n]
     assert np.max(np.abs(fit - values[sub])) <= 2 * tol
+
+
+@pytest.mark.parametrize("n,l,batch", [(70, 0, 5), (200, 4, 3), (333, 1, 2), (1000, 4, 2)])
+def test_dense_local_kernels_match_numpy(torch, n, l, batch):
+    """csrc/ras_dense.cu against numpy: Q^T A Q (fine_grid.hpp:71-81), the batched Cholesky factor and the local solve
+    lambda = Q (Q^T A Q)^-1 Q^T d (fine_grid.hpp:112-133) for symmetric positive definite blocks."""
+    from polatory_b200.ras import chol_batched, chol_solve_batched, reduce_q
+    rng = np.random.default_rng(n + l)
+    m = n + l
+    g = rng.standard_normal((batch, m, m))
+    a = g @ g.transpose(0, 2, 1) / m + 2.0 * np.eye(m)
+    q_top = rng.standard_normal((batch, l, n))
+    vals = rng.standard_normal((batch, m))
+    dev = torch.device("cuda")
+    d_a = torch.from_numpy(a).to(dev)
+    d_q = torch.from_numpy(q_top).to(dev) if l else None
+    fac = torch.empty((batch, n, n), dtype=torch.float64, device=dev)
+    if l:
+        reduce_q(d_a, d_q, fac)
+    else:
+        fac.copy_(d_a)
+    qm = np.concatenate([q_top, np.broadcast_to(np.eye(n), (batch, n, n))], axis=1)   # Q = [Q_top; I]  (m x n)
+    red = qm.transpose(0, 2, 1) @ a @ qm
+    assert np.max(np.abs(fac.cpu().numpy() - red)) <= 1e-12 * np.max(np.abs(red))
+    info = torch.zeros(batch, dtype=torch.int32, device=dev)
+    chol_batched(fac, info)
+    assert int(info.abs().max()) == 0
+    got_l = np.tril(fac.cpu().numpy())
+    ref_l = np.linalg.cholesky(red)
+    assert np.max(np.abs(got_l - ref_l)) <= 1e-11 * np.max(np.abs(ref_l))
+    lam = torch.empty((batch, m), dtype=torch.float64, device=dev)
+    chol_solve_batched(fac, d_q, torch.from_numpy(vals).to(dev), lam)
+    ref = np.stack([qm[b] @ np.linalg.solve(red[b], qm[b].T @ vals[b]) for b in range(batch)])
+    assert np.max(np.abs(lam.cpu().numpy() - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # a matrix that is not positive definite is reported, not silently factorised
+    bad = torch.from_numpy(a[:1, l:, l:].copy()).to(dev)
+    bad[0, n // 2, n // 2] = -1.0
+    chol_batched(bad, info[:1])
+    assert int(info[0]) == n // 2 + 1
