@@ -1389,7 +1389,7 @@ __global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
 // Register-blocked 3-D forward DFT of the multipoles (the mirror image of k_m2l_idft3):
 //   stage A: axis 2, p real -> p complex (half spectrum);  B: axis 1, p -> nf;  C: axis 0, p -> nf.
 // Zero padding from p to nf points is implicit (only p inputs per column are read).
-template <int ORDER, int NB>
+template <int ORDER, int NB, bool FLAGGED>
 __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int km, const double* __restrict__ M,
                                                 double2* __restrict__ Mhat, TwTable tw,
                                                 const unsigned char* __restrict__ flags) {
@@ -1403,7 +1403,7 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   const int nb = min(NB, total - w0);
   // partitioned upward pass: skip the cells whose spectrum this rank does not need
   __shared__ int s_on[NB];
-  if (flags) {
+  if constexpr (FLAGGED) {
     if (threadIdx.x < NB)
       s_on[threadIdx.x] = threadIdx.x < nb && (flags[first_cell + (w0 + threadIdx.x) / km] & kCellFlagMhat);
     __syncthreads();
@@ -1416,7 +1416,7 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   // stage A: column = (n0, n1)
   for (int item = threadIdx.x; item < nb * p * p; item += blockDim.x) {
     const int c = item / (p * p), col = item % (p * p);
-    if (flags && !s_on[c]) continue;
+    if (FLAGGED && !s_on[c]) continue;
     const double* in = Mc + static_cast<size_t>(c) * P + col * p;
     double x[p];
 #pragma unroll
@@ -1437,7 +1437,7 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   // stage B: column = (n0, k2), stride p
   for (int item = threadIdx.x; item < nb * p * p; item += blockDim.x) {
     const int c = item / (p * p), col = item % (p * p);
-    if (flags && !s_on[c]) continue;
+    if (FLAGGED && !s_on[c]) continue;
     const int n0 = col / p, k2 = col % p;
     const double2* in = Y1 + c * P + n0 * p * p + k2;
     double2 x[p];
@@ -1461,7 +1461,7 @@ __global__ void __launch_bounds__(256) k_m2hat3(int first_cell, int n_cells, int
   // stage C: column = (k1, k2), stride nf * p
   for (int item = threadIdx.x; item < nb * nf * p; item += blockDim.x) {
     const int c = item / (nf * p), col = item % (nf * p);
-    if (flags && !s_on[c]) continue;
+    if (FLAGGED && !s_on[c]) continue;
     const double2* in = Y2 + c * YN + col;
     double2 x[p];
 #pragma unroll
@@ -1773,9 +1773,15 @@ void launch_m2hat3(int first, int n_cells, int km, const double* tw_host, const 
   TwTable tw{};
   for (int i = 0; i < nf; ++i) tw.w[i] = make_double2(tw_host[2 * i], tw_host[2 * i + 1]);
   const size_t smem = sizeof(double2) * NB * (p * p * p + p * nf * p);
-  smem_opt_in((const void*)k_m2hat3<ORDER, NB>, smem);
-  PLT_LAUNCH(c, (k_m2hat3<ORDER, NB>), ceil_div(n_cells * km, NB), 256, smem, s, first, n_cells, km, M, Mhat, tw,
-             flags);
+  if (flags) {
+    smem_opt_in((const void*)k_m2hat3<ORDER, NB, true>, smem);
+    PLT_LAUNCH(c, (k_m2hat3<ORDER, NB, true>), ceil_div(n_cells * km, NB), 256, smem, s, first, n_cells, km, M, Mhat, tw,
+               flags);
+  } else {
+    smem_opt_in((const void*)k_m2hat3<ORDER, NB, false>, smem);
+    PLT_LAUNCH(c, (k_m2hat3<ORDER, NB, false>), ceil_div(n_cells * km, NB), 256, smem, s, first, n_cells, km, M, Mhat, tw,
+               flags);
+  }
 }
 }  // namespace
 

@@ -43,13 +43,16 @@ __global__ void k_reduce_q(const double* __restrict__ a, const double* __restric
   red[(static_cast<size_t>(b) * r + i) * r + j] = acc;
 }
 
-// Blocked right-looking Cholesky of one n x n matrix per CTA (lower triangle, in place).
+// Blocked right-looking Cholesky of one n x n matrix per CTA, in place.  Output format (internal to the solve
+// kernel below): off-diagonal blocks hold L in the lower triangle AND L^T mirrored in the upper triangle (so that a
+// column of L is a contiguous row segment); the kNB x kNB diagonal blocks hold L11^-1 (symmetric fill).
 //   for each panel of kNB columns: (1) factorise the diagonal block in shared memory, (2) triangular-solve the
 //   rows below it (one thread per row), (3) rank-kNB update of the trailing lower triangle in kTS x kTS tiles
 //   (both panel blocks staged in shared memory, 4 x 4 outputs per thread).
 __global__ void __launch_bounds__(kCholThreads) k_chol_batched(double* __restrict__ a_all, int n, int* __restrict__ info) {
   __shared__ double D[kNB][kNB + 1];
   __shared__ __align__(16) double PI[kNB][kTS + 4];  // panel block of the tile's rows, k-major
+  double (*Dinv)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(&PI[0][0]);  // PI is idle during the block step
   __shared__ __align__(16) double PJ[kNB][kTS + 4];  // panel block of the tile's columns
   __shared__ int s_bad;
   double* a = a_all + static_cast<size_t>(blockIdx.x) * n * n;
@@ -82,9 +85,20 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_batched(double* __restric
       }
       __syncthreads();
     }
+    // The solves only ever apply L11^-1 (a 32 x 32 triangular matrix-vector product, no dependent chain), so the
+    // diagonal block is stored INVERTED: column j of L11^-1 by forward substitution, one thread per column.
+    if (tid < nb) {
+      const int j = tid;
+      for (int i = j; i < nb; ++i) {
+        double sum = i == j ? 1.0 : 0.0;
+        for (int t = j; t < i; ++t) sum = fma(-D[i][t], Dinv[t][j], sum);
+        Dinv[i][j] = sum / D[i][i];
+      }
+    }
+    __syncthreads();
     for (int e = tid; e < nb * nb; e += kCholThreads) {
       const int i = e / nb, j = e - i * nb;
-      if (j <= i) a[static_cast<size_t>(k0 + i) * n + (k0 + j)] = D[i][j];
+      a[static_cast<size_t>(k0 + i) * n + (k0 + j)] = j <= i ? Dinv[i][j] : Dinv[j][i];  // symmetric fill
     }
     const int r0 = k0 + nb;   // first row below the panel's diagonal block
     if (r0 >= n) break;
@@ -112,6 +126,12 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_batched(double* __restric
         const int rr = e / kNB, k = e - rr * kNB;
         if (i0 + rr < n && k < nb)
           a[static_cast<size_t>(i0 + rr) * n + (k0 + k)] = rr < kTS ? PI[k][rr] : PJ[k][rr - kTS];
+      }
+      // mirror into the upper triangle (row k0 + k, columns i0 ...: contiguous): the solves read L by columns
+      for (int e = tid; e < 2 * kTS * kNB; e += kCholThreads) {
+        const int k = e / (2 * kTS), rr = e - k * (2 * kTS);
+        if (i0 + rr < n && k < nb)
+          a[static_cast<size_t>(k0 + k) * n + (i0 + rr)] = rr < kTS ? PI[k][rr] : PJ[k][rr - kTS];
       }
     }
     __syncthreads();
@@ -163,19 +183,21 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_batched(double* __restric
 }
 
 // One domain per CTA:  qtd = vals[l:] + Q_top^T vals[:l];  L y = qtd;  L^T gamma = y;  lambda = [Q_top gamma; gamma].
-// L: [B][n][n] lower triangular factor; q: [B][l][n] or null (l == 0); vals, lam: [B][l + n].
+// F: [B][n][n] factor in the format written by k_chol_batched; q: [B][l][n] or null (l == 0); vals, lam: [B][l + n].
+// Blocked substitution: the diagonal block is applied as y_blk = L11^-1 x_blk (one lane per row, no dependent chain),
+// the remaining rows are updated from the MIRRORED factor (thread per row, coalesced across the CTA).
 constexpr int kSolveThreads = 256;
-__global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __restrict__ L_all, int n,
+__global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __restrict__ F_all, int n,
                                                               const double* __restrict__ q_all, int l,
                                                               const double* __restrict__ vals_all,
                                                               double* __restrict__ lam_all) {
   extern __shared__ double sm[];
   double* x = sm;                      // [n] right-hand side / solution
-  double* Dg = x + ((n + 31) & ~31);   // [kNB][kNB + 1] diagonal block
-  double* part = Dg + kNB * (kNB + 1); // [warps][kNB] partial sums of the backward update
+  double* Dg = x + ((n + 31) & ~31);   // [kNB][kNB + 1] inverse of the diagonal block
+  double* yb = Dg + kNB * (kNB + 1);   // [kNB] solved block
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kSolveThreads / 32;
-  const double* Lm = L_all + static_cast<size_t>(b) * n * n;
+  const double* F = F_all + static_cast<size_t>(b) * n * n;
   const double* q = l ? q_all + static_cast<size_t>(b) * l * n : nullptr;
   const double* vals = vals_all + static_cast<size_t>(b) * (l + n);
   double* lam = lam_all + static_cast<size_t>(b) * (l + n);
@@ -190,25 +212,27 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
     __syncthreads();
     for (int e = tid; e < nb * nb; e += kSolveThreads) {
       const int i = e / nb, j = e - i * nb;
-      Dg[i * (kNB + 1) + j] = Lm[static_cast<size_t>(k0 + i) * n + (k0 + j)];
+      Dg[i * (kNB + 1) + j] = F[static_cast<size_t>(k0 + i) * n + (k0 + j)];
     }
     __syncthreads();
-    if (warp == 0) {
-      double xv = lane < nb ? x[k0 + lane] : 0.0;
-      for (int c = 0; c < nb; ++c) {
-        const double yc = __shfl_sync(0xffffffffu, xv, c) / Dg[c * (kNB + 1) + c];
-        if (lane == c) xv = yc;
-        if (lane > c && lane < nb) xv = fma(-Dg[lane * (kNB + 1) + c], yc, xv);
-      }
-      if (lane < nb) x[k0 + lane] = xv;
+    if (warp == 0 && lane < nb) {
+      double acc = 0.0;
+      for (int c = 0; c <= lane; ++c) acc = fma(Dg[lane * (kNB + 1) + c], x[k0 + c], acc);
+      yb[lane] = acc;
     }
     __syncthreads();
-    // rows below: x[i] -= L[i][k0 : k0 + nb] . y   (thread per row, the row segment is contiguous)
+    if (tid < nb) x[k0 + tid] = yb[tid];
+    // rows below: x[i] -= sum_c L[i][k0 + c] y[c],  L[i][k0 + c] = F[k0 + c][i] (mirror): coalesced over i
     for (int i = k0 + nb + tid; i < n; i += kSolveThreads) {
-      const double* row = Lm + static_cast<size_t>(i) * n + k0;
-      double s = 0.0;
-      for (int c = 0; c < nb; ++c) s = fma(row[c], x[k0 + c], s);
-      x[i] -= s;
+      const double* col = F + static_cast<size_t>(k0) * n + i;
+      double s0 = 0.0, s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < nb; c += 2) {
+        s0 = fma(col[static_cast<size_t>(c) * n], yb[c], s0);
+        s1 = fma(col[static_cast<size_t>(c + 1) * n], yb[c + 1], s1);
+      }
+      if (c < nb) s0 = fma(col[static_cast<size_t>(c) * n], yb[c], s0);
+      x[i] -= s0 + s1;
     }
   }
   // ---- backward: L^T gamma = y ----
@@ -216,28 +240,24 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
   for (int k0 = last; k0 >= 0; k0 -= kNB) {
     const int nb = min(kNB, n - k0);
     __syncthreads();
-    // x[k0 + j] -= sum_{i >= k0 + nb} L[i][k0 + j] gamma[i]: warps over rows, lanes over the nb columns
-    double acc = 0.0;
-    for (int i = k0 + nb + warp; i < n; i += NW)
-      if (lane < nb) acc = fma(Lm[static_cast<size_t>(i) * n + (k0 + lane)], x[i], acc);
-    part[warp * kNB + lane] = acc;
+    // x[k0 + j] -= sum_{i >= k0 + nb} L[i][k0 + j] gamma[i] = sum_i F[k0 + j][i] gamma[i]: warp per j, lanes over i
+    for (int j = warp; j < nb; j += NW) {
+      const double* rowj = F + static_cast<size_t>(k0 + j) * n;
+      double acc = 0.0;
+      for (int i = k0 + nb + lane; i < n; i += 32) acc = fma(rowj[i], x[i], acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) yb[j] = x[k0 + j] - acc;
+    }
     for (int e = tid; e < nb * nb; e += kSolveThreads) {
       const int i = e / nb, j = e - i * nb;
-      Dg[i * (kNB + 1) + j] = Lm[static_cast<size_t>(k0 + i) * n + (k0 + j)];
+      Dg[i * (kNB + 1) + j] = F[static_cast<size_t>(k0 + i) * n + (k0 + j)];
     }
     __syncthreads();
-    if (warp == 0) {
-      double xv = 0.0;
-      if (lane < nb) {
-        xv = x[k0 + lane];
-        for (int w = 0; w < NW; ++w) xv -= part[w * kNB + lane];
-      }
-      for (int c = nb - 1; c >= 0; --c) {
-        const double gc = __shfl_sync(0xffffffffu, xv, c) / Dg[c * (kNB + 1) + c];
-        if (lane == c) xv = gc;
-        if (lane < c) xv = fma(-Dg[c * (kNB + 1) + lane], gc, xv);   // L^T[lane][c] = L[c][lane]
-      }
-      if (lane < nb) x[k0 + lane] = xv;
+    // gamma_blk = L11^-T x_blk: lane r sums over c >= r of L11^-1[c][r] x[c]
+    if (warp == 0 && lane < nb) {
+      double acc = 0.0;
+      for (int c = lane; c < nb; ++c) acc = fma(Dg[c * (kNB + 1) + lane], yb[c], acc);
+      x[k0 + lane] = acc;
     }
   }
   __syncthreads();
@@ -295,7 +315,7 @@ int plt_chol_solve_batched(const double* factor, int64_t n_batch, int n, const d
   if (!factor || !vals || !lam || n_batch < 0 || n < 1 || l < 0 || (l > 0 && !q_top)) return PLT_ERR_INVALID;
   if (!is_dev(factor) || !is_dev(vals) || !is_dev(lam)) return PLT_ERR_INVALID;
   if (n_batch == 0) return PLT_OK;
-  const size_t smem = sizeof(double) * (((n + 31) & ~31) + kNB * (kNB + 1) + (kSolveThreads / 32) * kNB);
+  const size_t smem = sizeof(double) * (((n + 31) & ~31) + kNB * (kNB + 1) + kNB);
   if (smem > 40 * 1024 &&
       cudaFuncSetAttribute((const void*)k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
           cudaSuccess)

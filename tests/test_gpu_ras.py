@@ -359,9 +359,14 @@ def test_dense_local_kernels_match_numpy(torch, n, l, batch):
     info = torch.zeros(batch, dtype=torch.int32, device=dev)
     chol_batched(fac, info)
     assert int(info.abs().max()) == 0
-    got_l = np.tril(fac.cpu().numpy())
-    ref_l = np.linalg.cholesky(red)
-    assert np.max(np.abs(got_l - ref_l)) <= 1e-11 * np.max(np.abs(ref_l))
+    # factor format: L below the 32 x 32 diagonal blocks (mirrored above them), the diagonal blocks hold L11^-1
+    got, ref_l = fac.cpu().numpy(), np.linalg.cholesky(red)
+    for k0 in range(0, n, 32):
+        k1 = min(n, k0 + 32)
+        assert np.max(np.abs(got[:, k1:, k0:k1] - ref_l[:, k1:, k0:k1])) <= 1e-11 * np.max(np.abs(ref_l))
+        assert np.max(np.abs(got[:, k0:k1, k1:] - ref_l[:, k1:, k0:k1].transpose(0, 2, 1))) <= 1e-11 * np.max(np.abs(ref_l))
+        inv_blk = np.linalg.inv(ref_l[:, k0:k1, k0:k1])
+        assert np.max(np.abs(np.tril(got[:, k0:k1, k0:k1]) - inv_blk)) <= 1e-10 * np.max(np.abs(inv_blk))
     lam = torch.empty((batch, m), dtype=torch.float64, device=dev)
     chol_solve_batched(fac, d_q, torch.from_numpy(vals).to(dev), lam)
     ref = np.stack([qm[b] @ np.linalg.solve(red[b], qm[b].T @ vals[b]) for b in range(batch)])
