@@ -288,6 +288,11 @@ int plt_ras_reduce_q(const double* a, const double* q_top, int64_t n_batch, int 
 int plt_chol_batched(double* a, int64_t n_batch, int n, int* info, void* stream);
 int plt_chol_solve_batched(const double* factor, int64_t n_batch, int n, const double* q_top, int l, const double* vals,
                            double* lam, void* stream);
+/* ONE factor (as written by plt_chol_batched), n_rhs right-hand sides: out[k] = (L L^T)^-1 rhs[k]; rhs, out: [n_rhs][n].
+ * With the identity as right-hand sides this forms the explicit inverse of the coarse grid's matrix once per fit. */
+int plt_chol_solve_shared(const double* factor, int n, int64_t n_rhs, const double* rhs, double* out, void* stream);
+/* y = A x, A row-major [rows][cols], device pointers (applies the coarse grid's inverse, coarse_grid.hpp:84-128). */
+int plt_gemv(const double* a, int rows, int cols, const double* x, double* y, void* stream);
 
 /* The data points on which interpolation::ResidualEvaluator measures the residual exactly
  * (include/polatory/interpolation/residual_evaluator.hpp:123-136): out[0..n) = iota shuffled by a default-seeded

@@ -86,6 +86,8 @@ SYMBOLS = [
     ("plt_ras_reduce_q", ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     ("plt_chol_batched", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
     ("plt_chol_solve_batched", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp]),
+    ("plt_chol_solve_shared", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _vp, _vp, _vp]),
+    ("plt_gemv", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     ("plt_residual_sample_indices", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp]),
     ("plt_version", ctypes.c_int, []),
     ("plt_device_check", ctypes.c_int, []),

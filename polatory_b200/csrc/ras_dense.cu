@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_batched(double* __restric
 // Blocked substitution: the diagonal block is applied as y_blk = L11^-1 x_blk (one lane per row, no dependent chain),
 // the remaining rows are updated from the MIRRORED factor (thread per row, coalesced across the CTA).
 constexpr int kSolveThreads = 256;
-__global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __restrict__ F_all, int n,
+__global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __restrict__ F_all, size_t f_stride, int n,
                                                               const double* __restrict__ q_all, int l,
                                                               const double* __restrict__ vals_all,
                                                               double* __restrict__ lam_all) {
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
   double* yb = Dg + kNB * (kNB + 1);   // [kNB] solved block
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kSolveThreads / 32;
-  const double* F = F_all + static_cast<size_t>(b) * n * n;
+  const double* F = F_all + static_cast<size_t>(b) * f_stride;  // f_stride == 0: one factor, many right-hand sides
   const double* q = l ? q_all + static_cast<size_t>(b) * l * n : nullptr;
   const double* vals = vals_all + static_cast<size_t>(b) * (l + n);
   double* lam = lam_all + static_cast<size_t>(b) * (l + n);
@@ -215,23 +215,30 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
       Dg[i * (kNB + 1) + j] = F[static_cast<size_t>(k0 + i) * n + (k0 + j)];
     }
     __syncthreads();
-    if (warp == 0 && lane < nb) {
-      double acc = 0.0;
-      for (int c = 0; c <= lane; ++c) acc = fma(Dg[lane * (kNB + 1) + c], x[k0 + c], acc);
-      yb[lane] = acc;
+    if (warp == 0) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < kNB; c += 2) {  // entries above the diagonal of L11^-1 are multiplied by 0
+        a0 = fma(c <= lane && c < nb ? Dg[lane * (kNB + 1) + c] : 0.0, c < nb ? x[k0 + c] : 0.0, a0);
+        a1 = fma(c + 1 <= lane && c + 1 < nb ? Dg[lane * (kNB + 1) + c + 1] : 0.0, c + 1 < nb ? x[k0 + c + 1] : 0.0, a1);
+      }
+      yb[lane] = a0 + a1;
     }
     __syncthreads();
     if (tid < nb) x[k0 + tid] = yb[tid];
     // rows below: x[i] -= sum_c L[i][k0 + c] y[c],  L[i][k0 + c] = F[k0 + c][i] (mirror): coalesced over i
-    for (int i = k0 + nb + tid; i < n; i += kSolveThreads) {
+    // (a full panel below a partial one cannot occur: the partial panel is the last)
+    for (int i = k0 + kNB + tid; i < n; i += kSolveThreads) {
       const double* col = F + static_cast<size_t>(k0) * n + i;
+      double v[kNB];
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) v[c] = col[static_cast<size_t>(c) * n];  // kNB independent coalesced loads in flight
       double s0 = 0.0, s1 = 0.0;
-      int c = 0;
-      for (; c + 1 < nb; c += 2) {
-        s0 = fma(col[static_cast<size_t>(c) * n], yb[c], s0);
-        s1 = fma(col[static_cast<size_t>(c + 1) * n], yb[c + 1], s1);
+#pragma unroll
+      for (int c = 0; c < kNB; c += 2) {
+        s0 = fma(v[c], yb[c], s0);
+        s1 = fma(v[c + 1], yb[c + 1], s1);
       }
-      if (c < nb) s0 = fma(col[static_cast<size_t>(c) * n], yb[c], s0);
       x[i] -= s0 + s1;
     }
   }
@@ -243,8 +250,17 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
     // x[k0 + j] -= sum_{i >= k0 + nb} L[i][k0 + j] gamma[i] = sum_i F[k0 + j][i] gamma[i]: warp per j, lanes over i
     for (int j = warp; j < nb; j += NW) {
       const double* rowj = F + static_cast<size_t>(k0 + j) * n;
-      double acc = 0.0;
-      for (int i = k0 + nb + lane; i < n; i += 32) acc = fma(rowj[i], x[i], acc);
+      double acc = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      int i = k0 + nb + lane;
+      for (; i + 224 < n; i += 256) {  // 8 independent coalesced loads in flight per lane
+        const double v0 = rowj[i], v1 = rowj[i + 32], v2 = rowj[i + 64], v3 = rowj[i + 96];
+        const double v4 = rowj[i + 128], v5 = rowj[i + 160], v6 = rowj[i + 192], v7 = rowj[i + 224];
+        acc = fma(v0, x[i], acc); acc1 = fma(v1, x[i + 32], acc1); acc2 = fma(v2, x[i + 64], acc2);
+        acc3 = fma(v3, x[i + 96], acc3); acc = fma(v4, x[i + 128], acc); acc1 = fma(v5, x[i + 160], acc1);
+        acc2 = fma(v6, x[i + 192], acc2); acc3 = fma(v7, x[i + 224], acc3);
+      }
+      for (; i < n; i += 32) acc = fma(rowj[i], x[i], acc);
+      acc += acc1 + acc2 + acc3;
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) yb[j] = x[k0 + j] - acc;
     }
@@ -254,10 +270,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
     }
     __syncthreads();
     // gamma_blk = L11^-T x_blk: lane r sums over c >= r of L11^-1[c][r] x[c]
-    if (warp == 0 && lane < nb) {
-      double acc = 0.0;
-      for (int c = lane; c < nb; ++c) acc = fma(Dg[c * (kNB + 1) + lane], yb[c], acc);
-      x[k0 + lane] = acc;
+    if (warp == 0) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < kNB; c += 2) {
+        a0 = fma(c >= lane && c < nb ? Dg[c * (kNB + 1) + lane] : 0.0, c < nb ? yb[c] : 0.0, a0);
+        a1 = fma(c + 1 >= lane && c + 1 < nb ? Dg[(c + 1) * (kNB + 1) + lane] : 0.0, c + 1 < nb ? yb[c + 1] : 0.0, a1);
+      }
+      if (lane < nb) x[k0 + lane] = a0 + a1;
     }
   }
   __syncthreads();
@@ -269,6 +289,24 @@ __global__ void __launch_bounds__(kSolveThreads) k_chol_solve(const double* __re
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) lam[s] = acc;
   }
+}
+
+// y = A x, A row-major [rows][cols]: one warp per row (the coarse grid's explicit inverse, coarse_grid.hpp:84-128).
+__global__ void k_gemv(const double* __restrict__ A, int rows, int cols, const double* __restrict__ x,
+                       double* __restrict__ y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const double* a = A + static_cast<size_t>(row) * cols;
+  double acc0 = 0.0, acc1 = 0.0;
+  int j = lane;
+  for (; j + 32 < cols; j += 64) {
+    acc0 = fma(a[j], x[j], acc0);
+    acc1 = fma(a[j + 32], x[j + 32], acc1);
+  }
+  if (j < cols) acc0 = fma(a[j], x[j], acc0);
+  acc0 += acc1;
+  for (int o = 16; o > 0; o >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+  if (lane == 0) y[row] = acc0;
 }
 
 bool is_dev(const void* p) {
@@ -310,6 +348,27 @@ int plt_chol_batched(double* a, int64_t n_batch, int n, int* info, void* stream)
   return cudaGetLastError() == cudaSuccess ? PLT_OK : PLT_ERR_CUDA;
 }
 
+int plt_gemv(const double* a, int rows, int cols, const double* x, double* y, void* stream) {
+  if (!a || !x || !y || rows < 1 || cols < 1) return PLT_ERR_INVALID;
+  if (!is_dev(a) || !is_dev(x) || !is_dev(y)) return PLT_ERR_INVALID;
+  k_gemv<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, rows, cols, x, y);
+  return cudaGetLastError() == cudaSuccess ? PLT_OK : PLT_ERR_CUDA;
+}
+
+int plt_chol_solve_shared(const double* factor, int n, int64_t n_rhs, const double* rhs, double* out, void* stream) {
+  if (!factor || !rhs || !out || n < 1 || n_rhs < 0) return PLT_ERR_INVALID;
+  if (!is_dev(factor) || !is_dev(rhs) || !is_dev(out)) return PLT_ERR_INVALID;
+  if (n_rhs == 0) return PLT_OK;
+  const size_t smem = sizeof(double) * (((n + 31) & ~31) + kNB * (kNB + 1) + kNB);
+  if (smem > 40 * 1024 &&
+      cudaFuncSetAttribute((const void*)k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) !=
+          cudaSuccess)
+    return PLT_ERR_CUDA;
+  k_chol_solve<<<static_cast<unsigned>(n_rhs), kSolveThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      factor, 0, n, nullptr, 0, rhs, out);
+  return cudaGetLastError() == cudaSuccess ? PLT_OK : PLT_ERR_CUDA;
+}
+
 int plt_chol_solve_batched(const double* factor, int64_t n_batch, int n, const double* q_top, int l, const double* vals,
                            double* lam, void* stream) {
   if (!factor || !vals || !lam || n_batch < 0 || n < 1 || l < 0 || (l > 0 && !q_top)) return PLT_ERR_INVALID;
@@ -321,7 +380,7 @@ int plt_chol_solve_batched(const double* factor, int64_t n_batch, int n, const d
           cudaSuccess)
     return PLT_ERR_CUDA;
   k_chol_solve<<<static_cast<unsigned>(n_batch), kSolveThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      factor, n, q_top, l, vals, lam);
+      factor, static_cast<size_t>(n) * n, n, q_top, l, vals, lam);
   return cudaGetLastError() == cudaSuccess ? PLT_OK : PLT_ERR_CUDA;
 }
 

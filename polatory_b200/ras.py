@@ -77,6 +77,37 @@ def chol_solve_batched(factor, q_top, vals, lam):
     return lam
 
 
+def chol_inverse(factor):
+    """(L L^T)^-1 of ONE factor (n, n) written by chol_batched: the solve kernel on the n unit vectors."""
+    import ctypes
+    import torch
+    _lib, lib = _dense_lib()
+    n = int(factor.shape[0])
+    eye = torch.eye(n, dtype=torch.float64, device=factor.device)
+    out = torch.empty_like(eye)
+    st = lib.plt_chol_solve_shared(ctypes.c_void_p(factor.data_ptr()), n, n, ctypes.c_void_p(eye.data_ptr()),
+                                   ctypes.c_void_p(out.data_ptr()), None)
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_chol_solve_shared failed")
+    return out
+
+
+def gemv(a, x, out=None):
+    """y = A x with the library's own kernel (A (rows, cols) row-major CUDA tensor)."""
+    import ctypes
+    import torch
+    _lib, lib = _dense_lib()
+    rows, cols = int(a.shape[0]), int(a.shape[1])
+    x = x.contiguous()
+    assert a.is_contiguous() and x.numel() == cols
+    y = torch.empty(rows, dtype=torch.float64, device=a.device) if out is None else out
+    st = lib.plt_gemv(ctypes.c_void_p(a.data_ptr()), rows, cols, ctypes.c_void_p(x.data_ptr()),
+                      ctypes.c_void_p(y.data_ptr()), None)
+    if st != _lib.PLT_OK:
+        raise RuntimeError("plt_gemv failed")
+    return y
+
+
 K_FINE_TO_COARSE_RATIO = 10.0   # ras_preconditioner.hpp:53
 K_N_COARSEST_POINTS = 2048      # ras_preconditioner.hpp:54
 K_OVERLAP_QUOTA = 0.5           # domain_divider.hpp:25
@@ -354,15 +385,23 @@ class _CoarseGrid:
             self.q_top = None
             self.fac.copy_(a)
         chol_batched(self.fac, self.info)
+        # The coarse grid is solved ~2 n_levels times per application on ONE matrix: a single-CTA substitution is a
+        # latency chain, so its inverse is formed once (the solve kernel on the unit vectors, all SMs busy) and
+        # applied as a matrix-vector product.
+        self.inv = chol_inverse(self.fac[0])
 
     def solve(self, ras, residuals, weights):
         """CoarseGrid::solve + set_solution_to (coarse_grid.hpp:84-128)."""
         torch = ras.torch
         l = ras.l
-        vals = residuals[self.idx].contiguous()[None]              # (1, m)
-        lam = torch.empty_like(vals)
-        chol_solve_batched(self.fac, self.q_top, vals, lam)
-        lam = lam[0]
+        vals = residuals[self.idx].contiguous()                    # (m,)
+        if l > 0:
+            q = self.q_top[0]                                      # (l, m - l)
+            gamma = gemv(self.inv, vals[l:] + (q * vals[:l, None]).sum(dim=0))
+            lam = torch.cat([(q * gamma[None, :]).sum(dim=1), gamma])
+        else:
+            lam = gemv(self.inv, vals)
+        vals = vals[None]
         weights[self.idx] = lam
         if l > 0:
             # solve P c = d - A lambda at the polynomial points (l x l, l <= 10: element-wise products + sums)
