@@ -182,10 +182,17 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
 #pragma unroll
         for (int m = 0; m < KM; ++m) w[m] = dat[(DIM + m) * kSrcCap + q];
         if constexpr (FoldedPair<FAM, KIND>::value) {
-          // all kTG slots are evaluated (slots beyond nt repeat the last target and are not stored)
           const double c1e = k.c[1] + 1e-300;  // c^2 (+ the guard that keeps the seed finite at r = 0)
-          folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
-          folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
+          // (warp-uniform: slots up to the next multiple of 2 beyond nt are evaluated, not stored)
+          if (nt > kTG / 2) {
+            folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
+            if (nt > 3 * kTG / 4) folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
+            else folded_pairs<FAM, DIM, kTG / 4>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
+          } else if (nt > kTG / 4) {
+            folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
+          } else {
+            folded_pairs<FAM, DIM, kTG / 4>(c1e, sp, w[0], tp, v);
+          }
         } else if (nt == kTG) {
           // full group: branch-free, the kTG independent pair evaluations interleave
 #pragma unroll
