@@ -139,41 +139,111 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
   // DIM coordinates + KM weights, lane-contiguous (conflict-free LDS.64).  Every target group of the leaf then
   // streams it from there: no prefix search and no global load inside the pair loop.
   double* dat = s_dat + static_cast<size_t>(warp) * (DIM + KM) * kSrcCap;
+  // neighbour holding concatenated index jj (last nb with prefix[nb] <= jj) -> sorted source index
+  auto source_index = [&](int jj) {
+    int lo = 0, hi = NN - 1;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (pre[mid] <= jj) lo = mid; else hi = mid - 1;
+    }
+    return st[lo] + (jj - pre[lo]);
+  };
+  // the pair evaluations of one source against the target group in registers
+  auto eval_source = [&](const double (&sp)[DIM], const double (&w)[KM], const double (*tp)[DIM], double (*v)[KN],
+                         int nt) {
+    if constexpr (FoldedPair<FAM, KIND>::value) {
+      const double c1e = k.c[1] + 1e-300;  // c^2 (+ the guard that keeps the seed finite at r = 0)
+      // (warp-uniform: slots up to the next multiple of 2 beyond nt are evaluated, not stored)
+      if (nt > kTG / 2) {
+        folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
+        if (nt > 3 * kTG / 4) folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
+        else folded_pairs<FAM, DIM, kTG / 4>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
+      } else if (nt > kTG / 4) {
+        folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
+      } else {
+        folded_pairs<FAM, DIM, kTG / 4>(c1e, sp, w[0], tp, v);
+      }
+    } else if (nt == kTG) {
+      // full group: branch-free, the kTG independent pair evaluations interleave
+#pragma unroll
+      for (int u = 0; u < kTG; ++u) {
+        double d[DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
+        pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kTG; ++u) {
+        if (u < nt) {
+          double d[DIM];
+#pragma unroll
+          for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
+          pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
+        }
+      }
+    }
+  };
+  auto load_targets = [&](int tb, double (*tp)[DIM], double (*v)[KN]) {
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) {
+      const int t = min(tb + u, t1 - 1);
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) tp[u][a] = trg.pos[a * trg.n + t];
+#pragma unroll
+      for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
+    }
+  };
+  auto store_targets = [&](int tb, int nt, double (*v)[KN]) {
+#pragma unroll
+    for (int u = 0; u < kTG; ++u) {
+#pragma unroll
+      for (int b = 0; b < KN; ++b) {
+        double x = v[u][b];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && u < nt) vt[b * trg.n + tb + u] += x;
+      }
+    }
+  };
+  const double wscale = FoldedPair<FAM, KIND>::value ? (FAM == FAM_BH3 ? -k.c[0] : k.c[0]) : 1.0;  // slope folded in
+
+  const int tb0 = t0 + split * kTG;
+  if (tb0 + n_split * kTG >= t1) {
+    // ONE target group for this queue item (a few targets per leaf: grids, coarse samplers): the sources are used
+    // once, so they go from global memory straight into the pair loop.
+    double tp[kTG][DIM], v[kTG][KN];
+    load_targets(tb0, tp, v);
+    const int nt = min(kTG, t1 - tb0);
+    for (int jj = lane; jj < total; jj += 32) {
+      const int j = source_index(jj);
+      double sp[DIM], w[KM];
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
+#pragma unroll
+      for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j] * wscale;
+      eval_source(sp, w, tp, v, nt);
+    }
+    store_targets(tb0, nt, v);
+    continue;
+  }
+  // Several target groups: the concatenated source list is staged in shared memory once per (leaf, chunk of kSrcCap
+  // sources): SoA rows of DIM coordinates + KM weights, lane-contiguous (conflict-free LDS.64).  Every target group
+  // then streams it from there: no prefix search and no global load inside the pair loop.
   for (int c0 = 0; c0 < total; c0 += kSrcCap) {
     const int nc = min(kSrcCap, total - c0);
     __syncwarp();  // previous chunk no longer read
     for (int q = lane; q < nc; q += 32) {
-      const int jj = c0 + q;
-      // neighbour holding concatenated index jj: last nb with prefix[nb] <= jj
-      int lo = 0, hi = NN - 1;
-#pragma unroll
-      for (int it = 0; it < 5; ++it) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (pre[mid] <= jj) lo = mid; else hi = mid - 1;
-      }
-      const int j = st[lo] + (jj - pre[lo]);
+      const int j = source_index(c0 + q);
 #pragma unroll
       for (int a = 0; a < DIM; ++a) dat[a * kSrcCap + q] = src.pos[a * src.n + j];
 #pragma unroll
-      for (int m = 0; m < KM; ++m) {
-        double wv = swt[m * src.n + j];
-        if constexpr (FoldedPair<FAM, KIND>::value) wv *= (FAM == FAM_BH3 ? -k.c[0] : k.c[0]);  // slope folded in
-        dat[(DIM + m) * kSrcCap + q] = wv;
-      }
+      for (int m = 0; m < KM; ++m) dat[(DIM + m) * kSrcCap + q] = swt[m * src.n + j] * wscale;
     }
     __syncwarp();
-
-    for (int tb = t0 + split * kTG; tb < t1; tb += n_split * kTG) {
-      double tp[kTG][DIM];
-      double v[kTG][KN];
-#pragma unroll
-      for (int u = 0; u < kTG; ++u) {
-        const int t = min(tb + u, t1 - 1);
-#pragma unroll
-        for (int a = 0; a < DIM; ++a) tp[u][a] = trg.pos[a * trg.n + t];
-#pragma unroll
-        for (int b = 0; b < KN; ++b) v[u][b] = 0.0;
-      }
+    for (int tb = tb0; tb < t1; tb += n_split * kTG) {
+      double tp[kTG][DIM], v[kTG][KN];
+      load_targets(tb, tp, v);
       const int nt = min(kTG, t1 - tb);
       for (int q = lane; q < nc; q += 32) {
         double sp[DIM], w[KM];
@@ -181,48 +251,9 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
         for (int a = 0; a < DIM; ++a) sp[a] = dat[a * kSrcCap + q];
 #pragma unroll
         for (int m = 0; m < KM; ++m) w[m] = dat[(DIM + m) * kSrcCap + q];
-        if constexpr (FoldedPair<FAM, KIND>::value) {
-          const double c1e = k.c[1] + 1e-300;  // c^2 (+ the guard that keeps the seed finite at r = 0)
-          // (warp-uniform: slots up to the next multiple of 2 beyond nt are evaluated, not stored)
-          if (nt > kTG / 2) {
-            folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
-            if (nt > 3 * kTG / 4) folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
-            else folded_pairs<FAM, DIM, kTG / 4>(c1e, sp, w[0], tp + kTG / 2, v + kTG / 2);
-          } else if (nt > kTG / 4) {
-            folded_pairs<FAM, DIM, kTG / 2>(c1e, sp, w[0], tp, v);
-          } else {
-            folded_pairs<FAM, DIM, kTG / 4>(c1e, sp, w[0], tp, v);
-          }
-        } else if (nt == kTG) {
-          // full group: branch-free, the kTG independent pair evaluations interleave
-#pragma unroll
-          for (int u = 0; u < kTG; ++u) {
-            double d[DIM];
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
-            pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < kTG; ++u) {
-            if (u < nt) {
-              double d[DIM];
-#pragma unroll
-              for (int a = 0; a < DIM; ++a) d[a] = tp[u][a] - sp[a];
-              pair_accumulate<FAM, KIND, DIM>(k, d, w, v[u]);
-            }
-          }
-        }
+        eval_source(sp, w, tp, v, nt);
       }
-#pragma unroll
-      for (int u = 0; u < kTG; ++u) {
-#pragma unroll
-        for (int b = 0; b < KN; ++b) {
-          double x = v[u][b];
-          for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-          if (lane == 0 && u < nt) vt[b * trg.n + tb + u] += x;
-        }
-      }
+      store_targets(tb, nt, v);
     }
   }
   }
