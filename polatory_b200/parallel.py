@@ -33,12 +33,14 @@ def partition_keys(keys, world_size, dim, level, weights=None):
 
 def make_allgatherv(group, rank, owner=None):
     """The `plt_allgatherv_fn` of the C ABI over torch.distributed: in-place all-gather of uneven segments of a
-    device buffer.  Segments are padded to the longest one and exchanged with ONE all_gather_into_tensor (NCCL:
-    ncclAllGather over NVLink), then copied into place; issued on torch's current stream, which is the stream
-    the library works on."""
+    device buffer.  NCCL: one all_gather whose output tensors are the segments themselves (no staging); otherwise
+    (gloo, or an empty segment) segments are padded to the longest one, exchanged with one all_gather and copied
+    into place.  Issued on torch's current stream, which is the stream the library works on."""
     import torch
     import torch.distributed as dist
     from .krylov import _view
+
+    cache = {}
 
     def cb(_ctx, buf, offsets, world, _stream):
         try:
@@ -48,10 +50,20 @@ def make_allgatherv(group, rank, owner=None):
             if mx == 0:
                 return 0
             t = _view(buf, off[-1])
-            send = torch.zeros(mx, dtype=torch.float64, device=t.device)
+            if dist.get_backend(group) == "nccl" and min(lens) > 0:
+                # uneven segments straight into place: ONE grouped NCCL call (ProcessGroupNCCL coalesces the per-rank
+                # broadcasts of an all_gather with unequal sizes), no staging copies
+                dist.all_gather([t[off[r]:off[r + 1]] for r in range(world)], t[off[rank]:off[rank + 1]].clone(),
+                                group=group)
+                return 0
+            key = (mx, world, t.device)
+            if key not in cache:
+                cache.clear()
+                cache[key] = (torch.zeros(mx, dtype=torch.float64, device=t.device),
+                              torch.empty(world * mx, dtype=torch.float64, device=t.device))
+            send, recv = cache[key]
             send[:lens[rank]] = t[off[rank]:off[rank + 1]]
             if dist.get_backend(group) == "nccl":
-                recv = torch.empty(world * mx, dtype=torch.float64, device=t.device)
                 dist.all_gather_into_tensor(recv, send, group=group)
                 parts = [recv[r * mx:(r + 1) * mx] for r in range(world)]
             else:

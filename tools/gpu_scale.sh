@@ -11,7 +11,7 @@ for N in ${NS:-2 4 8}; do
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/${TAG}_bench_${N}gpu.json"))
+    d = json.loads([l for l in open("gpurun_out/${TAG}_bench_${N}gpu.json") if l.startswith("{")][-1])
     m = d["multi_gpu"]
     print("N=$N value", round(d["value"], 1), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), round(d["e2e"]["ms_per_step"], 3),
           "rel diff vs 1 GPU", m["n_gpu_vs_1_gpu_max_rel_diff"], "per-rank ms", m["step_ms_per_rank"], "upward", round(m["upward_ms_max"], 3),
