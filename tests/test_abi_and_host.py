@@ -331,3 +331,30 @@ def test_shim_overrides_compile_against_reference_headers(tmp_path):
                            "-I", ref_inc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                            "-L", libdir, "-lpolatory_b200", f"-Wl,-rpath,{libdir}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_partition_keys_balances_and_covers():
+    """polatory_b200/parallel.py::partition_keys: contiguous Morton key ranges cut on level-cut cell boundaries,
+    covering the whole key space, balanced by (weighted) point count; empty ranks allowed."""
+    from polatory_b200.parallel import partition_keys
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 4096, 200_000)
+    for world in (1, 2, 3, 8):
+        kb = partition_keys(keys, world, 3, 4)
+        assert kb[0] == 0 and kb[-1] == 4096 and (np.diff(kb.astype(np.int64)) >= 0).all()
+        counts = [int(((keys >= kb[r]) & (keys < kb[r + 1])).sum()) for r in range(world)]
+        assert sum(counts) == len(keys) and max(counts) - min(counts) <= 2 * len(keys) // 4096 + 1
+    # all points in one cell: one rank owns them, the others own empty ranges
+    kb = partition_keys(np.full(1000, 77), 4, 3, 4)
+    assert sum(int(kb[r] <= 77 < kb[r + 1]) for r in range(4)) == 1
+    # weighted
+    wts = np.where(keys < 2048, 3.0, 1.0)
+    kb = partition_keys(keys, 2, 3, 4, weights=wts)
+    assert kb[1] < 2048
+
+
+def test_tree_height_rule():
+    """src/fmm/utility.hpp:12-16 through the C ABI (host-only entry point)."""
+    from polatory_b200 import fmm
+    assert [fmm.tree_height(3, n) for n in (10, 1024, 100_000, 1_000_000, 10_031_040)] == [2, 3, 6, 7, 8]
+    assert [fmm.tree_height(2, n) for n in (1_000_000, 5_000_000, 20_000_000)] == [10, 11, 12]

@@ -597,3 +597,31 @@ def test_partitioned_symmetric_evaluator_shards_sum_to_full(pb, world, rng):
     assert np.array_equal(total, ref)
     ranges = [ev.target_shard_range() for ev in evs]
     assert ranges[0][0] == 0 and ranges[-1][1] == n and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+
+
+# ---------------------------------------------------------------------------------------
+# 10. 2-D at scale (config C5's evaluator): bh2, 1M sources, tree height 10, orders 10 and (12, 8)
+# ---------------------------------------------------------------------------------------
+def test_2d_bh2_one_million_points_matches_cpu_restatement(pb):
+    import torch
+    odir, ofmm, _ = _oracle()
+    dim, n, nt = 2, 1_000_000, 200_000
+    rng = np.random.default_rng(2024)
+    src = rng.uniform(0, 1, (n, dim))
+    trg = rng.uniform(0, 1, (nt, dim))
+    w = rng.uniform(-1, 1, n)
+    w -= w.mean()   # weights orthogonal to constants, as fitted bh2 weights are (keeps the sums O(1))
+    lo, hi = np.zeros(dim), np.ones(dim)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh2", [1.0, 0.0], dim), pb.Bbox(lo, hi))
+    ev.set_source_points(src)
+    ev.set_target_points(trg)
+    ev.set_weights(w)
+    for order, d, tol in ((10, -1, 1e-10), (12, 8, 5e-10)):
+        ev.force_config(order, d)
+        got = ev.evaluate()
+        assert ev.config() == {"tree_height": 10, "order": order, "d": d}
+        ref = ofmm.fmm("bh2", [1.0, 0.0], dim, 0, lo, hi, src, trg, w, order, d, 0)
+        assert _relerr(got, ref) < tol, (order, _relerr(got, ref))
+    sub = rng.choice(nt, 100, replace=False)
+    exact = ofmm.direct("bh2", [1.0, 0.0], dim, 0, src, trg[sub], w)
+    assert np.max(np.abs(got[sub] - exact)) < 1e-6 * max(np.max(np.abs(exact)), 1.0)
