@@ -686,7 +686,7 @@ struct plt_eval {
         }
         if (l > 2 && !compact_out) {
           if (timed) timer.begin("l2l", stream);
-          launch_l2l(dim, kn, tv, l, ip.dev, L, lo[l], hi[l], stream, ctr);
+          launch_l2l(dim, kn, tv, l, ip.dev, L, lo[l], hi[l], lo[l - 1], hi[l - 1], stream, ctr);
           if (timed) timer.end(stream);
         }
       }

@@ -640,6 +640,61 @@ __global__ void __launch_bounds__(leaf_threads(ORDER), ORDER <= 6 ? 6 : (ORDER <
 }
 
 // ------------------------------------------------------------------------------------
+// L2L of one level, 3-D, one CTA per PARENT cell: the first two axis contractions are shared between siblings
+// (axis 0: 2 variants, axis 1: 4), the last one produces all 2^dim children and adds them onto the children's locals
+// in HBM (which hold their own M2L result).  Register-blocked columns with the transfer matrices as kernel-parameter
+// constants, as in the fused leaf pass: 2 p^4 (1 + 2 + 4) FMAs per parent instead of 8 x 3 p^4 for child-wise CTAs,
+// 3 barriers per parent instead of 4 per child.
+// ------------------------------------------------------------------------------------
+template <int ORDER>
+__global__ void __launch_bounds__(leaf_threads(ORDER)) k_l2l_parent3(TreeView tr, int level, LeafTables tb, int kn,
+                                                                     double* __restrict__ L, int par_lo, int cell_lo,
+                                                                     int cell_hi) {
+  extern __shared__ double sm[];
+  constexpr int DIM = 3, NC = 8, p = ORDER, P = p * p * p, PC = p * p;
+  constexpr int NT = leaf_threads(ORDER);
+  double* lvl0 = sm;            // parent [P]
+  double* lvl1 = lvl0 + P;      // after axis 0: [2][P]
+  double* lvl2 = lvl1 + 2 * P;  // after axis 1: [4][P]
+  __shared__ int s_child[NC];
+  const int tid = threadIdx.x;
+  const int pl = level - 1;
+  const int pidx = par_lo + blockIdx.x;
+  const uint32_t pkey = tr.keys[tr.cell_off[pl] + pidx];
+  if (tid < NC) {
+    const int cidx = tr.dense[tr.dense_off[level] + ((pkey << DIM) | tid)];
+    s_child[tid] = (cidx >= cell_lo && cidx < cell_hi) ? cidx : -1;
+  }
+  for (int b = 0; b < kn; ++b) {
+    const double* Lp = L + (static_cast<size_t>(tr.cell_off[pl] + pidx) * kn + b) * P;
+    __syncthreads();  // previous component done with the stages; s_child written
+    for (int n = tid; n < P; n += NT) lvl0[n] = Lp[n];
+    __syncthreads();
+    for (int item = tid; item < 2 * PC; item += NT) {  // axis 0 (stride p^2)
+      const int v = item / PC, col = item - v * PC;
+      leaf_contract_col<p>(tb.child + v * p * p, lvl0 + col, PC, lvl1 + v * P + col);
+    }
+    __syncthreads();
+    for (int item = tid; item < 4 * PC; item += NT) {  // axis 1 (stride p): column = (i, k)
+      const int v = item / PC, col = item - v * PC;
+      const int i = col / p, k = col - i * p;
+      leaf_contract_col<p>(tb.child + (v & 1) * p * p, lvl1 + (v >> 1) * P + i * p * p + k, p, lvl2 + v * P + i * p * p + k);
+    }
+    __syncthreads();
+    for (int item = tid; item < NC * PC; item += NT) {  // axis 2 (stride 1) -> the children, accumulated in HBM
+      const int ch = item / PC, col = item - ch * PC;
+      const int cidx = s_child[ch];
+      if (cidx < 0) continue;
+      double out[p];
+      leaf_contract_col<p>(tb.child + (ch & 1) * p * p, lvl2 + (ch >> 1) * P + col * p, 1, out);
+      double* Lc = L + (static_cast<size_t>(tr.cell_off[level] + cidx) * kn + b) * P + col * p;
+#pragma unroll
+      for (int r = 0; r < p; ++r) Lc[r] += out[r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Leaf pass for the POLYNOMIAL interpolant (d = kClassic: orders 6, 8, 10), 3-D, without the last L2L.
 //
 // The parent's local expansion is the tensor polynomial F(x) = sum_m L_parent[m] S_m^parent(x) of degree
@@ -1647,9 +1702,27 @@ void launch_m2m(int dim, int km, const TreeView& tr, int level, const InterpDev&
 }
 
 void launch_l2l(int dim, int kn, const TreeView& tr, int level, const InterpDev& it, double* L, int cell_lo,
-                int cell_hi, cudaStream_t s, LaunchCounter& c) {
+                int cell_hi, int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c) {
   const int n = cell_hi - cell_lo;
   if (n <= 0) return;
+  static const bool no_parent = getenv("PLT_DEBUG_NO_L2L_PARENT") != nullptr;  // A/B switch
+  const int p = it.order;
+  if (dim == 3 && !no_parent && it.host_child && par_hi > par_lo && (p == 6 || p == 8 || p == 10 || p == 12)) {
+    LeafTables tb{};
+    for (int i = 0; i < 2 * p * p; ++i) tb.child[i] = it.host_child[i];
+    auto run = [&](auto od) {
+      constexpr int P_ = od.value;
+      const size_t bytes = sizeof(double) * 7 * P_ * P_ * P_;
+      smem_opt_in((const void*)k_l2l_parent3<P_>, bytes);
+      PLT_LAUNCH(c, (k_l2l_parent3<P_>), par_hi - par_lo, leaf_threads(P_), bytes, s, tr, level, tb, kn, L, par_lo,
+                 cell_lo, cell_hi);
+    };
+    if (p == 6) run(std::integral_constant<int, 6>{});
+    if (p == 8) run(std::integral_constant<int, 8>{});
+    if (p == 10) run(std::integral_constant<int, 10>{});
+    if (p == 12) run(std::integral_constant<int, 12>{});
+    return;
+  }
   const int P = nodes_per_cell(it.order, dim);
   size_t smem = sizeof(double) * (2 * it.order * it.order + 2 * static_cast<size_t>(P));
   PLT_REQUIRE(smem <= kSmemCap, "interpolation order too large for L2L shared-memory staging");

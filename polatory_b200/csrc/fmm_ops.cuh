@@ -86,8 +86,9 @@ void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsign
 void launch_m2l_idft(const M2LArgs& a, const InterpDev& it, cudaStream_t s, LaunchCounter& c);
 
 // ---- downward ----
+// children [cell_lo, cell_hi) of level child_level from their parents [par_lo, par_hi) of level child_level - 1
 void launch_l2l(int dim, int kn, const TreeView& tr, int child_level, const InterpDev& it, double* L,
-                int cell_lo, int cell_hi, cudaStream_t s, LaunchCounter& c);
+                int cell_lo, int cell_hi, int par_lo, int par_hi, cudaStream_t s, LaunchCounter& c);
 void launch_l2p(int dim, int kn, const TreeView& tr, const Box& box, const InterpDev& it, const double* L,
                 double* vt, int64_t lo, int64_t hi, cudaStream_t s, LaunchCounter& c);
 // Fused last level of the downward pass: for every parent of level leaf-1, L2L to its children
