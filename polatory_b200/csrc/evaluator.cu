@@ -211,6 +211,11 @@ struct Interpolator {
   DevBuf<double2> tw;
   DevBuf<double2> khat;  // [levels 2..height-1][7^dim][kn][km][F]
   size_t khat_level_stride = 0;
+  // Parent-block M2L (fmm_blk.cu): block operators [levels 2..height-1][27][kn][km][FB]; blk_ok = supported for this
+  // (dim, order) and every tabulated value is finite (the block sums touch k at distance 0).
+  DevBuf<double2> kblk, tw_blk;
+  size_t kblk_level_stride = 0;
+  bool blk_ok = false;
   InterpDev dev{};
   uint64_t last_use = 0;
 };
@@ -255,7 +260,7 @@ struct plt_eval {
   DevBuf<double> wt_sorted;    // [km][n_src] folded, sorted
   bool wt_dirty = true;
   DevBuf<double> M;
-  DevBuf<double2> Mhat;
+  DevBuf<double2> Mhat, Mblk;
 
   std::map<ConfigKey, std::unique_ptr<Interpolator>> interp_cache;
   uint64_t use_clock = 0;
@@ -462,7 +467,7 @@ struct plt_eval {
     const plt_config c = find_best_configuration(height);
     if (multipole_dirty || up_order != c.order || up_d != c.d) {
       Interpolator& ip = interpolator(height, c.order, c.d);
-      upward(src_tree, wt_sorted.get(), ip, M, Mhat, false);
+      upward(src_tree, wt_sorted.get(), ip, M, Mhat, Mblk, false);
       multipole_dirty = false;
       up_order = c.order;
       up_d = c.d;
@@ -525,6 +530,37 @@ struct plt_eval {
       for (int l = 2; l < height; ++l)
         launch_tabulate_m2l(kind, dim, rbf.k, box, l, ip->dev, ip->khat.get() + ip->khat_level_stride * (l - 2),
                             stream, ctr);
+      if (blk_supported(dim, order) && n_levels > 0) {
+        const int nb = blk_nf(order);
+        std::vector<double2> twb(nb);
+        const double pi = 3.14159265358979323846264338327950288;
+        for (int i = 0; i < nb; ++i) twb[i] = make_double2(std::cos(2.0 * pi * i / nb), -std::sin(2.0 * pi * i / nb));
+        ip->tw_blk.alloc(nb, stream);
+        PLT_CUDA(cudaMemcpyAsync(ip->tw_blk.get(), twb.data(), sizeof(double2) * nb, cudaMemcpyHostToDevice, stream));
+        ip->kblk_level_stride = static_cast<size_t>(27) * kn * km * blk_freqs(order);
+        ip->kblk.alloc(ip->kblk_level_stride * n_levels, stream);
+        ip->kblk.zero(stream);
+        for (int l = 2; l < height; ++l)
+          launch_tabulate_m2l_blk(kind, dim, rbf.k, box, l, order, ip->tw_blk.get(), ip->tw.get(),
+                                  ip->kblk.get() + ip->kblk_level_stride * (l - 2),
+                                  ip->khat.get() + ip->khat_level_stride * (l - 2), stream, ctr);
+        DevBuf<int> bad;
+        bad.alloc(1, stream);
+        bad.zero(stream);
+        launch_check_finite(reinterpret_cast<const double*>(ip->kblk.get()), 2 * ip->kblk.size(), bad.get(), stream, ctr);
+        launch_check_finite(reinterpret_cast<const double*>(ip->khat.get()), 2 * ip->khat.size(), bad.get(), stream, ctr);
+        int h_bad = 0;
+        PLT_CUDA(cudaMemcpyAsync(&h_bad, bad.get(), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLT_CUDA(cudaStreamSynchronize(stream));
+        ip->blk_ok = h_bad == 0;
+        if (!ip->blk_ok) {  // k is singular at distance 0 for this kind: list path; drop the near operators again
+          ip->kblk.release();
+          ip->khat.zero(stream);
+          for (int l = 2; l < height; ++l)
+            launch_tabulate_m2l(kind, dim, rbf.k, box, l, ip->dev, ip->khat.get() + ip->khat_level_stride * (l - 2),
+                                stream, ctr);
+        }
+      }
       it = interp_cache.emplace(key, std::move(ip)).first;
     }
     it->second->last_use = ++use_clock;
@@ -542,7 +578,7 @@ struct plt_eval {
   // P2M + M2M + multipole DFT (the reference's `fmm(src_tree, op, p2m | m2m)`,
   // src/fmm/fmm_evaluator.hpp:83-88).
   void upward(const Tree& st, const double* wt, Interpolator& ip, DevBuf<double>& M_, DevBuf<double2>& Mhat_,
-              bool timed, bool partitioned = false) {
+              DevBuf<double2>& Mblk_, bool timed, bool partitioned = false) {
     const int order = ip.host.order;
     const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
     TreeView sv = st.view();
@@ -583,7 +619,20 @@ struct plt_eval {
     if (timed) timer.begin("m2hat", stream);
     launch_m2hat(dim, km, sv, ip.dev, M_.get(), Mhat_.get(), stream, ctr);
     if (timed) timer.end(stream);
+    // block spectra of the cells of levels 1 .. height-2 (parent-block M2L); an empty buffer selects the list path
+    size_t blk_cells = 0;
+    for (int l = 1; l + 1 < st.height(); ++l) blk_cells += st.n_cells(l);
+    const size_t blk_elems = blk_cells * km * blk_freqs(order);
+    if (ip.blk_ok && blk_cells > 0 && blk_elems * sizeof(double2) <= kBlkSpectraBudget) {
+      Mblk_.alloc(blk_elems, stream);
+      if (timed) timer.begin("mblk", stream);
+      launch_mblk(km, sv, order, M_.get(), Mblk_.get(), stream, ctr);
+      if (timed) timer.end(stream);
+    } else {
+      Mblk_.alloc(0, stream);
+    }
   }
+  static constexpr size_t kBlkSpectraBudget = size_t{48} << 30;
 
   // In-place all-gather of M at the cut level: rank r's segment = the cells [own_cells[r], own_cells[r + 1]).
   void allgather_cut_level(const Tree& st, double* M_, size_t P) {
@@ -600,8 +649,8 @@ struct plt_eval {
 
   // M2L + L2L + L2P + P2P for the target leaves [leaf_lo, leaf_hi) -> vt (SoA [kn][n_trg], sorted).
   // vt must be zero on entry.
-  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const Tree& tt, const Plan& pl,
-                Interpolator& ip, double* vt, int leaf_lo, int leaf_hi, bool timed) {
+  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const DevBuf<double2>& Mblk_,
+                const Tree& tt, const Plan& pl, Interpolator& ip, double* vt, int leaf_lo, int leaf_hi, bool timed) {
     const int order = ip.host.order;
     const int height = tt.height(), leaf = height - 1;
     const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
@@ -644,12 +693,16 @@ struct plt_eval {
         L = arena.take<double>(std::max<size_t>(L_cells, 1) * kn * P);
         PLT_CUDA(cudaMemsetAsync(L, 0, sizeof(double) * L_cells * kn * P, stream));
       }
-      const size_t per_parent = static_cast<size_t>(nc) * kn * F;
-      const size_t budget = (size_t{8} << 30) / sizeof(double2);
+      const bool use_blk = ip.blk_ok && Mblk_.size() > 0 && pv.n_groups > 0;
+      const size_t FB = use_blk ? blk_freqs(order) : 0;
+      const size_t per_parent = static_cast<size_t>(nc) * kn * F + kn * FB;
+      const size_t budget = (static_cast<size_t>(use_blk ? 16 : 8) << 30) / sizeof(double2);
       const int chunk_parents = static_cast<int>(std::max<size_t>(1, budget / per_parent));
       int max_active = 0;
       for (int l = 2; l < height; ++l) max_active = std::max(max_active, shi[l] - slo[l]);
-      double2* Lhat = arena.take<double2>(static_cast<size_t>(std::min(chunk_parents, std::max(max_active, 1))) * per_parent);
+      const size_t chunk_cap = static_cast<size_t>(std::min(chunk_parents, std::max(max_active, 1)));
+      double2* Lhat = arena.take<double2>(chunk_cap * per_parent);
+      double2* Lhat_blk = Lhat + chunk_cap * nc * kn * F;
       // compact M2L result of the leaf level (fused path), indexed by slot - level_begin[leaf]
       double* Lc = nullptr;
       const int n_leaf_active = pl.n_active(leaf);
@@ -677,6 +730,31 @@ struct plt_eval {
           a.Lhat = Lhat;
           a.L = compact_out ? nullptr : L;
           a.Lc = compact_out ? Lc + (s0 - pv.level_begin[leaf]) * nc * kn * P : nullptr;
+          if (use_blk) {
+            // block sums over the neighbouring parents, minus the adjacent child pairs they contain (fmm_ops.cuh)
+            a.Mblk = Mblk_.get();
+            a.Kblk = ip.kblk.get() + ip.kblk_level_stride * (l - 2);
+            a.grp_first = pv.grp_first;
+            a.grp_slot = pv.grp_slot;
+            a.grp_src = pv.grp_src;
+            a.grp_lo = pv.grp_level_begin[l];
+            a.grp_hi = pv.grp_level_begin[l + 1];
+            a.slot0 = static_cast<int>(s0);
+            a.Lhat_blk = Lhat_blk;
+            if (timed) timer.begin("m2l_blk", stream);
+            launch_m2l_blk_hadamard(a, stream, ctr);
+            if (timed) timer.end(stream);
+            if (timed) timer.begin("m2l_near", stream);
+            launch_m2l_hadamard_near(a, stream, ctr);
+            if (timed) timer.end(stream);
+            if (timed) timer.begin("m2l_idft", stream);
+            launch_m2l_idft(a, ip.dev, stream, ctr);
+            if (timed) timer.end(stream);
+            if (timed) timer.begin("m2l_blk_idft", stream);
+            launch_m2l_blk_idft(a, stream, ctr);
+            if (timed) timer.end(stream);
+            continue;
+          }
           if (timed) timer.begin("m2l_hadamard", stream);
           launch_m2l_hadamard(a, stream, ctr);
           if (timed) timer.end(stream);
@@ -784,7 +862,7 @@ struct plt_eval {
     sample_plan.build(src_tree, sample_tree, stream, ctr);
     unsigned long long* d_err = arena.take<unsigned long long>(1);
     DevBuf<double> M_;
-    DevBuf<double2> Mhat_;
+    DevBuf<double2> Mhat_, Mblk_;
     plt_config found{0, 0, kClassic};
     for (int order = 8; order <= 20 && !found.order; order += 2) {
       const int min_d = order >= 12 ? 7 : kClassic;
@@ -792,9 +870,9 @@ struct plt_eval {
       for (int d = min_d; d <= max_d; ++d) {
         const auto inner_mark = arena.mark();
         Interpolator& ip = interpolator(height, order, d);
-        upward(src_tree, wt_sorted.get(), ip, M_, Mhat_, false);
+        upward(src_tree, wt_sorted.get(), ip, M_, Mhat_, Mblk_, false);
         PLT_CUDA(cudaMemsetAsync(approx_raw, 0, sizeof(double) * kn * nt, stream));
-        downward(src_tree, wt_sorted.get(), Mhat_, sample_tree, sample_plan, ip, approx_raw, 0,
+        downward(src_tree, wt_sorted.get(), Mhat_, Mblk_, sample_tree, sample_plan, ip, approx_raw, 0,
                  sample_tree.n_cells(height - 1), false);
         launch_finish_outputs(kind, dim, aniso, approx_raw, sample_tree.perm(), nt, 0, nt, approx, stream, ctr);
         PLT_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), stream));
@@ -1103,12 +1181,12 @@ struct plt_eval {
       plt_config c = find_best_configuration(height);
       Interpolator& ip = interpolator(height, c.order, c.d);
       if (height > 2 && (multipole_dirty || up_order != c.order || up_d != c.d)) {
-        upward(src_tree, wt_sorted.get(), ip, M, Mhat, true, part.on);
+        upward(src_tree, wt_sorted.get(), ip, M, Mhat, Mblk, true, part.on);
         multipole_dirty = false;
         up_order = c.order;
         up_d = c.d;
       }
-      downward(src_tree, wt_sorted.get(), Mhat, tt, plan, ip, vt, leaf_lo, leaf_hi, true);
+      downward(src_tree, wt_sorted.get(), Mhat, Mblk, tt, plan, ip, vt, leaf_lo, leaf_hi, true);
       config = c;
     }
     timer.begin("finish", stream);

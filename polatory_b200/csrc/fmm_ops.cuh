@@ -77,6 +77,15 @@ struct M2LArgs {
   double2* Lhat;         // scratch [n_active][2^dim][kn][F]
   double* L;             // target locals of the upper levels, indexed by global compact id (or null)
   double* Lc;            // compact leaf-level output [n_active][2^dim][kn][P] (used when L == null)
+  // Parent-block M2L (3-D, fmm_blk.cu); unused (null) on the list path.
+  const double2* Mblk = nullptr;   // block spectra of all source cells of levels 1 .. height-2 (id - cell_off[1])
+  const double2* Kblk = nullptr;   // this level's block operators [27][kn][km][FB]
+  const int* grp_first = nullptr;  // plan: first slot of each sibling group of active parents (all levels, ascending)
+  const int* grp_slot = nullptr;   // plan: [group][8] slot of the parent at sibling position tp, or -1
+  const int* grp_src = nullptr;    // plan: [group][64] Mblk row of the source parent at position sp of the 4^3 block, or -1
+  int grp_lo = 0, grp_hi = 0;      // this level's group range
+  int slot0 = 0;                   // plan slot of active[0] (groups are cut to the chunk [slot0, slot0 + n_active))
+  double2* Lhat_blk = nullptr;     // scratch [n_active][kn][FB]
 };
 // Fourier-space accumulation over the M2L lists of the children of the active parents.
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
@@ -84,6 +93,34 @@ void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
 void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
                        cudaStream_t s, LaunchCounter& c);
 void launch_m2l_idft(const M2LArgs& a, const InterpDev& it, cudaStream_t s, LaunchCounter& c);
+
+// ---- M2L by parent blocks (3-D; fmm_blk.cu) ----
+// The equispaced nodes of the 8 children of a cell form ONE equispaced grid of (2 order - 1)^3 distinct nodes (the
+// children share their boundary planes).  The interaction of all children of a source parent with all children of a
+// neighbouring target parent is therefore a single Toeplitz operator on that grid, diagonalised by a DFT of length
+// 4 order - 3 per axis: one complex multiply-add per frequency and parent pair instead of one per CHILD pair and child
+// frequency (9.6 x fewer at order 6).  That sum also contains the ADJACENT child pairs of different parents, which do
+// not belong to the M2L list; they are subtracted by the child-level Hadamard kernel run over the near offsets with
+// negated operators (launch_m2l_hadamard_near).  Exact up to rounding; needs k finite at distance 0 (touching cells
+// have coincident nodes), which the caller checks on the tabulated operators.
+inline int blk_nodes(int order) { return 2 * order - 1; }
+inline int blk_nf(int order) { return 4 * order - 3; }
+inline size_t blk_freqs(int order) { return static_cast<size_t>(blk_nf(order)) * blk_nf(order) * blk_nodes(order); }
+bool blk_supported(int dim, int order);
+// Block operators of one level: Kblk[D][b][a][f], D over the 3^3 parent offsets (centre unused), and the negated
+// child-level operators of the 3^3 near offsets written into Khat_level (which the far tabulation leaves at zero).
+void launch_tabulate_m2l_blk(int kind, int dim, const RbfConst& k, const Box& box, int level, int order,
+                             const double2* tw_blk, const double2* tw_child, double2* Kblk_level, double2* Khat_level,
+                             cudaStream_t s, LaunchCounter& c);
+// flag[0] |= 1 if any of the n doubles is not finite.
+void launch_check_finite(const double* x, size_t n, int* flag, cudaStream_t s, LaunchCounter& c);
+// Block spectra of all source cells of levels 1 .. height-2 from the multipoles of their children.
+void launch_mblk(int km, const TreeView& src, int order, const double* M, double2* Mblk, cudaStream_t s,
+                 LaunchCounter& c);
+void launch_m2l_blk_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
+void launch_m2l_hadamard_near(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
+// L (or Lc) of the children += pruned inverse DFT of Lhat_blk; runs after launch_m2l_idft (which stores).
+void launch_m2l_blk_idft(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
 
 // ---- downward ----
 // children [cell_lo, cell_hi) of level child_level from their parents [par_lo, par_hi) of level child_level - 1

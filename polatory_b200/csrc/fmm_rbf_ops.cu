@@ -306,22 +306,28 @@ __device__ __forceinline__ void dft_c2c_axis(const double2* in, double2* out, in
   }
 }
 
+// mode 0: the 7^dim child offsets, far ones only (the M2L lists);
+// mode 1: only the 3^dim - 1 near child offsets, NEGATED (correction pass of the parent-block M2L, fmm_blk.cu);
+// mode 2: the 3^dim - 1 parent offsets of the parent-block M2L (`it` then describes the block grid: order = 2p - 1
+//         nodes, nf = 4p - 3, cell_w = the parent's width).
 template <int FAM, int KIND, int DIM>
 __global__ void __launch_bounds__(128) k_tabulate_m2l(RbfConst k, double cell_w, InterpDev it,
                                                       double2* __restrict__ Khat, double* scratch_t,
-                                                      double2* scratch_c) {
+                                                      double2* scratch_c, int mode) {
   constexpr int KM = KindTraits<KIND, DIM>::km;
   constexpr int KN = KindTraits<KIND, DIM>::kn;
   const int p = it.order, nf = it.nf;
+  const int base = mode == 2 ? 3 : 7, half = mode == 2 ? 1 : 3;
   int o3[DIM], r = blockIdx.x;
-  bool near = true;
+  bool near = true, zero = true;
 #pragma unroll
   for (int a = DIM - 1; a >= 0; --a) {
-    o3[a] = (r % 7) - 3;
-    r /= 7;
+    o3[a] = (r % base) - half;
+    r /= base;
     near = near && o3[a] >= -1 && o3[a] <= 1;
+    zero = zero && o3[a] == 0;
   }
-  if (near) return;
+  if (zero || (mode == 0 && near) || (mode == 1 && !near)) return;
   int NT = 1, F = p;
   for (int a = 0; a < DIM; ++a) NT *= nf;
   for (int a = 0; a + 1 < DIM; ++a) F *= nf;
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(128) k_tabulate_m2l(RbfConst k, double cell_w,
   double2* bufA = scratch_c + static_cast<size_t>(blockIdx.x) * 2 * F;
   double2* bufB = bufA + F;
   const double h = cell_w / (p - 1);
-  double scale = 1.0;
+  double scale = mode == 1 ? -1.0 : 1.0;
   for (int a = 0; a < DIM; ++a) scale /= nf;
   for (int comp = 0; comp < KN * KM; ++comp) {
     for (int e = threadIdx.x; e < NT; e += blockDim.x) {
@@ -340,7 +346,10 @@ __global__ void __launch_bounds__(128) k_tabulate_m2l(RbfConst k, double cell_w,
         int ia = rr % nf;
         rr /= nf;
         int delta = ia < p ? ia : ia - nf;
-        d[a] = h * delta - cell_w * o3[a];
+        // modes 1 and 2 take the distance from the INTEGER node offset, so that a node pair seen through the block grid
+        // and through the child grid gets the same bits and coincident nodes of touching cells are at distance exactly 0
+        // (kernels that are discontinuous there, e.g. the gradient of |r|, must cancel exactly between the two passes)
+        d[a] = mode == 0 ? h * delta - cell_w * o3[a] : h * static_cast<double>(delta - (p - 1) * o3[a]);
       }
       double blk[KN * KM];
       kernel_block<FAM, KIND, DIM>(k, d, blk);
@@ -407,7 +416,34 @@ void launch_tabulate_m2l(int kind, int dim, const RbfConst& k, const Box& box, i
   const double cell_w = box.width / static_cast<double>(1 << level);
   dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
     PLT_LAUNCH(c, (k_tabulate_m2l<fam.value, knd.value, dm.value>), noff, 128, 0, s, k, cell_w, it, Khat_level,
-               st.get(), sc.get());
+               st.get(), sc.get(), 0);
+  });
+}
+
+void launch_tabulate_m2l_blk(int kind, int dim, const RbfConst& k, const Box& box, int level, int order,
+                             const double2* tw_blk, const double2* tw_child, double2* Kblk_level, double2* Khat_level,
+                             cudaStream_t s, LaunchCounter& c) {
+  const double cell_w = box.width / static_cast<double>(1 << level);
+  InterpDev child{};  // only order, nf and tw are read by the tabulation
+  child.order = order;
+  child.nf = 2 * order - 1;
+  child.tw = tw_child;
+  InterpDev blk{};
+  blk.order = blk_nodes(order);
+  blk.nf = blk_nf(order);
+  blk.tw = tw_blk;
+  const int noff = ipow(7, dim), noff_b = ipow(3, dim);
+  const size_t NT = ipow(child.nf, dim), F = freqs_per_cell(order, dim);
+  const size_t NTB = ipow(blk.nf, dim), FB = blk_freqs(order);
+  DevBuf<double> st;
+  DevBuf<double2> sc;
+  st.alloc(std::max(noff * NT, noff_b * NTB), s);
+  sc.alloc(std::max(noff * 2 * F, noff_b * 2 * FB), s);
+  dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
+    PLT_LAUNCH(c, (k_tabulate_m2l<fam.value, knd.value, dm.value>), noff, 128, 0, s, k, cell_w, child, Khat_level,
+               st.get(), sc.get(), 1);
+    PLT_LAUNCH(c, (k_tabulate_m2l<fam.value, knd.value, dm.value>), noff_b, 128, 0, s, k, 2.0 * cell_w, blk, Kblk_level,
+               st.get(), sc.get(), 2);
   });
 }
 

@@ -68,8 +68,34 @@ __global__ void k_plan_p2p_mark(TreeView src, TreeView trg, int* __restrict__ fl
   flags[i] = found;
 }
 
-// counts: [0] n_active, [1] n_p2p, [2 + l] level_begin[l] for l = 0 .. height.
-__global__ void k_plan_bounds(TreeView trg, const int* __restrict__ raw, int* __restrict__ counts) {
+__device__ __forceinline__ int level_of_parent(const TreeView& trg, int g) {
+  const int leaf = trg.height - 1;
+  int l = 1;
+  while (l + 1 < leaf && g >= trg.cell_off[l + 1]) ++l;
+  return l;
+}
+
+// Sibling groups (plan.cuh): flags[i] = 1 if the i-th active parent starts a run of parents with a common parent.
+__global__ void k_plan_grp_flags(TreeView trg, const int* __restrict__ raw, const int* __restrict__ counts, int n_par,
+                                 int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_par) return;
+  int f = 0;
+  if (i < counts[0]) {
+    f = 1;
+    if (i > 0) {
+      const int g = raw[i] + trg.cell_off[1], gp = raw[i - 1] + trg.cell_off[1];
+      f = level_of_parent(trg, g) != level_of_parent(trg, gp) || (trg.keys[g] >> trg.dim) != (trg.keys[gp] >> trg.dim);
+    }
+  }
+  flags[i] = f;
+}
+
+// counts: [0] n_active, [1] n_p2p, [2 + l] level_begin[l] for l = 0 .. height, [27] n_groups,
+// [28 + l] grp_level_begin[l] (grp_first == nullptr: no groups).
+constexpr int kCountGroups = 27, kCountsSize = 28 + 25;
+__global__ void k_plan_bounds(TreeView trg, const int* __restrict__ raw, const int* __restrict__ grp_first,
+                              int* __restrict__ counts) {
   const int l = threadIdx.x;
   if (l > trg.height) return;
   const int n = counts[0];
@@ -89,6 +115,44 @@ __global__ void k_plan_bounds(TreeView trg, const int* __restrict__ raw, int* __
     v = lo;
   }
   counts[2 + l] = v;
+  int gv = 0;
+  if (grp_first) {  // first group whose first slot is >= level_begin[l] (a group never spans two levels)
+    int lo = 0, hi = counts[kCountGroups];
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (grp_first[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    gv = lo;
+  }
+  counts[kCountGroups + 1 + l] = gv;
+}
+
+// grp_slot / grp_src (plan.cuh), 3-D: one thread per (group, position of the 4^3 source block).
+__global__ void k_plan_grp_fill(TreeView src, TreeView trg, const int* __restrict__ raw, const int* __restrict__ grp_first,
+                                int n_groups, int n_active, int* __restrict__ grp_slot, int* __restrict__ grp_src) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int grp = static_cast<int>(t >> 6), e = static_cast<int>(t & 63);
+  if (grp >= n_groups) return;
+  const int head = grp_first[grp];
+  const int next = grp + 1 < n_groups ? grp_first[grp + 1] : n_active;
+  const int g = raw[head] + trg.cell_off[1];
+  const int pl = level_of_parent(trg, g);
+  int gc[3];
+  morton_decode<3>(trg.keys[g] >> 3, gc);
+  const int nside = 1 << pl;
+  int q[3] = {2 * gc[0] + (e >> 4) - 1, 2 * gc[1] + ((e >> 2) & 3) - 1, 2 * gc[2] + (e & 3) - 1};
+  int id = -1;
+  if (q[0] >= 0 && q[0] < nside && q[1] >= 0 && q[1] < nside && q[2] >= 0 && q[2] < nside) {
+    const int ci = src.dense[src.dense_off[pl] + morton_encode<3>(q)];
+    if (ci >= 0) id = src.cell_off[pl] + ci - src.cell_off[1];
+  }
+  grp_src[static_cast<size_t>(grp) * 64 + e] = id;
+  if (e < 8) {
+    int slot = -1;
+    for (int j = head; j < next; ++j)
+      if ((trg.keys[raw[j] + trg.cell_off[1]] & 7u) == static_cast<unsigned>(e)) slot = j;
+    grp_slot[static_cast<size_t>(grp) * 8 + e] = slot;
+  }
 }
 
 struct LevelBegin {
@@ -173,7 +237,7 @@ void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCo
   const int dim = tv.dim, height = tv.height, leaf = height - 1;
   const int nn = dim == 1 ? 3 : (dim == 2 ? 9 : 27), nc = 1 << dim;
   view_ = PlanView{};
-  counts_.alloc(2 + 25, stream);
+  counts_.alloc(kCountsSize, stream);
   counts_.zero(stream);
 
   // ---- phase 1: flags + compaction (M2L parents of all levels at once; P2P leaves) ----
@@ -192,7 +256,20 @@ void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCo
     PLT_CUDA(cub::DeviceSelect::Flagged(tmp_.get(), tmp_bytes, iota, flags_.get(), active_.get(), counts_.get(), n_par,
                                         stream));
     ctr.n += 1;
+    if (dim == 3) {  // sibling groups of the active parents
+      grp_flags_.alloc(n_par, stream);
+      grp_first_.alloc(n_par, stream);
+      PLT_LAUNCH(ctr, k_plan_grp_flags, ceil_div(n_par, 256), 256, 0, stream, tv, active_.get(), counts_.get(), n_par,
+                 grp_flags_.get());
+      PLT_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, grp_flags_.get(), grp_first_.get(),
+                                          counts_.get() + kCountGroups, n_par, stream));
+      if (tmp_bytes > tmp_.size()) tmp_.alloc(tmp_bytes, stream);
+      PLT_CUDA(cub::DeviceSelect::Flagged(tmp_.get(), tmp_bytes, iota, grp_flags_.get(), grp_first_.get(),
+                                          counts_.get() + kCountGroups, n_par, stream));
+      ctr.n += 1;
+    }
   }
+  const bool grouped = n_par > 0 && dim == 3;
   const int n_leaf = tv.n_cells[leaf];
   p2p_flags_.alloc(n_leaf, stream);
   p2p_leaves_.alloc(n_leaf, stream);
@@ -205,9 +282,10 @@ void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCo
   PLT_CUDA(cub::DeviceSelect::Flagged(tmp_.get(), tmp_bytes, iota, p2p_flags_.get(), p2p_leaves_.get(),
                                       counts_.get() + 1, n_leaf, stream));
   ctr.n += 1;
-  PLT_LAUNCH(ctr, k_plan_bounds, 1, 32, 0, stream, tv, active_.get(), counts_.get());
+  PLT_LAUNCH(ctr, k_plan_bounds, 1, 32, 0, stream, tv, active_.get(), grouped ? grp_first_.get() : nullptr,
+             counts_.get());
 
-  int host[2 + 25];
+  int host[kCountsSize];
   PLT_CUDA(cudaMemcpyAsync(host, counts_.get(), sizeof(host), cudaMemcpyDeviceToHost, stream));
   PLT_CUDA(cudaStreamSynchronize(stream));  // the one synchronisation of the plan
   const int n_active = host[0];
@@ -217,6 +295,8 @@ void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCo
     view_.level_begin[l] = host[2 + l];
   }
   view_.n_active = n_active;
+  view_.n_groups = grouped ? host[kCountGroups] : 0;
+  for (int l = 0; l <= height; ++l) view_.grp_level_begin[l] = grouped ? host[kCountGroups + 1 + l] : 0;
   view_.n_p2p = host[1];
   view_.p2p_leaves = p2p_leaves_.get();
 
@@ -232,6 +312,15 @@ void Plan::build(const Tree& src, const Tree& trg, cudaStream_t stream, LaunchCo
       if (dim == 1) PLT_LAUNCH(ctr, k_plan_fill<1>, ceil_div(threads, 256), 256, 0, stream, sv, tv, active_.get(), lb, n_active, active_out, src_ids_.get(), trg_mask_.get(), leaf_slot_.get());
       if (dim == 2) PLT_LAUNCH(ctr, k_plan_fill<2>, ceil_div(threads, 256), 256, 0, stream, sv, tv, active_.get(), lb, n_active, active_out, src_ids_.get(), trg_mask_.get(), leaf_slot_.get());
       if (dim == 3) PLT_LAUNCH(ctr, k_plan_fill<3>, ceil_div(threads, 256), 256, 0, stream, sv, tv, active_.get(), lb, n_active, active_out, src_ids_.get(), trg_mask_.get(), leaf_slot_.get());
+    }
+    if (view_.n_groups > 0) {
+      grp_slot_.alloc(static_cast<size_t>(view_.n_groups) * 8, stream);
+      grp_src_.alloc(static_cast<size_t>(view_.n_groups) * 64, stream);
+      PLT_LAUNCH(ctr, k_plan_grp_fill, ceil_div(static_cast<int64_t>(view_.n_groups) * 64, 256), 256, 0, stream, sv, tv,
+                 active_.get(), grp_first_.get(), view_.n_groups, n_active, grp_slot_.get(), grp_src_.get());
+      view_.grp_first = grp_first_.get();
+      view_.grp_slot = grp_slot_.get();
+      view_.grp_src = grp_src_.get();
     }
     view_.active = active_out;
     view_.src_ids = src_ids_.get();

@@ -29,6 +29,14 @@ struct PlanView {
   const int* leaf_meta;
   int level_begin[25];
   int n_active;
+  // Sibling groups of active parents (3-D parent-block M2L, fmm_blk.cu): maximal runs of active parents with the same
+  // parent (they are consecutive in Morton order).  Level l: groups [grp_level_begin[l], grp_level_begin[l + 1]).
+  const int* grp_first = nullptr;  // [n_groups] first slot
+  const int* grp_slot = nullptr;   // [n_groups][8] slot of the sibling at position tp = key & 7, or -1
+  const int* grp_src = nullptr;    // [n_groups][64] source cell (global id - cell_off[1]) at position sp = (sx * 4 + sy) * 4 + sz
+                                   // of the 4^3 block of cells around the group (s = coordinate - 2 * grandparent + 1), or -1
+  int grp_level_begin[25];
+  int n_groups = 0;
   // P2P: target leaves with at least one non-empty adjacent source leaf (ascending).
   const int* p2p_leaves;
   int n_p2p;
@@ -47,6 +55,7 @@ class Plan {
   bool built_ = false;
   PlanView view_{};
   DevBuf<int> flags_, active_, src_ids_, leaf_slot_, leaf_meta_, p2p_flags_, p2p_leaves_, counts_;
+  DevBuf<int> grp_flags_, grp_first_, grp_slot_, grp_src_;
   DevBuf<unsigned char> trg_mask_, tmp_;
 };
 

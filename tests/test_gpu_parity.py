@@ -420,7 +420,7 @@ def test_device_resident_io_and_weight_update(pb, rng):
         ref = ofmm.fmm("bh3", [1.0, 0.0], dim, 0, -np.ones(dim), np.ones(dim), src, trg, w, 8, -1, 0)
         assert _relerr(out.cpu().numpy(), ref) < 1e-10
     assert ev.launch_count() > 0
-    assert "m2l_hadamard" in ev.phase_times()
+    assert {"m2l_hadamard", "m2l_blk"} & set(ev.phase_times())  # list path or parent-block path
 
 
 # ---------------------------------------------------------------------------------------
