@@ -202,6 +202,14 @@ int64_t plt_eval_launch_count(plt_eval* h);
  * on the calling thread).  Never NULL. */
 const char* plt_last_error(plt_eval* h);
 
+/* M2L by parent blocks (3-D, orders 6 and 8; polatory_b200/csrc/fmm_blk.cu): a level of the far field is computed
+ * through the block spectra of sibling cells when the source tree fills at least `min_fill` of the cells of that
+ * level and that level has at least 8192 source cells (dense tables: volume clouds), else through the per-pair
+ * lists.  Process-wide; default 0.25; 0 = wherever supported, > 1 = never.  Both paths evaluate the same sums (rounding
+ * differs); the choice depends on the source tree only, so every rank of a partition takes the same one.
+ * Returns the previous value. */
+double plt_set_block_m2l_min_fill(double min_fill);
+
 /* FP64 FMA peak of the current device, measured with a DFMA-chain microbenchmark (TFLOP/s);
  * the denominator of the FP64 roofline. */
 int plt_measure_fp64_peak(double* tflops);

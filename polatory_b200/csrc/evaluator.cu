@@ -205,6 +205,12 @@ struct ConfigKey {
 // Counterpart of scalfmm::interpolation::interpolator(kernel, order, tree_height, box_width, d)
 // cached like the reference's LruCache<InterpolatorConfiguration, Interpolator>(2)
 // (src/fmm/fmm_evaluator.hpp:249-252,292).
+// Block spectra of the parent-block M2L and the children levels they were built for (bit l).
+struct BlkSpectra {
+  DevBuf<double2> buf;
+  unsigned levels = 0;
+};
+
 struct Interpolator {
   InterpTables host;
   DevBuf<double> beta, child;
@@ -260,7 +266,8 @@ struct plt_eval {
   DevBuf<double> wt_sorted;    // [km][n_src] folded, sorted
   bool wt_dirty = true;
   DevBuf<double> M;
-  DevBuf<double2> Mhat, Mblk;
+  DevBuf<double2> Mhat;
+  BlkSpectra Mblk;
 
   std::map<ConfigKey, std::unique_ptr<Interpolator>> interp_cache;
   uint64_t use_clock = 0;
@@ -578,7 +585,7 @@ struct plt_eval {
   // P2M + M2M + multipole DFT (the reference's `fmm(src_tree, op, p2m | m2m)`,
   // src/fmm/fmm_evaluator.hpp:83-88).
   void upward(const Tree& st, const double* wt, Interpolator& ip, DevBuf<double>& M_, DevBuf<double2>& Mhat_,
-              DevBuf<double2>& Mblk_, bool timed, bool partitioned = false) {
+              BlkSpectra& Mblk_, bool timed, bool partitioned = false) {
     const int order = ip.host.order;
     const size_t P = nodes_per_cell(order, dim), F = freqs_per_cell(order, dim);
     TreeView sv = st.view();
@@ -619,17 +626,30 @@ struct plt_eval {
     if (timed) timer.begin("m2hat", stream);
     launch_m2hat(dim, km, sv, ip.dev, M_.get(), Mhat_.get(), stream, ctr);
     if (timed) timer.end(stream);
-    // block spectra of the cells of levels 1 .. height-2 (parent-block M2L); an empty buffer selects the list path
+    // block spectra (parent-block M2L) of the parents of the levels that are dense enough, stored for the cells of
+    // levels 1 .. deepest such parent level; an empty buffer selects the list path everywhere
+    int blk_top = 0;  // deepest children level on the block path
+    if (ip.blk_ok)
+      for (int l = 2; l < st.height(); ++l)
+        if (blk_level_dense(l, st.n_cells(l))) blk_top = l;
     size_t blk_cells = 0;
-    for (int l = 1; l + 1 < st.height(); ++l) blk_cells += st.n_cells(l);
+    for (int l = 1; l < blk_top; ++l) blk_cells += st.n_cells(l);
     const size_t blk_elems = blk_cells * km * blk_freqs(order);
-    if (ip.blk_ok && blk_cells > 0 && blk_elems * sizeof(double2) <= kBlkSpectraBudget) {
-      Mblk_.alloc(blk_elems, stream);
+    Mblk_.levels = 0;
+    if (blk_top >= 2 && blk_elems * sizeof(double2) <= kBlkSpectraBudget) {
+      Mblk_.buf.alloc(blk_elems, stream);
       if (timed) timer.begin("mblk", stream);
-      launch_mblk(km, sv, order, M_.get(), Mblk_.get(), stream, ctr);
+      for (int l = 2; l <= blk_top; ++l)  // runs of consecutive dense levels share a launch
+        if (blk_level_dense(l, st.n_cells(l))) {
+          int hi = l;
+          while (hi + 1 <= blk_top && blk_level_dense(hi + 1, st.n_cells(hi + 1))) ++hi;
+          launch_mblk(km, sv, order, l - 1, hi - 1, M_.get(), Mblk_.buf.get(), stream, ctr);
+          for (int q = l; q <= hi; ++q) Mblk_.levels |= 1u << q;
+          l = hi;
+        }
       if (timed) timer.end(stream);
     } else {
-      Mblk_.alloc(0, stream);
+      Mblk_.buf.alloc(0, stream);
     }
   }
   static constexpr size_t kBlkSpectraBudget = size_t{48} << 30;
@@ -649,7 +669,7 @@ struct plt_eval {
 
   // M2L + L2L + L2P + P2P for the target leaves [leaf_lo, leaf_hi) -> vt (SoA [kn][n_trg], sorted).
   // vt must be zero on entry.
-  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const DevBuf<double2>& Mblk_,
+  void downward(const Tree& st, const double* wt, const DevBuf<double2>& Mhat_, const BlkSpectra& Mblk_,
                 const Tree& tt, const Plan& pl, Interpolator& ip, double* vt, int leaf_lo, int leaf_hi, bool timed) {
     const int order = ip.host.order;
     const int height = tt.height(), leaf = height - 1;
@@ -693,7 +713,7 @@ struct plt_eval {
         L = arena.take<double>(std::max<size_t>(L_cells, 1) * kn * P);
         PLT_CUDA(cudaMemsetAsync(L, 0, sizeof(double) * L_cells * kn * P, stream));
       }
-      const bool use_blk = ip.blk_ok && Mblk_.size() > 0 && pv.n_groups > 0;
+      const bool use_blk = ip.blk_ok && Mblk_.levels != 0 && pv.n_groups > 0;
       const size_t FB = use_blk ? blk_freqs(order) : 0;
       const size_t per_parent = static_cast<size_t>(nc) * kn * F + kn * FB;
       const size_t budget = (static_cast<size_t>(use_blk ? 16 : 8) << 30) / sizeof(double2);
@@ -730,9 +750,9 @@ struct plt_eval {
           a.Lhat = Lhat;
           a.L = compact_out ? nullptr : L;
           a.Lc = compact_out ? Lc + (s0 - pv.level_begin[leaf]) * nc * kn * P : nullptr;
-          if (use_blk) {
+          if (use_blk && ((Mblk_.levels >> l) & 1u)) {
             // block sums over the neighbouring parents, minus the adjacent child pairs they contain (fmm_ops.cuh)
-            a.Mblk = Mblk_.get();
+            a.Mblk = Mblk_.buf.get();
             a.Kblk = ip.kblk.get() + ip.kblk_level_stride * (l - 2);
             a.grp_first = pv.grp_first;
             a.grp_slot = pv.grp_slot;
@@ -862,7 +882,8 @@ struct plt_eval {
     sample_plan.build(src_tree, sample_tree, stream, ctr);
     unsigned long long* d_err = arena.take<unsigned long long>(1);
     DevBuf<double> M_;
-    DevBuf<double2> Mhat_, Mblk_;
+    DevBuf<double2> Mhat_;
+    BlkSpectra Mblk_;
     plt_config found{0, 0, kClassic};
     for (int order = 8; order <= 20 && !found.order; order += 2) {
       const int min_d = order >= 12 ? 7 : kClassic;
@@ -1291,6 +1312,8 @@ int plt_eval_set_accuracy(plt_eval* h, double accuracy) {
 int plt_eval_evaluate(plt_eval* h, double* out, int64_t len) {
   return guarded(h, [&] { h->evaluate(out, len); });
 }
+
+double plt_set_block_m2l_min_fill(double min_fill) { return blk_set_min_fill(min_fill); }
 
 int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_override) {
   return guarded(h, [&] {

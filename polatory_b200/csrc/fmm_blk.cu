@@ -48,8 +48,8 @@ __device__ __forceinline__ int level_of_cell(const TreeView& tr, int g, int last
 // twiddles are kernel-parameter constants.
 // ------------------------------------------------------------------------------------
 template <int ORDER>
-__global__ void __launch_bounds__(256) k_mblk3(TreeView src, int km, const double* __restrict__ M,
-                                               double2* __restrict__ Mblk, TwBlk tw) {
+__global__ void __launch_bounds__(256) k_mblk3(TreeView src, int km, int first_cell, int n_par,
+                                               const double* __restrict__ M, double2* __restrict__ Mblk, TwBlk tw) {
   constexpr int p = ORDER, n = 2 * p - 1, NB = 4 * p - 3, P = p * p * p;
   constexpr size_t FB = static_cast<size_t>(NB) * NB * n;
   extern __shared__ double2 sm2[];
@@ -59,9 +59,8 @@ __global__ void __launch_bounds__(256) k_mblk3(TreeView src, int km, const doubl
   __shared__ int s_child[8];
   __shared__ int s_on;
   const int leaf = src.height - 1;
-  const int n_par = src.cell_off[leaf] - src.cell_off[1];
   for (int w = blockIdx.x; w < n_par * km; w += gridDim.x) {
-    const int cell = w / km, comp = w - cell * km;
+    const int cell = first_cell + w / km, comp = w % km;  // cell: global id - cell_off[1]
     __syncthreads();  // previous pass done with the buffers and the child table
     if (threadIdx.x < 8) {
       const int g = src.cell_off[1] + cell;
@@ -271,7 +270,12 @@ __global__ void __launch_bounds__(kGrpWarps * 32, VEC ? 1 : 2) k_m2l_grouped3(M2
   const int glo = s_g[0], n_g = s_g[1] - s_g[0];
   if (n_g <= 0) return;
 
-  const long long n_items = static_cast<long long>(n_ftiles) * n_g;
+  // Work items = (block of kGrpWarps frequency tiles, group), tile-block-major, cut into equal contiguous ranges per CTA.
+  // The warps of a CTA take the SAME groups at kGrpWarps neighbouring tiles: identical control flow (they walk through
+  // the ~40 KB of straight-line position code together and share its instruction-cache lines; with every warp on its
+  // own group the kernel stalled on instruction fetch) and 4 KB contiguous of every spectrum row per CTA.
+  const int n_tb = (n_ftiles + kGrpWarps - 1) / kGrpWarps;
+  const long long n_items = static_cast<long long>(n_tb) * n_g;
   const long long q_lo = n_items * blockIdx.x / gridDim.x, q_hi = n_items * (blockIdx.x + 1) / gridDim.x;
   const double2** ptrs = s_ptr[warp];
   const double2* ring = &s_ring[warp][0][lane];
@@ -282,11 +286,13 @@ __global__ void __launch_bounds__(kGrpWarps * 32, VEC ? 1 : 2) k_m2l_grouped3(M2
   const double2* ops = NEAR ? a.Khat : a.Kblk;
   double2* result = NEAR ? a.Lhat : a.Lhat_blk;
   for (long long q0 = q_lo; q0 < q_hi;) {
-    const int ftile = static_cast<int>(q0 / n_g);
-    const int g_lo = static_cast<int>(q0 - static_cast<long long>(ftile) * n_g);
-    const long long seg_end = min(q_hi, static_cast<long long>(ftile + 1) * n_g);
+    const int tb = static_cast<int>(q0 / n_g);
+    const int g_lo = static_cast<int>(q0 - static_cast<long long>(tb) * n_g);
+    const long long seg_end = min(q_hi, static_cast<long long>(tb + 1) * n_g);
     const int g_hi = g_lo + static_cast<int>(seg_end - q0);
     q0 = seg_end;
+    const int ftile = tb * kGrpWarps + warp;
+    if (ftile >= n_ftiles) continue;  // last tile block: no CTA-wide barrier below
     const int f = ftile * kGrpTF + lane;
     const bool fok = f < F;
     const int fl = fok ? f : F - 1;  // idle lanes of the last tile compute on a valid address and store nothing
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, VEC ? 1 : 2) k_m2l_grouped3(M2
       const size_t rstride = static_cast<size_t>(km) * F;
       const unsigned long long lane_off = static_cast<unsigned long long>(fl) * sizeof(double2);
 
-      for (int g = g_lo + warp; g < g_hi; g += kGrpWarps) {
+      for (int g = g_lo; g < g_hi; ++g) {
         // ---- targets and source rows of this group ----
         int local = -1;     // lane tp < 8: index of target tp in the result (or -1)
         int r0, r1;         // spectrum rows of the source positions lane and lane + 32 (or -1)
@@ -514,14 +520,16 @@ __global__ void k_check_finite(const double* __restrict__ x, size_t n, int* __re
 }
 
 template <int ORDER>
-void launch_mblk_t(int km, const TreeView& src, const double* M, double2* Mblk, cudaStream_t s, LaunchCounter& c) {
+void launch_mblk_t(int km, const TreeView& src, int par_lo, int par_hi, const double* M, double2* Mblk, cudaStream_t s,
+                   LaunchCounter& c) {
   constexpr int n = 2 * ORDER - 1, NB = 4 * ORDER - 3;
-  const int n_par = src.cell_off[src.height - 1] - src.cell_off[1];
+  const int first_cell = src.cell_off[par_lo] - src.cell_off[1];
+  const int n_par = src.cell_off[par_hi + 1] - src.cell_off[par_lo];
   if (n_par <= 0) return;
   const size_t smem = sizeof(double2) * (n * n * n + n * NB * n);
   smem_opt_in((const void*)k_mblk3<ORDER>, smem);
   const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(n_par) * km, kNumSM * 16));
-  PLT_LAUNCH(c, (k_mblk3<ORDER>), grid, 256, smem, s, src, km, M, Mblk, make_tw_blk(ORDER));
+  PLT_LAUNCH(c, (k_mblk3<ORDER>), grid, 256, smem, s, src, km, first_cell, n_par, M, Mblk, make_tw_blk(ORDER));
 }
 
 template <int ORDER>
@@ -534,6 +542,19 @@ void launch_idft_blk_t(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
 
 }  // namespace
 
+namespace {
+double g_blk_min_fill = [] {
+  const char* e = getenv("PLT_BLK_MIN_FILL");
+  return e ? atof(e) : 0.25;
+}();
+}  // namespace
+double blk_min_fill() { return g_blk_min_fill; }
+double blk_set_min_fill(double v) {
+  const double old = g_blk_min_fill;
+  g_blk_min_fill = v;
+  return old;
+}
+
 bool blk_supported(int dim, int order) {
   static const bool off = getenv("PLT_DEBUG_NO_BLK") != nullptr;  // A/B switch for parity bisection
   return !off && dim == 3 && (order == 6 || order == 8);
@@ -544,12 +565,13 @@ void launch_check_finite(const double* x, size_t n, int* flag, cudaStream_t s, L
   PLT_LAUNCH(c, k_check_finite, static_cast<int>(std::min<size_t>((n + 255) / 256, kNumSM * 8)), 256, 0, s, x, n, flag);
 }
 
-void launch_mblk(int km, const TreeView& src, int order, const double* M, double2* Mblk, cudaStream_t s,
-                 LaunchCounter& c) {
-  if (src.height <= 2) return;
+void launch_mblk(int km, const TreeView& src, int order, int par_lo, int par_hi, const double* M, double2* Mblk,
+                 cudaStream_t s, LaunchCounter& c) {
+  if (src.height <= 2 || par_hi < par_lo) return;
+  PLT_REQUIRE(par_lo >= 1 && par_hi <= src.height - 2, "block spectra: parent levels out of range");
   switch (order) {
-    case 6: launch_mblk_t<6>(km, src, M, Mblk, s, c); return;
-    case 8: launch_mblk_t<8>(km, src, M, Mblk, s, c); return;
+    case 6: launch_mblk_t<6>(km, src, par_lo, par_hi, M, Mblk, s, c); return;
+    case 8: launch_mblk_t<8>(km, src, par_lo, par_hi, M, Mblk, s, c); return;
     default: throw Error(PLT_ERR_INVALID, "parent-block M2L: unsupported order");
   }
 }
@@ -558,7 +580,7 @@ namespace {
 template <bool NEAR>
 void launch_grouped(const M2LArgs& a, int F, int n_groups, cudaStream_t s, LaunchCounter& c) {
   const int n_ftiles = ceil_div(F, kGrpTF);
-  const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(n_groups, kGrpWarps);
+  const long long rounds = static_cast<long long>(ceil_div(n_ftiles, kGrpWarps)) * n_groups;
   if (a.kn * a.km == 1) {
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(2 * kNumSM, rounds)));
     PLT_LAUNCH(c, (k_m2l_grouped3<false, NEAR>), grid, kGrpWarps * 32, 0, s, a, F, n_ftiles);

@@ -107,6 +107,18 @@ inline int blk_nodes(int order) { return 2 * order - 1; }
 inline int blk_nf(int order) { return 4 * order - 3; }
 inline size_t blk_freqs(int order) { return static_cast<size_t>(blk_nf(order)) * blk_nf(order) * blk_nodes(order); }
 bool blk_supported(int dim, int order);
+// Process-wide density threshold (plt_set_block_m2l_min_fill) and the per-level decision: the children level l goes
+// through the block path when the source tree has at least min_fill * 8^l cells there.
+double blk_min_fill();
+double blk_set_min_fill(double v);
+// Small levels stay on the list path unless the block path is forced (min_fill <= 0): their launches are
+// latency-bound either way and the extra passes do not pay (measured on config #3: +0.4 ms for levels 2 - 4).
+constexpr int kBlkMinCells = 8192;
+inline bool blk_level_dense(int level, int n_src_cells) {
+  const double f = blk_min_fill();
+  return static_cast<double>(n_src_cells) >= f * static_cast<double>(1ll << (3 * level)) &&
+         (f <= 0.0 || n_src_cells >= kBlkMinCells);
+}
 // Block operators of one level: Kblk[D][b][a][f], D over the 3^3 parent offsets (centre unused), and the negated
 // child-level operators of the 3^3 near offsets written into Khat_level (which the far tabulation leaves at zero).
 void launch_tabulate_m2l_blk(int kind, int dim, const RbfConst& k, const Box& box, int level, int order,
@@ -115,8 +127,9 @@ void launch_tabulate_m2l_blk(int kind, int dim, const RbfConst& k, const Box& bo
 // flag[0] |= 1 if any of the n doubles is not finite.
 void launch_check_finite(const double* x, size_t n, int* flag, cudaStream_t s, LaunchCounter& c);
 // Block spectra of all source cells of levels 1 .. height-2 from the multipoles of their children.
-void launch_mblk(int km, const TreeView& src, int order, const double* M, double2* Mblk, cudaStream_t s,
-                 LaunchCounter& c);
+// (parents whose level is in [par_lo, par_hi] only; Mblk is indexed by global cell id - cell_off[1])
+void launch_mblk(int km, const TreeView& src, int order, int par_lo, int par_hi, const double* M, double2* Mblk,
+                 cudaStream_t s, LaunchCounter& c);
 void launch_m2l_blk_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
 void launch_m2l_hadamard_near(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
 // L (or Lc) of the children += pruned inverse DFT of Lhat_blk; runs after launch_m2l_idft (which stores).

@@ -144,6 +144,50 @@ def test_fmm_branch_of_remaining_rbfs(pb, dim, name, params, kind, rng):
 # ---------------------------------------------------------------------------------------
 # 3. the reference's own test shapes
 # ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cloud", ["surface", "volume"])
+@pytest.mark.parametrize("kind", [0, 1, 3])
+def test_block_and_list_m2l_agree_with_cpu_restatement(pb, cloud, kind, rng):
+    """Parent-block M2L (fmm_blk.cu) forced on (min_fill 0) and off (min_fill 2) on a sparse surface cloud and a dense
+    volume cloud, orders 6 and 8: both must equal the oracle's per-pair M2L (fmm_oracle.c) to 1e-10; the default
+    (min_fill 0.25) picks per level from the source tree."""
+    from polatory_b200 import _lib
+    _, ofmm, _ = _oracle()
+    dim, n = 3, 30000
+    if cloud == "surface":
+        src = rng.normal(size=(n, dim))
+        src /= np.linalg.norm(src, axis=1)[:, None]
+        src *= 0.9
+    else:
+        src = rng.uniform(-1, 1, (n, dim))
+    trg = rng.uniform(-1, 1, (8000, dim))
+    # (gradient / Hessian of bh3 with c = 0 are not finite at distance 0: such kinds stay on the list path)
+    name, params = ("bh3", [1.0, 0.0]) if kind == 0 else ("th3", [1.0, 0.01])
+    from oracle import direct as odir
+    w = rng.uniform(-1, 1, n * odir.kind_km(kind, dim))
+    lib = _lib.load()
+    prev = lib.plt_set_block_m2l_min_fill(0.25)
+    try:
+        for order in (6, 8):
+            ref = ofmm.fmm(name, params, dim, kind, -np.ones(dim), np.ones(dim), src, trg, w, order, -1, 0)
+            phases = {}
+            for min_fill in (0.0, 2.0, 0.25):
+                lib.plt_set_block_m2l_min_fill(min_fill)
+                ev = pb.FmmGenericEvaluator(kind, pb.make_rbf(name, params, dim), pb.Bbox(-np.ones(dim), np.ones(dim)))
+                ev.set_source_points(src)
+                ev.set_target_points(trg)
+                ev.set_weights(w)
+                ev.force_config(order, -1)
+                got = ev.evaluate()
+                assert ev.config()["tree_height"] == ofmm.tree_height(dim, n)
+                assert _relerr(got, ref) < 1e-10, (order, min_fill, _relerr(got, ref))
+                phases[min_fill] = set(ev.phase_times())
+            assert "m2l_blk" in phases[0.0] and "m2l_hadamard" not in phases[0.0]
+            assert "m2l_hadamard" in phases[2.0] and "m2l_blk" not in phases[2.0]
+            assert "m2l_blk" not in phases[0.25]  # levels of fewer than 8192 source cells stay on the lists
+    finally:
+        lib.plt_set_block_m2l_min_fill(prev)
+
+
 def test_reference_evaluator_test_shape(pb, rng):
     """test/interpolation/test_evaluator.cpp:27-75: th3, random anisotropy, 1024 points + 1024
     gradient points -> 1024 + 1024 gradient targets in [-1,1]^3, accuracy 1e-4 (values and
@@ -513,8 +557,20 @@ def _emulated_ranks(pb, make, world, cut, key_begin, setup):
 
 
 @pytest.mark.parametrize("world,cut", [(2, 2), (3, 3), (8, 4)])
-@pytest.mark.parametrize("kind", [0, 3])
+@pytest.mark.parametrize("kind", [0, 3, "0-blocks"])
 def test_partitioned_generic_evaluator_is_bit_identical(pb, world, cut, kind, rng):
+    if kind == "0-blocks":  # the same with the parent-block M2L forced on every level
+        from polatory_b200 import _lib
+        prev = _lib.load().plt_set_block_m2l_min_fill(0.0)
+        try:
+            _partitioned_generic_evaluator_is_bit_identical(pb, world, cut, 0, rng, blocks=True)
+        finally:
+            _lib.load().plt_set_block_m2l_min_fill(prev)
+    else:
+        _partitioned_generic_evaluator_is_bit_identical(pb, world, cut, kind, rng)
+
+
+def _partitioned_generic_evaluator_is_bit_identical(pb, world, cut, kind, rng, blocks=False):
     """Each rank gets the targets of its own Morton key range, computes only the multipoles it owns or needs and
     receives the level-cut expansions of the others: the results equal the single-GPU evaluation of the same
     targets bit for bit (1-vs-N-GPU parity), and a rank skips most of the upward pass."""
@@ -557,6 +613,7 @@ def test_partitioned_generic_evaluator_is_bit_identical(pb, world, cut, kind, rn
     for r in range(world):
         assert evs[r].config()["tree_height"] == height and evs[r].allgather_count() == 2
         assert np.array_equal(outs[r], ref[own[r]]), (r, np.max(np.abs(outs[r] - ref[own[r]])))
+        assert ("m2l_blk" in evs[r].phase_times()) == blocks
     if world == 8:
         # the upward pass of a rank touches a fraction of the source cells
         t_full = sum(full.phase_times().get(k, 0.0) for k in ("p2m", "m2m", "m2hat"))
