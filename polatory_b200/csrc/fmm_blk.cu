@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(kGrpWarps * 32, VEC ? 1 : 2) k_m2l_grouped3(M2
   const int glo = s_g[0], n_g = s_g[1] - s_g[0];
   if (n_g <= 0) return;
 
-  // Work items = (block of kGrpWarps frequency tiles, group), tile-block-major, cut into equal contiguous ranges per CTA.
-  // The warps of a CTA take the SAME groups at kGrpWarps neighbouring tiles: identical control flow (they walk through
-  // the ~40 KB of straight-line position code together and share its instruction-cache lines; with every warp on its
-  // own group the kernel stalled on instruction fetch) and 4 KB contiguous of every spectrum row per CTA.
+  // Schedule: the warps of a CTA take the SAME group at kGrpWarps neighbouring frequency tiles (identical control flow:
+  // they walk through the ~40 KB of straight-line position code together and share its instruction-cache lines; 4 KB
+  // contiguous of every spectrum row per CTA), and the whole grid works on ONE block of kGrpWarps tiles at a time, CTA c
+  // on the groups c, c + gridDim.x, ...: the CTAs in flight then cover a window of consecutive (Morton-neighbouring)
+  // groups, whose source rows overlap and stay in L2.  With contiguous (tile block, group) ranges per CTA the rows
+  // were re-read from DRAM 4 - 5 times (ncu: 13.4 GB against 2.9 GB of unique block spectra on a dense 1M-point cloud).
   const int n_tb = (n_ftiles + kGrpWarps - 1) / kGrpWarps;
-  const long long n_items = static_cast<long long>(n_tb) * n_g;
-  const long long q_lo = n_items * blockIdx.x / gridDim.x, q_hi = n_items * (blockIdx.x + 1) / gridDim.x;
   const double2** ptrs = s_ptr[warp];
   const double2* ring = &s_ring[warp][0][lane];
   const unsigned ring_addr = static_cast<unsigned>(__cvta_generic_to_shared(ring));
@@ -285,12 +285,8 @@ __global__ void __launch_bounds__(kGrpWarps * 32, VEC ? 1 : 2) k_m2l_grouped3(M2
   const double2* spectra = NEAR ? a.Mhat : a.Mblk;
   const double2* ops = NEAR ? a.Khat : a.Kblk;
   double2* result = NEAR ? a.Lhat : a.Lhat_blk;
-  for (long long q0 = q_lo; q0 < q_hi;) {
-    const int tb = static_cast<int>(q0 / n_g);
-    const int g_lo = static_cast<int>(q0 - static_cast<long long>(tb) * n_g);
-    const long long seg_end = min(q_hi, static_cast<long long>(tb + 1) * n_g);
-    const int g_hi = g_lo + static_cast<int>(seg_end - q0);
-    q0 = seg_end;
+  for (int tb = 0; tb < n_tb; ++tb) {
+    const int g_lo = blockIdx.x, g_hi = n_g;
     const int ftile = tb * kGrpWarps + warp;
     if (ftile >= n_ftiles) continue;  // last tile block: no CTA-wide barrier below
     const int f = ftile * kGrpTF + lane;
@@ -309,7 +305,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, VEC ? 1 : 2) k_m2l_grouped3(M2
       const size_t rstride = static_cast<size_t>(km) * F;
       const unsigned long long lane_off = static_cast<unsigned long long>(fl) * sizeof(double2);
 
-      for (int g = g_lo; g < g_hi; ++g) {
+      for (int g = g_lo; g < g_hi; g += gridDim.x) {
         // ---- targets and source rows of this group ----
         int local = -1;     // lane tp < 8: index of target tp in the result (or -1)
         int r0, r1;         // spectrum rows of the source positions lane and lane + 32 (or -1)
@@ -580,12 +576,11 @@ namespace {
 template <bool NEAR>
 void launch_grouped(const M2LArgs& a, int F, int n_groups, cudaStream_t s, LaunchCounter& c) {
   const int n_ftiles = ceil_div(F, kGrpTF);
-  const long long rounds = static_cast<long long>(ceil_div(n_ftiles, kGrpWarps)) * n_groups;
   if (a.kn * a.km == 1) {
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(2 * kNumSM, rounds)));
+    const int grid = std::max(1, std::min(2 * kNumSM, n_groups));
     PLT_LAUNCH(c, (k_m2l_grouped3<false, NEAR>), grid, kGrpWarps * 32, 0, s, a, F, n_ftiles);
   } else {
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
+    const int grid = std::max(1, std::min(kNumSM, n_groups));
     PLT_LAUNCH(c, (k_m2l_grouped3<true, NEAR>), grid, kGrpWarps * 32, 0, s, a, F, n_ftiles);
   }
 }
