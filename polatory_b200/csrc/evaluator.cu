@@ -128,6 +128,46 @@ __global__ void k_need_mask(TreeView trg, int cut, unsigned char* __restrict__ n
   }
 }
 
+// The same from the raw target points (before their tree exists, so that the partitioned upward pass can run while the
+// target tree is being built): occ[key] = 1 for the level-`cut` cell of every point -- the leaf cell of tree.cu's
+// k_point_keys, shifted up -- then the dilation by one cell.
+template <int DIM>
+__global__ void k_cut_cells_of_points(const double* __restrict__ pos, int64_t n, Box box, int leaf, int cut,
+                                      unsigned char* __restrict__ occ) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int nside = 1 << leaf;
+  const double inv_w = static_cast<double>(nside) / box.width;
+  int c[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) {
+    const double x = (pos[a * n + i] - (box.center[a] - 0.5 * box.width)) * inv_w;
+    c[a] = min(max(static_cast<int>(floor(x)), 0), nside - 1);
+  }
+  const uint32_t key = morton_encode<DIM>(c) >> (DIM * (leaf - cut));
+  if (!occ[key]) occ[key] = 1;
+}
+template <int DIM>
+__global__ void k_dilate_need(const unsigned char* __restrict__ occ, int cut, unsigned char* __restrict__ need) {
+  const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= (1u << (DIM * cut)) || !occ[key]) return;
+  int c[DIM];
+  morton_decode<DIM>(key, c);
+  const int nside = 1 << cut;
+  constexpr int NN = DIM == 1 ? 3 : (DIM == 2 ? 9 : 27);
+  for (int e = 0; e < NN; ++e) {
+    int q[DIM], r = e;
+    bool ok = true;
+#pragma unroll
+    for (int a = DIM - 1; a >= 0; --a) {
+      q[a] = c[a] + (r % 3) - 1;
+      r /= 3;
+      ok = ok && q[a] >= 0 && q[a] < nside;
+    }
+    if (ok) need[morton_encode<DIM>(q)] = 1;
+  }
+}
+
 // Work flags of every source cell (tree.cuh: kCellFlagM / kCellFlagMhat) for rank `rank` of a partition of the
 // level-`cut` key space into the ranges [key_begin[r], key_begin[r + 1]):
 //   levels <  cut : M by M2M from the all-gathered level `cut` and Mhat on every rank (a handful of cells)
@@ -201,16 +241,16 @@ struct ConfigKey {
   bool operator<(const ConfigKey& o) const { return std::tie(height, order, d) < std::tie(o.height, o.order, o.d); }
 };
 
-// Device-resident interpolator for one (height, order, d): tables + per-level M2L operators.
-// Counterpart of scalfmm::interpolation::interpolator(kernel, order, tree_height, box_width, d)
-// cached like the reference's LruCache<InterpolatorConfiguration, Interpolator>(2)
-// (src/fmm/fmm_evaluator.hpp:249-252,292).
 // Block spectra of the parent-block M2L and the children levels they were built for (bit l).
 struct BlkSpectra {
   DevBuf<double2> buf;
   unsigned levels = 0;
 };
 
+// Device-resident interpolator for one (height, order, d): tables + per-level M2L operators.
+// Counterpart of scalfmm::interpolation::interpolator(kernel, order, tree_height, box_width, d)
+// cached like the reference's LruCache<InterpolatorConfiguration, Interpolator>(2)
+// (src/fmm/fmm_evaluator.hpp:249-252,292).
 struct Interpolator {
   InterpTables host;
   DevBuf<double> beta, child;
@@ -243,6 +283,17 @@ struct plt_eval {
   int force_order = 0, force_d = kClassic, force_height = 0;
   bool force_direct = false;  // always take the brute-force branch (exact sums: the fit's residual sample)
   cudaStream_t stream = nullptr;
+  // Side stream for the target tree + plan, concurrent with the upward pass (evaluate_device).  Declared before the
+  // trees and the plan: their buffers are stream-ordered allocations of this stream and must be freed before it goes.
+  struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    ~SideStream() {
+      if (fork) cudaEventDestroy(fork);
+      if (join) cudaEventDestroy(join);
+      if (s) cudaStreamDestroy(s);
+    }
+  } side;
   LaunchCounter ctr;
   std::string err;
   PhaseTimer timer;
@@ -299,6 +350,7 @@ struct plt_eval {
     if (copy_ready) cudaEventDestroy(copy_ready);
     if (copy_done) cudaEventDestroy(copy_done);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+
   }
 
   // -------------------------------------------------------------------------------
@@ -1021,12 +1073,19 @@ struct plt_eval {
   }
 
   // Builds the source / target trees of the FMM (or compact) branch if they are not current.
-  void ensure_trees() {
+  int planned_height() const {
     const bool compact = std::isfinite(rbf.support_radius);
-    const int64_t nt = targets();
     int height = compact ? compact_height()
-                         : fmm_tree_height(dim, symmetric ? n_src : std::max(n_src, nt));
+                         : fmm_tree_height(dim, symmetric ? n_src : std::max(n_src, targets()));
     if (force_height > 0) height = force_height;
+    return height;
+  }
+  void ensure_trees() {
+    ensure_src_tree();
+    ensure_trg_tree(stream);
+  }
+  void ensure_src_tree() {
+    const int height = planned_height();
     if (!src_tree.built() || src_tree.height() != height) {
       src_tree.build(dim, height, box, src_pos_c.get(), n_src, stream, ctr);
       wt_dirty = true;
@@ -1035,8 +1094,14 @@ struct plt_eval {
       if (symmetric) shard_cache.valid = false;
       own_cells_valid = cell_flags_valid = false;
     }
-    if (!symmetric && (!trg_tree.built() || trg_tree.height() != height)) {
-      trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, stream, ctr);
+  }
+  bool trg_tree_stale() const {
+    return !symmetric && (!trg_tree.built() || trg_tree.height() != planned_height());
+  }
+  void ensure_trg_tree(cudaStream_t s) {
+    const int height = planned_height();
+    if (trg_tree_stale()) {
+      trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, s, ctr);
       plan.reset();
       shard_cache.valid = false;
       if (part.on) {  // another set of needed source cells: the cached multipoles may not cover it
@@ -1072,14 +1137,28 @@ struct plt_eval {
       cell_flags_valid = false;
     }
     if (!cell_flags_valid) {
-      const TreeView tv = target_tree().view();
       const size_t n_keys = size_t{1} << (dim * cut);
       need_mask.alloc(n_keys, stream);
       need_mask.zero(stream);
-      const int nt = tv.n_cells[cut];
-      if (dim == 1) PLT_LAUNCH(ctr, k_need_mask<1>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
-      if (dim == 2) PLT_LAUNCH(ctr, k_need_mask<2>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
-      if (dim == 3) PLT_LAUNCH(ctr, k_need_mask<3>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+      if (!symmetric && !trg_tree.built()) {
+        // the target tree is built concurrently (evaluate_device): take the cells from the points themselves
+        unsigned char* occ = arena.take<unsigned char>(n_keys);
+        PLT_CUDA(cudaMemsetAsync(occ, 0, n_keys, stream));
+        const int leaf = src_tree.height() - 1;
+        const int gp = ceil_div(n_trg, 256), gk = ceil_div(static_cast<int64_t>(n_keys), 128);
+        if (dim == 1) PLT_LAUNCH(ctr, k_cut_cells_of_points<1>, gp, 256, 0, stream, trg_pos_c.get(), n_trg, box, leaf, cut, occ);
+        if (dim == 2) PLT_LAUNCH(ctr, k_cut_cells_of_points<2>, gp, 256, 0, stream, trg_pos_c.get(), n_trg, box, leaf, cut, occ);
+        if (dim == 3) PLT_LAUNCH(ctr, k_cut_cells_of_points<3>, gp, 256, 0, stream, trg_pos_c.get(), n_trg, box, leaf, cut, occ);
+        if (dim == 1) PLT_LAUNCH(ctr, k_dilate_need<1>, gk, 128, 0, stream, occ, cut, need_mask.get());
+        if (dim == 2) PLT_LAUNCH(ctr, k_dilate_need<2>, gk, 128, 0, stream, occ, cut, need_mask.get());
+        if (dim == 3) PLT_LAUNCH(ctr, k_dilate_need<3>, gk, 128, 0, stream, occ, cut, need_mask.get());
+      } else {
+        const TreeView tv = target_tree().view();
+        const int nt = tv.n_cells[cut];
+        if (dim == 1) PLT_LAUNCH(ctr, k_need_mask<1>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+        if (dim == 2) PLT_LAUNCH(ctr, k_need_mask<2>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+        if (dim == 3) PLT_LAUNCH(ctr, k_need_mask<3>, ceil_div(nt, 128), 128, 0, stream, tv, cut, need_mask.get());
+      }
       cell_flags.alloc(src_tree.total_cells(), stream);
       PLT_LAUNCH(ctr, k_cell_flags, ceil_div(src_tree.total_cells(), 256), 256, 0, stream, sv, cut, need_mask.get(),
                  own_key_lo, own_key_hi, cell_flags.get());
@@ -1175,11 +1254,58 @@ struct plt_eval {
       return;
     }
 
+    // Source side first.  When the targets are new as well (bulk evaluation: every call) and the multipoles have to be
+    // recomputed, the target tree and the plan are built on a side stream WHILE the upward pass runs on the main
+    // one: both are chains of small, latency-bound kernels (0.9 + 0.45 ms against 1.0 ms on config #3; at 8 GPUs they are
+    // a quarter of the step) and neither depends on the other -- the partitioned upward pass takes the cells it needs
+    // from the target points themselves (ensure_partition_tables).
     timer.begin("tree", stream);
-    ensure_trees();
+    ensure_src_tree();
     const int height = src_tree.height();
     ensure_sorted_weights();
     timer.end(stream);
+    static const bool no_overlap = getenv("PLT_DEBUG_NO_OVERLAP") != nullptr;  // A/B switch
+    bool upward_done = false;
+    if (!no_overlap && !symmetric && !compact && height > 2 && trg_tree_stale()) {
+      const plt_config c = find_best_configuration(height);
+      // (partitioned: new targets need another set of source cells, ensure_trg_tree)
+      if (multipole_dirty || up_order != c.order || up_d != c.d || part.on) {
+        Interpolator& ip = interpolator(height, c.order, c.d);
+        if (!side.s) {
+          PLT_CUDA(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+          PLT_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+          PLT_CUDA(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
+        }
+        cudaStream_t side_stream = side.s;
+        cudaEvent_t side_fork = side.fork, side_join = side.join;
+        if (part.on) {  // (cell flags from the target points; cleared by ensure_trg_tree below, rebuilt identically)
+          trg_tree.reset();
+          cell_flags_valid = false;
+        }
+        PLT_CUDA(cudaEventRecord(side_fork, stream));  // source tree, weights and target positions are in place
+        PLT_CUDA(cudaStreamWaitEvent(side_stream, side_fork, 0));
+        upward(src_tree, wt_sorted.get(), ip, M, Mhat, Mblk, true, part.on);  // asynchronous, main stream
+        const bool flags_ok = cell_flags_valid;
+        timer.begin("tree", side_stream);
+        ensure_trg_tree(side_stream);
+        timer.end(side_stream);
+        timer.begin("plan", side_stream);
+        plan.build(src_tree, trg_tree, side_stream, ctr);
+        timer.end(side_stream);
+        PLT_CUDA(cudaEventRecord(side_join, side_stream));
+        PLT_CUDA(cudaStreamWaitEvent(stream, side_join, 0));
+        cell_flags_valid = flags_ok;  // the flags the upward pass has just used are those of this target set
+        multipole_dirty = false;
+        up_order = c.order;
+        up_d = c.d;
+        upward_done = true;
+      }
+    }
+    if (!upward_done) {
+      timer.begin("tree", stream);
+      ensure_trg_tree(stream);
+      timer.end(stream);
+    }
     const Tree& tt = target_tree();
     if (!plan.built()) {
       timer.begin("plan", stream);

@@ -212,19 +212,24 @@ k_p2p(RbfConst k, TreeView src, const double* __restrict__ swt, TreeView trg, do
   if (tb0 + n_split * kTG >= t1) {
     // ONE target group for this queue item (a few targets per leaf: grids, coarse samplers): the sources are used
     // once, so they go from global memory straight into the pair loop.
-    double tp[kTG][DIM], v[kTG][KN];
-    load_targets(tb0, tp, v);
+    // (reduced and added per kSrcCap sources like the staged path below, so that a target gets the same bits whichever
+    // path its leaf takes: per-layer batches of the isosurface sampler equal the one-shot evaluation exactly)
     const int nt = min(kTG, t1 - tb0);
-    for (int jj = lane; jj < total; jj += 32) {
-      const int j = source_index(jj);
-      double sp[DIM], w[KM];
+    for (int c0 = 0; c0 < total; c0 += kSrcCap) {
+      double tp[kTG][DIM], v[kTG][KN];
+      load_targets(tb0, tp, v);
+      const int c1 = min(total, c0 + kSrcCap);
+      for (int jj = c0 + lane; jj < c1; jj += 32) {
+        const int j = source_index(jj);
+        double sp[DIM], w[KM];
 #pragma unroll
-      for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
+        for (int a = 0; a < DIM; ++a) sp[a] = src.pos[a * src.n + j];
 #pragma unroll
-      for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j] * wscale;
-      eval_source(sp, w, tp, v, nt);
+        for (int m = 0; m < KM; ++m) w[m] = swt[m * src.n + j] * wscale;
+        eval_source(sp, w, tp, v, nt);
+      }
+      store_targets(tb0, nt, v);
     }
-    store_targets(tb0, nt, v);
     continue;
   }
   // Several target groups: the concatenated source list is staged in shared memory once per (leaf, chunk of kSrcCap
