@@ -312,9 +312,10 @@ def main():
     h_out = torch.empty(n_trg, dtype=torch.float64).pin_memory()
 
     def step_host():
+        # interpolation::Evaluator::evaluate(points) = set_target_points + evaluate (evaluator.hpp:83-87), as one ABI
+        # call: on one GPU the library streams the host targets in slabs (copy-in / evaluate / copy-out pipeline)
         ev.set_weights(h_w.numpy())
-        ev.set_target_points(h_trg.numpy())
-        ev.evaluate(h_out.numpy())
+        ev.evaluate_points(h_trg.numpy(), h_out.numpy())
 
     if args.no_e2e:
         e2e_ms, e2e_value, host_ok = None, None, None

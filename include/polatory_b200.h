@@ -108,6 +108,14 @@ int plt_eval_set_accuracy(plt_eval* h, double accuracy);
 /* evaluate (fmm_evaluator.hpp:32): writes kn * n_targets doubles. */
 int plt_eval_evaluate(plt_eval* h, double* out, int64_t len);
 
+/* set_target_points(points) + evaluate(out) in one call: the sequence of interpolation::Evaluator::evaluate(points)
+ * (include/polatory/interpolation/evaluator.hpp:83-87).  With HOST buffers (pinned ones for full overlap) on the FMM
+ * branch the targets are streamed in caller-order slabs through a copy-in / evaluate / copy-out pipeline on three
+ * streams; every slab is evaluated against the octree of the whole problem, so the values are bit-identical to the two
+ * separate calls.  Device pointers, small problems, symmetric / partitioned / compact-support evaluators take the two
+ * calls as they are.  On return the evaluator is in the state the two calls leave it in. */
+int plt_eval_evaluate_points(plt_eval* h, const double* points, int64_t n, double* out, int64_t len);
+
 /* Additions with no reference counterpart. */
 
 /* Bypass the accuracy search with a fixed (order, d); order 0 restores the search.

@@ -88,6 +88,12 @@ class Evaluator {
     evaluate(out.data(), static_cast<int64_t>(out.size()));
     return out;
   }
+  // set_target_points(points) + evaluate(out) as one call (interpolation/evaluator.hpp:83-87); host buffers are
+  // streamed in slabs through a copy-in / evaluate / copy-out pipeline.
+  void evaluate_points(const double* points, int64_t n, double* out, int64_t len) {
+    check(plt_eval_evaluate_points(h_, points, n, out, len));
+    n_trg_ = n;
+  }
 
  private:
   void check(int status) const {

@@ -35,6 +35,7 @@ SYMBOLS = [
     ("plt_eval_set_weights", ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     ("plt_eval_set_accuracy", ctypes.c_int, [_vp, ctypes.c_double]),
     ("plt_eval_evaluate", ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
+    ("plt_eval_evaluate_points", ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64]),
     ("plt_eval_force_config", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     ("plt_eval_force_direct", ctypes.c_int, [_vp, ctypes.c_int]),
     ("plt_eval_get_config", ctypes.c_int, [_vp, ctypes.POINTER(PltConfig)]),

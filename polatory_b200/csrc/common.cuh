@@ -176,6 +176,20 @@ class Arena {
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 constexpr int kMaxDim = 3;
-constexpr int kNumSM = 148;  // B200
+constexpr int kNumSM = 148;  // B200 (compile-time bound for fixed-size reduction grids)
+
+// SM count of the current device (persistent grids are sized from it), queried once.
+inline int num_sm() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      cudaGetLastError();
+      return kNumSM;
+    }
+    return v;
+  }();
+  return n;
+}
 
 }  // namespace plt

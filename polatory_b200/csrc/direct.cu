@@ -211,7 +211,7 @@ void launch_gram_batched(int dim, const RbfConst& k, const double* aniso, const 
 
 int direct_plan_chunks(int64_t ns, int64_t nt) {
   const int64_t t_blocks = (nt + kThreads * kTPT - 1) / (kThreads * kTPT);
-  const int64_t want = 4 * kNumSM;
+  const int64_t want = 4 * num_sm();
   int64_t chunks = (want + t_blocks - 1) / t_blocks;
   const int64_t max_chunks = std::max<int64_t>(1, ns / 1024);
   chunks = std::max<int64_t>(1, std::min(chunks, max_chunks));

@@ -312,6 +312,18 @@ struct plt_eval {
   DevBuf<double> stage;  // host -> device staging of caller points
   cudaStream_t copy_stream = nullptr;  // H2D of host targets, overlapped with the upward pass
   cudaEvent_t copy_ready = nullptr, copy_done = nullptr;
+  // Slab streaming of host targets (evaluate_points): two staging buffers, the slab's transformed positions, a
+  // stream for the D2H of finished slabs and three events per slab (copied in / staging buffer free / values ready).
+  struct SlabPipe {
+    cudaStream_t out_stream = nullptr;
+    std::vector<cudaEvent_t> ev;
+    DevBuf<double> stage[2], pos;
+    const double* trg_pos = nullptr;  // positions the target tree is built from while a slab is evaluated
+    ~SlabPipe() {
+      for (auto e : ev) cudaEventDestroy(e);
+      if (out_stream) cudaStreamDestroy(out_stream);
+    }
+  } slabs;
   bool multipole_dirty = true;
   int up_order = 0, up_d = 0;  // configuration the cached multipoles were built with
   DevBuf<double> wt_sorted;    // [km][n_src] folded, sorted
@@ -456,6 +468,13 @@ struct plt_eval {
     if (!dev) PLT_CUDA(cudaStreamSynchronize(stream));
   }
 
+  void ensure_copy_stream() {
+    if (copy_stream) return;
+    PLT_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    PLT_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
+    PLT_CUDA(cudaEventCreateWithFlags(&copy_done, cudaEventDisableTiming));
+  }
+
   // -------------------------------------------------------------------------------
   void set_points_impl(const double* pts, int64_t n, bool source) {
     PLT_REQUIRE(n >= 0 && (n == 0 || pts), "points");
@@ -472,11 +491,7 @@ struct plt_eval {
         // Host targets: their H2D copy (PCIe-bound, the longest single item of a host-buffer
         // evaluation) runs on a copy stream while this stream does the source-side upward pass,
         // which does not depend on the targets.
-        if (!copy_stream) {
-          PLT_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-          PLT_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
-          PLT_CUDA(cudaEventCreateWithFlags(&copy_done, cudaEventDisableTiming));
-        }
+        ensure_copy_stream();
         PLT_CUDA(cudaEventRecord(copy_ready, stream));  // staging buffer allocated, previous use finished
         PLT_CUDA(cudaStreamWaitEvent(copy_stream, copy_ready, 0));
         prefetch_upward(n);                             // asynchronous launches on `stream`
@@ -996,6 +1011,127 @@ struct plt_eval {
     }
   }
 
+  // Bulk evaluation at new points: set_target_points(points) + evaluate(out) as ONE call -- the sequence of
+  // interpolation::Evaluator::evaluate(points) (include/polatory/interpolation/evaluator.hpp:83-87).  With HOST buffers
+  // on the FMM branch the targets are streamed in caller-order slabs: slab i+1 is copied in on the copy stream and the
+  // values of slab i-1 are copied out on a third stream while slab i is evaluated.  Every slab is evaluated against
+  // the octree of the WHOLE problem (same height, hence the same cells, lists and kernels), so the values are
+  // bit-identical to the one-shot evaluation; the multipoles are computed once (while slab 0 is on its way in).
+  // On return the evaluator is in the state set_target_points(points) + evaluate() leave it in.
+  static constexpr int64_t kSlabMinTargets = int64_t{1} << 20;
+  int slab_count(const double* pts, int64_t n, const double* out) const {
+    static const char* env = getenv("PLT_SLABS");  // A/B switch: 1 = off, k = k slabs
+    if (!can_prefetch_upward() || force_direct || shard_world > 1) return 1;
+    if (n < 2 * kSlabMinTargets || is_device_pointer(pts) || is_device_pointer(out)) return 1;
+    const int height = force_height > 0 ? force_height : fmm_tree_height(dim, std::max(n_src, n));
+    if (height <= 2) return 1;
+    // Every slab pays ~1 ms of fixed cost (its own target tree, plan and per-level launches), measured on config #3
+    // (profiles/r02_j_slabs.md): two slabs from 2M targets, three (half-size edge slabs) from 6M.
+    const int k = env ? atoi(env) : (n >= 6 * kSlabMinTargets ? 3 : 2);
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(k, n / kSlabMinTargets)));
+  }
+
+  void evaluate_points(const double* pts, int64_t n, double* out, int64_t len) {
+    PLT_REQUIRE(!symmetric, "evaluate_points is not available on a symmetric evaluator");
+    PLT_REQUIRE(n >= 0 && (n == 0 || pts), "points");
+    PLT_REQUIRE(len == kn * n, "output length must be kn * n_trg_points");
+    const int n_slabs = slab_count(pts, n, out);
+    if (n_slabs < 2) {
+      set_points_impl(pts, n, false);
+      evaluate(out, len);
+      return;
+    }
+    timer.reset();
+    arena.reset();
+    SlabPipe& sp = slabs;
+    ensure_copy_stream();
+    if (!sp.out_stream) PLT_CUDA(cudaStreamCreateWithFlags(&sp.out_stream, cudaStreamNonBlocking));
+    while (sp.ev.size() < static_cast<size_t>(3 * n_slabs)) {
+      cudaEvent_t e;
+      PLT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      sp.ev.push_back(e);
+    }
+    // The first slab's copy-in and the last slab's copy-out are the exposed ends of the pipeline: edge slabs are
+    // smaller than the inner ones (weights e, 1, ..., 1, e).
+    static const double edge = getenv("PLT_SLAB_EDGE") ? atof(getenv("PLT_SLAB_EDGE")) : 0.5;
+    std::vector<int64_t> bound(n_slabs + 1, 0);
+    {
+      const double e = n_slabs > 2 ? std::min(1.0, std::max(0.05, edge)) : 1.0;
+      const double total = 2.0 * e + (n_slabs - 2);
+      double acc = 0.0;
+      for (int i = 0; i < n_slabs; ++i) {
+        acc += (i == 0 || i == n_slabs - 1) ? e : 1.0;
+        bound[i + 1] = std::min<int64_t>(n, static_cast<int64_t>(std::llround(acc / total * static_cast<double>(n))));
+      }
+      bound[n_slabs] = n;
+    }
+    auto first = [&](int i) { return bound[std::min(i, n_slabs)]; };
+    int64_t per = 0;
+    for (int i = 0; i < n_slabs; ++i) per = std::max(per, bound[i + 1] - bound[i]);
+    sp.stage[0].alloc(static_cast<size_t>(per) * dim, stream);
+    sp.stage[1].alloc(static_cast<size_t>(per) * dim, stream);
+    sp.pos.alloc(static_cast<size_t>(per) * dim, stream);
+    trg_pos_c.alloc(static_cast<size_t>(n) * dim, stream);
+    double* dst = arena.take<double>(len);
+    PLT_CUDA(cudaEventRecord(copy_ready, stream));  // buffers allocated, their previous uses finished
+    PLT_CUDA(cudaStreamWaitEvent(copy_stream, copy_ready, 0));
+    PLT_CUDA(cudaStreamWaitEvent(sp.out_stream, copy_ready, 0));
+    auto copy_in = [&](int i) {
+      const int64_t o = first(i), m = first(i + 1) - o;
+      PLT_CUDA(cudaMemcpyAsync(sp.stage[i & 1].get(), pts + o * dim, sizeof(double) * m * dim, cudaMemcpyHostToDevice,
+                               copy_stream));
+      PLT_CUDA(cudaEventRecord(sp.ev[3 * i], copy_stream));
+    };
+    const int saved_height = force_height;
+    const int height = saved_height > 0 ? saved_height : fmm_tree_height(dim, std::max(n_src, n));
+    auto restore = [&] {
+      force_height = saved_height;
+      sp.trg_pos = nullptr;
+      n_trg = n;            // as set_target_points(points) leaves it: positions in place, tree and plan stale
+      trg_tree.reset();
+      plan.reset();
+    };
+    try {
+      copy_in(0);
+      prefetch_upward(n);   // main stream: the upward pass does not depend on the targets
+      copy_in(1);
+      force_height = height;
+      for (int i = 0; i < n_slabs; ++i) {
+        const int64_t o = first(i), m = first(i + 1) - o;
+        if (m == 0) break;
+        PLT_CUDA(cudaStreamWaitEvent(stream, sp.ev[3 * i], 0));
+        launch_transform_points(dim, aniso, sp.stage[i & 1].get(), m, sp.pos.get(), stream, ctr);
+        launch_transform_points(dim, aniso, sp.stage[i & 1].get(), m, trg_pos_c.get() + o, stream, ctr, n);
+        PLT_CUDA(cudaEventRecord(sp.ev[3 * i + 1], stream));
+        if (i + 2 < n_slabs && first(i + 2) < n) {
+          PLT_CUDA(cudaStreamWaitEvent(copy_stream, sp.ev[3 * i + 1], 0));
+          copy_in(i + 2);
+        }
+        n_trg = m;
+        sp.trg_pos = sp.pos.get();
+        trg_tree.reset();
+        plan.reset();
+        const auto mark = arena.mark();
+        evaluate_device(dst + kn * o);
+        arena.rewind(mark);
+        PLT_CUDA(cudaEventRecord(sp.ev[3 * i + 2], stream));
+        PLT_CUDA(cudaStreamWaitEvent(sp.out_stream, sp.ev[3 * i + 2], 0));
+        PLT_CUDA(cudaMemcpyAsync(out + kn * o, dst + kn * o, sizeof(double) * kn * m, cudaMemcpyDeviceToHost,
+                                 sp.out_stream));
+      }
+    } catch (...) {
+      restore();
+      cudaStreamSynchronize(copy_stream);
+      cudaStreamSynchronize(stream);
+      cudaStreamSynchronize(sp.out_stream);
+      throw;
+    }
+    restore();
+    PLT_CUDA(cudaStreamSynchronize(copy_stream));
+    PLT_CUDA(cudaStreamSynchronize(stream));
+    PLT_CUDA(cudaStreamSynchronize(sp.out_stream));
+  }
+
   // Leaf range [leaf_lo, leaf_hi) and sorted point range [p_lo, p_hi) of the current target shard.
   // Cached per (target tree build, rank, world): the steady-state sharded matvec has no extra sync.
   struct ShardBounds {
@@ -1101,7 +1237,7 @@ struct plt_eval {
   void ensure_trg_tree(cudaStream_t s) {
     const int height = planned_height();
     if (trg_tree_stale()) {
-      trg_tree.build(dim, height, box, trg_pos_c.get(), n_trg, s, ctr);
+      trg_tree.build(dim, height, box, slabs.trg_pos ? slabs.trg_pos : trg_pos_c.get(), n_trg, s, ctr);
       plan.reset();
       shard_cache.valid = false;
       if (part.on) {  // another set of needed source cells: the cached multipoles may not cover it
@@ -1437,6 +1573,10 @@ int plt_eval_set_accuracy(plt_eval* h, double accuracy) {
 
 int plt_eval_evaluate(plt_eval* h, double* out, int64_t len) {
   return guarded(h, [&] { h->evaluate(out, len); });
+}
+
+int plt_eval_evaluate_points(plt_eval* h, const double* points, int64_t n, double* out, int64_t len) {
+  return guarded(h, [&] { h->evaluate_points(points, n, out, len); });
 }
 
 double plt_set_block_m2l_min_fill(double min_fill) { return blk_set_min_fill(min_fill); }

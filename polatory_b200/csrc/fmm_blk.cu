@@ -524,7 +524,7 @@ void launch_mblk_t(int km, const TreeView& src, int par_lo, int par_hi, const do
   if (n_par <= 0) return;
   const size_t smem = sizeof(double2) * (n * n * n + n * NB * n);
   smem_opt_in((const void*)k_mblk3<ORDER>, smem);
-  const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(n_par) * km, kNumSM * 16));
+  const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(n_par) * km, num_sm() * 16));
   PLT_LAUNCH(c, (k_mblk3<ORDER>), grid, 256, smem, s, src, km, first_cell, n_par, M, Mblk, make_tw_blk(ORDER));
 }
 
@@ -558,7 +558,7 @@ bool blk_supported(int dim, int order) {
 
 void launch_check_finite(const double* x, size_t n, int* flag, cudaStream_t s, LaunchCounter& c) {
   if (n == 0) return;
-  PLT_LAUNCH(c, k_check_finite, static_cast<int>(std::min<size_t>((n + 255) / 256, kNumSM * 8)), 256, 0, s, x, n, flag);
+  PLT_LAUNCH(c, k_check_finite, static_cast<int>(std::min<size_t>((n + 255) / 256, num_sm() * 8)), 256, 0, s, x, n, flag);
 }
 
 void launch_mblk(int km, const TreeView& src, int order, int par_lo, int par_hi, const double* M, double2* Mblk,
@@ -577,10 +577,10 @@ template <bool NEAR>
 void launch_grouped(const M2LArgs& a, int F, int n_groups, cudaStream_t s, LaunchCounter& c) {
   const int n_ftiles = ceil_div(F, kGrpTF);
   if (a.kn * a.km == 1) {
-    const int grid = std::max(1, std::min(2 * kNumSM, n_groups));
+    const int grid = std::max(1, std::min(2 * num_sm(), n_groups));
     PLT_LAUNCH(c, (k_m2l_grouped3<false, NEAR>), grid, kGrpWarps * 32, 0, s, a, F, n_ftiles);
   } else {
-    const int grid = std::max(1, std::min(kNumSM, n_groups));
+    const int grid = std::max(1, std::min(num_sm(), n_groups));
     PLT_LAUNCH(c, (k_m2l_grouped3<true, NEAR>), grid, kGrpWarps * 32, 0, s, a, F, n_ftiles);
   }
 }

@@ -29,7 +29,7 @@ struct Mat3 {
 // ------------------------------------------------------------------------------------
 // Point pre/post processing
 // ------------------------------------------------------------------------------------
-__global__ void k_transform_points(int dim, Mat3 A, const double* __restrict__ pts, int64_t n,
+__global__ void k_transform_points(int dim, Mat3 A, const double* __restrict__ pts, int64_t n, int64_t ld,
                                    double* __restrict__ pos) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
@@ -39,7 +39,7 @@ __global__ void k_transform_points(int dim, Mat3 A, const double* __restrict__ p
     // geometry/point3d.hpp:36-40: p * A^T  => component a = sum_b A[a][b] p[b]
     double s = 0.0;
     for (int b = 0; b < dim; ++b) s += p[b] * A.a[a * dim + b];
-    pos[a * n + i] = s;
+    pos[a * ld + i] = s;
   }
 }
 
@@ -1655,9 +1655,10 @@ void dispatch_dim_order(int dim, int order, F&& f) {
 // Launchers
 // ------------------------------------------------------------------------------------
 void launch_transform_points(int dim, const double* aniso, const double* pts, int64_t n, double* pos,
-                             cudaStream_t s, LaunchCounter& c) {
+                             cudaStream_t s, LaunchCounter& c, int64_t ld) {
   if (n == 0) return;
-  PLT_LAUNCH(c, k_transform_points, ceil_div(n, 256), 256, 0, s, dim, make_mat3(dim, aniso), pts, n, pos);
+  PLT_LAUNCH(c, k_transform_points, ceil_div(n, 256), 256, 0, s, dim, make_mat3(dim, aniso), pts, n, ld > 0 ? ld : n,
+             pos);
 }
 
 void launch_prepare_weights(int kind, int dim, const double* aniso, const double* w, const int* perm, int64_t n,
@@ -1832,7 +1833,7 @@ DftScratch plan_dft_scratch(int order, int dim, int work_items, cudaStream_t s) 
   size_t smem = sizeof(double2) * (nf + 2 * static_cast<size_t>(elems));
   d.global = smem > kSmemCap;
   d.smem = d.global ? sizeof(double2) * nf : smem;
-  d.grid = std::max(1, std::min(work_items, d.global ? 4 * kNumSM : work_items));
+  d.grid = std::max(1, std::min(work_items, d.global ? 4 * num_sm() : work_items));
   if (d.global) d.buf.alloc(static_cast<size_t>(d.grid) * 2 * elems, s);
   return d;
 }
@@ -1907,7 +1908,7 @@ void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounte
   const int n_ftiles = ceil_div(F, kHadTF);
   // one persistent CTA per SM; fewer when there is not a warp-round of parents per CTA
   const long long rounds = static_cast<long long>(n_ftiles) * ceil_div(a.n_active, kHadWarps);
-  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(kNumSM, rounds)));
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(num_sm(), rounds)));
   const size_t smem = sizeof(double2) * NOFF * kHadTF + sizeof(int2) * (NN * NC + (NN * NC - NC) * kHadWarps);
   if (a.kn * a.km == 1) {
     smem_opt_in((const void*)k_m2l_hadamard_tiled<DIM, false>, smem);

@@ -39,9 +39,9 @@ inline int nodes_per_cell(int order, int dim) { return ipow(order, dim); }
 inline int freqs_per_cell(int order, int dim) { return ipow(2 * order - 1, dim - 1) * order; }
 
 // ---- point pre/post processing ----
-// pos_out[a][i] = sum_b A[a][b] * points[i][b]   (caller order, SoA)
+// pos_out[a][i] = sum_b A[a][b] * points[i][b]   (caller order, SoA; rows `ld` apart, ld = 0: n)
 void launch_transform_points(int dim, const double* aniso, const double* points_rowmajor, int64_t n,
-                             double* pos_soa, cudaStream_t s, LaunchCounter& c);
+                             double* pos_soa, cudaStream_t s, LaunchCounter& c, int64_t ld = 0);
 // wt[m][i] = folded weights of sorted point i  (perm == nullptr: caller order)
 void launch_prepare_weights(int kind, int dim, const double* aniso, const double* weights, const int* perm,
                             int64_t n, double* wt_soa, cudaStream_t s, LaunchCounter& c);

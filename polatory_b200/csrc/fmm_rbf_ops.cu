@@ -396,7 +396,7 @@ void launch_p2p(int kind, int dim, const RbfConst& k, const TreeView& src, const
   const int64_t avg_targets = trg.n / std::max(1, trg.n_cells[trg.height - 1]);
   const int n_split = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(16, avg_targets / 32)));
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div(static_cast<int64_t>(n_leaves) * n_split, kP2PWarps),
-                                                      kNumSM * 8));
+                                                      num_sm() * 8));
   dispatch_fkd(k.family, kind, dim, [&](auto fam, auto knd, auto dm) {
     constexpr int km = KindTraits<knd.value, dm.value>::km;
     const size_t smem = sizeof(double) * kP2PWarps * (dm.value + km) * kSrcCap;

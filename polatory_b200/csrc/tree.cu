@@ -76,6 +76,19 @@ __global__ void k_finish_levels(const int* __restrict__ occ, const int* __restri
   }
 }
 
+// base[l] = first compact cell id of level l, [height] = number of cells, [height + 1] = "a point outside the box".
+__global__ void k_level_summary(const int* __restrict__ scan, const int* __restrict__ occ,
+                                const int64_t* __restrict__ off, int height, const int* __restrict__ outside,
+                                int* __restrict__ out) {
+  const int l = threadIdx.x;
+  if (l < height) out[l] = scan[off[l]];
+  if (l == height) {
+    const int64_t total = off[height];
+    out[height] = scan[total - 1] + occ[total - 1];
+    out[height + 1] = *outside;
+  }
+}
+
 __global__ void k_leaf_start(const uint32_t* __restrict__ pkey, int64_t n, const int* __restrict__ dense_leaf,
                              int n_leaf, int* __restrict__ leaf_start) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -144,20 +157,22 @@ void Tree::build(int dim, int height, const Box& box, const double* pos_caller, 
   PLT_CUDA(cub::DeviceScan::ExclusiveSum(tmp_.get(), scan_bytes, occ.get(), scan.get(), static_cast<int>(total), stream));
   ctr.n += 1;
 
-  // Cell counts per level (one small D2H copy; the only sync of the build).
-  std::vector<int> base(height + 1, 0);
-  for (int l = 0; l < height; ++l)
-    PLT_CUDA(cudaMemcpyAsync(&base[l], scan.get() + dense_off_[l], sizeof(int), cudaMemcpyDeviceToHost, stream));
-  int last_scan = 0, last_occ = 0, any_outside = 0;
-  PLT_CUDA(cudaMemcpyAsync(&last_scan, scan.get() + total - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  PLT_CUDA(cudaMemcpyAsync(&last_occ, occ.get() + total - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  PLT_CUDA(cudaMemcpyAsync(&any_outside, outside, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  // Cell counts per level: gathered on the device, ONE small copy into pinned memory; the only sync of the build.
+  summary_.alloc(height + 2, stream);
+  PLT_LAUNCH(ctr, k_level_summary, 1, 32, 0, stream, scan.get(), occ.get(), d_off.get(), height, outside,
+             summary_.get());
+  if (!h_summary_) {
+    int* p = nullptr;
+    PLT_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p), sizeof(int) * 32, cudaHostAllocDefault));
+    h_summary_.reset(p);
+  }
+  PLT_CUDA(cudaMemcpyAsync(h_summary_.get(), summary_.get(), sizeof(int) * (height + 2), cudaMemcpyDeviceToHost, stream));
   PLT_CUDA(cudaStreamSynchronize(stream));
-  if (any_outside) {
+  std::vector<int> base(h_summary_.get(), h_summary_.get() + height + 1);
+  if (h_summary_.get()[height + 1]) {
     height_ = 0;
     throw Error(PLT_ERR_INVALID, "a point lies outside the bounding box the evaluator was created with");
   }
-  base[height] = last_scan + last_occ;
   total_cells_ = base[height];
   cell_off_.assign(height + 1, 0);
   n_cells_.assign(height, 0);

@@ -12,6 +12,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -133,6 +134,11 @@ class Tree {
   DevBuf<int> idx_tmp_;
   DevBuf<int> occ_, scan_;
   DevBuf<int64_t> d_off_;
+  DevBuf<int> summary_;
+  struct HostFree {
+    void operator()(int* p) const { cudaFreeHost(p); }
+  };
+  std::unique_ptr<int, HostFree> h_summary_;  // pinned landing buffer of the level summary
   std::vector<int64_t> dense_off_;
   std::vector<int> cell_off_, n_cells_;
   int total_cells_ = 0;

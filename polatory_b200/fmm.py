@@ -235,6 +235,24 @@ class FmmGenericEvaluator(_EvaluatorBase):
         _lib.check(self._h, self._lib.plt_eval_set_target_points(self._h, p, n))
         self._n_trg = n
 
+    def evaluate_points(self, points, out=None):
+        """set_target_points(points) + evaluate(out) as one call (interpolation/evaluator.hpp:83-87): host arrays
+        are streamed through the device in slabs (plt_eval_evaluate_points); same values, bit for bit."""
+        p, n, keep = self._points(points)
+        m = self.kn * n
+        if out is not None and _is_torch_cuda(out):
+            import torch
+            assert out.dtype == torch.float64 and out.is_contiguous() and out.numel() == m
+            q = ctypes.c_void_p(out.data_ptr())
+            res = out
+        else:
+            res = np.empty(m, dtype=np.float64) if out is None else out
+            assert res.dtype == np.float64 and res.flags.c_contiguous and res.size == m
+            q = ctypes.c_void_p(res.ctypes.data)
+        _lib.check(self._h, self._lib.plt_eval_evaluate_points(self._h, p, n, q, m))
+        self._n_trg = n
+        return res
+
 
 class FmmGenericSymmetricEvaluator(_EvaluatorBase):
     """FmmGenericSymmetricEvaluator<Kernel> (src/fmm/fmm_symmetric_evaluator.hpp:31-275)."""

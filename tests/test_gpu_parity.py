@@ -682,3 +682,71 @@ def test_2d_bh2_one_million_points_matches_cpu_restatement(pb):
     sub = rng.choice(nt, 100, replace=False)
     exact = ofmm.direct("bh2", [1.0, 0.0], dim, 0, src, trg[sub], w)
     assert np.max(np.abs(got[sub] - exact)) < 1e-6 * max(np.max(np.abs(exact)), 1.0)
+
+
+# ---------------------------------------------------------------------------------------
+# Slab-streamed bulk evaluation (plt_eval_evaluate_points) == set_target_points + evaluate
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kind,pinned", [("bh3", "K", True), ("bh3", "K", False), ("th3", "FT", True)])
+def test_evaluate_points_streams_host_slabs_bit_identically(pb, name, kind, pinned):
+    """interpolation::Evaluator::evaluate(points) is set_target_points(points) + evaluate()
+    (include/polatory/interpolation/evaluator.hpp:83-87); the one-call form streams host targets in slabs against
+    the octree of the whole problem and must give the same bits, pageable or pinned buffers, scalar or vector
+    outputs, and leave the evaluator in the state of the two calls."""
+    import torch
+    rng = np.random.default_rng(11)
+    dim, n_src, n_trg = 3, 60000, 2300000
+    src = rng.uniform(-1, 1, (n_src, dim))
+    trg = rng.uniform(-1, 1, (n_trg, dim))
+    w = rng.uniform(-1, 1, n_src)
+    rbf = pb.make_rbf(name, [1.0])
+    if kind == "FT":
+        rbf.set_anisotropy(np.diag([1.0, 1.3, 0.8]))
+    box = pb.Bbox(-np.ones(dim), np.ones(dim))
+    make = pb.make_fmm_evaluator if kind == "K" else pb.make_fmm_gradient_transpose_evaluator
+    ev = make(rbf, box)
+    ev.set_source_points(src)
+    ev.set_weights(w)
+    ev.set_target_points(trg)
+    ref = ev.evaluate().copy()
+    cfg = ev.config()
+
+    ev2 = make(rbf, box)
+    ev2.set_source_points(src)
+    ev2.set_weights(w)
+    if pinned:
+        h_trg = torch.from_numpy(trg).pin_memory()
+        h_out = torch.empty(ev2.kn * n_trg, dtype=torch.float64).pin_memory()
+        got = ev2.evaluate_points(h_trg.numpy(), h_out.numpy())
+    else:
+        got = ev2.evaluate_points(trg)
+    assert ev2.config() == cfg
+    assert np.array_equal(got, ref)
+    assert ev2.launch_count() > ev.launch_count()  # several slabs were evaluated
+    again = ev2.evaluate()                           # targets are still set: one-shot evaluation of the same points
+    assert np.array_equal(again, ref)
+    # new weights, same call again: the multipoles are recomputed once, the slabs reuse them
+    w2 = rng.uniform(-1, 1, n_src)
+    ev.set_weights(w2)
+    ev2.set_weights(w2)
+    assert np.array_equal(ev2.evaluate_points(trg), ev.evaluate())
+
+
+def test_evaluate_points_small_and_device_inputs_take_the_two_calls(pb, rng):
+    import torch
+    dim = 3
+    src = rng.uniform(-1, 1, (20000, dim))
+    trg = rng.uniform(-1, 1, (15000, dim))
+    w = rng.uniform(-1, 1, 20000)
+    ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    ev.set_source_points(src)
+    ev.set_weights(w)
+    ev.set_target_points(trg)
+    ref = ev.evaluate().copy()
+    assert np.array_equal(ev.evaluate_points(trg), ref)
+    out = torch.empty(15000, dtype=torch.float64, device="cuda")
+    ev.evaluate_points(torch.from_numpy(trg).cuda(), out)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    sym = pb.make_fmm_symmetric_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+    with pytest.raises(AttributeError):
+        sym.evaluate_points(trg)

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Final-state evidence of a tag: full GPU test suite, smoke, both bench arms.  usage: TAG=r02_j bash tools/gpu_final.sh
+set -u
+TAG=${TAG:-r02_j}
+mkdir -p gpurun_out
+echo "== tests"
+( time timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -6 ) 2>&1 | tee gpurun_out/${TAG}_tests.log
+echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
+echo "== bench"
+( time timeout 900 python bench.py 2> gpurun_out/${TAG}_bench.err | tail -1 > gpurun_out/${TAG}_bench.json ) 2>&1 | tail -3
+cut -c1-600 gpurun_out/${TAG}_bench.json
+echo "== bench reference arm"
+( time timeout 600 python bench.py --impl reference 2> gpurun_out/${TAG}_bench_reference.err | tail -1 > gpurun_out/${TAG}_bench_reference.json ) 2>&1 | tail -3
+cut -c1-400 gpurun_out/${TAG}_bench_reference.json
