@@ -302,6 +302,7 @@ def main():
     clocks = sampler.stop()
     phases = ev.phase_times()
     cfg = ev.config()
+    work = ev.work_stats()   # of the plan of the timed steps (the host-buffer leg below rebuilds plans per slab)
     ms_step = ms_total / args.steps
     value = n_trg_global / (ms_step * 1e-3) / 1e6
     allgathers = ev.allgather_count()
@@ -339,7 +340,7 @@ def main():
     _lib.load().plt_measure_fp64_peak(ctypes.byref(tf))
     fp64_peak = float(tf.value)
     dominant = max(phases, key=phases.get) if phases else None
-    roofline = roofline_for(dominant, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, ev)
+    roofline = roofline_for(dominant, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, work)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -358,7 +359,7 @@ def main():
         "fp64_peak_tflops_measured": fp64_peak,
     }
 
-    line["phase_rooflines"] = phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, ev)
+    line["phase_rooflines"] = phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, work)
     if world > 1:
         line["multi_gpu"] = multi_gpu_report(args, ev, dist, dev, world, rank, shard, d_w, d_trg, d_out, d_src,
                                              trg_full, allgathers, ms_step, timed, barrier)
@@ -546,13 +547,12 @@ def fit_once(points, dev, tol=1e-4):
             "matvec_phases_ms": {k: round(v, 4) for k, v in ph.items()}}
 
 
-def phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, ev):
+def phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, work):
     """Roofline fractions of the secondary phases whose algorithmic work is known from the device counters
     (DESIGN.md section 5): the pruned inverse DFT and the fused leaf pass against HBM, the near field against FP64
     (SURVEY 8d counting rule: 12 flop per bh3 pair)."""
     out = {}
     try:
-        stats = ev.work_stats()
         p = cfg.get("order") or 0
         F, P = (2 * p - 1) ** 2 * p, p ** 3
         if phases.get("m2l_idft") and stats.get("m2l_target_cells"):
@@ -563,12 +563,12 @@ def phase_rooflines(phases, cfg, n_trg, hbm_peak, fp64_peak, ev):
             nb = 8.0 * P * stats.get("m2l_target_cells", 0) + 8.0 * (3 + 1) * n_trg
             gbs = nb / (phases["l2l_l2p_leaf"] * 1e-3) / 1e9
             out["l2l_l2p_leaf"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                                   "frac": gbs / hbm_peak, "note": "latency-bound (5 CTA barriers per parent), DESIGN.md"}
+                                   "frac": gbs / hbm_peak, "note": "shared-memory bound (LDS.128 of the expansions), DESIGN.md"}
         if phases.get("p2p") and stats.get("p2p_pairs"):
             tf = 12.0 * stats["p2p_pairs"] / (phases["p2p"] * 1e-3) / 1e12
             out["p2p"] = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": tf / fp64_peak if fp64_peak else None,
-                          "note": "12 flop per pair by the counting rule; 15 FP64-pipe instructions per pair in SASS"}
+                          "note": "12 flop per pair by the counting rule; 12 FP64-pipe instructions per pair in SASS"}
     except Exception as e:  # diagnostics only
         out["error"] = str(e)
     return out
@@ -584,14 +584,13 @@ def measured_traffic(kernel):
         return None
 
 
-def roofline_for(name, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, ev):
+def roofline_for(name, phases, cfg, n_src, n_trg, hbm_peak, hbm_src, fp64_peak, stats):
     """Algorithmic work of the dominant kernel / its CUDA-event time
     (sum over the kernel's launches of one step, events on the launching stream)."""
     if not name:
         return None
     ms = phases[name]
     p = cfg.get("order") or 0
-    stats = ev.work_stats()
     out = {"kernel": name, "ms": ms, "work": stats}
     F = (2 * p - 1) ** 2 * p
     P = p ** 3
