@@ -218,6 +218,11 @@ const char* plt_last_error(plt_eval* h);
  * Returns the previous value. */
 double plt_set_block_m2l_min_fill(double min_fill);
 
+/* Experimental: scalar 3-D Hadamard M2L with the operators of most pairs in Tensor Memory (tcgen05.ld; csrc/fmm_had_tmem.cu).
+ * Off by default (parity-green, but slower than the shared-memory kernel on B200: profiles/r02_k_hadamard_tmem.md);
+ * PLT_HAD_TMEM=1 in the environment or this switch turn it on.  Returns the previous setting. */
+int plt_set_hadamard_tmem(int on);
+
 /* FP64 FMA peak of the current device, measured with a DFMA-chain microbenchmark (TFLOP/s);
  * the denominator of the FP64 roofline. */
 int plt_measure_fp64_peak(double* tflops);

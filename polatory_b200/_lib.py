@@ -56,6 +56,7 @@ SYMBOLS = [
     ("plt_eval_launch_count", ctypes.c_int64, [_vp]),
     ("plt_last_error", ctypes.c_char_p, [_vp]),
     ("plt_set_block_m2l_min_fill", ctypes.c_double, [ctypes.c_double]),
+    ("plt_set_hadamard_tmem", ctypes.c_int, [ctypes.c_int]),
     ("plt_measure_fp64_peak", ctypes.c_int, [_c_double_p]),
     ("plt_fgmres_create", ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.POINTER(_vp)]),
     ("plt_fgmres_destroy", None, [_vp]),

@@ -1581,6 +1581,8 @@ int plt_eval_evaluate_points(plt_eval* h, const double* points, int64_t n, doubl
 
 double plt_set_block_m2l_min_fill(double min_fill) { return blk_set_min_fill(min_fill); }
 
+int plt_set_hadamard_tmem(int on) { return hadamard_tmem_set(on); }
+
 int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_override) {
   return guarded(h, [&] {
     PLT_REQUIRE(order == 0 || (order >= 2 && order <= kMaxOrder), "order out of range");

@@ -1925,6 +1925,7 @@ void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   const int F = freqs_per_cell(a.order, a.dim);
   static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
   if (!no_tiled) {
+    if (launch_m2l_hadamard_tmem(a, F, s, c)) return;
     if (a.dim == 1) launch_hadamard_tiled<1>(a, F, s, c);
     if (a.dim == 2) launch_hadamard_tiled<2>(a, F, s, c);
     if (a.dim == 3) launch_hadamard_tiled<3>(a, F, s, c);

@@ -89,6 +89,10 @@ struct M2LArgs {
 };
 // Fourier-space accumulation over the M2L lists of the children of the active parents.
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
+// Scalar 3-D variant with the operators of most pairs in Tensor Memory (fmm_had_tmem.cu); false = not applicable.
+bool launch_m2l_hadamard_tmem(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c);
+bool hadamard_tmem_enabled();
+int hadamard_tmem_set(int on);  // returns the previous setting
 // counters[0] += M2L pairs, [1] += target cells with a non-empty M2L list, [2] += P2P pairs.
 void launch_count_work(int dim, const TreeView& src, const TreeView& trg, unsigned long long* counters,
                        cudaStream_t s, LaunchCounter& c);

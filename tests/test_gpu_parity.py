@@ -750,3 +750,46 @@ def test_evaluate_points_small_and_device_inputs_take_the_two_calls(pb, rng):
     sym = pb.make_fmm_symmetric_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
     with pytest.raises(AttributeError):
         sym.evaluate_points(trg)
+
+
+# ---------------------------------------------------------------------------------------
+# Experimental Tensor-Memory Hadamard kernel (tcgen05.ld operands, conjugate-symmetric half table)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cloud", ["surface", "volume"])
+def test_hadamard_tmem_kernel_matches_list_kernel_and_cpu_restatement(pb, cloud):
+    """plt_set_hadamard_tmem(1) routes the scalar 3-D M2L lists through k_m2l_hadamard_tmem3 (operators of the offsets
+    with at most one axis at +-3 in Tensor Memory, Khat[-o] = conj Khat[o]); same sums as the shared-memory kernel up to
+    rounding, and the same distance to the CPU restatement."""
+    from polatory_b200 import _lib
+    _, ofmm, _ = _oracle()
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    dim, n_src, n_trg = 3, 40000, 50000
+    if cloud == "surface":
+        src = rng.normal(size=(n_src, dim))
+        src /= np.linalg.norm(src, axis=1)[:, None]
+        src *= 0.9
+    else:
+        src = rng.uniform(-1, 1, (n_src, dim))
+    trg = rng.uniform(-1, 1, (n_trg, dim))
+    w = rng.uniform(-1, 1, n_src)
+    box = pb.Bbox(-np.ones(dim), np.ones(dim))
+    prev_fill = lib.plt_set_block_m2l_min_fill(2.0)  # lists on every level
+    try:
+        out = {}
+        for on in (0, 1):
+            prev = lib.plt_set_hadamard_tmem(on)
+            try:
+                ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), box)
+                ev.set_source_points(src)
+                ev.set_target_points(trg)
+                ev.set_weights(w)
+                out[on] = ev.evaluate().copy()
+                assert ev.config()["order"] == 6 and ev.config()["tree_height"] >= 5
+            finally:
+                lib.plt_set_hadamard_tmem(prev)
+    finally:
+        lib.plt_set_block_m2l_min_fill(prev_fill)
+    ref = ofmm.fmm("bh3", [1.0, 0.0], dim, 0, -np.ones(dim), np.ones(dim), src, trg, w, 6, -1, 0)
+    assert _relerr(out[1], out[0]) < 1e-13
+    assert _relerr(out[1], ref) < 1e-10
