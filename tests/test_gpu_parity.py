@@ -793,3 +793,46 @@ def test_hadamard_tmem_kernel_matches_list_kernel_and_cpu_restatement(pb, cloud)
     ref = ofmm.fmm("bh3", [1.0, 0.0], dim, 0, -np.ones(dim), np.ones(dim), src, trg, w, 6, -1, 0)
     assert _relerr(out[1], out[0]) < 1e-13
     assert _relerr(out[1], ref) < 1e-10
+
+
+@pytest.mark.parametrize("world,cut", [(2, 3), (8, 5)])
+def test_partitioned_2d_evaluator_is_bit_identical(pb, world, cut, rng):
+    """Config C5's shape (bh2 terrain, 2-D): the Morton-range partition with the partitioned upward pass and the
+    all-gather of the level-cut expansions gives the single-GPU values bit for bit in two dimensions as well."""
+    from polatory_b200.parallel import partition_keys
+    dim, n = 2, 60000
+    src = rng.uniform(0, 1, (n, dim))
+    g = np.linspace(0.0, 1.0, 300)
+    trg = np.ascontiguousarray(np.stack(np.meshgrid(g, g, indexing="ij"), axis=-1).reshape(-1, dim))
+    w = rng.uniform(-1, 1, n)
+    w -= w.mean()
+    bbox = pb.Bbox(np.zeros(dim), np.ones(dim))
+    rbf = pb.make_rbf("bh2", [1.0, 0.0], dim)
+    height = pb.fmm.tree_height(dim, len(trg))
+    assert height > cut
+
+    full = pb.FmmGenericEvaluator(0, rbf, bbox)
+    full.set_source_points(src)
+    full.set_target_points(trg)
+    full.set_weights(w)
+    ref = full.evaluate().copy()
+    keys = full.point_keys(trg, cut)
+    kb = partition_keys(keys, world, dim, cut)
+    own = [np.nonzero((keys >= kb[r]) & (keys < kb[r + 1]))[0] for r in range(world)]
+    assert sum(len(o) for o in own) == len(trg) and min(len(o) for o in own) > 0
+
+    def setup(ev, r):
+        ev.set_source_points(src)
+        ev.force_config(0, -1, height)
+        ev.set_target_points(trg[own[r]])
+        ev.set_weights(w)
+
+    evs = _emulated_ranks(pb, lambda: pb.FmmGenericEvaluator(0, rbf, bbox), world, cut, kb, setup)
+    for _ in range(2):
+        outs = []
+        for r, ev in enumerate(evs):
+            ev.set_weights(w)
+            outs.append(ev.evaluate().copy())
+    for r in range(world):
+        assert evs[r].config()["tree_height"] == height and evs[r].allgather_count() == 2
+        assert np.array_equal(outs[r], ref[own[r]]), (r, np.max(np.abs(outs[r] - ref[own[r]])))
