@@ -218,6 +218,15 @@ const char* plt_last_error(plt_eval* h);
  * Returns the previous value. */
 double plt_set_block_m2l_min_fill(double min_fill);
 
+/* Work-space blocks of destroyed evaluators are kept in a process-wide cache (up to a quarter of the device memory by
+ * default) and reused by the next evaluators that ask for about the same size: a second fit or a second sampler in the
+ * same process then performs no cudaMalloc / cudaFree of multi-GB blocks.  plt_release_cached_memory returns the cache to
+ * the driver (bytes freed; also done automatically when an allocation fails), plt_cached_memory reports its size,
+ * plt_set_cached_memory_limit(0) switches it off. */
+int64_t plt_release_cached_memory(void);
+int64_t plt_cached_memory(void);
+void plt_set_cached_memory_limit(int64_t bytes);
+
 /* Experimental: scalar 3-D Hadamard M2L with the operators of most pairs in Tensor Memory (tcgen05.ld; csrc/fmm_had_tmem.cu).
  * Off by default (parity-green, but slower than the shared-memory kernel on B200: profiles/r02_k_hadamard_tmem.md);
  * PLT_HAD_TMEM=1 in the environment or this switch turn it on.  Returns the previous setting. */
@@ -314,6 +323,38 @@ int plt_chol_solve_batched(const double* factor, int64_t n_batch, int n, const d
 int plt_chol_solve_shared(const double* factor, int n, int64_t n_rhs, const double* rhs, double* out, void* stream);
 /* y = A x, A row-major [rows][cols], device pointers (applies the coarse grid's inverse, coarse_grid.hpp:84-128). */
 int plt_gemv(const double* a, int rows, int cols, const double* x, double* y, void* stream);
+
+/* RasPreconditioner::operator() (include/polatory/preconditioner/ras_preconditioner.hpp:183-246) as ONE call on a
+ * stream: the multiplicative level sweep -- coarse-grid solves (coarse_grid.hpp:84-128), batched fine-level solves
+ * (fine_grid.hpp:103-147), update_residuals through resident evaluators (:287-321), orthogonalize (:267-285).
+ * The handle references (does not own) DEVICE tables set up through the entry points above:
+ *   set_level_rows: rows of the global system [mu values | dim * sigma gradient components] of a level's value points and,
+ *                   point-major, of the components of its gradient points;
+ *   set_fine:       a level >= 1: idx [n_domains][m] rows of every domain (the l polynomial rows first, padded), cnt
+ *                   valid rows per domain, the factors written by plt_chol_batched [n_domains][m-l][m-l], q_top
+ *                   [n_domains][l][m-l] (NULL for l = 0), and the (row, position in the [n_domains][m] solution) pairs
+ *                   of the points each domain owns;
+ *   set_coarse:     level 0: rows idx[m], the explicit inverse of Q^T A Q [(m-l)^2], q_top [l][m-l], the first l rows of
+ *                   mat_a [l][m], the inverse of the polynomial matrix at the polynomial points [l][l];
+ *   add_transfer:   an evaluator (kind 0 = K, 1 = F, 2 = F^T, 3 = H) whose sources are src_level's points and whose
+ *                   targets are trg_level's points, both already set (several per pair: one model with several RBFs);
+ *   set_poly:       monomials, orthonormalised monomials and A p at every row, [m_rows][l] row-major;
+ *   apply:          out = M^-1 v, v and out: m_rows + l doubles on the device. */
+typedef struct plt_ras_sweep plt_ras_sweep;
+int plt_ras_sweep_create(int64_t m_rows, int l, int n_levels, plt_ras_sweep** out);
+void plt_ras_sweep_destroy(plt_ras_sweep* h);
+int plt_ras_sweep_set_level_rows(plt_ras_sweep* h, int level, const int64_t* value_rows, int64_t n_value,
+                                 const int64_t* grad_rows, int64_t n_grad);
+int plt_ras_sweep_set_fine(plt_ras_sweep* h, int level, int64_t n_domains, int m, const int64_t* idx, const int32_t* cnt,
+                           const double* factor, const double* q_top, const int64_t* inner_glob,
+                           const int64_t* inner_loc, int64_t n_inner);
+int plt_ras_sweep_set_coarse(plt_ras_sweep* h, int m, const int64_t* idx, const double* inverse, const double* q_top,
+                             const double* a_top, const double* p_top_inv);
+int plt_ras_sweep_add_transfer(plt_ras_sweep* h, int src_level, int trg_level, int kind, plt_eval* ev);
+int plt_ras_sweep_set_poly(plt_ras_sweep* h, const double* p_mono, const double* p_orth, const double* a_p);
+int plt_ras_sweep_apply(plt_ras_sweep* h, const double* v, double* out, void* stream);
+int64_t plt_ras_sweep_launch_count(plt_ras_sweep* h);
+const char* plt_ras_sweep_last_error(plt_ras_sweep* h);
 
 /* The data points on which interpolation::ResidualEvaluator measures the residual exactly
  * (include/polatory/interpolation/residual_evaluator.hpp:123-136): out[0..n) = iota shuffled by a default-seeded

@@ -57,6 +57,9 @@ SYMBOLS = [
     ("plt_last_error", ctypes.c_char_p, [_vp]),
     ("plt_set_block_m2l_min_fill", ctypes.c_double, [ctypes.c_double]),
     ("plt_set_hadamard_tmem", ctypes.c_int, [ctypes.c_int]),
+    ("plt_release_cached_memory", ctypes.c_int64, []),
+    ("plt_cached_memory", ctypes.c_int64, []),
+    ("plt_set_cached_memory_limit", None, [ctypes.c_int64]),
     ("plt_measure_fp64_peak", ctypes.c_int, [_c_double_p]),
     ("plt_fgmres_create", ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.POINTER(_vp)]),
     ("plt_fgmres_destroy", None, [_vp]),
@@ -91,6 +94,17 @@ SYMBOLS = [
     ("plt_chol_solve_batched", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp]),
     ("plt_chol_solve_shared", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, _vp, _vp, _vp]),
     ("plt_gemv", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    ("plt_ras_sweep_create", ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("plt_ras_sweep_destroy", None, [_vp]),
+    ("plt_ras_sweep_set_level_rows", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64, _vp, ctypes.c_int64]),
+    ("plt_ras_sweep_set_fine", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp,
+                                              _vp, ctypes.c_int64]),
+    ("plt_ras_sweep_set_coarse", ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
+    ("plt_ras_sweep_add_transfer", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    ("plt_ras_sweep_set_poly", ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    ("plt_ras_sweep_apply", ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    ("plt_ras_sweep_launch_count", ctypes.c_int64, [_vp]),
+    ("plt_ras_sweep_last_error", ctypes.c_char_p, [_vp]),
     ("plt_residual_sample_indices", ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp]),
     ("plt_version", ctypes.c_int, []),
     ("plt_device_check", ctypes.c_int, []),

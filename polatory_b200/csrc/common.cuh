@@ -9,6 +9,8 @@
 #include <string>
 #include <algorithm>
 #include <utility>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/polatory_b200.h"
@@ -45,6 +47,8 @@ struct LaunchCounter {
     PLT_CUDA(cudaGetLastError());                                            \
   } while (0)
 
+size_t release_cached_arena_blocks();  // ArenaBlockCache::release_all (below)
+
 // Stream-ordered RAII device buffer (cudaMallocAsync pool: reuse without device syncs).
 template <class T>
 class DevBuf {
@@ -72,7 +76,11 @@ class DevBuf {
     stream_ = s;
     if (n > 0) {
       void* p = nullptr;
-      PLT_CUDA(cudaMallocAsync(&p, n * sizeof(T), s));
+      if (cudaMallocAsync(&p, n * sizeof(T), s) != cudaSuccess) {  // out of memory: drop the cached arena blocks, retry
+        cudaGetLastError();
+        release_cached_arena_blocks();
+        PLT_CUDA(cudaMallocAsync(&p, n * sizeof(T), s));
+      }
       ptr_ = static_cast<T*>(p);
     }
     n_ = cap_ = n;
@@ -104,24 +112,112 @@ class DevBuf {
   cudaStream_t stream_ = nullptr;
 };
 
+// Process-wide cache of arena blocks.  An evaluator's arena settles at ONE block of its steady-state size; a fit creates
+// and destroys a few dozen evaluators (matvec and residual operators, the level transfers of the preconditioner), and
+// the next fit -- or the next sampler over another model -- asks for exactly the same sizes again.  cudaMalloc / cudaFree
+// of multi-GB blocks cost 10 - 100 ms each and synchronise the device, so released blocks are kept here (up to a
+// quarter of the device memory, plt_set_cached_memory_limit) and handed out again when a request of about that size
+// comes (at most 25 % larger than asked).  plt_release_cached_memory() returns everything to the driver; an allocation
+// failure does the same before it retries.
+class ArenaBlockCache {
+ public:
+  static ArenaBlockCache& get() {
+    static ArenaBlockCache* c = new ArenaBlockCache();  // never destroyed: the CUDA context may be gone by then
+    return *c;
+  }
+  void* take(size_t want, size_t& cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu_);
+    for (auto it = free_.lower_bound(want); it != free_.end() && it->first <= want + want / 4; ++it) {
+      if (it->second.dev != dev) continue;
+      void* p = it->second.ptr;
+      cap = it->first;
+      total_ -= cap;
+      free_.erase(it);
+      return p;
+    }
+    return nullptr;
+  }
+  // The caller has synchronised the device: no kernel still uses the block.
+  void give(void* p, size_t cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      if (limit_ == kUnset) {
+        size_t free_b = 0, total_b = 0;
+        limit_ = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 4 : 0;
+        cudaGetLastError();
+      }
+      if (total_ + cap <= limit_) {
+        free_.emplace(cap, Entry{p, dev});
+        total_ += cap;
+        return;
+      }
+    }
+    cudaFree(p);
+  }
+  size_t release_all() {
+    std::multimap<size_t, Entry> drop;
+    size_t bytes = 0;
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      drop.swap(free_);
+      bytes = total_;
+      total_ = 0;
+    }
+    for (auto& e : drop) cudaFree(e.second.ptr);
+    cudaGetLastError();
+    return bytes;
+  }
+  void set_limit(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      limit_ = bytes;
+    }
+    if (cached() > bytes) release_all();
+  }
+  size_t cached() {
+    std::lock_guard<std::mutex> lock(mu_);
+    return total_;
+  }
+
+ private:
+  static constexpr size_t kUnset = ~size_t{0};
+  struct Entry {
+    void* ptr;
+    int dev;
+  };
+  std::mutex mu_;
+  std::multimap<size_t, Entry> free_;
+  size_t total_ = 0, limit_ = kUnset;
+};
+
+inline size_t release_cached_arena_blocks() { return ArenaBlockCache::get().release_all(); }
+
 // Grow-only bump arena for the temporaries of one evaluate(): after the first call with a given
 // problem shape the steady state performs no allocation at all (no cudaMalloc, no pool
 // traffic); reset() rewinds it.  Blocks are 256-byte aligned.  Growth adds a block; the next
-// reset() coalesces the blocks into one (the only place that synchronises the device).
+// reset() coalesces the blocks into one (the only place that synchronises the device).  Blocks come from and go back to
+// the process-wide ArenaBlockCache.
 class Arena {
  public:
   Arena() = default;
   Arena(const Arena&) = delete;
   Arena& operator=(const Arena&) = delete;
   ~Arena() {
-    for (auto& b : blocks_) cudaFree(b.ptr);
+    if (blocks_.empty()) return;
+    cudaDeviceSynchronize();  // (errors ignored: at interpreter exit the context may be gone)
+    cudaGetLastError();
+    for (auto& b : blocks_) ArenaBlockCache::get().give(b.ptr, b.cap);
   }
   void reset() {
     if (blocks_.size() > 1) {
       size_t total = 0;
       for (auto& b : blocks_) total += b.cap;
       PLT_CUDA(cudaDeviceSynchronize());
-      for (auto& b : blocks_) cudaFree(b.ptr);
+      for (auto& b : blocks_) ArenaBlockCache::get().give(b.ptr, b.cap);
       blocks_.clear();
       add_block(total);
     }
@@ -165,9 +261,17 @@ class Arena {
     size_t cap, used;
   };
   void add_block(size_t cap) {
-    void* p = nullptr;
-    PLT_CUDA(cudaMalloc(&p, cap));
-    blocks_.push_back(Block{p, cap, 0});
+    size_t got = cap;
+    void* p = ArenaBlockCache::get().take(cap, got);
+    if (!p) {
+      got = cap;
+      if (cudaMalloc(&p, cap) != cudaSuccess) {  // out of memory: give the cached blocks back to the driver first
+        cudaGetLastError();
+        ArenaBlockCache::get().release_all();
+        PLT_CUDA(cudaMalloc(&p, cap));
+      }
+    }
+    blocks_.push_back(Block{p, got, 0});
   }
   std::vector<Block> blocks_;
   size_t high_ = 0;

@@ -1583,6 +1583,12 @@ double plt_set_block_m2l_min_fill(double min_fill) { return blk_set_min_fill(min
 
 int plt_set_hadamard_tmem(int on) { return hadamard_tmem_set(on); }
 
+int64_t plt_release_cached_memory(void) { return static_cast<int64_t>(ArenaBlockCache::get().release_all()); }
+
+int64_t plt_cached_memory(void) { return static_cast<int64_t>(ArenaBlockCache::get().cached()); }
+
+void plt_set_cached_memory_limit(int64_t bytes) { ArenaBlockCache::get().set_limit(bytes < 0 ? 0 : static_cast<size_t>(bytes)); }
+
 int plt_eval_force_config(plt_eval* h, int order, int d, int tree_height_override) {
   return guarded(h, [&] {
     PLT_REQUIRE(order == 0 || (order >= 2 && order <= kMaxOrder), "order out of range");

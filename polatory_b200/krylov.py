@@ -46,7 +46,11 @@ class Fgmres:
         self._max_iter = int(max_iter)
         self._x0 = None
         self._group = group
-        self._error = None
+        self._slots = []     # the callables behind the ctypes callbacks, cleared when the solver goes: a ctypes
+                             # function pointer sits in a reference cycle of its own, and through the closure it
+                             # would keep the operator / preconditioner (and their device memory) alive until a gc pass
+        self._err = [None]   # shared with the callbacks (they must not capture `self`: a cycle would keep the
+                             # operator, the preconditioner and their device memory alive until a gc pass)
         h = ctypes.c_void_p()
         st = self._lib.plt_fgmres_create(self._n, self._max_iter, ctypes.byref(h))
         if st != _lib.PLT_OK:
@@ -60,12 +64,14 @@ class Fgmres:
         if group is not None:
             import torch.distributed as dist
 
+            err = self._err
+
             def allreduce(_ctx, buf, count):
                 try:
                     dist.all_reduce(_view(buf, count), op=dist.ReduceOp.SUM, group=group)
                     return 0
                 except Exception as e:  # noqa: BLE001 -- reported through the status code
-                    self._error = e
+                    err[0] = e
                     return 1
 
             self._ar_cb = _lib.ALLREDUCE_FN(allreduce)
@@ -76,25 +82,29 @@ class Fgmres:
         if h:
             self._lib.plt_fgmres_destroy(h)
             self._h = None
+        for slot in getattr(self, "_slots", []):
+            slot[0] = None
 
     def _wrap(self, f):
-        apply = f.apply if hasattr(f, "apply") else f
+        slot = [f.apply if hasattr(f, "apply") else f]
+        self._slots.append(slot)
         n = self._n
+        err = self._err
 
         def cb(_ctx, x, y):
             try:
-                apply(_view(x, n), _view(y, n))
+                slot[0](_view(x, n), _view(y, n))
                 return 0
             except Exception as e:  # noqa: BLE001
-                self._error = e
+                err[0] = e
                 return 1
 
         return _lib.LINOP_FN(cb)
 
     def _check(self, st):
         if st != _lib.PLT_OK:
-            if self._error is not None:
-                e, self._error = self._error, None
+            if self._err[0] is not None:
+                e, self._err[0] = self._err[0], None
                 raise e
             msg = self._lib.plt_fgmres_last_error(self._h)
             raise _lib.PolatoryB200Error(st, msg.decode() if msg else f"status {st}")

@@ -25,6 +25,7 @@ need ~19 GB here), and the level transfers
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -413,10 +414,13 @@ class RasPreconditioner:
     """preconditioner::RasPreconditioner; `apply(v, out)` on CUDA tensors laid out as the operator's vectors
     [mu values | dim * sigma gradient components | l polynomial coefficients]."""
 
-    def __init__(self, model, points, grad_points=None, device=None, verbose=False, transfer_config=None):
+    def __init__(self, model, points, grad_points=None, device=None, verbose=False, transfer_config=None,
+                 native_sweep=True):
         """transfer_config: optional (order, d) forced on the level-transfer evaluators, or "direct" for exact
         sums (default: the reference's accuracy = infinity, i.e. order 6) -- used by the parity tests to
-        separate the FMM discretisation error of the transfers from everything else."""
+        separate the FMM discretisation error of the transfers from everything else.
+        native_sweep: apply() is ONE call into the library (plt_ras_sweep_apply, csrc/ras_sweep.cu); False keeps the
+        torch re-expression of the same sweep below (the checker of the native one in the tests)."""
         import time
         import torch
         self.transfer_config = transfer_config
@@ -539,6 +543,61 @@ class RasPreconditioner:
                 fin.apply(self.p[:, i].contiguous(), col)
                 self.ap[:, i] = col
             del fin
+        self._sweep = None
+        if native_sweep and os.environ.get("PLT_RAS_PY_SWEEP") is None:
+            self._build_native_sweep()
+
+    def __del__(self):
+        h = getattr(self, "_sweep", None)
+        if h:
+            self._sweep_lib.plt_ras_sweep_destroy(h)
+            self._sweep = None
+
+    def _build_native_sweep(self):
+        """Hands the level structure to the library (device pointers into tensors this object keeps alive)."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        ptr = lambda t: None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        n = self.n_levels
+        h = ctypes.c_void_p()
+        if lib.plt_ras_sweep_create(self.m_rows, self.l, n, ctypes.byref(h)) != _lib.PLT_OK:
+            raise RuntimeError("plt_ras_sweep_create failed")
+        self._sweep_lib = lib
+
+        def ok(st):
+            if st != _lib.PLT_OK:
+                msg = lib.plt_ras_sweep_last_error(h)
+                raise RuntimeError("RAS sweep: " + (msg.decode() if msg else f"status {st}"))
+
+        keep = []
+        for level in range(n):
+            v, g = self.idx_dev[level].contiguous(), self.grows_dev[level].contiguous()
+            keep += [v, g]
+            ok(lib.plt_ras_sweep_set_level_rows(h, level, ptr(v), v.numel(), ptr(g), g.numel()))
+        for level in range(1, n):
+            f = self.fine[level]
+            ok(lib.plt_ras_sweep_set_fine(h, level, f.n_dom, f.m, ptr(f.idx), ptr(f.cnt), ptr(f.fac), ptr(f.q_top),
+                                          ptr(f.inner_glob), ptr(f.inner_loc), f.inner_glob.numel()))
+        c = self.coarse
+        if self.l > 0:
+            q0 = c.q_top[0].contiguous()
+            keep += [q0]
+            ok(lib.plt_ras_sweep_set_coarse(h, c.m, ptr(c.idx), ptr(c.inv), ptr(q0), ptr(c.a_top), ptr(c.p_top_inv)))
+        else:
+            ok(lib.plt_ras_sweep_set_coarse(h, c.m, ptr(c.idx), ptr(c.inv), None, None, None))
+        pairs = [(0, n - 1)] if n > 1 else []
+        pairs += [(level, n - 1) for level in range(1, n - 1)]
+        pairs += [(level, level - 1) for level in range(n - 1, 0, -1)]
+        pairs += [(0, level - 1) for level in range(n - 1, 1, -1)]
+        kind_of = {"a": 0, "f": 1, "ft": 2, "h": 3}
+        for src, trg in dict.fromkeys(pairs):
+            for name, ev, _fit in self._evaluator(src, trg):
+                ok(lib.plt_ras_sweep_add_transfer(h, src, trg, kind_of[name], ev._h))
+        if n > 1 and self.l > 0:
+            ok(lib.plt_ras_sweep_set_poly(h, ptr(self.p_mono), ptr(self.p), ptr(self.ap)))
+        self._sweep_keep = keep
+        self._sweep = h
 
     # -- helpers ---------------------------------------------------------------------------
     def _configure_transfer(self, ev):
@@ -642,6 +701,19 @@ class RasPreconditioner:
 
     # -- RasPreconditioner::operator() (ras_preconditioner.hpp:183-246) -----------------------
     def apply(self, v, out):
+        if self._sweep:
+            import ctypes
+            assert v.is_contiguous() and out.is_contiguous() and v.numel() == self.m_rows + self.l == out.numel()
+            st = self._sweep_lib.plt_ras_sweep_apply(self._sweep, ctypes.c_void_p(v.data_ptr()),
+                                                     ctypes.c_void_p(out.data_ptr()), None)
+            if st != 0:
+                msg = self._sweep_lib.plt_ras_sweep_last_error(self._sweep)
+                raise RuntimeError("RAS sweep: " + (msg.decode() if msg else f"status {st}"))
+            return out
+        return self.apply_reference(v, out)
+
+    def apply_reference(self, v, out):
+        """The same sweep as torch operations around the library's kernels (checker of the native sweep)."""
         n = self.n_levels
         residuals = v[:self.m_rows].clone()
         if n == 1:

@@ -836,3 +836,43 @@ def test_partitioned_2d_evaluator_is_bit_identical(pb, world, cut, rng):
     for r in range(world):
         assert evs[r].config()["tree_height"] == height and evs[r].allgather_count() == 2
         assert np.array_equal(outs[r], ref[own[r]]), (r, np.max(np.abs(outs[r] - ref[own[r]])))
+
+
+def test_arena_blocks_are_cached_across_evaluators(pb, rng):
+    """Work-space blocks of a destroyed evaluator are reused by the next one that asks for the same size (no cudaMalloc
+    / cudaFree between two fits or samplers in one process); plt_release_cached_memory gives them back."""
+    import gc
+    from polatory_b200 import _lib
+    lib = _lib.load()
+    dim = 3
+    src = rng.uniform(-1, 1, (30000, dim))
+    trg = rng.uniform(-1, 1, (40000, dim))
+    w = rng.uniform(-1, 1, 30000)
+
+    def run():
+        ev = pb.make_fmm_evaluator(pb.make_rbf("bh3", [1.0]), pb.Bbox(-np.ones(dim), np.ones(dim)))
+        ev.set_source_points(src)
+        ev.set_target_points(trg)
+        ev.set_weights(w)
+        out = ev.evaluate().copy()
+        out2 = ev.evaluate().copy()      # second call: the arena has settled at one block
+        assert np.array_equal(out, out2)
+        del ev
+        gc.collect()
+        return out
+
+    lib.plt_release_cached_memory()
+    assert lib.plt_cached_memory() == 0
+    a = run()
+    cached = lib.plt_cached_memory()
+    assert cached > 0
+    b = run()                            # takes its blocks from the cache
+    assert np.array_equal(a, b)
+    assert lib.plt_cached_memory() >= cached
+    assert lib.plt_release_cached_memory() >= cached and lib.plt_cached_memory() == 0
+    lib.plt_set_cached_memory_limit(0)   # off: blocks go straight back to the driver
+    try:
+        c = run()
+        assert np.array_equal(a, c) and lib.plt_cached_memory() == 0
+    finally:
+        lib.plt_set_cached_memory_limit(45 << 30)

@@ -17,7 +17,9 @@ dev = torch.device("cuda", 0)
 def T():
     torch.cuda.synchronize(); return time.perf_counter()
 
-for run in range(2):
+import gc
+for run in range(3):
+    free, tot = torch.cuda.mem_get_info(); print('free GB', round(free / 2**30, 1), 'torch reserved GB', round(torch.cuda.memory_reserved() / 2**30, 1))
     model = Model(pb.make_rbf("bh3", [1.0, 0.0]), poly_degree=0, nugget=0.0)
     bbox = pb.Bbox(points.min(axis=0), points.max(axis=0))
     t = [T()]
@@ -41,3 +43,4 @@ for run in range(2):
     print("run", run, {k: round(t[i + 1] - t[i], 3) for i, k in enumerate(names)}, "total", round(t[-1] - t[0], 3))
     print("   ", log, "ras breakdown", {k: round(v, 3) for k, v in pc.setup_seconds.items()})
     del solver, pc, op, res_op, res_eval
+    if os.environ.get('DEV_GC'): gc.collect()
