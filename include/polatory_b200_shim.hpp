@@ -161,6 +161,50 @@ class Fgmres {
   int max_iter_;
 };
 
+// preconditioner::RasPreconditioner::operator() (include/polatory/preconditioner/ras_preconditioner.hpp:183-246) over the
+// device tables of a set-up made through plt_ras_* / plt_chol_* / plt_eval_gram_* (INTEGRATION.md section 5): usable
+// directly as the right preconditioner of plt::Fgmres (`RasSweep::linop`, ctx = the object).
+class RasSweep {
+ public:
+  RasSweep(int64_t m_rows, int l, int n_levels) {
+    int st = plt_ras_sweep_create(m_rows, l, n_levels, &h_);
+    if (st != PLT_OK) throw_status(st, "plt_ras_sweep_create");
+  }
+  ~RasSweep() { plt_ras_sweep_destroy(h_); }
+  RasSweep(const RasSweep&) = delete;
+  RasSweep& operator=(const RasSweep&) = delete;
+
+  void set_level_rows(int level, const int64_t* value_rows, int64_t n_value, const int64_t* grad_rows, int64_t n_grad) {
+    check(plt_ras_sweep_set_level_rows(h_, level, value_rows, n_value, grad_rows, n_grad));
+  }
+  void set_fine(int level, int64_t n_domains, int m, const int64_t* idx, const int32_t* cnt, const double* factor,
+                const double* q_top, const int64_t* inner_glob, const int64_t* inner_loc, int64_t n_inner) {
+    check(plt_ras_sweep_set_fine(h_, level, n_domains, m, idx, cnt, factor, q_top, inner_glob, inner_loc, n_inner));
+  }
+  void set_coarse(int m, const int64_t* idx, const double* inverse, const double* q_top, const double* a_top,
+                  const double* p_top_inv) {
+    check(plt_ras_sweep_set_coarse(h_, m, idx, inverse, q_top, a_top, p_top_inv));
+  }
+  void add_transfer(int src_level, int trg_level, int kind, plt_eval* ev) {
+    check(plt_ras_sweep_add_transfer(h_, src_level, trg_level, kind, ev));
+  }
+  void set_poly(const double* p_mono, const double* p_orth, const double* a_p) {
+    check(plt_ras_sweep_set_poly(h_, p_mono, p_orth, a_p));
+  }
+  void operator()(const double* v_dev, double* out_dev, void* stream = nullptr) {
+    check(plt_ras_sweep_apply(h_, v_dev, out_dev, stream));
+  }
+  static int linop(void* ctx, const double* x_dev, double* y_dev) {
+    return plt_ras_sweep_apply(static_cast<RasSweep*>(ctx)->h_, x_dev, y_dev, nullptr);
+  }
+
+ private:
+  void check(int st) const {
+    if (st != PLT_OK) throw_status(st, plt_ras_sweep_last_error(h_));
+  }
+  plt_ras_sweep* h_ = nullptr;
+};
+
 }  // namespace plt
 
 #ifdef POLATORY_B200_WITH_POLATORY

@@ -234,6 +234,8 @@ def test_cpp_shim_compiles_and_links(tmp_path):
         "    ev.set_source_points(lo, 1); ev.set_target_points(hi, 1); ev.set_weights(lo, 1); ev.set_accuracy(0.0);\n"
         "    plt::Fgmres solver([](void*, const double*, double*) { return 0; }, nullptr, lo, 3, 5);\n"
         "    solver.set_initial_solution(hi); solver.setup(); solver.iterate_process();\n"
+        "    plt::RasSweep sweep(3, 0, 1);  // RasPreconditioner::operator() as the solver's right preconditioner\n"
+        "    solver.set_right_preconditioner(&plt::RasSweep::linop, &sweep); sweep(lo, hi); ev.evaluate_points(lo, 1, hi, 1);\n"
         "    return static_cast<int>(ev.evaluate().size()) + solver.iteration_count() + static_cast<int>(solver.solution_vector().size());\n"
         "  }\n"
         "  return plt_version() == 200 ? 0 : 3;\n"
@@ -243,6 +245,27 @@ def test_cpp_shim_compiles_and_links(tmp_path):
     subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
                            "-o", str(exe), "-L", libdir, "-lpolatory_b200", f"-Wl,-rpath,{libdir}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_ras_sweep_handle_error_paths():
+    """plt_ras_sweep_*: argument checks that need no device (status codes, message through _last_error)."""
+    import ctypes
+    from polatory_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.plt_ras_sweep_create(0, 0, 1, ctypes.byref(h)) == _lib.PLT_ERR_INVALID
+    assert lib.plt_ras_sweep_create(10, 1, 2, ctypes.byref(h)) == _lib.PLT_OK and h
+    rows = np.arange(10, dtype=np.int64)
+    assert lib.plt_ras_sweep_set_level_rows(h, 2, rows.ctypes.data, 10, None, 0) == _lib.PLT_ERR_INVALID   # no such level
+    assert lib.plt_ras_sweep_set_level_rows(h, 1, rows.ctypes.data, 10, None, 0) == _lib.PLT_OK
+    assert lib.plt_ras_sweep_set_fine(h, 0, 1, 5, None, None, None, None, None, None, 0) == _lib.PLT_ERR_INVALID  # level 0 = coarse
+    assert lib.plt_ras_sweep_set_coarse(h, 1, rows.ctypes.data, rows.ctypes.data, None, None, None) == _lib.PLT_ERR_INVALID  # m <= l
+    assert lib.plt_ras_sweep_add_transfer(h, 0, 1, 7, None) == _lib.PLT_ERR_INVALID
+    assert lib.plt_ras_sweep_apply(h, None, None, None) == _lib.PLT_ERR_INVALID
+    assert lib.plt_ras_sweep_last_error(h)
+    assert lib.plt_ras_sweep_launch_count(h) == 0
+    lib.plt_ras_sweep_destroy(h)
+    assert lib.plt_cached_memory() == 0 and lib.plt_release_cached_memory() == 0
 
 
 def test_host_side_abi_error_paths():
