@@ -795,9 +795,46 @@ struct plt_eval {
       const int n_leaf_active = pl.n_active(leaf);
       if (fused) Lc = arena.take<double>(static_cast<size_t>(std::max(n_leaf_active, 1)) * nc * kn * P);
 
+      // The levels above the leaf level in ONE Hadamard launch (list path, all their slots at once): each of them is
+      // a few hundred parents, latency-bound when launched one by one -- which is what a slab, a sampler batch or the
+      // share of one rank of eight pays per evaluation.  Their spectra sit side by side in Lhat; the inverse
+      // transforms and L2L then run level by level as before (same arithmetic per slot: bit-identical).
+      const bool full_range = leaf_lo == 0 && leaf_hi == tt.n_cells(leaf);
+      bool merged = false;
+      const int n_upper = leaf - 2;  // levels 2 .. leaf-1
+      if (full_range && n_upper >= 2 && n_upper <= 8 && m2l_hadamard_multi_level_supported()) {
+        bool lists_only = true;
+        for (int l = 2; l < leaf; ++l) lists_only = lists_only && !(use_blk && ((Mblk_.levels >> l) & 1u));
+        const int total_upper = shi[leaf - 1] - slo[2];
+        if (lists_only && total_upper > 0 && static_cast<size_t>(total_upper) <= chunk_cap) {
+          M2LArgs a{};
+          a.trg = tv;
+          a.level = 2;
+          a.order = order;
+          a.dim = dim;
+          a.km = km;
+          a.kn = kn;
+          a.Mhat = Mhat_.get();
+          a.Khat = ip.khat.get();
+          a.khat_level_stride = ip.khat_level_stride;
+          a.active = pv.active + slo[2];
+          a.src_ids = pv.src_ids + static_cast<size_t>(slo[2]) * nn * nc;
+          a.trg_mask = pv.trg_mask + slo[2];
+          a.n_active = total_upper;
+          a.Lhat = Lhat;
+          a.n_lvls = n_upper;
+          for (int i = 0; i < n_upper; ++i) a.lvl_slot_end[i] = shi[2 + i] - slo[2];
+          if (timed) timer.begin("m2l_hadamard", stream);
+          launch_m2l_hadamard(a, stream, ctr);
+          if (timed) timer.end(stream);
+          merged = true;
+        }
+      }
+
       for (int l = 2; l < height; ++l) {
         const int n_active = shi[l] - slo[l];
         const bool compact_out = fused && l == leaf;
+        const bool had_done = merged && l < leaf;  // this level's spectra are already in Lhat
         for (int c0 = 0; c0 < n_active; c0 += chunk_parents) {
           const int ncnk = std::min(chunk_parents, n_active - c0);
           const size_t s0 = static_cast<size_t>(slo[l]) + c0;
@@ -814,7 +851,7 @@ struct plt_eval {
           a.src_ids = pv.src_ids + s0 * nn * nc;
           a.trg_mask = pv.trg_mask + s0;
           a.n_active = ncnk;
-          a.Lhat = Lhat;
+          a.Lhat = had_done ? Lhat + static_cast<size_t>(slo[l] - slo[2]) * nc * kn * F : Lhat;
           a.L = compact_out ? nullptr : L;
           a.Lc = compact_out ? Lc + (s0 - pv.level_begin[leaf]) * nc * kn * P : nullptr;
           if (use_blk && ((Mblk_.levels >> l) & 1u)) {
@@ -842,9 +879,11 @@ struct plt_eval {
             if (timed) timer.end(stream);
             continue;
           }
-          if (timed) timer.begin("m2l_hadamard", stream);
-          launch_m2l_hadamard(a, stream, ctr);
-          if (timed) timer.end(stream);
+          if (!had_done) {
+            if (timed) timer.begin("m2l_hadamard", stream);
+            launch_m2l_hadamard(a, stream, ctr);
+            if (timed) timer.end(stream);
+          }
           if (timed) timer.begin("m2l_idft", stream);
           launch_m2l_idft(a, ip.dev, stream, ctr);
           if (timed) timer.end(stream);

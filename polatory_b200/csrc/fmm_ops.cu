@@ -1186,7 +1186,14 @@ __global__ void __launch_bounds__(HadCfg<DIM>::kWarps * 32, 1) k_m2l_hadamard_ti
   for (long long q0 = q_lo; q0 < q_hi;) {
     const int ftile = static_cast<int>(q0 / a.n_active);
     const int slot_lo = static_cast<int>(q0 - static_cast<long long>(ftile) * a.n_active);
-    const long long seg_end = min(q_hi, static_cast<long long>(ftile + 1) * a.n_active);
+    // a segment ends with the CTA's range, the tile or the level (another level = another operator slice)
+    int lv = 0, lv_end = a.n_active;
+    if (a.n_lvls > 1) {
+      while (lv + 1 < a.n_lvls && slot_lo >= a.lvl_slot_end[lv]) ++lv;
+      lv_end = a.lvl_slot_end[lv];
+    }
+    const double2* Khat_l = a.Khat + static_cast<size_t>(lv) * a.khat_level_stride;
+    const long long seg_end = min(q_hi, static_cast<long long>(ftile) * a.n_active + lv_end);
     const int slot_hi = slot_lo + static_cast<int>(seg_end - q0);
     q0 = seg_end;
     const int f = ftile * kHadTF + lane;
@@ -1206,7 +1213,7 @@ __global__ void __launch_bounds__(HadCfg<DIM>::kWarps * 32, 1) k_m2l_hadamard_ti
         if (lane == 0) mbar_expect_tx(&s_bar, static_cast<uint32_t>(NOFF) * valid * sizeof(double2));
         __syncwarp();
         for (int oi = lane; oi < NOFF; oi += 32)
-          bulk_g2s(Ks + oi * kHadTF, a.Khat + (static_cast<size_t>(oi) * kn * km + comp) * F + ftile * kHadTF,
+          bulk_g2s(Ks + oi * kHadTF, Khat_l + (static_cast<size_t>(oi) * kn * km + comp) * F + ftile * kHadTF,
                    valid * sizeof(double2), &s_bar);
       }
       if (valid < kHadTF)
@@ -1217,7 +1224,7 @@ __global__ void __launch_bounds__(HadCfg<DIM>::kWarps * 32, 1) k_m2l_hadamard_ti
     } else {
       for (int e = threadIdx.x; e < NOFF * kHadTF; e += blockDim.x) {
         const int oi = e / kHadTF, ff = ftile * kHadTF + (e % kHadTF);
-        Ks[e] = ff < F ? a.Khat[(static_cast<size_t>(oi) * kn * km + comp) * F + ff] : make_double2(0.0, 0.0);
+        Ks[e] = ff < F ? Khat_l[(static_cast<size_t>(oi) * kn * km + comp) * F + ff] : make_double2(0.0, 0.0);
       }
     }
     __syncthreads();
@@ -1949,8 +1956,14 @@ void launch_hadamard_tiled(const M2LArgs& a, int F, cudaStream_t s, LaunchCounte
 }
 }  // namespace
 
+bool m2l_hadamard_multi_level_supported() {
+  static const bool ok = getenv("PLT_DEBUG_NO_TILED") == nullptr && getenv("PLT_DEBUG_NO_MULTI_LEVEL") == nullptr;
+  return ok && !hadamard_tmem_enabled();
+}
+
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c) {
   if (a.n_active == 0) return;
+  PLT_REQUIRE(a.n_lvls == 1 || m2l_hadamard_multi_level_supported(), "multi-level Hadamard launch not available");
   const int F = freqs_per_cell(a.order, a.dim);
   static const bool no_tiled = getenv("PLT_DEBUG_NO_TILED") != nullptr;  // A/B switch for parity bisection
   if (!no_tiled) {

@@ -86,9 +86,17 @@ struct M2LArgs {
   int grp_lo = 0, grp_hi = 0;      // this level's group range
   int slot0 = 0;                   // plan slot of active[0] (groups are cut to the chunk [slot0, slot0 + n_active))
   double2* Lhat_blk = nullptr;     // scratch [n_active][kn][FB]
+  // Several consecutive levels in ONE Hadamard launch (the levels above the leaf level are a few launches of a few
+  // hundred parents each, latency-bound one by one): slots [lvl_slot_end[i-1], lvl_slot_end[i]) of the chunk belong to
+  // level `level + i`, whose operators are Khat + i * khat_level_stride.  n_lvls = 1: the chunk is one level.
+  int n_lvls = 1;
+  int lvl_slot_end[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t khat_level_stride = 0;
 };
 // Fourier-space accumulation over the M2L lists of the children of the active parents.
 void launch_m2l_hadamard(const M2LArgs& a, cudaStream_t s, LaunchCounter& c);
+// May a chunk span several levels (M2LArgs::n_lvls > 1)?  (the tiled list kernel only)
+bool m2l_hadamard_multi_level_supported();
 // Scalar 3-D variant with the operators of most pairs in Tensor Memory (fmm_had_tmem.cu); false = not applicable.
 bool launch_m2l_hadamard_tmem(const M2LArgs& a, int F, cudaStream_t s, LaunchCounter& c);
 bool hadamard_tmem_enabled();

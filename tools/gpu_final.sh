@@ -12,3 +12,11 @@ cut -c1-600 gpurun_out/${TAG}_bench.json
 echo "== bench reference arm"
 ( time timeout 600 python bench.py --impl reference 2> gpurun_out/${TAG}_bench_reference.err | tail -1 > gpurun_out/${TAG}_bench_reference.json ) 2>&1 | tail -3
 cut -c1-400 gpurun_out/${TAG}_bench_reference.json
+echo "== ncu launches"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-fit --no-sampler > gpurun_out/${TAG}_ncu_launches.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_launches.log | cut -c1-120
+echo "== ncu full: k_m2l_hadamard_tiled (leaf-level launch)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_m2l_hadamard_tiled -s 5 -c 1 -f -o gpurun_out/${TAG}_prof_hadamard \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-fit --no-sampler > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_full.log | cut -c1-120
