@@ -827,6 +827,10 @@ struct plt_eval {
           if (timed) timer.begin("m2l_hadamard", stream);
           launch_m2l_hadamard(a, stream, ctr);
           if (timed) timer.end(stream);
+          a.L = L;  // inverse transforms of all those levels in one launch as well (a slot knows its level)
+          if (timed) timer.begin("m2l_idft", stream);
+          launch_m2l_idft(a, ip.dev, stream, ctr);
+          if (timed) timer.end(stream);
           merged = true;
         }
       }
@@ -834,7 +838,7 @@ struct plt_eval {
       for (int l = 2; l < height; ++l) {
         const int n_active = shi[l] - slo[l];
         const bool compact_out = fused && l == leaf;
-        const bool had_done = merged && l < leaf;  // this level's spectra are already in Lhat
+        const bool had_done = merged && l < leaf;  // this level's spectra and locals are already done
         for (int c0 = 0; c0 < n_active; c0 += chunk_parents) {
           const int ncnk = std::min(chunk_parents, n_active - c0);
           const size_t s0 = static_cast<size_t>(slo[l]) + c0;
@@ -879,11 +883,10 @@ struct plt_eval {
             if (timed) timer.end(stream);
             continue;
           }
-          if (!had_done) {
-            if (timed) timer.begin("m2l_hadamard", stream);
-            launch_m2l_hadamard(a, stream, ctr);
-            if (timed) timer.end(stream);
-          }
+          if (had_done) continue;  // spectra and inverse transforms of this level were done with the others
+          if (timed) timer.begin("m2l_hadamard", stream);
+          launch_m2l_hadamard(a, stream, ctr);
+          if (timed) timer.end(stream);
           if (timed) timer.begin("m2l_idft", stream);
           launch_m2l_idft(a, ip.dev, stream, ctr);
           if (timed) timer.end(stream);

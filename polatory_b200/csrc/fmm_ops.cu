@@ -1302,6 +1302,13 @@ __global__ void __launch_bounds__(HadCfg<DIM>::kWarps * 32, 1) k_m2l_hadamard_ti
   }
 }
 
+// Level of a slot of a (possibly multi-level) chunk, M2LArgs::n_lvls / lvl_slot_end.
+__device__ __forceinline__ int m2l_slot_level(const M2LArgs& a, int slot) {
+  int lv = 0;
+  while (lv + 1 < a.n_lvls && slot >= a.lvl_slot_end[lv]) ++lv;
+  return a.level + lv;
+}
+
 // Inverse DFT of the accumulated spectra, pruned to the order^dim nodes:  L[cell][b][:] = IDFT(Lhat)
 // One CTA per (slot, child, b).
 template <int DIM, int ORDER>
@@ -1327,10 +1334,10 @@ __global__ void __launch_bounds__(kBlock) k_m2l_idft(M2LArgs a, InterpDev it, do
     const double2* in0 = a.Lhat + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * F;
     double* Lc;
     if (a.L) {
-      const int pidx = a.active[slot];
-      const uint32_t pkey = a.trg.keys[a.trg.cell_off[a.level - 1] + pidx];
-      const int cidx = a.trg.dense[a.trg.dense_off[a.level] + ((pkey << DIM) | ct)];
-      Lc = a.L + (static_cast<size_t>(a.trg.cell_off[a.level] + cidx) * a.kn + b) * P;
+      const int pidx = a.active[slot], lvl = m2l_slot_level(a, slot);
+      const uint32_t pkey = a.trg.keys[a.trg.cell_off[lvl - 1] + pidx];
+      const int cidx = a.trg.dense[a.trg.dense_off[lvl] + ((pkey << DIM) | ct)];
+      Lc = a.L + (static_cast<size_t>(a.trg.cell_off[lvl] + cidx) * a.kn + b) * P;
     } else {
       Lc = a.Lc + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * P;
     }
@@ -1386,10 +1393,10 @@ __global__ void __launch_bounds__(256) k_m2l_idft3(M2LArgs a, TwTable tw) {
       if ((a.trg_mask[slot] >> ct) & 1u) {
         in = a.Lhat + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * F;
         if (a.L) {
-          const int pidx = a.active[slot];
-          const uint32_t pkey = a.trg.keys[a.trg.cell_off[a.level - 1] + pidx];
-          const int cidx = a.trg.dense[a.trg.dense_off[a.level] + ((pkey << DIM) | ct)];
-          out = a.L + (static_cast<size_t>(a.trg.cell_off[a.level] + cidx) * a.kn + b) * P;
+          const int pidx = a.active[slot], lvl = m2l_slot_level(a, slot);
+          const uint32_t pkey = a.trg.keys[a.trg.cell_off[lvl - 1] + pidx];
+          const int cidx = a.trg.dense[a.trg.dense_off[lvl] + ((pkey << DIM) | ct)];
+          out = a.L + (static_cast<size_t>(a.trg.cell_off[lvl] + cidx) * a.kn + b) * P;
         } else {
           out = a.Lc + ((static_cast<size_t>(slot) * NC + ct) * a.kn + b) * P;
         }
