@@ -787,7 +787,10 @@ struct plt_eval {
       const int chunk_parents = static_cast<int>(std::max<size_t>(1, budget / per_parent));
       int max_active = 0;
       for (int l = 2; l < height; ++l) max_active = std::max(max_active, shi[l] - slo[l]);
-      const size_t chunk_cap = static_cast<size_t>(std::min(chunk_parents, std::max(max_active, 1)));
+      const bool full_range_early = leaf_lo == 0 && leaf_hi == tt.n_cells(leaf);
+      // (room for all levels side by side when that fits one chunk: the merged launches below)
+      const int all_active = full_range_early ? shi[leaf] - slo[2] : 0;
+      const size_t chunk_cap = static_cast<size_t>(std::min(chunk_parents, std::max(std::max(max_active, all_active), 1)));
       double2* Lhat = arena.take<double2>(chunk_cap * per_parent);
       double2* Lhat_blk = Lhat + chunk_cap * nc * kn * F;
       // compact M2L result of the leaf level (fused path), indexed by slot - level_begin[leaf]
@@ -800,13 +803,16 @@ struct plt_eval {
       // share of one rank of eight pays per evaluation.  Their spectra sit side by side in Lhat; the inverse
       // transforms and L2L then run level by level as before (same arithmetic per slot: bit-identical).
       const bool full_range = leaf_lo == 0 && leaf_hi == tt.n_cells(leaf);
-      bool merged = false;
+      bool merged = false, merged_leaf = false;
       const int n_upper = leaf - 2;  // levels 2 .. leaf-1
-      if (full_range && n_upper >= 2 && n_upper <= 8 && m2l_hadamard_multi_level_supported()) {
-        bool lists_only = true;
+      if (full_range && n_upper >= 1 && n_upper < 8 && m2l_hadamard_multi_level_supported()) {
+        bool lists_only = true, leaf_lists = !(use_blk && ((Mblk_.levels >> leaf) & 1u));
         for (int l = 2; l < leaf; ++l) lists_only = lists_only && !(use_blk && ((Mblk_.levels >> l) & 1u));
-        const int total_upper = shi[leaf - 1] - slo[2];
-        if (lists_only && total_upper > 0 && static_cast<size_t>(total_upper) <= chunk_cap) {
+        const int total_upper = shi[leaf - 1] - slo[2], total_all = shi[leaf] - slo[2];
+        // a small evaluation (a sampler batch, the share of one rank of eight) takes the leaf level along: it fits the
+        // Lhat chunk as well, and one launch instead of two is worth 0.07 ms of a 0.6 ms batch
+        const bool with_leaf = leaf_lists && static_cast<size_t>(total_all) <= chunk_cap;
+        if (lists_only && total_upper > 0 && static_cast<size_t>(total_upper) <= chunk_cap && (n_upper >= 2 || with_leaf)) {
           M2LArgs a{};
           a.trg = tv;
           a.level = 2;
@@ -820,18 +826,23 @@ struct plt_eval {
           a.active = pv.active + slo[2];
           a.src_ids = pv.src_ids + static_cast<size_t>(slo[2]) * nn * nc;
           a.trg_mask = pv.trg_mask + slo[2];
-          a.n_active = total_upper;
+          a.n_active = with_leaf ? total_all : total_upper;
           a.Lhat = Lhat;
-          a.n_lvls = n_upper;
-          for (int i = 0; i < n_upper; ++i) a.lvl_slot_end[i] = shi[2 + i] - slo[2];
+          a.n_lvls = n_upper + (with_leaf ? 1 : 0);
+          for (int i = 0; i < a.n_lvls; ++i) a.lvl_slot_end[i] = shi[2 + i] - slo[2];
           if (timed) timer.begin("m2l_hadamard", stream);
           launch_m2l_hadamard(a, stream, ctr);
           if (timed) timer.end(stream);
-          a.L = L;  // inverse transforms of all those levels in one launch as well (a slot knows its level)
+          // inverse transforms of the upper levels in one launch as well (a slot knows its level); the leaf level's go
+          // to the compact buffer of the fused leaf pass and keep their own launch
+          a.n_active = total_upper;
+          a.n_lvls = n_upper;
+          a.L = L;
           if (timed) timer.begin("m2l_idft", stream);
           launch_m2l_idft(a, ip.dev, stream, ctr);
           if (timed) timer.end(stream);
           merged = true;
+          merged_leaf = with_leaf;
         }
       }
 
@@ -884,9 +895,13 @@ struct plt_eval {
             continue;
           }
           if (had_done) continue;  // spectra and inverse transforms of this level were done with the others
-          if (timed) timer.begin("m2l_hadamard", stream);
-          launch_m2l_hadamard(a, stream, ctr);
-          if (timed) timer.end(stream);
+          if (merged_leaf && l == leaf) {
+            a.Lhat = Lhat + static_cast<size_t>(slo[l] - slo[2]) * nc * kn * F;  // spectra already there
+          } else {
+            if (timed) timer.begin("m2l_hadamard", stream);
+            launch_m2l_hadamard(a, stream, ctr);
+            if (timed) timer.end(stream);
+          }
           if (timed) timer.begin("m2l_idft", stream);
           launch_m2l_idft(a, ip.dev, stream, ctr);
           if (timed) timer.end(stream);
