@@ -12,6 +12,7 @@ cut -c1-600 gpurun_out/${TAG}_bench.json
 echo "== bench reference arm"
 ( time timeout 600 python bench.py --impl reference 2> gpurun_out/${TAG}_bench_reference.err | tail -1 > gpurun_out/${TAG}_bench_reference.json ) 2>&1 | tail -3
 cut -c1-400 gpurun_out/${TAG}_bench_reference.json
+[ -n "${SKIP_NCU:-}" ] && exit 0
 echo "== ncu launches"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-fit --no-sampler > gpurun_out/${TAG}_ncu_launches.log 2>&1
