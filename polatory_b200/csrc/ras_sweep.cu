@@ -154,7 +154,7 @@ __global__ void k_coarse_post(const double* __restrict__ gamma, const double* __
   }
 }
 
-inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>((n + kT - 1) / kT); }
+inline unsigned blocks_for(int64_t n) { return static_cast<unsigned>(std::max<int64_t>(1, (n + kT - 1) / kT)); }
 
 }  // namespace
 }  // namespace plt
