@@ -34,6 +34,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -584,6 +585,9 @@ int orc_fmm(int rbf_id, int part, int dim, const double* params, const double* a
   for (int64_t i = 0; i < ns; ++i)
     for (int a = 0; a < km; ++a) ws[i * km + a] = w[st.perm[i] * km + a];
 
+  /* (ORC_TIMING=1 in the environment prints the wall time of the three phases: the CPU baseline's own profile) */
+  const int timing = getenv("ORC_TIMING") != NULL;
+  const double t_up0 = omp_get_wtime();
   /* ---- upward: P2M at the leaves, M2M to level 2 ---- */
   double*** M = (double***)calloc(tree_height, sizeof(double**));
   cplx*** Mh = (cplx***)calloc(tree_height, sizeof(cplx**));
@@ -650,6 +654,7 @@ int orc_fmm(int rbf_id, int part, int dim, const double* params, const double* a
     }
   }
 
+  const double t_down0 = omp_get_wtime();
   /* ---- downward ---- */
   double*** L = (double***)calloc(tree_height, sizeof(double**));
   for (int l = 2; l < tree_height; ++l) L[l] = (double**)calloc(cells_at(dim, l), sizeof(double*));
@@ -739,6 +744,7 @@ int orc_fmm(int rbf_id, int part, int dim, const double* params, const double* a
   }
   free(Kh);
 
+  const double t_leaf0 = omp_get_wtime();
   /* ---- leaves: L2P + P2P ---- */
   {
     const int64_t nleaf = cells_at(dim, leaf);
@@ -783,6 +789,10 @@ int orc_fmm(int rbf_id, int part, int dim, const double* params, const double* a
     }
   }
 
+  if (timing)
+    fprintf(stderr, "orc_fmm: upward (P2M, M2M, forward DFTs) %.3f s, downward (operators, M2L, inverse DFTs, L2L) %.3f s, "
+                    "leaves (L2P, P2P) %.3f s, %d threads\n",
+            t_down0 - t_up0, t_leaf0 - t_down0, omp_get_wtime() - t_leaf0, omp_get_max_threads());
   for (int l = 2; l < tree_height; ++l) {
     for (int64_t c = 0; c < cells_at(dim, l); ++c) { free(M[l][c]); free(Mh[l][c]); free(L[l][c]); }
     free(M[l]); free(Mh[l]); free(L[l]);
