@@ -46,6 +46,109 @@ void parallel_for(size_t n, F&& f) {
   for (auto& th : pool) th.join();
 }
 
+unsigned hardware_threads() { return std::max(1u, std::thread::hardware_concurrency()); }
+
+// Multi-rank selection with several threads.  On return, for every rank r of `ranks` (ascending) a[r] is the element a
+// full sort would put there, everything left of it is smaller and everything right of it larger -- what successive
+// std::nth_element calls on the right remainders give.  `less` must be a strict TOTAL order (ties broken by the index),
+// so the sets on either side of a cut do not depend on how they were found.
+// The first levels of a bisection have fewer clusters than cores; a serial selection over 10^6 items costs 40 - 75 ms
+// there.  Sample sort without the sort: ~1000 sorted splitters, every thread bins its chunk (binary search) and
+// scatters it bucket by bucket, then only the buckets that contain a rank are selected serially.
+template <class T, class Less>
+void parallel_select(T* a, size_t n, std::initializer_list<size_t> ranks, Less less, unsigned threads) {
+  auto serial = [&] {
+    size_t lo = 0;
+    for (size_t r : ranks) {
+      if (r > lo && r < n) std::nth_element(a + lo, a + r, a + n, less);
+      lo = std::max(lo, std::min(r, n));
+    }
+  };
+  threads = std::min(threads, 64u);
+  if (threads <= 1 || n < (size_t{1} << 17)) return serial();
+  // Thresholds that bracket every rank: from a sorted sample of m elements, the sample quantile of the rank -+ 4 standard
+  // deviations of its position (0.5 sqrt(m) sample positions).  Should a rank fall outside its bracket, the selection
+  // below simply runs on the (larger) class that does contain it -- the result is exact either way.
+  const size_t m = 8192, margin = 4 * 46;
+  std::vector<T> sample(m);
+  for (size_t k = 0; k < m; ++k) sample[k] = a[(2 * k + 1) * n / (2 * m)];
+  std::sort(sample.begin(), sample.end(), less);
+  std::vector<size_t> cut_at;
+  for (size_t r : ranks) {
+    if (r == 0 || r >= n) continue;
+    const size_t p = static_cast<size_t>(static_cast<double>(r) / static_cast<double>(n) * m);
+    cut_at.push_back(p > margin ? p - margin : 0);
+    cut_at.push_back(std::min(m - 1, p + margin));
+  }
+  std::sort(cut_at.begin(), cut_at.end());
+  cut_at.erase(std::unique(cut_at.begin(), cut_at.end()), cut_at.end());
+  std::vector<T> thr;
+  for (size_t c : cut_at) thr.push_back(sample[c]);
+  const size_t C = thr.size() + 1;  // classes: number of thresholds smaller than the element
+  if (C == 1) return serial();
+  std::unique_ptr<uint8_t[]> cls(new uint8_t[n]);
+  std::vector<size_t> count(static_cast<size_t>(threads) * C, 0);
+  auto chunk = [&](size_t t, size_t& lo, size_t& hi) {
+    lo = n * t / threads;
+    hi = n * (t + 1) / threads;
+  };
+  parallel_for(threads, [&](size_t t) {
+    size_t lo, hi;
+    chunk(t, lo, hi);
+    size_t* c = count.data() + t * C;
+    for (size_t k = lo; k < hi; ++k) {
+      size_t b = 0;
+      while (b < thr.size() && less(thr[b], a[k])) ++b;  // a handful of thresholds, the big classes first: predictable
+      cls[k] = static_cast<uint8_t>(b);
+      ++c[b];
+    }
+  });
+  std::vector<size_t> start(C + 1, 0), offset(static_cast<size_t>(threads) * C);
+  for (size_t b = 0; b < C; ++b) {
+    size_t at = start[b];
+    for (unsigned t = 0; t < threads; ++t) {
+      offset[static_cast<size_t>(t) * C + b] = at;
+      at += count[static_cast<size_t>(t) * C + b];
+    }
+    start[b + 1] = at;
+  }
+  std::unique_ptr<T[]> tmp(new T[n]);  // (uninitialised: its pages are first touched by the scattering threads)
+  parallel_for(threads, [&](size_t t) {
+    size_t lo, hi;
+    chunk(t, lo, hi);
+    size_t* o = offset.data() + t * C;
+    for (size_t k = lo; k < hi; ++k) tmp[o[cls[k]]++] = a[k];
+  });
+  parallel_for(threads, [&](size_t t) {
+    size_t lo, hi;
+    chunk(t, lo, hi);
+    std::copy(tmp.get() + lo, tmp.get() + hi, a + lo);
+  });
+  size_t done = 0;  // everything left of `done` is final
+  for (size_t r : ranks) {
+    if (r <= done || r >= n) {
+      done = std::max(done, std::min(r, n));
+      continue;
+    }
+    const size_t b = std::upper_bound(start.begin(), start.end(), r) - start.begin() - 1;  // start[b] <= r < start[b + 1]
+    const size_t lo = std::max(start[b], done), hi = start[b + 1];
+    std::nth_element(a + lo, a + r, a + hi, less);
+    done = r;
+  }
+}
+
+template <class T>
+void parallel_copy(const T* src, size_t n, T* dst, unsigned threads) {
+  if (threads <= 1 || n < (size_t{1} << 16)) {
+    std::copy(src, src + n, dst);
+    return;
+  }
+  parallel_for(threads, [&](size_t t) {
+    const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
+    std::copy(src + lo, src + hi, dst + lo);
+  });
+}
+
 // Axes by decreasing bounding-box width (stable for equal widths), and the box itself.
 struct BoxInfo {
   std::array<double, 3> lo, hi;
@@ -104,49 +207,125 @@ size_t split_position(size_t size) {
   return a % 2 == 0 ? a : a + 1;
 }
 
-struct Cluster {
-  std::vector<int64_t> idx;
-  std::array<int, 3> axes;  // by decreasing width of the cluster's box
-  double volume;
-  int64_t centre;
+// ---- value data: clusters and domains over COMPACT items (coordinates + index side by side) -------------------------
+// The selections below touch every point of a level log2(n / leaf) times; going through idx -> pv.row(idx) is a random
+// access into the point array per comparison, a compact item array is streamed.  Same order (coordinates along the
+// axes, then the index), hence the same sets on either side of every cut.
+struct Item {
+  double x[3];
+  int64_t i;
 };
 
-// bbox, axes and centre (the point nearest to the box centre).
-void init_cluster(const PointsView& pv, Cluster& c) {
-  const BoxInfo b = box_of(pv, c.idx.data(), c.idx.size());
-  double best = std::numeric_limits<double>::infinity();
-  c.centre = c.idx.empty() ? -1 : c.idx[0];
-  c.volume = 1.0;
-  for (int a = 0; a < pv.dim; ++a) c.volume *= b.hi[a] - b.lo[a];
-  for (int64_t i : c.idx) {
-    const double* r = pv.row(i);
-    double d2 = 0.0;
-    for (int a = 0; a < pv.dim; ++a) {
-      const double d = r[a] - 0.5 * (b.lo[a] + b.hi[a]);
-      d2 += d * d;
+struct ItemLess {
+  std::array<int, 3> axes;
+  int dim;
+  bool operator()(const Item& p, const Item& q) const {
+    for (int k = 0; k < dim; ++k) {
+      const int a = axes[k];
+      if (p.x[a] != q.x[a]) return p.x[a] < q.x[a];
     }
-    if (d2 < best) {
-      best = d2;
-      c.centre = i;
-    }
+    return p.i < q.i;
   }
+};
+
+template <class It>
+BoxInfo box_of_items(const It* it, size_t n, int dim, unsigned threads = 1) {
+  BoxInfo b;
+  for (int a = 0; a < 3; ++a) {
+    b.lo[a] = std::numeric_limits<double>::infinity();
+    b.hi[a] = -std::numeric_limits<double>::infinity();
+  }
+  if (threads <= 1 || n < (size_t{1} << 16)) {
+    for (size_t k = 0; k < n; ++k)
+      for (int a = 0; a < dim; ++a) {
+        b.lo[a] = std::min(b.lo[a], it[k].x[a]);
+        b.hi[a] = std::max(b.hi[a], it[k].x[a]);
+      }
+  } else {
+    std::vector<BoxInfo> part(threads, b);
+    parallel_for(threads, [&](size_t t) {
+      BoxInfo& q = part[t];
+      for (size_t k = n * t / threads; k < n * (t + 1) / threads; ++k)
+        for (int a = 0; a < dim; ++a) {
+          q.lo[a] = std::min(q.lo[a], it[k].x[a]);
+          q.hi[a] = std::max(q.hi[a], it[k].x[a]);
+        }
+    });
+    for (const BoxInfo& q : part)
+      for (int a = 0; a < dim; ++a) {
+        b.lo[a] = std::min(b.lo[a], q.lo[a]);
+        b.hi[a] = std::max(b.hi[a], q.hi[a]);
+      }
+  }
+  for (int a = 0; a < 3; ++a) b.axes[a] = a;
+  std::stable_sort(b.axes.begin(), b.axes.begin() + dim,
+                   [&](int i, int j) { return b.hi[i] - b.lo[i] > b.hi[j] - b.lo[j]; });
+  return b;
+}
+
+// A cluster is a range of ONE item array: splitting is a selection in place, no copies.
+struct RangeCluster {
+  size_t lo = 0, hi = 0;
+  std::array<int, 3> axes{{0, 1, 2}};
+  double volume = 0.0;
+  int64_t centre = -1;
+  size_t size() const { return hi - lo; }
+};
+
+void init_range_cluster(const Item* items, int dim, RangeCluster& c, unsigned threads = 1) {
+  const Item* it = items + c.lo;
+  const size_t n = c.size();
+  const BoxInfo b = box_of_items(it, n, dim, threads);
+  c.volume = 1.0;
+  for (int a = 0; a < dim; ++a) c.volume *= b.hi[a] - b.lo[a];
+  // the FIRST point nearest to the box centre (per-thread candidates are merged in position order)
+  auto nearest = [&](size_t lo, size_t hi, double& best, size_t& at) {
+    for (size_t k = lo; k < hi; ++k) {
+      double d2 = 0.0;
+      for (int a = 0; a < dim; ++a) {
+        const double d = it[k].x[a] - 0.5 * (b.lo[a] + b.hi[a]);
+        d2 += d * d;
+      }
+      if (d2 < best) {
+        best = d2;
+        at = k;
+      }
+    }
+  };
+  double best = std::numeric_limits<double>::infinity();
+  size_t at = 0;
+  if (threads <= 1 || n < (size_t{1} << 16)) {
+    nearest(0, n, best, at);
+  } else {
+    std::vector<double> pb(threads, std::numeric_limits<double>::infinity());
+    std::vector<size_t> pa(threads, 0);
+    parallel_for(threads, [&](size_t t) { nearest(n * t / threads, n * (t + 1) / threads, pb[t], pa[t]); });
+    for (unsigned t = 0; t < threads; ++t)
+      if (pb[t] < best) {
+        best = pb[t];
+        at = pa[t];
+      }
+  }
+  c.centre = n ? it[at].i : -1;
   c.axes = b.axes;
 }
 
-// Splits c at the reference's mid rank into (l, r).
-void split_cluster(const PointsView& pv, Cluster& c, Cluster& l, Cluster& r) {
-  const size_t mid = c.idx.size() > 1 ? split_position(c.idx.size()) : 0;
-  select_ranks(pv, c.axes, c.idx.data(), c.idx.size(), {mid});
-  l.idx.assign(c.idx.begin(), c.idx.begin() + mid);
-  r.idx.assign(c.idx.begin() + mid, c.idx.end());
-  // The centre is the FIRST point nearest to the box centre in the reference's order (the parent's sorted order);
-  // exact distance ties are the rule for two-point clusters (both are equidistant from their midpoint), so small
-  // children are put in that order before their centre is chosen.
-  const AxisLess less{pv, c.axes};
-  if (l.idx.size() <= 8) std::sort(l.idx.begin(), l.idx.end(), less);
-  if (r.idx.size() <= 8) std::sort(r.idx.begin(), r.idx.end(), less);
-  if (!l.idx.empty()) init_cluster(pv, l);
-  if (!r.idx.empty()) init_cluster(pv, r);
+void split_range_cluster(Item* items, int dim, const RangeCluster& c, RangeCluster& l, RangeCluster& r,
+                         unsigned threads = 1) {
+  const size_t n = c.size(), mid = n > 1 ? split_position(n) : 0;
+  const ItemLess less{c.axes, dim};
+  Item* it = items + c.lo;
+  if (mid > 0 && mid < n) parallel_select(it, n, {mid}, less, threads);
+  l.lo = c.lo;
+  l.hi = c.lo + mid;
+  r.lo = c.lo + mid;
+  r.hi = c.hi;
+  // (the centre is the FIRST nearest point in the parent's sorted order; exact ties are the rule for two-point
+  // clusters, so small children are put in that order before their centre is chosen)
+  if (l.size() <= 8) std::sort(items + l.lo, items + l.hi, less);
+  if (r.size() <= 8) std::sort(items + r.lo, items + r.hi, less);
+  if (l.size()) init_range_cluster(items, dim, l, threads);
+  if (r.size()) init_range_cluster(items, dim, r, threads);
 }
 
 double round_half_to_even(double d) { return std::ceil((d - 0.5) / 2.0) + std::floor((d + 0.5) / 2.0); }
@@ -172,27 +351,35 @@ int plt_ras_choose_coarse_points(const double* a_points, int dim, const int64_t*
                                  const int64_t* poly, int64_t n_poly, int64_t n_coarse, int64_t* out) {
   if (!a_points || !idcs || !out || dim < 1 || dim > 3 || n_coarse < 1) return PLT_ERR_INVALID;
   try {
-    const PointsView pv{a_points, dim};
     std::vector<int64_t> poly_sorted(poly, poly + n_poly);
     std::sort(poly_sorted.begin(), poly_sorted.end());
-    Cluster root;
-    root.idx.reserve(n_idcs);
-    for (int64_t k = 0; k < n_idcs; ++k)
-      if (!std::binary_search(poly_sorted.begin(), poly_sorted.end(), idcs[k])) root.idx.push_back(idcs[k]);
-    if (static_cast<int64_t>(root.idx.size()) < n_coarse) return PLT_ERR_INVALID;
-    init_cluster(pv, root);
-    std::vector<Cluster> level;
-    level.push_back(std::move(root));
+    std::vector<Item> items;
+    items.reserve(n_idcs);
+    for (int64_t k = 0; k < n_idcs; ++k) {
+      if (std::binary_search(poly_sorted.begin(), poly_sorted.end(), idcs[k])) continue;
+      Item it{{0.0, 0.0, 0.0}, idcs[k]};
+      for (int a = 0; a < dim; ++a) it.x[a] = a_points[idcs[k] * dim + a];
+      items.push_back(it);
+    }
+    if (static_cast<int64_t>(items.size()) < n_coarse) return PLT_ERR_INVALID;
+    RangeCluster root;
+    root.hi = items.size();
+    init_range_cluster(items.data(), dim, root, hardware_threads());
+    std::vector<RangeCluster> level{root};
     // Whole levels are split while the count stays below the target (the queue orders by level first).
     for (;;) {
       size_t splittable = 0;
-      for (auto& c : level) splittable += c.idx.size() > 1 ? 1 : 0;
+      for (auto& c : level) splittable += c.size() > 1 ? 1 : 0;
       if (level.size() + splittable > static_cast<size_t>(n_coarse) || splittable == 0) break;
-      std::vector<Cluster> next(level.size() * 2);
-      parallel_for(level.size(), [&](size_t i) { split_cluster(pv, level[i], next[2 * i], next[2 * i + 1]); });
+      std::vector<RangeCluster> next(level.size() * 2);
+      // (the first levels have fewer clusters than cores: the cores go into the selection of each cluster)
+      const unsigned inner = static_cast<unsigned>(std::max<size_t>(1, hardware_threads() / level.size()));
+      parallel_for(level.size(), [&](size_t i) {
+        split_range_cluster(items.data(), dim, level[i], next[2 * i], next[2 * i + 1], inner);
+      });
       level.clear();
       for (auto& c : next)
-        if (!c.idx.empty()) level.push_back(std::move(c));
+        if (c.size()) level.push_back(c);
     }
     // Last, partial level: the largest boxes are split first until the target count is reached.
     std::vector<size_t> order(level.size());
@@ -201,10 +388,11 @@ int plt_ras_choose_coarse_points(const double* a_points, int dim, const int64_t*
     const size_t need = static_cast<size_t>(n_coarse) - level.size();
     std::vector<size_t> to_split;
     for (size_t k = 0; k < order.size() && to_split.size() < need; ++k)
-      if (level[order[k]].idx.size() > 1) to_split.push_back(order[k]);
-    std::vector<Cluster> children(to_split.size() * 2);
-    parallel_for(to_split.size(),
-                 [&](size_t i) { split_cluster(pv, level[to_split[i]], children[2 * i], children[2 * i + 1]); });
+      if (level[order[k]].size() > 1) to_split.push_back(order[k]);
+    std::vector<RangeCluster> children(to_split.size() * 2);
+    parallel_for(to_split.size(), [&](size_t i) {
+      split_range_cluster(items.data(), dim, level[to_split[i]], children[2 * i], children[2 * i + 1]);
+    });
     std::vector<char> was_split(level.size(), 0);
     for (size_t i : to_split) was_split[i] = 1;
     int64_t w = 0;
@@ -227,69 +415,84 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
                            int64_t n_poly, int64_t max_leaf, double overlap_quota, plt_ras_domains** out) {
   if (!a_points || !idcs || !out || dim < 1 || dim > 3 || max_leaf < 2) return PLT_ERR_INVALID;
   try {
-    const PointsView pv{a_points, dim};
-    struct Dom {
-      std::vector<int64_t> idx;
-      std::vector<uint8_t> inner;
+    // compact items again (see Item): coordinates, index and the ownership flag side by side
+    struct DItem {
+      double x[3];
+      int64_t i;
+      uint8_t inner;
     };
-    std::vector<Dom> level(1), leaves;
-    level[0].idx.assign(idcs, idcs + n_idcs);
-    level[0].inner.assign(n_idcs, 1);
+    struct DBuf {  // (uninitialised storage: its pages are first touched by the threads that fill it)
+      std::unique_ptr<DItem[]> p;
+      size_t n = 0;
+      void alloc(size_t m) {
+        p.reset(new DItem[m]);
+        n = m;
+      }
+      size_t size() const { return n; }
+      DItem* data() { return p.get(); }
+      const DItem* data() const { return p.get(); }
+      DItem& operator[](size_t k) { return p[k]; }
+      const DItem& operator[](size_t k) const { return p[k]; }
+    };
+    struct Dom {
+      DBuf it;
+    };
+    std::vector<Dom> level(1), leaf_items;
+    level[0].it.alloc(n_idcs);
+    parallel_for(16, [&](size_t t) {
+      const int64_t lo = n_idcs * static_cast<int64_t>(t) / 16, hi = n_idcs * static_cast<int64_t>(t + 1) / 16;
+      for (int64_t k = lo; k < hi; ++k) {
+        DItem& d = level[0].it[k];
+        d.x[0] = d.x[1] = d.x[2] = 0.0;
+        for (int a = 0; a < dim; ++a) d.x[a] = a_points[idcs[k] * dim + a];
+        d.i = idcs[k];
+        d.inner = 1;
+      }
+    });
     while (!level.empty()) {
       std::vector<Dom> next(level.size() * 2);
       std::vector<char> is_leaf(level.size(), 0);
+      const unsigned inner_threads = static_cast<unsigned>(std::max<size_t>(1, hardware_threads() / level.size()));
       parallel_for(level.size(), [&](size_t i) {
         Dom& d = level[i];
-        const int64_t n = static_cast<int64_t>(d.idx.size());
+        const int64_t n = static_cast<int64_t>(d.it.size());
         if (n <= max_leaf) {
           is_leaf[i] = 1;
           return;
         }
-        const BoxInfo b = box_of(pv, d.idx.data(), d.idx.size());
+        const BoxInfo b = box_of_items(d.it.data(), d.it.size(), dim, inner_threads);
         // domain_divider.hpp:209-225 with unit multiplicities
         const double q = overlap_quota * static_cast<double>(max_leaf) / static_cast<double>(n);
         const int64_t n_sub = static_cast<int64_t>(round_half_to_even((1.0 + q) / 2.0 * static_cast<double>(n)));
         const int64_t left_part = n - n_sub, right_part = n_sub;
         const int64_t mid = static_cast<int64_t>(round_half_to_even(static_cast<double>(left_part + right_part) / 2.0));
         {
-          // order (index, inner) pairs by rank classes [0, left_part) [left_part, mid) [mid, right_part) [right_part, n)
-          std::vector<int64_t> perm(n);
-          std::iota(perm.begin(), perm.end(), 0);
+          // rank classes [0, left_part) [left_part, mid) [mid, right_part) [right_part, n): selections, not a sort
           const std::array<int, 3> axes = b.axes;
-          auto less = [&](int64_t x, int64_t y) {
-            const double *p = pv.row(d.idx[x]), *q = pv.row(d.idx[y]);
+          auto less = [&](const DItem& p, const DItem& r) {
             for (int k = 0; k < dim; ++k) {
               const int a = axes[k];
-              if (p[a] != q[a]) return p[a] < q[a];
+              if (p.x[a] != r.x[a]) return p.x[a] < r.x[a];
             }
-            return d.idx[x] < d.idx[y];
+            return p.i < r.i;
           };
-          size_t lo = 0;
-          for (int64_t r : {left_part, mid, right_part}) {
-            if (static_cast<size_t>(r) > lo && r < n) std::nth_element(perm.begin() + lo, perm.begin() + r, perm.end(), less);
-            lo = std::max<size_t>(lo, static_cast<size_t>(std::min<int64_t>(r, n)));
-          }
-          std::vector<int64_t> idx2(n);
-          std::vector<uint8_t> in2(n);
-          for (int64_t k = 0; k < n; ++k) {
-            idx2[k] = d.idx[perm[k]];
-            in2[k] = d.inner[perm[k]];
-          }
-          d.idx.swap(idx2);
-          d.inner.swap(in2);
+          parallel_select(d.it.data(), static_cast<size_t>(n),
+                          {static_cast<size_t>(left_part), static_cast<size_t>(mid), static_cast<size_t>(right_part)}, less,
+                          inner_threads);
         }
         Dom &l = next[2 * i], &r = next[2 * i + 1];
-        l.idx.assign(d.idx.begin(), d.idx.begin() + right_part);
-        l.inner.resize(right_part);
-        for (int64_t k = 0; k < right_part; ++k) l.inner[k] = d.inner[k] && k < mid;
-        r.idx.assign(d.idx.begin() + left_part, d.idx.end());
-        r.inner.resize(n - left_part);
-        for (int64_t k = left_part; k < n; ++k) r.inner[k - left_part] = d.inner[k] && k >= mid;
+        l.it.alloc(right_part);
+        parallel_copy(d.it.data(), static_cast<size_t>(right_part), l.it.data(), inner_threads);
+        for (int64_t k = mid; k < right_part; ++k) l.it[k].inner = 0;
+        r.it.alloc(n - left_part);
+        parallel_copy(d.it.data() + left_part, static_cast<size_t>(n - left_part), r.it.data(), inner_threads);
+        for (int64_t k = left_part; k < mid; ++k) r.it[k - left_part].inner = 0;
+        d.it.p.reset();
       });
       std::vector<Dom> keep;
       for (size_t i = 0; i < level.size(); ++i) {
         if (is_leaf[i]) {
-          leaves.push_back(std::move(level[i]));
+          leaf_items.push_back(std::move(level[i]));
         } else {
           keep.push_back(std::move(next[2 * i]));
           keep.push_back(std::move(next[2 * i + 1]));
@@ -297,10 +500,24 @@ int plt_ras_divide_domains(const double* a_points, int dim, const int64_t* idcs,
       }
       level.swap(keep);
     }
+    struct Leaf {
+      std::vector<int64_t> idx;
+      std::vector<uint8_t> inner;
+    };
+    std::vector<Leaf> leaves(leaf_items.size());
+    parallel_for(leaf_items.size(), [&](size_t i) {
+      const auto& src = leaf_items[i].it;
+      leaves[i].idx.resize(src.size());
+      leaves[i].inner.resize(src.size());
+      for (size_t k = 0; k < src.size(); ++k) {
+        leaves[i].idx[k] = src[k].i;
+        leaves[i].inner[k] = src[k].inner;
+      }
+    });
     // merge_poly_points: points sorted by index, the poly points first (inner flag carried over)
     std::vector<int64_t> poly_v(poly, poly + n_poly);
     parallel_for(leaves.size(), [&](size_t i) {
-      Dom& d = leaves[i];
+      Leaf& d = leaves[i];
       const size_t n = d.idx.size();
       std::vector<size_t> perm(n);
       std::iota(perm.begin(), perm.end(), 0);
